@@ -1,0 +1,133 @@
+/*
+ * univst_b200 -- C ABI of the B200 (sm_100a) kernels behind UniVST's three-branch DDIM denoising hot path.
+ *
+ * The reference (QuanjianSong/UniVST) is pure Python on top of torch/diffusers: it has no FFI of its own.
+ * Every entry point below therefore names the reference *Python call site* it replaces (file:line relative to
+ * the reference checkout); INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every function returns 0 (UNIVST_OK) or a negative error code and never throws;
+ *     univst_last_error() returns a human-readable message for the last failure on the calling thread;
+ *   - all tensor pointers are DEVICE pointers owned by the caller, fp16 unless the name says otherwise,
+ *     16-byte aligned; activations are frames-major / channels-last: [images, H, W, C] == [tokens, C];
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - no global mutable state besides a per-process cache of device properties: thread-compatible.
+ */
+#ifndef UNIVST_B200_H_
+#define UNIVST_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UNIVST_OK 0
+#define UNIVST_ERR_INVALID (-1)  /* bad argument / unsupported shape */
+#define UNIVST_ERR_CUDA (-2)     /* a CUDA runtime / driver call failed */
+#define UNIVST_ERR_NO_DEVICE (-3)/* not running on an sm_100 device */
+
+#define UNIVST_ABI_VERSION 1
+
+int univst_abi_version(void);
+const char* univst_last_error(void);
+/* 0 when the current device is compute capability 10.x, UNIVST_ERR_NO_DEVICE otherwise. */
+int univst_device_check(void);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused epilogue of the tensor-core GEMM / implicit-GEMM convolution:
+ *   y = (acc + bias[col] + rowvec[row / rows_per_group][col] + residual[row][col]) * out_scale
+ *   geglu != 0 : the weight rows were interleaved per tile so that each BN-wide tile holds BN/2 value columns
+ *                followed by BN/2 gate columns; y = (val + bias) * gelu_erf(gate + bias), N_out = N / 2
+ *   bias2      : y = fp16(y) + bias2[col]   (the algebraically dead temporal attention of the SD backbone,
+ *                models/attention.py:331-346 -- to_out weight is zero so it reduces to its bias)
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct univst_epilogue {
+  const void* bias;     /* fp16 [N] or NULL */
+  const void* rowvec;   /* fp16 [M / rows_per_group, rowvec_ld] or NULL (time-embedding projection per branch) */
+  int32_t rows_per_group;
+  int32_t rowvec_ld;    /* row stride of rowvec in halves */
+  int32_t act;          /* 1: y = silu(fp16(y)) (time-embedding MLP, unet_3d_condition.py:359-365, resnet.py:355) */
+  const void* residual; /* fp16 [M, ldr] or NULL */
+  int32_t ldr;
+  const void* bias2;    /* fp16 [N_out] or NULL */
+  int32_t geglu;
+  float out_scale;      /* 1 / output_scale_factor (resnet.py:392) */
+} univst_epilogue_t;
+
+/* D[M, N_out] = epilogue( [A | A2][M, K] * W[N, K]^T ).  A covers K columns [0, K1), A2 (optional) [K1, K):
+ * the skip-connection concat of the up blocks (unet_3d_blocks.py:523) is folded into the K loop.
+ * Replaces nn.Linear / 1x1 PseudoConv3d call sites: attention.py:123,127,141,143 (proj_in/out),
+ * pnp_utils.py:39-43,97 and attention.py:375-377,425 (to_q/k/v/out), diffusers FeedForward (attention.py:329),
+ * resnet.py:390 (conv_shortcut). */
+int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32_t lda2, int32_t K1, const void* W, int32_t M,
+                    int32_t N, int32_t K, void* D, int32_t ldd, const univst_epilogue_t* ep, void* stream);
+
+/* Y[NB*H*W, Cout] = epilogue( conv3x3(X, Wt[Cout, 3, 3, C1 + C2], padding 1) ), H x W = OUTPUT size (powers of two).
+ * Implicit GEMM: the 9 taps are 4-D TMA boxes over the NHWC activation with out-of-bounds zero fill (no im2col).
+ *   stride 1: X is [NB, H, W, C1]; X2 (optional) is [NB, H, W, C2] -- the skip-connection concat of the up blocks
+ *             (unet_3d_blocks.py:523,618) is folded into the K loop, the concatenated tensor never exists.
+ *   stride 2: X holds the four input parity planes [4 = (row parity, col parity)][NB, H, W, C1] produced by
+ *             univst_space_to_depth2 (downsamplers, resnet.py:216, padding 1).
+ * Replaces PseudoConv3d.forward (resnet.py:57-80; the temporal Conv1d is a Dirac identity and is skipped). */
+int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int32_t W, int32_t C1, int32_t C2,
+                       const void* Wt, int32_t Cout, int32_t stride, void* Y, int32_t ldy,
+                       const univst_epilogue_t* ep, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Fused sparse-causal attention: O[img] = softmax(Q[img] K^T / sqrt(d)) V, where the K/V sequence of image `img` is
+ * the concatenation of the K/V of the images kv_src[img * nsrc + 0 .. nsrc) (never materialised: every KV tile is a
+ * TMA box over the source image).  Q: [NI * N, ldq] with head h at columns [h d, (h+1) d); K, V: [NIkv * Nkv, ldkv].
+ * kv_src is a DEVICE int32 array.  Replaces pnp_utils.py:59-92 (patched attn1, sources [max(f-1,0), 0]),
+ * models/attention.py:384-420 (stock SparseCausalAttention, sources [max(f-1,0), f, 0]) and the cross-attention
+ * SDPA of attention.py:316-323 (one shared 77-token source).
+ * ---------------------------------------------------------------------------------------------------------- */
+int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
+                            int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const int32_t* kv_src,
+                            int32_t nsrc, void* O, int32_t ldo, void* stream);
+
+/* AdaIN-guided attention shift of the edit branch, in place on the fused [3 F N, ld] = [Q | K | V] buffer
+ * (branch-major: 0 content, 1 style, 2 edit).  Replaces pnp_utils.py:47-57 + attention_adain :114-125. */
+int64_t univst_attn_shift_workspace_bytes(int32_t F, int32_t C);
+int univst_attn_shift_f16(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t C, float alpha, float beta, float gamma,
+                          void* workspace, void* stream);
+
+/* GroupNorm(+SiLU) over [NB, rows, C1 + C2] channels-last (second source optional = skip-connection concat):
+ * statistics per (batch, group) over rows x channels-per-group.  resnet.py:338,369 / unet_3d_condition.py:439
+ * (NB = branches, rows = F H W: statistics span the frames) and attention.py:121 (NB = images, rows = H W). */
+int64_t univst_groupnorm_workspace_bytes(int32_t NB, int32_t groups);
+int univst_groupnorm_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
+                         int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu, void* Y,
+                         void* workspace, void* stream);
+/* LayerNorm over the last axis of [rows, C] (attention.py:290,312,329). */
+int univst_layernorm_f16(const void* X, int32_t rows, int32_t C, const void* gamma, const void* beta, float eps, void* Y,
+                         void* stream);
+
+/* Nearest x2 upsample of [NB, H, W, C] (resnet.py:145) and the parity-plane rearrangement feeding the stride-2 conv. */
+int univst_upsample2x_f16(const void* X, int32_t NB, int32_t H, int32_t W, int32_t C, void* Y, void* stream);
+int univst_space_to_depth2_f16(const void* X, int32_t NB, int32_t Ho, int32_t Wo, int32_t C, void* Y, void* stream);
+
+/* (B, C, F, hw) latents <-> channels-last [(b f) hw, Cpad] (Z: HOST array of B device pointers). */
+int univst_pack_latents_f16(const void* const* Z, int32_t B, int32_t C, int32_t F, int32_t HW, int32_t Cpad, void* out,
+                            void* stream);
+int univst_unpack_latents_f16(const void* X, int32_t ld, int32_t B, int32_t C, int32_t F, int32_t HW, void* Y,
+                              void* stream);
+/* diffusers Timesteps(dim, flip_sin_to_cos=True, freq_shift=0) for B fp32 timesteps (unet_3d_condition.py:359). */
+int univst_timestep_embedding_f16(const float* t, int32_t B, int32_t dim, void* out, void* stream);
+
+/* Per-step latent arithmetic of video_style_transfer (stable_diffusion.py:687-704, :761) on (C, F, hw) fp16 latents. */
+int univst_mask_resize_u8(const uint8_t* mask, int32_t F, int32_t Hin, int32_t Win, int32_t Hout, int32_t Wout,
+                          void* out, void* stream);
+int univst_latent_blend_f16(const void* a, const void* b, const void* mask, int32_t C, int32_t F, int32_t HW, void* out,
+                            void* stream);
+int univst_latent_adain_f16(const void* cnt, const void* sty, int32_t C, int32_t F, int32_t HW, void* out, void* stream);
+/* DDIM step, eta = 0 (diffusers DDIMScheduler.step) and, with the alphas swapped, next_step of
+ * inversion_tools/ddim_inversion.py:190-204.  eps is read from the channels-last conv_out buffer of `branch`. */
+int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t ld, int32_t branch, int32_t C, int32_t F,
+                         int32_t HW, float alpha_t, float alpha_prev, void* z_out, void* x0_out, void* stream);
+int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n, void* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UNIVST_B200_H_ */

@@ -1,0 +1,360 @@
+// Fused sparse-causal attention for sm_100a: O = softmax(Q K^T / sqrt(d)) V with the K/V sequence of an image
+// being the concatenation of the K/V of up to three *source frames* (previous / self / first).  The concat
+// is never materialised: each KV tile is a TMA box addressed through a per-image source table, so the same
+// kernel serves the patched attn1 of the reference (pnp_utils.py:59-92, KV = [prev, first]), the stock
+// SparseCausalAttention (models/attention.py:384-420, KV = [prev, self, first]), plain self-attention and the
+// 77-token cross-attention (attention.py:316-323; one shared K/V "image").
+//
+// Structure (FlashAttention-4 style, one CTA per (q-tile group, head, image)):
+//   warp 0        TMA producer: Q tiles once, K and V tiles through two 2-deep rings
+//   warp 1        tcgen05.mma issuer: S = Q K^T into a TMEM slot, O += P V with P read from shared memory
+//   warps 2..     softmax groups of 128 threads, one thread per query row: TMEM -> registers, running max with
+//                 lazy (thresholded) rescale of the TMEM-resident O, exp2, fp16 P tile written 128B-swizzled
+//   NQ = 2: two query tiles per CTA ping-pong on the tensor pipe (slot = q tile);
+//   NQ = 1: one query tile, the two S slots alternate between consecutive KV tiles.
+// Head dims that are not multiples of 64 (SD-1.5: 40 / 80 / 160) are zero-filled by TMA out-of-bounds
+// handling; nothing is padded in global memory.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace uv {
+
+struct AttnParams {
+  int NI;        // images (query side)
+  int H;         // heads
+  int d;         // true head dim
+  int N;         // query tokens per image
+  int Nkv;       // key tokens per source image
+  int nsrc;      // sources per image
+  const int* kv_src;  // [NI][nsrc] image index into the K/V tensors
+  __half* O;     // [NI*N][ldo]
+  int ldo;
+  float scale_log2;  // d^-0.5 * log2(e)
+};
+
+static constexpr uint32_t kSlotCols = 128;  // TMEM columns per S slot
+static constexpr uint32_t kOBase = 256;     // TMEM column of the first O accumulator
+static constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 before a forced rescale
+
+template <int NQ, int BKV>
+struct AttnSmem {
+  static constexpr int kQChunkBytes = 128 * 128;      // [128 rows][64 halves]
+  static constexpr int kKVChunkBytes = BKV * 128;     // [BKV rows][64 halves]
+  static constexpr int kPBytes = 128 * BKV * 2;       // [128 rows][BKV halves] as BKV/64 swizzled chunks
+};
+
+template <int NQ, int BKV>
+__global__ void __launch_bounds__(64 + 128 * NQ, 1)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  using L = AttnSmem<NQ, BKV>;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+
+  const int dch = (p.d + 63) >> 6;                    // 64-column chunks of the head dim
+  const int dpad = (p.d + 15) & ~15;                  // head dim rounded to the UMMA K / N granularity
+  const uint32_t q_bytes = (uint32_t)dch * L::kQChunkBytes;        // one Q tile
+  const uint32_t kv_bytes = (uint32_t)dch * L::kKVChunkBytes;      // one K (or V) tile
+  uint8_t* sQ = smem;                                  // [NQ][dch][128][64]
+  uint8_t* sK = sQ + NQ * q_bytes;                     // [2][dch][BKV][64]
+  uint8_t* sV = sK + 2 * kv_bytes;                     // [2][dch][BKV][64]
+  uint8_t* sP = sV + 2 * kv_bytes;                     // [2][BKV/64][128][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * L::kPBytes);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* p_full = bars + 11;       // 2
+  uint64_t* o_done = bars + 13;       // NQ (<= 2)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int qt0 = blockIdx.x * NQ;     // first 128-row query tile of this CTA
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int tps = (p.Nkv + BKV - 1) / BKV;   // KV tiles per source
+  const int T = p.nsrc * tps;                // KV tiles in total
+  const int I = T * NQ;                      // work items (q, j), q fastest
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&o_done[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t opad = (uint32_t)dpad;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer
+      mbar_expect_tx(q_full, NQ * q_bytes);
+      for (int q = 0; q < NQ; ++q)
+        for (int c = 0; c < dch; ++c)
+          tma_load_4d(sQ + q * q_bytes + c * L::kQChunkBytes, &tmQ, q_full, c * 64, head, (qt0 + q) * 128, img);
+      const int* src = p.kv_src + (size_t)img * p.nsrc;
+      uint32_t phase = 0;
+      for (int j = 0; j < T; ++j) {
+        const int s = j & 1;
+        const int simg = src[j / tps];
+        const int row0 = (j % tps) * BKV;
+        mbar_wait(&k_empty[s], phase ^ 1);
+        mbar_expect_tx(&k_full[s], kv_bytes);
+        for (int c = 0; c < dch; ++c)
+          tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &tmK, &k_full[s], c * 64, head, row0, simg);
+        mbar_wait(&v_empty[s], phase ^ 1);
+        mbar_expect_tx(&v_full[s], kv_bytes);
+        for (int c = 0; c < dch; ++c)
+          tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &tmV, &v_full[s], c * 64, head, row0, simg);
+        if (s == 1) phase ^= 1;
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer
+      const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
+      const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
+      auto issue_s = [&](int i) {
+        const int q = i % NQ, j = i / NQ, ks = j & 1, slot = i & 1;
+        if (q == 0) {
+          mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
+          tc_fence_after();
+        }
+        const uint32_t qa = smem_u32(sQ + q * q_bytes);
+        const uint32_t ka = smem_u32(sK + ks * kv_bytes);
+        int step = 0;
+        for (int c = 0; c < dch; ++c) {
+          const int nk = min(64, dpad - c * 64) >> 4;
+          const uint64_t da = make_smem_desc_sw128(qa + c * L::kQChunkBytes, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(ka + c * L::kKVChunkBytes, 16, 1024);
+          for (int k = 0; k < nk; ++k, ++step)
+            umma_f16_ss(tmem_base + slot * kSlotCols, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s,
+                        step ? 1u : 0u);
+        }
+        if (q == NQ - 1) tc_commit(&k_empty[ks]);
+        tc_commit(&s_full[slot]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int i = 0; i < I; ++i) {
+        if (i + 1 < I) issue_s(i + 1);
+        const int q = i % NQ, j = i / NQ, vs = j & 1, slot = i & 1;
+        // P of item i is the (i/2)-th use of its slot
+        mbar_wait(&p_full[slot], (uint32_t)((i >> 1) & 1));
+        if (q == 0) mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP + slot * L::kPBytes);
+        const uint32_t va = smem_u32(sV + vs * kv_bytes);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          // A: P chunk (k / 4), 32-byte step inside the swizzle row.  B: V, 16 keys = 2 KiB further down;
+          // the next 64 head-dim columns are a whole chunk away (LBO).
+          const uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(va + k * 2048, L::kKVChunkBytes, 1024);
+          umma_f16_ss(tmem_base + kOBase + q * opad, da, db, idesc_o, (j | k) ? 1u : 0u);
+        }
+        if (q == NQ - 1) tc_commit(&v_empty[vs]);
+        tc_commit(&o_done[q]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax groups
+    const int g = (int)(warp - 2) >> 2;                 // group index (== q tile when NQ == 2)
+    const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
+    const uint32_t r = quad * 32 + lane;                // row inside the 128-row tile
+    const uint32_t lane_off = (quad * 32) << 16;
+    const uint32_t o_addr = tmem_base + kOBase + g * opad + lane_off;
+    float m_used = -INFINITY;   // max baked into O and l
+    float l = 0.0f;
+    for (int j = 0; j < T; ++j) {
+      const int i = j * NQ + g;
+      const int slot = i & 1;
+      mbar_wait(&s_full[slot], (uint32_t)((i >> 1) & 1));
+      tc_fence_after();
+      float s[BKV];
+      {
+        const uint32_t sa = tmem_base + slot * kSlotCols + lane_off;
+#pragma unroll
+        for (int c = 0; c < BKV / 32; ++c) {
+          uint32_t t[32];
+          tmem_ld32(sa + c * 32, t);
+          tc_wait_ld();
+#pragma unroll
+          for (int x = 0; x < 32; ++x) s[c * 32 + x] = __uint_as_float(t[x]) * p.scale_log2;
+        }
+      }
+      const int valid = min(BKV, p.Nkv - (j % tps) * BKV);
+      if (valid < BKV) {
+#pragma unroll
+        for (int x = 0; x < BKV; ++x)
+          if (x >= valid) s[x] = -INFINITY;
+      }
+      float mx = s[0];
+#pragma unroll
+      for (int x = 1; x < BKV; ++x) mx = fmaxf(mx, s[x]);
+      // previous P V of this query tile must have landed before O may be touched / P slot reused
+      if (j > 0) {
+        mbar_wait(&o_done[g], (uint32_t)((j - 1) & 1));
+        tc_fence_after();
+      }
+      const bool need = mx > m_used + kRescaleThreshold;   // first tile: m_used = -inf -> always true
+      if (__any_sync(0xffffffffu, need)) {
+        const float m_new = fmaxf(m_used, mx);
+        if (j > 0) {
+          const float alpha = exp2f(m_used - m_new);       // lanes that did not need it: alpha <= 1, harmless
+          l *= alpha;
+          for (uint32_t c = 0; c < opad; c += 16) {
+            uint32_t t[16];
+            tmem_ld16(o_addr + c, t);
+            tc_wait_ld();
+#pragma unroll
+            for (int x = 0; x < 16; ++x) t[x] = __float_as_uint(__uint_as_float(t[x]) * alpha);
+            tmem_st16(o_addr + c, t);
+          }
+          tc_wait_st();
+        }
+        m_used = m_new;
+      }
+      // P = exp2(s - m_used), fp16, written as swizzled K-major chunks: chunk kc holds keys [64 kc, 64 kc + 64)
+      uint8_t* prow = sP + slot * L::kPBytes + r * 128;
+      float lsum = 0.0f;
+#pragma unroll
+      for (int c16 = 0; c16 < BKV / 8; ++c16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          const float e0 = exp2f(s[c16 * 8 + 2 * x] - m_used);
+          const float e1 = exp2f(s[c16 * 8 + 2 * x + 1] - m_used);
+          lsum += e0 + e1;
+          w[x] = pack_half2(e0, e1);
+        }
+        const int kc = c16 >> 3, cc = c16 & 7;
+        *reinterpret_cast<uint4*>(prow + kc * (128 * 128) + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+      l += lsum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[slot]);
+    }
+    // ------------------------------------------------------------------ epilogue: O / l -> global
+    mbar_wait(&o_done[g], (uint32_t)((T - 1) & 1));
+    tc_fence_after();
+    const float inv_l = 1.0f / l;
+    const int qrow = (qt0 + g) * 128 + (int)r;
+    const bool row_ok = qrow < p.N;
+    __half* orow = p.O + ((size_t)img * p.N + qrow) * p.ldo + head * p.d;
+    for (uint32_t c = 0; c < opad; c += 16) {
+      uint32_t t[16];
+      tmem_ld16(o_addr + c, t);
+      tc_wait_ld();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        const int col = (int)c + h8 * 8;
+        if (col < p.d) {
+          uint32_t w[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x)
+            w[x] = pack_half2(__uint_as_float(t[h8 * 8 + 2 * x]) * inv_l, __uint_as_float(t[h8 * 8 + 2 * x + 1]) * inv_l);
+          *reinterpret_cast<uint4*>(orow + col) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NQ, int BKV>
+static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                       cudaStream_t stream) {
+  using L = AttnSmem<NQ, BKV>;
+  const int dch = (p.d + 63) / 64;
+  const size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes + 2 * L::kPBytes +
+                      16 * sizeof(uint64_t) + 1024;
+  UV_REQUIRE(smem <= 227 * 1024, "attention: tile configuration needs %zu bytes of shared memory", smem);
+  static bool configured = false;
+  if (!configured) {
+    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       227 * 1024));
+    configured = true;
+  }
+  dim3 grid((p.N + 128 * NQ - 1) / (128 * NQ), p.H, p.NI);
+  attention_tc_kernel<NQ, BKV><<<grid, 64 + 128 * NQ, smem, stream>>>(tq, tk, tv, p);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+}  // namespace uv
+
+using namespace uv;
+
+extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv,
+                                       int32_t NI, int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv,
+                                       const int32_t* kv_src, int32_t nsrc, void* O, int32_t ldo, void* stream) {
+  UV_REQUIRE(Q && K && V && O && kv_src, "sc_attention: null pointer");
+  UV_REQUIRE(NI > 0 && NIkv > 0 && H > 0 && N > 0 && Nkv > 0 && nsrc > 0, "sc_attention: empty shape");
+  UV_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "sc_attention: head dim must be a multiple of 8 in [8, 192]");
+  UV_REQUIRE(ldq % 8 == 0 && ldkv % 8 == 0 && ldo % 8 == 0, "sc_attention: row strides must be multiples of 8");
+  UV_REQUIRE(((uintptr_t)Q | (uintptr_t)K | (uintptr_t)V | (uintptr_t)O) % 16 == 0, "sc_attention: 16-byte alignment");
+  AttnParams p{};
+  p.NI = NI;
+  p.H = H;
+  p.d = d;
+  p.N = N;
+  p.Nkv = Nkv;
+  p.nsrc = nsrc;
+  p.kv_src = kv_src;
+  p.O = (__half*)O;
+  p.ldo = ldo;
+  p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+
+  const int bkv = (d <= 64) ? 128 : 64;
+  CUtensorMap tq, tk, tv;
+  {
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)N, (uint64_t)NI};
+    uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ldq * 2, (uint64_t)N * ldq * 2};
+    uint32_t box[4] = {64, 1, 128, 1};
+    int r = make_tmap_f16(&tq, Q, 4, dims, str, box, true);
+    if (r) return r;
+  }
+  {
+    uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)Nkv, (uint64_t)NIkv};
+    uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ldkv * 2, (uint64_t)Nkv * ldkv * 2};
+    uint32_t box[4] = {64, 1, (uint32_t)bkv, 1};
+    int r = make_tmap_f16(&tk, K, 4, dims, str, box, true);
+    if (r) return r;
+    r = make_tmap_f16(&tv, V, 4, dims, str, box, true);
+    if (r) return r;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d <= 64) return launch_attn<2, 128>(tq, tk, tv, p, st);
+  if (d <= 128) return launch_attn<2, 64>(tq, tk, tv, p, st);
+  return launch_attn<1, 64>(tq, tk, tv, p, st);
+}

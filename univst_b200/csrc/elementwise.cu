@@ -1,0 +1,298 @@
+// Small HBM-bound kernels around the UNet: resampling of channels-last activations, latent pack / unpack
+// between the reference's (B, 4, F, h, w) layout and the kernels' [(b f), h, w, C], the sinusoidal timestep
+// embedding, and the per-step latent arithmetic of the denoising loop (mask blend, late latent AdaIN, DDIM step).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace uv {
+
+// ---------------------------------------------------------------------------------------------- resampling
+// nearest x2 upsample, NHWC (resnet.py:145, F.interpolate(scale_factor=2, mode="nearest"))
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int NB, int H, int W, int nvec) {
+  const size_t total = (size_t)NB * 4 * H * W * nvec;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    size_t t = i / nvec;
+    const int ox = (int)(t % (2 * W));
+    t /= 2 * W;
+    const int oy = (int)(t % (2 * H));
+    const int n = (int)(t / (2 * H));
+    y[i] = __ldg(x + (((size_t)n * H + (oy >> 1)) * W + (ox >> 1)) * nvec + v);
+  }
+}
+
+// [NB, 2H, 2W, C] -> four parity planes [(row parity, col parity)][NB, H, W, C] (input of the stride-2 conv)
+__global__ void space_to_depth2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int NB, int H, int W,
+                                       int nvec) {
+  const size_t plane = (size_t)NB * H * W * nvec;
+  const size_t total = plane * 4;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int v = (int)(i % nvec);
+    size_t t = i / nvec;
+    const int ix = (int)(t % (2 * W));
+    t /= 2 * W;
+    const int iy = (int)(t % (2 * H));
+    const int n = (int)(t / (2 * H));
+    const int p = (iy & 1) * 2 + (ix & 1);
+    y[p * plane + (((size_t)n * H + (iy >> 1)) * W + (ix >> 1)) * nvec + v] = __ldg(x + i);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- latents
+struct PackSrc {
+  const __half* z[4];
+};
+// out[(b f), hw, Cpad] = z_b[c, f, hw] (c < C), zero elsewhere
+__global__ void pack_latents_kernel(PackSrc src, int B, int C, int F, int HW, int Cpad, __half* __restrict__ out) {
+  const size_t total = (size_t)B * F * HW * Cpad;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i % Cpad);
+    size_t t = i / Cpad;
+    const int hw = (int)(t % HW);
+    t /= HW;
+    const int f = (int)(t % F);
+    const int b = (int)(t / F);
+    out[i] = (c < C) ? src.z[b][((size_t)c * F + f) * HW + hw] : __float2half(0.0f);
+  }
+}
+
+// y[b, c, f, hw] = x[(b f) hw, c]  (x row stride ld)
+__global__ void unpack_latents_kernel(const __half* __restrict__ x, int ld, int B, int C, int F, int HW,
+                                      __half* __restrict__ y) {
+  const size_t total = (size_t)B * C * F * HW;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int hw = (int)(i % HW);
+    size_t t = i / HW;
+    const int f = (int)(t % F);
+    t /= F;
+    const int c = (int)(t % C);
+    const int b = (int)(t / C);
+    y[i] = x[(((size_t)b * F + f) * HW + hw) * ld + c];
+  }
+}
+
+// Timesteps(dim, flip_sin_to_cos=True, freq_shift=0): out[b] = [cos(t f_k) | sin(t f_k)], f_k = exp(-ln(1e4) k / half)
+__global__ void timestep_embedding_kernel(const float* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+  const int half_dim = dim / 2;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < B * half_dim; i += gridDim.x * blockDim.x) {
+    const int b = i / half_dim, k = i % half_dim;
+    const float freq = expf(-logf(10000.0f) * (float)k / (float)half_dim);
+    const float e = t[b] * freq;
+    out[(size_t)b * dim + k] = __float2half_rn(cosf(e));
+    out[(size_t)b * dim + half_dim + k] = __float2half_rn(sinf(e));
+  }
+}
+
+// bilinear (align_corners=False, no antialias) resize of a {0,1} mask, u8 [F, Hin, Win] -> fp16 [F, Hout, Wout]
+// (stable_diffusion.py:689 F.interpolate(mask, size=latent, mode='bilinear'); load_mask src/util.py:133-144 maps
+// any non-zero pixel to 1 through its uint8 * 255 wrap-around)
+__global__ void mask_resize_kernel(const uint8_t* __restrict__ m, int F, int Hin, int Win, int Hout, int Wout,
+                                   __half* __restrict__ out) {
+  const float sy = (float)Hin / (float)Hout, sx = (float)Win / (float)Wout;
+  const int total = F * Hout * Wout;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int ox = i % Wout, oy = (i / Wout) % Hout, f = i / (Wout * Hout);
+    float fy = ((float)oy + 0.5f) * sy - 0.5f, fx = ((float)ox + 0.5f) * sx - 0.5f;
+    fy = fmaxf(fy, 0.0f);
+    fx = fmaxf(fx, 0.0f);
+    const int y0 = (int)fy, x0 = (int)fx;
+    const int y1 = min(y0 + 1, Hin - 1), x1 = min(x0 + 1, Win - 1);
+    const float ly = fy - (float)y0, lx = fx - (float)x0;
+    const uint8_t* p = m + (size_t)f * Hin * Win;
+    const float v00 = p[y0 * Win + x0] ? 1.0f : 0.0f, v01 = p[y0 * Win + x1] ? 1.0f : 0.0f;
+    const float v10 = p[y1 * Win + x0] ? 1.0f : 0.0f, v11 = p[y1 * Win + x1] ? 1.0f : 0.0f;
+    const float v = (1.0f - ly) * ((1.0f - lx) * v00 + lx * v01) + ly * ((1.0f - lx) * v10 + lx * v11);
+    out[i] = __float2half_rn(v);
+  }
+}
+
+// out = (1 - m) * a + m * b, m[f, hw] broadcast over the C channels of (C, F, HW) latents (stable_diffusion.py:692)
+__global__ void latent_blend_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                    const __half* __restrict__ m, int C, int FHW, __half* __restrict__ out) {
+  const int total = C * FHW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const float w = __half2float(m[i % FHW]);
+    out[i] = __float2half_rn((1.0f - w) * __half2float(a[i]) + w * __half2float(b[i]));
+  }
+}
+
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+  v = warp_sum(v);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  float r = 0.0f;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) r += sh[i];
+  return r;
+}
+
+// latent_adain (pnp_utils.py:128-139): out = IN_{F,H,W}(cnt) * std_s[c, f] + mean_s[c, f]; IN biased / eps 1e-5,
+// style statistics unbiased over (H, W) per (channel, frame).  One block per channel.
+__global__ void latent_adain_kernel(const __half* __restrict__ cnt, const __half* __restrict__ sty, int F, int HW,
+                                    __half* __restrict__ out) {
+  __shared__ float sh[32];
+  __shared__ float s_mean[64], s_std[64];
+  const int c = blockIdx.x;
+  const __half* x = cnt + (size_t)c * F * HW;
+  const __half* s = sty + (size_t)c * F * HW;
+  const int n = F * HW;
+  float a = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) a += __half2float(x[i]);
+  const float mean = block_sum(a, sh) / (float)n;
+  float q = 0.0f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float d = __half2float(x[i]) - mean;
+    q += d * d;
+  }
+  const float rstd = rsqrtf(block_sum(q, sh) / (float)n + 1e-5f);
+  for (int f = 0; f < F; ++f) {
+    float sa = 0.0f;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) sa += __half2float(s[(size_t)f * HW + i]);
+    const float sm = block_sum(sa, sh) / (float)HW;
+    float sq = 0.0f;
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      const float d = __half2float(s[(size_t)f * HW + i]) - sm;
+      sq += d * d;
+    }
+    const float sv = block_sum(sq, sh) / (float)(HW - 1);
+    if (threadIdx.x == 0) {
+      // the reference keeps the statistics as fp16 tensors
+      s_mean[f] = __half2float(__float2half_rn(sm));
+      s_std[f] = __half2float(__float2half_rn(sqrtf(sv)));
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int f = i / HW;
+    const float v = __half2float(__float2half_rn((__half2float(x[i]) - mean) * rstd));
+    out[(size_t)c * n + i] = __float2half_rn(v * s_std[f] + s_mean[f]);
+  }
+}
+
+// DDIM step (eta = 0): x0 = (z - sqrt(1 - a_t) eps) / sqrt(a_t); z' = sqrt(a_p) x0 + sqrt(1 - a_p) eps.
+// The same kernel is the inversion step with (a_t, a_p) swapped in meaning (ddim_inversion.py:190-204).
+// eps is read straight from the channels-last conv_out buffer of the chosen branch.
+__global__ void ddim_step_kernel(const __half* __restrict__ z, const __half* __restrict__ eps_nhwc, int ld,
+                                 int branch_row0, int C, int F, int HW, float c_x0_z, float c_x0_e, float c_p_x0,
+                                 float c_p_e, __half* __restrict__ z_out, __half* __restrict__ x0_out) {
+  const int total = C * F * HW;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int hw = i % HW, f = (i / HW) % F, c = i / (HW * F);
+    const float e = __half2float(eps_nhwc[((size_t)branch_row0 + (size_t)f * HW + hw) * ld + c]);
+    const float x0 = c_x0_z * __half2float(z[i]) - c_x0_e * e;
+    if (x0_out) x0_out[i] = __float2half_rn(x0);
+    z_out[i] = __float2half_rn(c_p_x0 * x0 + c_p_e * e);
+  }
+}
+
+__global__ void axpby_kernel(const __half* __restrict__ a, const __half* __restrict__ b, float wa, float wb, int n,
+                             __half* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    out[i] = __float2half_rn(wa * __half2float(a[i]) + wb * __half2float(b[i]));
+}
+
+static inline int grid_for(size_t total, int threads) {
+  size_t b = (total + threads - 1) / threads;
+  const size_t cap = (size_t)num_sms() * 16;
+  return (int)(b < cap ? (b ? b : 1) : cap);
+}
+
+}  // namespace uv
+
+using namespace uv;
+
+extern "C" int univst_upsample2x_f16(const void* X, int32_t NB, int32_t H, int32_t W, int32_t C, void* Y, void* stream) {
+  UV_REQUIRE(X && Y && NB > 0 && H > 0 && W > 0 && C % 8 == 0, "upsample2x: bad arguments");
+  const size_t total = (size_t)NB * 4 * H * W * (C / 8);
+  upsample2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)X, (uint4*)Y, NB, H, W, C / 8);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_space_to_depth2_f16(const void* X, int32_t NB, int32_t Ho, int32_t Wo, int32_t C, void* Y,
+                                          void* stream) {
+  UV_REQUIRE(X && Y && NB > 0 && Ho > 0 && Wo > 0 && C % 8 == 0, "space_to_depth2: bad arguments");
+  const size_t total = (size_t)NB * 4 * Ho * Wo * (C / 8);
+  space_to_depth2_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const uint4*)X, (uint4*)Y, NB, Ho, Wo,
+                                                                               C / 8);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_pack_latents_f16(const void* const* Z, int32_t B, int32_t C, int32_t F, int32_t HW, int32_t Cpad,
+                                       void* out, void* stream) {
+  UV_REQUIRE(Z && out && B > 0 && B <= 4 && C > 0 && C <= Cpad, "pack_latents: bad arguments");
+  PackSrc src{};
+  for (int b = 0; b < B; ++b) {
+    UV_REQUIRE(Z[b], "pack_latents: null latent");
+    src.z[b] = (const __half*)Z[b];
+  }
+  const size_t total = (size_t)B * F * HW * Cpad;
+  pack_latents_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(src, B, C, F, HW, Cpad, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_unpack_latents_f16(const void* X, int32_t ld, int32_t B, int32_t C, int32_t F, int32_t HW, void* Y,
+                                         void* stream) {
+  UV_REQUIRE(X && Y && B > 0 && C > 0 && C <= ld, "unpack_latents: bad arguments");
+  const size_t total = (size_t)B * C * F * HW;
+  unpack_latents_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)X, ld, B, C, F, HW,
+                                                                             (__half*)Y);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_timestep_embedding_f16(const float* t, int32_t B, int32_t dim, void* out, void* stream) {
+  UV_REQUIRE(t && out && B > 0 && dim % 2 == 0, "timestep_embedding: bad arguments");
+  timestep_embedding_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(t, B, dim, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_mask_resize_u8(const uint8_t* mask, int32_t F, int32_t Hin, int32_t Win, int32_t Hout,
+                                     int32_t Wout, void* out, void* stream) {
+  UV_REQUIRE(mask && out && F > 0 && Hin > 0 && Win > 0 && Hout > 0 && Wout > 0, "mask_resize: bad arguments");
+  mask_resize_kernel<<<grid_for((size_t)F * Hout * Wout, 256), 256, 0, (cudaStream_t)stream>>>(mask, F, Hin, Win, Hout,
+                                                                                              Wout, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_latent_blend_f16(const void* a, const void* b, const void* mask, int32_t C, int32_t F, int32_t HW,
+                                       void* out, void* stream) {
+  UV_REQUIRE(a && b && mask && out && C > 0 && F > 0 && HW > 0, "latent_blend: bad arguments");
+  latent_blend_kernel<<<grid_for((size_t)C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)a, (const __half*)b, (const __half*)mask, C, F * HW, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_latent_adain_f16(const void* cnt, const void* sty, int32_t C, int32_t F, int32_t HW, void* out,
+                                       void* stream) {
+  UV_REQUIRE(cnt && sty && out && C > 0 && F > 0 && F <= 64 && HW > 1, "latent_adain: bad arguments (F <= 64)");
+  latent_adain_kernel<<<C, 1024, 0, (cudaStream_t)stream>>>((const __half*)cnt, (const __half*)sty, F, HW, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t ld, int32_t branch, int32_t C, int32_t F,
+                                    int32_t HW, float alpha_t, float alpha_prev, void* z_out, void* x0_out,
+                                    void* stream) {
+  UV_REQUIRE(z && eps_nhwc && z_out && C > 0 && C <= ld && alpha_t > 0.0f && alpha_prev > 0.0f, "ddim_step: bad arguments");
+  const float sa = sqrtf(alpha_t), sb = sqrtf(1.0f - alpha_t);
+  ddim_step_kernel<<<grid_for((size_t)C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)z, (const __half*)eps_nhwc, ld, branch * F * HW, C, F, HW, 1.0f / sa, sb / sa, sqrtf(alpha_prev),
+      sqrtf(1.0f - alpha_prev), (__half*)z_out, (__half*)x0_out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n, void* out, void* stream) {
+  UV_REQUIRE(a && b && out && n > 0 && n < (1ll << 31), "axpby: bad arguments");
+  axpby_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, wa, wb,
+                                                                         (int)n, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}

@@ -1,0 +1,496 @@
+// tcgen05 GEMM / implicit-GEMM 3x3 convolution for sm_100a.
+//
+//   D[M, N_out] = epilogue( A[M, K] * W[N, K]^T )        fp16 operands, fp32 accumulation in TMEM
+//
+// One CTA owns one 128 x BN output tile.  Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM
+// allocator + tcgen05.mma issuer (one lane), warps 2..5 = epilogue (TMEM -> registers -> global).
+// Operand tiles are 128B-swizzled K-major [rows][64 halves]; the A tile of the convolution is a 4-D TMA
+// box over the NHWC activation shifted by the filter tap, with out-of-bounds zero fill standing in for
+// the padding -- no im2col buffer exists.  The skip-connection concat of the UNet up blocks is a second
+// tensor map consumed by the same K loop.
+//
+// Reference call sites replaced: see include/univst_b200.h (univst_gemm_f16 / univst_conv3x3_f16).
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace uv {
+
+static constexpr int kBM = 128;   // rows per tile (UMMA_M, cta_group::1)
+static constexpr int kBK = 64;    // halves per k-block = one 128-byte swizzle row
+static constexpr int kThreads = 192;
+
+struct GemmParams {
+  int M, N, N_out, BN;
+  int num_kb;           // k-blocks of 64
+  int mode;             // 0 = linear A[M,K]; 1 = conv taps over NHWC
+  int kb_split;         // linear: first k-block served by A2; conv: channel blocks per tap served by A (cbs1)
+  int K1;               // linear: K columns in A; conv: channels in A (C1)
+  int cbs;              // conv: channel blocks per tap (cbs1 + cbs2)
+  int Cin;              // conv: total input channels (weight K index = tap * Cin + channel)
+  int HW, W;            // conv: output pixels per image, output width (== box width)
+  int plane_stride;     // conv: images per parity plane (stride-2 input was rearranged into 4 planes)
+  int8_t tap_dy[9], tap_dx[9], tap_plane[9];
+  int stages;
+  // epilogue
+  const __half* bias;
+  const __half* rowvec;
+  int rows_per_group;
+  int rowvec_ld;
+  int act;              // 1: SiLU applied to the fp16-rounded result
+  const __half* residual;
+  int ldr;
+  const __half* bias2;
+  int geglu;
+  float out_scale;
+  __half* D;
+  int ldd;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [stages][A 16 KB | B BN*128 B], then barriers
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t a_bytes = kBM * kBK * 2;
+  const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int tile_m = blockIdx.x;
+  const int tile_n = blockIdx.y;
+  const int m0 = tile_m * kBM;
+  const int n0 = tile_n * p.BN;
+
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmA2);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------ TMA producer
+      int cn = 0, cy = 0;
+      if (p.mode == 1) {
+        cn = m0 / p.HW;
+        cy = (m0 % p.HW) / p.W;
+      }
+      uint32_t phase = 0;
+      int s = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[s], phase ^ 1);
+        uint8_t* sa = smem + (size_t)s * stage_bytes;
+        uint8_t* sb = sa + a_bytes;
+        mbar_expect_tx(&full_bar[s], stage_bytes);
+        int kw;  // K coordinate into the weight matrix
+        if (p.mode == 0) {
+          kw = kb * kBK;
+          if (kb < p.kb_split)
+            tma_load_2d(sa, &tmA, &full_bar[s], kb * kBK, m0);
+          else
+            tma_load_2d(sa, &tmA2, &full_bar[s], kb * kBK - p.K1, m0);
+        } else {
+          const int tap = kb / p.cbs;
+          const int cb = kb - tap * p.cbs;
+          const int x = p.tap_dx[tap], y = cy + p.tap_dy[tap], n = cn + p.tap_plane[tap] * p.plane_stride;
+          if (cb < p.kb_split) {
+            kw = tap * p.Cin + cb * kBK;
+            tma_load_4d(sa, &tmA, &full_bar[s], cb * kBK, x, y, n);
+          } else {
+            kw = tap * p.Cin + p.K1 + (cb - p.kb_split) * kBK;
+            tma_load_4d(sa, &tmA2, &full_bar[s], (cb - p.kb_split) * kBK, x, y, n);
+          }
+        }
+        tma_load_2d(sb, &tmB, &full_bar[s], kw, n0);
+        if (++s == p.stages) {
+          s = 0;
+          phase ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------ MMA issuer
+      const uint32_t idesc = make_idesc_f16(kBM, (uint32_t)p.BN, 0, 0);
+      uint32_t phase = 0;
+      int s = 0;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&full_bar[s], phase);
+        tc_fence_after();
+        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t sb = sa + a_bytes;
+        const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+          umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+        }
+        tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        if (++s == p.stages) {
+          s = 0;
+          phase ^= 1;
+        }
+      }
+      tc_commit(tmem_full_bar);
+    }
+  } else {
+    // -------------------------------------------------- epilogue warps 2..5 (TMEM lane quadrant = warp % 4)
+    const uint32_t q = warp & 3;
+    const int row = m0 + (int)(q * 32 + lane);
+    mbar_wait(tmem_full_bar, 0);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + ((q * 32) << 16);
+    const bool row_ok = row < p.M;
+    const __half* rv = (p.rowvec && row_ok) ? p.rowvec + (size_t)(row / p.rows_per_group) * p.rowvec_ld : nullptr;
+    const __half* res = (p.residual && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
+    __half* drow = p.D + (size_t)row * p.ldd;
+
+    if (!p.geglu) {
+      for (int c0 = 0; c0 < p.BN; c0 += 32) {
+        if (n0 + c0 >= p.N_out) break;  // warp-uniform
+        uint32_t acc[32];
+        tmem_ld32(taddr + c0, acc);
+        tc_wait_ld();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n0 + c0 + g * 8;
+          if (n >= p.N_out) break;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+          if (n + 8 <= p.N_out) {
+            if (p.bias) {
+              const uint4 b = *reinterpret_cast<const uint4*>(p.bias + n);
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(bw[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (rv) {
+              const uint4 b = *reinterpret_cast<const uint4*>(rv + n);
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(bw[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (res) {
+              const uint4 b = *reinterpret_cast<const uint4*>(res + n);
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(bw[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j] * p.out_scale, v[2 * j + 1] * p.out_scale);
+            if (p.act) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 y = unpack_half2(o[j]);
+                o[j] = pack_half2(y.x / (1.0f + __expf(-y.x)), y.y / (1.0f + __expf(-y.y)));
+              }
+            }
+            if (p.bias2) {
+              const uint4 b = *reinterpret_cast<const uint4*>(p.bias2 + n);
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(bw[j]);
+                float2 y = unpack_half2(o[j]);
+                o[j] = pack_half2(y.x + f.x, y.y + f.y);
+              }
+            }
+            *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+            for (int j = 0; j < 8 && n + j < p.N_out; ++j) {
+              float x = v[j];
+              if (p.bias) x += __half2float(p.bias[n + j]);
+              if (rv) x += __half2float(rv[n + j]);
+              if (res) x += __half2float(res[n + j]);
+              __half y = __float2half_rn(x * p.out_scale);
+              if (p.act) {
+                const float yf = __half2float(y);
+                y = __float2half_rn(yf / (1.0f + __expf(-yf)));
+              }
+              if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(p.bias2[n + j]));
+              drow[n + j] = y;
+            }
+          }
+        }
+      }
+    } else {
+      // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates (weights packed that way).
+      const int half_bn = p.BN >> 1;
+      const int no0 = tile_n * half_bn;
+      for (int c0 = 0; c0 < half_bn; c0 += 32) {
+        if (no0 + c0 >= p.N_out) break;
+        uint32_t av[32], ag[32];
+        tmem_ld32(taddr + c0, av);
+        tmem_ld32(taddr + half_bn + c0, ag);
+        tc_wait_ld();
+        if (!row_ok) continue;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int c = c0 + g * 8;
+          const int n = no0 + c;
+          if (n >= p.N_out) break;
+          float v[8], gt[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            v[j] = __uint_as_float(av[g * 8 + j]);
+            gt[j] = __uint_as_float(ag[g * 8 + j]);
+            if (p.bias) {
+              v[j] += __half2float(p.bias[n0 + c + j]);
+              gt[j] += __half2float(p.bias[n0 + half_bn + c + j]);
+            }
+            // the reference rounds the projection to fp16 before h * gelu(gate)
+            v[j] = __half2float(__float2half_rn(v[j]));
+            gt[j] = __half2float(__float2half_rn(gt[j]));
+            v[j] = v[j] * __half2float(__float2half_rn(gelu_erf(gt[j])));
+          }
+          if (n + 8 <= p.N_out) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+            *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+            for (int j = 0; j < 8 && n + j < p.N_out; ++j) drow[n + j] = __float2half_rn(v[j]);
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------------------
+static int pick_bn(int N, int geglu) {
+  if (geglu) return (N % 256 == 0) ? 256 : 128;
+  if (N <= 32) return 32;
+  if (N <= 64) return 64;
+  if (N % 256 == 0) return 256;
+  if (N % 160 == 0) return 160;
+  if (N % 128 == 0) return 128;
+  if (N % 96 == 0) return 96;
+  if (N % 64 == 0) return 64;
+  return 128;
+}
+
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, GemmParams& p,
+                  cudaStream_t stream) {
+  const uint32_t stage_bytes = kBM * kBK * 2 + (uint32_t)p.BN * kBK * 2;
+  // up to two co-resident CTAs per SM when the tile is narrow, so one CTA's epilogue hides behind the other's MMAs
+  const uint32_t budget = (p.BN <= 160) ? 108 * 1024 : 200 * 1024;
+  int stages = (int)(budget / stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages > p.num_kb) stages = p.num_kb;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  static size_t configured = 0;
+  if (smem > configured) {
+    UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = 227 * 1024;
+  }
+  dim3 grid((p.M + kBM - 1) / kBM, (p.N + p.BN - 1) / p.BN);
+  gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+static void fill_epilogue(GemmParams& p, const univst_epilogue_t* ep) {
+  p.bias = p.rowvec = p.residual = p.bias2 = nullptr;
+  p.rows_per_group = 1;
+  p.rowvec_ld = 0;
+  p.act = 0;
+  p.ldr = 0;
+  p.geglu = 0;
+  p.out_scale = 1.0f;
+  if (ep) {
+    p.bias = (const __half*)ep->bias;
+    p.rowvec = (const __half*)ep->rowvec;
+    p.rows_per_group = ep->rows_per_group > 0 ? ep->rows_per_group : 1;
+    p.rowvec_ld = ep->rowvec_ld;
+    p.act = ep->act;
+    p.residual = (const __half*)ep->residual;
+    p.ldr = ep->ldr;
+    p.bias2 = (const __half*)ep->bias2;
+    p.geglu = ep->geglu;
+    p.out_scale = ep->out_scale != 0.0f ? ep->out_scale : 1.0f;
+  }
+}
+
+}  // namespace uv
+
+using namespace uv;
+
+extern "C" int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32_t lda2, int32_t K1, const void* W,
+                               int32_t M, int32_t N, int32_t K, void* D, int32_t ldd, const univst_epilogue_t* ep,
+                               void* stream) {
+  UV_REQUIRE(A && W && D && M > 0 && N > 0 && K > 0, "gemm: null pointer or empty shape");
+  UV_REQUIRE(lda % 8 == 0 && K % 8 == 0 && ldd % 8 == 0, "gemm: lda, K, ldd must be multiples of 8 (16-byte rows)");
+  UV_REQUIRE(!A2 || (K1 % kBK == 0 && K1 > 0 && K1 < K && lda2 % 8 == 0), "gemm: K1 must be a multiple of 64");
+  GemmParams p{};
+  fill_epilogue(p, ep);
+  UV_REQUIRE(!p.geglu || N % 128 == 0, "gemm: GEGLU needs N %% 128 == 0");
+  UV_REQUIRE(!p.residual || p.ldr % 8 == 0, "gemm: residual ld must be a multiple of 8");
+  p.M = M;
+  p.N = N;
+  p.BN = pick_bn(N, p.geglu);
+  p.N_out = p.geglu ? N / 2 : N;
+  p.mode = 0;
+  p.K1 = A2 ? K1 : K;
+  p.num_kb = (K + kBK - 1) / kBK;
+  p.kb_split = A2 ? K1 / kBK : p.num_kb;
+  p.D = (__half*)D;
+  p.ldd = ldd;
+
+  CUtensorMap tmA, tmA2, tmB;
+  {
+    uint64_t dims[2] = {(uint64_t)p.K1, (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda * 2};
+    uint32_t box[2] = {kBK, kBM};
+    int r = make_tmap_f16(&tmA, A, 2, dims, str, box, true);
+    if (r) return r;
+  }
+  if (A2) {
+    uint64_t dims[2] = {(uint64_t)(K - K1), (uint64_t)M};
+    uint64_t str[1] = {(uint64_t)lda2 * 2};
+    uint32_t box[2] = {kBK, kBM};
+    int r = make_tmap_f16(&tmA2, A2, 2, dims, str, box, true);
+    if (r) return r;
+  } else {
+    tmA2 = tmA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
+    uint64_t str[1] = {(uint64_t)K * 2};
+    uint32_t box[2] = {kBK, (uint32_t)p.BN};
+    int r = make_tmap_f16(&tmB, W, 2, dims, str, box, true);
+    if (r) return r;
+  }
+  return launch(tmA, tmA2, tmB, p, (cudaStream_t)stream);
+}
+
+extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int32_t W, int32_t C1,
+                                  int32_t C2, const void* Wt, int32_t Cout, int32_t stride, void* Y, int32_t ldy,
+                                  const univst_epilogue_t* ep, void* stream) {
+  UV_REQUIRE(X && Wt && Y && NB > 0 && Cout > 0 && C1 > 0, "conv3x3: null pointer or empty shape");
+  UV_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
+  UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && ldy % 8 == 0, "conv3x3: channel counts and ldy must be multiples of 8");
+  UV_REQUIRE(!X2 || C1 % kBK == 0, "conv3x3: with a second source, C1 must be a multiple of 64");
+  UV_REQUIRE(stride == 1 || !X2, "conv3x3: stride 2 takes a single (parity-plane) source");
+  // output geometry; for stride 2 the caller passes the 4 parity planes [4][NB][H/2][W/2][C] and H, W of the OUTPUT
+  const int Ho = H, Wo = W;
+  UV_REQUIRE((Wo & (Wo - 1)) == 0 && Wo <= 128 && (Ho & (Ho - 1)) == 0, "conv3x3: H and W must be powers of two, W <= 128");
+  GemmParams p{};
+  fill_epilogue(p, ep);
+  UV_REQUIRE(!p.geglu, "conv3x3: no GEGLU epilogue");
+  const int Cin = C1 + (X2 ? C2 : 0);
+  p.M = NB * Ho * Wo;
+  p.N = Cout;
+  p.N_out = Cout;
+  p.BN = pick_bn(Cout, 0);
+  p.mode = 1;
+  p.K1 = C1;
+  p.Cin = Cin;
+  const int cbs1 = (C1 + kBK - 1) / kBK;
+  const int cbs2 = X2 ? (C2 + kBK - 1) / kBK : 0;
+  p.kb_split = cbs1;
+  p.cbs = cbs1 + cbs2;
+  p.num_kb = 9 * p.cbs;
+  p.HW = Ho * Wo;
+  p.W = Wo;
+  p.plane_stride = NB;
+  for (int ky = 0; ky < 3; ++ky)
+    for (int kx = 0; kx < 3; ++kx) {
+      const int t = ky * 3 + kx;
+      if (stride == 1) {
+        p.tap_dy[t] = (int8_t)(ky - 1);
+        p.tap_dx[t] = (int8_t)(kx - 1);
+        p.tap_plane[t] = 0;
+      } else {
+        // input row 2*oy + ky - 1: ky=0 -> odd row of pair oy-1; ky=1 -> even row of pair oy; ky=2 -> odd row of pair oy
+        const int hp = (ky == 1) ? 0 : 1, wp = (kx == 1) ? 0 : 1;
+        p.tap_dy[t] = (int8_t)(ky == 0 ? -1 : 0);
+        p.tap_dx[t] = (int8_t)(kx == 0 ? -1 : 0);
+        p.tap_plane[t] = (int8_t)(hp * 2 + wp);
+      }
+    }
+  p.D = (__half*)Y;
+  p.ldd = ldy;
+
+  const int bw = Wo;
+  const int bh = (Ho * Wo >= kBM) ? kBM / bw : Ho;
+  const int bn = kBM / (bw * bh);
+  const int planes = (stride == 2) ? 4 : 1;
+  CUtensorMap tmA, tmA2, tmB;
+  {
+    uint64_t dims[4] = {(uint64_t)C1, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NB * planes};
+    uint64_t str[3] = {(uint64_t)C1 * 2, (uint64_t)C1 * Wo * 2, (uint64_t)C1 * Wo * Ho * 2};
+    uint32_t box[4] = {kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    int r = make_tmap_f16(&tmA, X, 4, dims, str, box, true);
+    if (r) return r;
+  }
+  if (X2) {
+    uint64_t dims[4] = {(uint64_t)C2, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)NB};
+    uint64_t str[3] = {(uint64_t)C2 * 2, (uint64_t)C2 * Wo * 2, (uint64_t)C2 * Wo * Ho * 2};
+    uint32_t box[4] = {kBK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
+    int r = make_tmap_f16(&tmA2, X2, 4, dims, str, box, true);
+    if (r) return r;
+  } else {
+    tmA2 = tmA;
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
+    uint64_t str[1] = {(uint64_t)9 * Cin * 2};
+    uint32_t box[2] = {kBK, (uint32_t)p.BN};
+    int r = make_tmap_f16(&tmB, Wt, 2, dims, str, box, true);
+    if (r) return r;
+  }
+  return launch(tmA, tmA2, tmB, p, (cudaStream_t)stream);
+}

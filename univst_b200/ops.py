@@ -1,0 +1,305 @@
+"""Tensor-facing wrappers over the C ABI (``include/univst_b200.h``).
+
+PyTorch is used for device memory and streams only: every function takes CUDA fp16 tensors, passes raw
+pointers / sizes / the current stream through ctypes and returns the output tensor.  Activations are
+channels-last: ``[images, H, W, C]`` viewed as ``[tokens, C]``.  Nothing here falls back to PyTorch math.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import Epilogue, check
+
+_vp, _i32, _f32, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
+_lib.register("univst_sc_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp])
+_lib.register("univst_attn_shift_workspace_bytes", [_i32, _i32], _i64)
+_lib.register("univst_attn_shift_f16", [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp])
+_lib.register("univst_groupnorm_workspace_bytes", [_i32, _i32], _i64)
+_lib.register("univst_groupnorm_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp])
+_lib.register("univst_layernorm_f16", [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp])
+_lib.register("univst_upsample2x_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_space_to_depth2_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_pack_latents_f16", [C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_unpack_latents_f16", [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_timestep_embedding_f16", [_vp, _i32, _i32, _vp, _vp])
+_lib.register("univst_mask_resize_u8", [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_latent_blend_f16", [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_latent_adain_f16", [_vp, _vp, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp])
+_lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
+
+# number of kernels launched through this module (bench.py reports it as ``gpu_launches``)
+launch_count = 0
+_LAUNCHES = {
+    "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 2, "layernorm": 1, "upsample2x": 1,
+    "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
+    "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1,
+}
+
+
+def _count(name):
+    global launch_count
+    launch_count += _LAUNCHES[name]
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _chk(t: torch.Tensor, name: str, dtype=torch.float16):
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise ValueError(f"{name}: expected a contiguous CUDA {dtype} tensor, got {t.dtype} {t.device} "
+                         f"contiguous={t.is_contiguous()}")
+
+
+def make_epilogue(bias=None, rowvec=None, rows_per_group=1, residual=None, bias2=None, geglu=False, out_scale=1.0,
+                  act=False) -> Epilogue:
+    ep = Epilogue()
+    ep.bias = _ptr(bias)
+    ep.rowvec = _ptr(rowvec)
+    ep.rows_per_group = rows_per_group
+    ep.rowvec_ld = rowvec.stride(0) if rowvec is not None else 0
+    ep.act = 1 if act else 0
+    ep.residual = _ptr(residual)
+    ep.ldr = residual.stride(0) if residual is not None else 0
+    ep.bias2 = _ptr(bias2)
+    ep.geglu = 1 if geglu else 0
+    ep.out_scale = out_scale
+    return ep
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         bias=None, rowvec=None, rows_per_group=1, residual=None, bias2=None, geglu=False, out_scale=1.0, act=False):
+    """``out[M, N_out] = epilogue([a | a2] @ w.T)``; ``a``/``a2``/``residual``/``out`` may be row-strided 2-D views."""
+    _lib.require_device()
+    M, K1 = a.shape
+    K = K1 + (a2.shape[1] if a2 is not None else 0)
+    N = w.shape[0]
+    assert w.shape[1] == K and w.is_contiguous() and a.stride(1) == 1
+    n_out = N // 2 if geglu else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    ep = make_epilogue(bias, rowvec, rows_per_group, residual, bias2, geglu, out_scale, act)
+    check(_lib.lib().univst_gemm_f16(a.data_ptr(), a.stride(0), _ptr(a2), a2.stride(0) if a2 is not None else 0, K1,
+                                     w.data_ptr(), M, N, K, out.data_ptr(), out.stride(0), C.byref(ep), _stream()),
+          "univst_gemm_f16")
+    _count("gemm")
+    return out
+
+
+def conv3x3(x: torch.Tensor, w: torch.Tensor, *, x2: Optional[torch.Tensor] = None, stride: int = 1,
+            out: Optional[torch.Tensor] = None, bias=None, rowvec=None, rows_per_group=1, residual=None,
+            out_scale=1.0):
+    """3x3 conv, padding 1.  ``x``: [NB, H, W, C1] (stride 1) or the parity planes [4, NB, H/2, W/2, C1] from
+    :func:`space_to_depth2` (stride 2); ``w``: [Cout, 3, 3, C1 + C2] flattened to [Cout, 9 (C1 + C2)]."""
+    _lib.require_device()
+    _chk(x, "x")
+    if stride == 1:
+        NB, H, W, C1 = x.shape
+    else:
+        _, NB, H, W, C1 = x.shape
+    C2 = x2.shape[-1] if x2 is not None else 0
+    Cout = w.shape[0]
+    assert w.is_contiguous() and w.numel() == Cout * 9 * (C1 + C2)
+    if out is None:
+        out = torch.empty((NB * H * W, Cout), dtype=torch.float16, device=x.device)
+    ep = make_epilogue(bias, rowvec, rows_per_group, residual, None, False, out_scale)
+    check(_lib.lib().univst_conv3x3_f16(x.data_ptr(), _ptr(x2), NB, H, W, C1, C2, w.data_ptr(), Cout, stride,
+                                        out.data_ptr(), out.stride(0), C.byref(ep), _stream()), "univst_conv3x3_f16")
+    _count("conv3x3")
+    return out
+
+
+def sc_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: torch.Tensor, *, NI: int, NIkv: int, H: int,
+                 d: int, N: int, Nkv: int, out: Optional[torch.Tensor] = None):
+    """``q``: [NI*N, >= H*d] (row-strided view), ``k``/``v``: [NIkv*Nkv, .] views sharing one row stride;
+    ``kv_src``: int32 CUDA [NI, nsrc] source-image table."""
+    _lib.require_device()
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1 and k.stride(0) == v.stride(0)
+    assert kv_src.dtype == torch.int32 and kv_src.is_cuda and kv_src.is_contiguous() and kv_src.shape[0] == NI
+    if out is None:
+        out = torch.empty((NI * N, H * d), dtype=torch.float16, device=q.device)
+    check(_lib.lib().univst_sc_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), NI, NIkv,
+                                             H, d, N, Nkv, kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(),
+                                             out.stride(0), _stream()), "univst_sc_attention_f16")
+    _count("sc_attention")
+    return out
+
+
+_workspaces = {}
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    key = (device, torch.cuda.current_stream().cuda_stream)
+    ws = _workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _workspaces[key] = ws
+    return ws
+
+
+def attn_shift_(qkv: torch.Tensor, F: int, N: int, C_: int, alpha: float, beta: float, gamma: float):
+    """In-place AdaIN-guided shift of the edit branch of the fused [3 F N, 3 C] projection buffer."""
+    _lib.require_device()
+    _chk(qkv, "qkv")
+    assert qkv.shape[0] == 3 * F * N
+    ws = _workspace(_lib.lib().univst_attn_shift_workspace_bytes(F, C_), qkv.device)
+    check(_lib.lib().univst_attn_shift_f16(qkv.data_ptr(), qkv.stride(0), F, N, C_, alpha, beta, gamma, ws.data_ptr(),
+                                           _stream()), "univst_attn_shift_f16")
+    _count("attn_shift")
+    return qkv
+
+
+def groupnorm(x1: torch.Tensor, gamma, beta, *, NB: int, rows: int, groups: int = 32, eps: float = 1e-5,
+              silu: bool = False, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
+    _lib.require_device()
+    _chk(x1, "x1")
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    if out is None:
+        out = torch.empty((NB * rows, C1 + C2), dtype=torch.float16, device=x1.device)
+    ws = _workspace(_lib.lib().univst_groupnorm_workspace_bytes(NB, groups), x1.device)
+    check(_lib.lib().univst_groupnorm_f16(x1.data_ptr(), _ptr(x2), C1, C2, NB, rows, groups, gamma.data_ptr(),
+                                          beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
+                                          _stream()), "univst_groupnorm_f16")
+    _count("groupnorm")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, out: Optional[torch.Tensor] = None):
+    _lib.require_device()
+    _chk(x, "x")
+    rows, C_ = x.shape
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().univst_layernorm_f16(x.data_ptr(), rows, C_, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
+                                          _stream()), "univst_layernorm_f16")
+    _count("layernorm")
+    return out
+
+
+def upsample2x(x: torch.Tensor):
+    _lib.require_device()
+    _chk(x, "x")
+    NB, H, W, C_ = x.shape
+    out = torch.empty((NB, 2 * H, 2 * W, C_), dtype=torch.float16, device=x.device)
+    check(_lib.lib().univst_upsample2x_f16(x.data_ptr(), NB, H, W, C_, out.data_ptr(), _stream()), "univst_upsample2x_f16")
+    _count("upsample2x")
+    return out
+
+
+def space_to_depth2(x: torch.Tensor):
+    _lib.require_device()
+    _chk(x, "x")
+    NB, H, W, C_ = x.shape
+    out = torch.empty((4, NB, H // 2, W // 2, C_), dtype=torch.float16, device=x.device)
+    check(_lib.lib().univst_space_to_depth2_f16(x.data_ptr(), NB, H // 2, W // 2, C_, out.data_ptr(), _stream()),
+          "univst_space_to_depth2_f16")
+    _count("space_to_depth2")
+    return out
+
+
+def pack_latents(zs, Cpad: int = 64):
+    """zs: list of B latents (C, F, h, w) (or (1, C, F, h, w)) -> [(b f), h, w, Cpad] zero-padded channels."""
+    _lib.require_device()
+    B = len(zs)
+    z0 = zs[0]
+    C_, F, h, w = z0.shape[-4:]
+    for z in zs:
+        _chk(z, "latent")
+    arr = (_vp * B)(*[z.data_ptr() for z in zs])
+    out = torch.empty((B * F, h, w, Cpad), dtype=torch.float16, device=z0.device)
+    check(_lib.lib().univst_pack_latents_f16(arr, B, C_, F, h * w, Cpad, out.data_ptr(), _stream()), "univst_pack_latents_f16")
+    _count("pack_latents")
+    return out
+
+
+def unpack_latents(x: torch.Tensor, B: int, C_: int, F: int, h: int, w: int):
+    """x: [(b f) h w, ld] channels-last rows -> (B, C, F, h, w)."""
+    _lib.require_device()
+    out = torch.empty((B, C_, F, h, w), dtype=torch.float16, device=x.device)
+    check(_lib.lib().univst_unpack_latents_f16(x.data_ptr(), x.stride(0), B, C_, F, h * w, out.data_ptr(), _stream()),
+          "univst_unpack_latents_f16")
+    _count("unpack_latents")
+    return out
+
+
+def timestep_embedding(t: torch.Tensor, dim: int):
+    _lib.require_device()
+    _chk(t, "t", torch.float32)
+    out = torch.empty((t.numel(), dim), dtype=torch.float16, device=t.device)
+    check(_lib.lib().univst_timestep_embedding_f16(t.data_ptr(), t.numel(), dim, out.data_ptr(), _stream()),
+          "univst_timestep_embedding_f16")
+    _count("timestep_embedding")
+    return out
+
+
+def mask_resize(mask_u8: torch.Tensor, h: int, w: int):
+    """mask_u8: [F, Hin, Win] uint8 (non-zero = inside) -> fp16 [F, h, w] bilinear, align_corners=False."""
+    _lib.require_device()
+    _chk(mask_u8, "mask", torch.uint8)
+    F, Hin, Win = mask_u8.shape
+    out = torch.empty((F, h, w), dtype=torch.float16, device=mask_u8.device)
+    check(_lib.lib().univst_mask_resize_u8(mask_u8.data_ptr(), F, Hin, Win, h, w, out.data_ptr(), _stream()),
+          "univst_mask_resize_u8")
+    _count("mask_resize")
+    return out
+
+
+def latent_blend(a, b, mask, out=None):
+    """(1 - m) * a + m * b on (.., C, F, h, w) latents, m: [F, h, w]."""
+    _lib.require_device()
+    _chk(a, "a"), _chk(b, "b"), _chk(mask, "mask")
+    C_, F, h, w = a.shape[-4:]
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.lib().univst_latent_blend_f16(a.data_ptr(), b.data_ptr(), mask.data_ptr(), C_, F, h * w, out.data_ptr(),
+                                             _stream()), "univst_latent_blend_f16")
+    _count("latent_blend")
+    return out
+
+
+def latent_adain(cnt, sty, out=None):
+    _lib.require_device()
+    _chk(cnt, "cnt"), _chk(sty, "sty")
+    C_, F, h, w = cnt.shape[-4:]
+    if out is None:
+        out = torch.empty_like(cnt)
+    check(_lib.lib().univst_latent_adain_f16(cnt.data_ptr(), sty.data_ptr(), C_, F, h * w, out.data_ptr(), _stream()),
+          "univst_latent_adain_f16")
+    _count("latent_adain")
+    return out
+
+
+def ddim_step(z, eps_rows, branch: int, alpha_t: float, alpha_prev: float, out=None, x0_out=None):
+    """z: (.., C, F, h, w); eps_rows: channels-last conv_out rows [(b f) h w, ld]."""
+    _lib.require_device()
+    _chk(z, "z")
+    C_, F, h, w = z.shape[-4:]
+    if out is None:
+        out = torch.empty_like(z)
+    check(_lib.lib().univst_ddim_step_f16(z.data_ptr(), eps_rows.data_ptr(), eps_rows.stride(0), branch, C_, F, h * w,
+                                          float(alpha_t), float(alpha_prev), out.data_ptr(), _ptr(x0_out), _stream()),
+          "univst_ddim_step_f16")
+    _count("ddim_step")
+    return out
+
+
+def axpby(a, b, wa: float, wb: float, out=None):
+    _lib.require_device()
+    _chk(a, "a"), _chk(b, "b")
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.lib().univst_axpby_f16(a.data_ptr(), b.data_ptr(), wa, wb, a.numel(), out.data_ptr(), _stream()),
+          "univst_axpby_f16")
+    _count("axpby")
+    return out
