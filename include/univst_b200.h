@@ -68,7 +68,7 @@ int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32_t lda2, in
  *   stride 1: X is [NB, H, W, C1]; X2 (optional) is [NB, H, W, C2] -- the skip-connection concat of the up blocks
  *             (unet_3d_blocks.py:523,618) is folded into the K loop, the concatenated tensor never exists.
  *   stride 2: X holds the four input parity planes [4 = (row parity, col parity)][NB, H, W, C1] produced by
- *             univst_space_to_depth2 (downsamplers, resnet.py:216, padding 1).
+ *             univst_space_to_depth2_f16 (downsamplers, resnet.py:216, padding 1).
  * Replaces PseudoConv3d.forward (resnet.py:57-80; the temporal Conv1d is a Dirac identity and is skipped). */
 int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int32_t W, int32_t C1, int32_t C2,
                        const void* Wt, int32_t Cout, int32_t stride, void* Y, int32_t ldy,

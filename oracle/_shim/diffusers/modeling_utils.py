@@ -1,0 +1,11 @@
+import torch
+
+
+class ModelMixin(torch.nn.Module):
+    @property
+    def dtype(self):
+        return next(self.parameters()).dtype
+
+    @property
+    def device(self):
+        return next(self.parameters()).device

@@ -1,0 +1,80 @@
+"""CPU tests: the oracle restatements against the golden vectors generated from the reference's own code
+(oracle/gen_golden.py; the reference ships no tests of its own), and host-side logic that needs no GPU."""
+import os
+
+import pytest
+import torch
+
+from oracle import unet_oracle as uo
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.fixture(scope="module")
+def unet_golden():
+    return torch.load(os.path.join(GOLDEN, "unet_tiny.pt"), weights_only=True)
+
+
+@pytest.fixture(scope="module")
+def tiny_sd(unet_golden):
+    return uo.seeded_state_dict(uo.TINY_CONFIG, seed=unet_golden["seed"])
+
+
+@pytest.mark.parametrize("case", ["stock_t981", "patched_idx0_t981", "patched_idx13_t721", "patched_idx25_t481",
+                                  "patched_idx26_t461"])
+def test_unet_oracle_matches_reference_module(unet_golden, tiny_sd, case):
+    """fp32, tolerance 5e-5 absolute on outputs of magnitude ~3 (reduction-order noise only)."""
+    g = unet_golden
+    t = int(case.split("_t")[-1])
+    patched = case.startswith("patched")
+    idx = int(case.split("idx")[1].split("_")[0]) if patched else None
+    with torch.no_grad():
+        y = uo.unet_forward(tiny_sd, uo.TINY_CONFIG, g["x"], t, g["ctx"], patched=patched, idx=idx)
+    ref = g["cases"][case]
+    assert y.shape == ref.shape
+    assert (y - ref).abs().max().item() < 5e-5
+
+
+def test_shift_is_live_in_the_goldens(unet_golden):
+    """idx 25 (shift on, beta = 0.1) and idx 26 (shift off) differ: the goldens really exercise the patch window."""
+    c = unet_golden["cases"]
+    assert (c["patched_idx0_t981"] - c["stock_t981"]).abs().max() > 1e-3
+
+
+def test_pnp_utils_goldens():
+    g = torch.load(os.path.join(GOLDEN, "pnp_utils.pt"), weights_only=True)
+    assert torch.allclose(uo.attention_adain(g["cnt"], g["sty"]), g["attention_adain"], atol=1e-6)
+    assert torch.allclose(uo.latent_adain(g["zc"], g["zs"]), g["latent_adain"], atol=1e-6)
+    a = g["attn1"]
+    sd = {"attn1." + k: v for k, v in a["weights"].items()}
+    for idx, ref in a["out"].items():
+        with torch.no_grad():
+            y = uo.sc_attention(sd, "attn1.", a["x"], a["heads"], a["F"], True, idx)
+        assert torch.allclose(y, ref, atol=2e-5), idx
+    # beta schedule: 0.9 at idx 0 -> 0.1 at idx 25, window closed at 26 (pnp_utils.py:47-50)
+    assert uo.shift_params(0)[2] == pytest.approx(0.9) and uo.shift_params(25)[2] == pytest.approx(0.1)
+    assert uo.shift_params(25)[0] and not uo.shift_params(26)[0]
+
+
+def test_frame_sources_clip_at_first_frame():
+    s = uo.frame_sources(4, [-1, 0, "first"])
+    assert [x.tolist() for x in s] == [[0, 0, 1, 2], [0, 1, 2, 3], [0, 0, 0, 0]]
+    from univst_b200.unet import kv_source_table
+    t = kv_source_table(2, 3, "prev_self_first")
+    assert t.tolist() == [[0, 0, 0], [0, 1, 0], [1, 2, 0], [3, 3, 3], [3, 4, 3], [4, 5, 3]]
+    assert kv_source_table(2, 2, "prev_first").tolist() == [[0, 0], [0, 0], [2, 2], [2, 2]]
+
+
+def test_library_exports_every_declared_symbol():
+    """The C-ABI library loads without a GPU and exports every function include/univst_b200.h declares."""
+    import re
+    from univst_b200 import _lib, build, ops  # noqa: F401  (ops registers its prototypes)
+    build.build()
+    lib = _lib.lib()
+    header = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "univst_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(univst_[a-z0-9_]+)\s*\(", header, re.M))
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert lib.univst_abi_version() == 1
+    assert set(_lib.PROTOTYPES) <= declared

@@ -421,7 +421,7 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
                                   const univst_epilogue_t* ep, void* stream) {
   UV_REQUIRE(X && Wt && Y && NB > 0 && Cout > 0 && C1 > 0, "conv3x3: null pointer or empty shape");
   UV_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
-  UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && ldy % 8 == 0, "conv3x3: channel counts and ldy must be multiples of 8");
+  UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && (ldy % 8 == 0 || Cout < 8), "conv3x3: channel counts and ldy must be multiples of 8");
   UV_REQUIRE(!X2 || C1 % kBK == 0, "conv3x3: with a second source, C1 must be a multiple of 64");
   UV_REQUIRE(stride == 1 || !X2, "conv3x3: stride 2 takes a single (parity-plane) source");
   // output geometry; for stride 2 the caller passes the 4 parity planes [4][NB][H/2][W/2][C] and H, W of the OUTPUT
