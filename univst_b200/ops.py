@@ -46,6 +46,43 @@ def _count(name):
     launch_count += _LAUNCHES[name]
 
 
+# Optional per-kernel device timing (bench.py): CUDA events recorded on the launching stream around selected kernels.
+_profile = None
+
+
+def profile_start(names):
+    """Start recording (start, end, meta) CUDA-event triples for the kernels in ``names`` (e.g. {"sc_attention"})."""
+    global _profile
+    _profile = {n: [] for n in names}
+
+
+def profile_stop():
+    """Stop recording; returns {name: [(milliseconds, meta), ...]} (synchronises)."""
+    global _profile
+    prof, _profile = _profile, None
+    torch.cuda.synchronize()
+    return {n: [(a.elapsed_time(b), meta) for a, b, meta in ev] for n, ev in (prof or {}).items()}
+
+
+class _Timed:
+    def __init__(self, name, meta):
+        self.rec = _profile.get(name) if _profile is not None else None
+        self.meta = meta
+
+    def __enter__(self):
+        if self.rec is not None:
+            self.a = torch.cuda.Event(enable_timing=True)
+            self.a.record()
+        return self
+
+    def __exit__(self, *exc):
+        if self.rec is not None:
+            b = torch.cuda.Event(enable_timing=True)
+            b.record()
+            self.rec.append((self.a, b, self.meta))
+        return False
+
+
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
 
@@ -89,9 +126,10 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
         out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
     assert out.shape == (M, n_out) and out.stride(1) == 1
     ep = make_epilogue(bias, rowvec, rows_per_group, residual, bias2, geglu, out_scale, act)
-    check(_lib.lib().univst_gemm_f16(a.data_ptr(), a.stride(0), _ptr(a2), a2.stride(0) if a2 is not None else 0, K1,
-                                     w.data_ptr(), M, N, K, out.data_ptr(), out.stride(0), C.byref(ep), _stream()),
-          "univst_gemm_f16")
+    with _Timed("gemm", (M, N, K)):
+        check(_lib.lib().univst_gemm_f16(a.data_ptr(), a.stride(0), _ptr(a2), a2.stride(0) if a2 is not None else 0, K1,
+                                         w.data_ptr(), M, N, K, out.data_ptr(), out.stride(0), C.byref(ep), _stream()),
+              "univst_gemm_f16")
     _count("gemm")
     return out
 
@@ -113,8 +151,9 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, x2: Optional[torch.Tensor] = No
     if out is None:
         out = torch.empty((NB * H * W, Cout), dtype=torch.float16, device=x.device)
     ep = make_epilogue(bias, rowvec, rows_per_group, residual, None, False, out_scale)
-    check(_lib.lib().univst_conv3x3_f16(x.data_ptr(), _ptr(x2), NB, H, W, C1, C2, w.data_ptr(), Cout, stride,
-                                        out.data_ptr(), out.stride(0), C.byref(ep), _stream()), "univst_conv3x3_f16")
+    with _Timed("conv3x3", (NB * H * W, Cout, 9 * (C1 + C2))):
+        check(_lib.lib().univst_conv3x3_f16(x.data_ptr(), _ptr(x2), NB, H, W, C1, C2, w.data_ptr(), Cout, stride,
+                                            out.data_ptr(), out.stride(0), C.byref(ep), _stream()), "univst_conv3x3_f16")
     _count("conv3x3")
     return out
 
@@ -128,9 +167,10 @@ def sc_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: torc
     assert kv_src.dtype == torch.int32 and kv_src.is_cuda and kv_src.is_contiguous() and kv_src.shape[0] == NI
     if out is None:
         out = torch.empty((NI * N, H * d), dtype=torch.float16, device=q.device)
-    check(_lib.lib().univst_sc_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), NI, NIkv,
-                                             H, d, N, Nkv, kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(),
-                                             out.stride(0), _stream()), "univst_sc_attention_f16")
+    with _Timed("sc_attention", (NI, H, d, N, Nkv * kv_src.shape[1])):
+        check(_lib.lib().univst_sc_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), NI,
+                                                 NIkv, H, d, N, Nkv, kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(),
+                                                 out.stride(0), _stream()), "univst_sc_attention_f16")
     _count("sc_attention")
     return out
 

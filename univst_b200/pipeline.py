@@ -1,0 +1,122 @@
+"""Mirror of ``SpatioTemporalStableDiffusionPipeline`` (backbones/video_diffusion_sd/pipelines/stable_diffusion.py:45)
+for the denoising loops on the hot path: ``video_style_transfer`` (:631-780) and ``reconstruction`` (:479-628).
+
+Same method names and keyword arguments.  What differs, deliberately:
+* the per-step ``torch.load`` of two latents and the re-decoding of 32 mask PNGs (:683-689) are hoisted out of the
+  loop: trajectories and the resized mask are loaded once and stay in HBM;
+* scheduler scalars are Python floats, so the loop never synchronises with the device;
+* while the AdaIN-guided shift is inactive (``idx > eta2 * 50``) the content and style branches cannot influence the
+  edit branch (every op is per-sample; their predictions are discarded at :712), so with ``skip_dead_branches=True``
+  only the edit branch is evaluated on those steps -- bit-identical edit output, 32 % fewer FLOPs;
+* the VAE / CLIP encoders are third-party networks whose weights are not available offline: ``prompt_embeds`` may be
+  passed directly and decoding happens only when a ``vae`` was supplied (``output.latents`` is always returned).
+"""
+from __future__ import annotations
+
+from types import SimpleNamespace
+from typing import List, Optional, Union
+
+import torch
+
+from . import ops
+from .pnp_utils import register_time
+from .scheduler import DDIMScheduler
+from .util import load_ddim_latents_at_t, load_mask
+
+
+class SpatioTemporalStableDiffusionPipeline:
+    def __init__(self, unet, scheduler: Optional[DDIMScheduler] = None, vae=None, text_encoder=None, tokenizer=None):
+        self.unet = unet
+        self.scheduler = scheduler or DDIMScheduler()
+        self.vae, self.text_encoder, self.tokenizer = vae, text_encoder, tokenizer
+        self.device = unet.device
+
+    # ------------------------------------------------------------------------------------------ helpers
+    def _encode_prompt(self, prompt, prompt_embeds=None):
+        if prompt_embeds is not None:
+            return prompt_embeds.to(self.device, torch.float16)
+        if self.text_encoder is None or self.tokenizer is None:
+            raise ValueError("no text encoder was given: pass prompt_embeds=(1, 77, D)")
+        ids = self.tokenizer([prompt], padding="max_length", max_length=self.tokenizer.model_max_length,
+                             truncation=True, return_tensors="pt").input_ids
+        return self.text_encoder(ids.to(self.device))[0].to(torch.float16)
+
+    def _trajectory(self, path_or_list, n):
+        """Latents x_0 .. x_n of an inversion: a directory of ``ddim_latents_{k}.pt`` or a list of tensors."""
+        if isinstance(path_or_list, (list, tuple)):
+            lat = list(path_or_list)
+        else:
+            lat = [load_ddim_latents_at_t(k, path_or_list) for k in range(1, n + 1)]
+            lat = [None] + lat
+        return [None if z is None else z.to(self.device, torch.float16).contiguous() for z in lat]
+
+    def _mask(self, mask, F, h, w):
+        if mask is None or (isinstance(mask, str) and not mask):
+            return None
+        m = load_mask(mask, n_frames=F) if isinstance(mask, str) else mask
+        m = m.reshape(-1, m.shape[-2], m.shape[-1])
+        return ops.mask_resize((m != 0).to(torch.uint8).to(self.device).contiguous(), h, w)
+
+    # ------------------------------------------------------------------------------------------ hot loop
+    @torch.no_grad()
+    def video_style_transfer(self, prompt: Union[str, List[str]], num_inference_steps: int = 50, latents=None,
+                             content_inv_path=None, style_inv_path=None, mask_path=None, prompt_embeds=None,
+                             output_type="tensor", skip_dead_branches: bool = False, callback=None, **kwargs):
+        """stable_diffusion.py:631-780.  ``content_inv_path`` / ``style_inv_path``: directory with the inversion's
+        ``ddim_latents_{k}.pt`` files (reference format) or an in-memory list [x_0 .. x_n]; ``mask_path``: directory
+        of ``%05d.png`` masks or a (F, H, W) tensor (non-zero = keep content)."""
+        n = num_inference_steps
+        emb = self._encode_prompt(prompt, prompt_embeds)
+        emb_inv = self._encode_prompt("", prompt_embeds)
+        ctx = torch.cat([emb_inv, emb_inv, emb])  # :668
+        self.scheduler.set_timesteps(n)
+        timesteps = [int(t) for t in self.scheduler.timesteps]
+        z = latents.to(self.device, torch.float16).contiguous().clone()
+        _, C, F, h, w = z.shape
+        zc_traj, zs_traj = self._trajectory(content_inv_path, n), self._trajectory(style_inv_path, n)
+        m = self._mask(mask_path, F, h, w)
+        for i, t in enumerate(timesteps):
+            zc, zs = zc_traj[n - i], zs_traj[n - i]
+            if m is not None and i <= 0.9 * n:  # localized latent blending, :687-692
+                z = ops.latent_blend(z, zc, m)
+            if i > 0.8 * n and i <= 0.9 * n:  # late latent AdaIN, :694-702
+                za = ops.latent_adain(z, zs)
+                z = ops.latent_blend(za, zc, m) if m is not None else za
+            register_time(self, i)  # :707
+            a1 = self.unet.up_blocks[1].attentions[1].transformer_blocks[0].attn1
+            shift_live = (not a1.patched) or (a1.idx >= a1.eta1 and a1.idx <= a1.eta2 * 50)
+            if skip_dead_branches and a1.patched and not shift_live:
+                self.unet(z, t, encoder_hidden_states=ctx[2:3])
+                branch = 0
+            else:
+                self.unet(torch.cat([zc, zs, z]), t, encoder_hidden_states=ctx)
+                branch = 2
+            a_t, a_prev = self.scheduler.step_alphas(t)
+            z = ops.ddim_step(z, self.unet.last_eps_rows, branch, a_t, a_prev)  # :761, eta = 0
+            if callback is not None:
+                callback(i, t, z)
+        images = self.decode_latents(z) if self.vae is not None else None
+        return SimpleNamespace(images=images, latents=z, nsfw_content_detected=None)
+
+    @torch.no_grad()
+    def reconstruction(self, prompt, latents=None, video_length=None, num_inference_steps: int = 50,
+                       guidance_scale: float = 1.0, prompt_embeds=None, **kwargs):
+        """stable_diffusion.py:479-628 with guidance_scale = 1 (how ddim_inversion.py:40 calls it): plain DDIM sampling."""
+        if guidance_scale != 1.0:
+            raise NotImplementedError("classifier-free guidance is not used on the UniVST path")
+        ctx = self._encode_prompt(prompt, prompt_embeds)
+        self.scheduler.set_timesteps(num_inference_steps)
+        z = latents.to(self.device, torch.float16).contiguous().clone()
+        for t in [int(t) for t in self.scheduler.timesteps]:
+            self.unet(z, t, encoder_hidden_states=ctx)
+            a_t, a_prev = self.scheduler.step_alphas(t)
+            z = ops.ddim_step(z, self.unet.last_eps_rows, 0, a_t, a_prev)
+        images = self.decode_latents(z) if self.vae is not None else None
+        return SimpleNamespace(images=images, latents=z)
+
+    def decode_latents(self, latents):
+        """stable_diffusion.py:369-394 -- third-party VAE (SVD temporal decoder); runs only when one was supplied."""
+        lat = (1 / 0.18215 * latents).permute(0, 2, 1, 3, 4).flatten(0, 1)
+        video = self.vae.decode(lat.to(self.vae.dtype), num_frames=lat.shape[0]).sample
+        video = video.view(latents.shape[0], -1, *video.shape[1:]).permute(0, 1, 3, 4, 2)
+        return ((video / 2 + 0.5).clamp(0, 1)).float().cpu()

@@ -1,0 +1,57 @@
+"""Host-side DDIM scheduler scalars, mirroring diffusers' ``DDIMScheduler`` as SD-1.5's scheduler_config.json sets it
+up (third-party to the reference: called at stable_diffusion.py:670,761; semantics in SURVEY.md Appendix B).
+All per-step coefficients are Python floats, so stepping never synchronises with the device; the arithmetic on the
+latents is the ``univst_ddim_step_f16`` kernel."""
+from __future__ import annotations
+
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+
+class DDIMScheduler:
+    order = 1
+    init_noise_sigma = 1.0
+
+    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
+                 set_alpha_to_one=False, steps_offset=1, clip_sample=False, prediction_type="epsilon",
+                 timestep_spacing="leading"):
+        if prediction_type != "epsilon" or clip_sample or timestep_spacing != "leading":
+            raise NotImplementedError("only the epsilon / no-clip / leading configuration of the reference is mirrored")
+        self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, steps_offset=steps_offset,
+                                      clip_sample=clip_sample, prediction_type=prediction_type,
+                                      timestep_spacing=timestep_spacing, beta_schedule=beta_schedule,
+                                      set_alpha_to_one=set_alpha_to_one)
+        if beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, num_train_timesteps, dtype=torch.float32) ** 2
+        elif beta_schedule == "linear":
+            betas = torch.linspace(beta_start, beta_end, num_train_timesteps, dtype=torch.float32)
+        else:
+            raise NotImplementedError(beta_schedule)
+        self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
+        self._alphas = [float(a) for a in self.alphas_cumprod]
+        self.num_inference_steps = None
+        self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
+
+    def set_timesteps(self, num_inference_steps: int, device=None):
+        self.num_inference_steps = num_inference_steps
+        ratio = self.config.num_train_timesteps // num_inference_steps
+        ts = (np.arange(0, num_inference_steps) * ratio).round()[::-1].copy().astype(np.int64) + self.config.steps_offset
+        self.timesteps = torch.from_numpy(ts)  # kept on the host: indexing it must not touch the device
+
+    def scale_model_input(self, sample, timestep=None):
+        return sample
+
+    def alpha(self, t: int) -> float:
+        return self._alphas[t] if t >= 0 else float(self.final_alpha_cumprod)
+
+    def step_alphas(self, t: int):
+        """(alpha_t, alpha_prev) of DDIMScheduler.step."""
+        return self.alpha(int(t)), self.alpha(int(t) - self.config.num_train_timesteps // self.num_inference_steps)
+
+    def inversion_alphas(self, t: int):
+        """(alpha_cur, alpha_next) of next_step (inversion_tools/ddim_inversion.py:190-196)."""
+        cur = min(int(t) - self.config.num_train_timesteps // self.num_inference_steps, 999)
+        return self.alpha(cur), self.alpha(int(t))
