@@ -39,3 +39,7 @@ def register_to_config(init):
         init(self, *args, **kwargs)
 
     return inner
+
+
+class FrozenDict(dict):
+    pass

@@ -1,0 +1,2 @@
+class AutoencoderKL:  # type annotation only on the reference path
+    pass

@@ -41,3 +41,12 @@ class DDIMScheduler:
         x0 = (sample - (1 - a_t) ** 0.5 * model_output) / a_t ** 0.5
         prev = a_p ** 0.5 * x0 + (1 - a_p) ** 0.5 * model_output
         return SimpleNamespace(prev_sample=prev, pred_original_sample=x0)
+
+
+class _Unused:
+    def __init__(self, *a, **k):
+        raise NotImplementedError("only DDIMScheduler is on the UniVST path")
+
+
+DPMSolverMultistepScheduler = EulerAncestralDiscreteScheduler = EulerDiscreteScheduler = _Unused
+LMSDiscreteScheduler = PNDMScheduler = DDPMScheduler = _Unused

@@ -29,3 +29,7 @@ logging = _Logging()
 
 def deprecate(*args, **kwargs):
     return None
+
+
+def is_accelerate_available():
+    return False

@@ -1,0 +1,87 @@
+"""Golden vectors for the loops around the UNet, produced by the REFERENCE's own ``video_style_transfer``
+(stable_diffusion.py:631-780) and ``ddim_loop`` / ``ddim_loop_plus`` (ddim_inversion.py:88-167), imported on the
+test-only shim and driven with the tiny seeded UNet.  Called from oracle/gen_golden.py (build container only)."""
+import os
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+
+def _tiny_reference_unet():
+    from backbones.video_diffusion_sd.models.unet_3d_condition import UNetPseudo3DConditionModel
+    from oracle import unet_oracle as uo
+    cfg = uo.TINY_CONFIG
+    m = UNetPseudo3DConditionModel(block_out_channels=cfg["block_out_channels"], attention_head_dim=cfg["attention_head_dim"],
+                                   cross_attention_dim=cfg["cross_attention_dim"], sample_size=8).eval()
+    m.load_state_dict(uo.seeded_state_dict(cfg, seed=33))
+    return m, cfg
+
+
+def gen_style_transfer(save):
+    from PIL import Image
+    from backbones.video_diffusion_sd import pnp_utils
+    from backbones.video_diffusion_sd.pipelines.stable_diffusion import SpatioTemporalStableDiffusionPipeline as P
+    from diffusers import DDIMScheduler
+    from oracle import pipeline_oracle as po
+
+    m, cfg = _tiny_reference_unet()
+    F_, hw, n, seed = 16, 8, 50, 77  # the reference hard-codes 16 mask frames (src/util.py:133) and 50 steps (eta2 * 50)
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(seed, F_, hw, n)
+    g = torch.Generator().manual_seed(seed + 1)
+    emb = torch.randn(1, 77, cfg["cross_attention_dim"], generator=g)
+    with tempfile.TemporaryDirectory() as tmp:
+        cdir, sdir, mdir = (os.path.join(tmp, d) for d in ("c", "s", "m"))
+        for d in (cdir, sdir, mdir):
+            os.makedirs(d)
+        for k in range(1, n + 1):
+            torch.save(traj_c[k], os.path.join(cdir, f"ddim_latents_{k}.pt"))
+            torch.save(traj_s[k], os.path.join(sdir, f"ddim_latents_{k}.pt"))
+        for f in range(F_):
+            Image.fromarray(mask_u8[f], mode="L").save(os.path.join(mdir, "%05d.png" % f))
+        pipe = P.__new__(P)
+        pipe.unet, pipe.scheduler = m, DDIMScheduler()
+        pipe._encode_prompt = lambda *a, **k: emb
+        final = []
+        pipe.decode_latents = lambda lat: (final.append(lat.clone()), np.zeros((1, 1, 1, 1, 3), np.float32))[1]
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        z_T = pnp_utils.latent_adain(traj_c[n], traj_s[n])
+        rec = {}
+        with torch.no_grad():
+            pipe.video_style_transfer("", latents=z_T, num_inference_steps=n, content_inv_path=cdir, style_inv_path=sdir,
+                                      mask_path=mdir, callback=lambda i, t, lat: rec.__setitem__(i, lat.clone()))
+    keep = {i: rec[i] for i in (0, 25, 26, 41, 46, 49)}
+    save("style_transfer_tiny.pt", {"seed": seed, "F": F_, "hw": hw, "n": n, "emb": emb, "z_T": z_T, "final": final[0],
+                                    "steps": keep})
+
+
+def gen_inversion(save):
+    import inversion_tools.ddim_inversion as di
+    from diffusers import DDIMScheduler
+    from oracle import pipeline_oracle as po
+
+    m, cfg = _tiny_reference_unet()
+    F_, hw, n, seed = 4, 8, 10, 5  # BASELINE.json configs[0] scaled down: 4 frames, 10 steps, CPU
+    traj_c, _, _ = po.synthetic_inputs(seed, F_, hw, 50)
+    g = torch.Generator().manual_seed(seed + 1)
+    emb = torch.randn(1, 77, cfg["cross_attention_dim"], generator=g)
+    di.init_prompt = lambda pipeline, prompt: torch.cat([emb, emb])  # CLIP is a third-party network: fixed embeddings
+    sch = DDIMScheduler()
+    sch.set_timesteps(n)
+    pipe = types.SimpleNamespace(unet=m)
+    out = {"seed": seed, "F": F_, "hw": hw, "n": n, "emb": emb}
+    with tempfile.TemporaryDirectory() as tmp:
+        with torch.no_grad():
+            lat = di.ddim_loop(pipe, sch, traj_c[0], n, "", tmp, ft_indices=[2], ft_timesteps=[301], ft_path=tmp)
+            out["files"] = sorted(os.listdir(tmp))
+            out["feature"] = torch.load(os.path.join(tmp, "inversion_feature_map_2_block_301_step.pt"))
+            lat_plus = di.ddim_loop_plus(pipe, sch, traj_c[0], n, "", None)
+    out["ddim_loop"] = torch.stack(lat[1:])
+    out["ddim_loop_plus"] = torch.stack(lat_plus[1:])
+    save("ddim_inversion_tiny.pt", out)
+
+
+def main(save):
+    gen_style_transfer(save)
+    gen_inversion(save)

@@ -78,3 +78,66 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert lib.univst_abi_version() == 1
     assert set(_lib.PROTOTYPES) <= declared
+
+
+# ------------------------------------------------------------------------------------------------ loops around the UNet
+def _tiny_unet_fn(sd):
+    def fn(x, t, ctx, idx):
+        with torch.no_grad():
+            return uo.unet_forward(sd, uo.TINY_CONFIG, x, t, ctx.expand(x.shape[0], -1, -1), patched=idx is not None, idx=idx)
+    return fn
+
+
+def test_video_style_transfer_oracle_matches_reference_pipeline(tiny_sd):
+    """The reference's own video_style_transfer (50 steps, 16 frames, mask blend, late AdaIN, shift window) vs the
+    oracle loop: fp32, 2e-4 absolute on latents of magnitude ~4 after 50 steps."""
+    from oracle import pipeline_oracle as po
+    g = torch.load(os.path.join(GOLDEN, "style_transfer_tiny.pt"), weights_only=True)
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], g["n"])
+    z_T = uo.latent_adain(traj_c[g["n"]], traj_s[g["n"]])
+    assert torch.allclose(z_T, g["z_T"], atol=1e-6)
+    rec = {i: None for i in g["steps"]}
+    ctx3 = g["emb"].repeat(3, 1, 1)
+    z = po.video_style_transfer(_tiny_unet_fn(tiny_sd), z_T, traj_c, traj_s, po.load_mask_values(mask_u8), ctx3, g["n"], rec)
+    for i, ref in g["steps"].items():
+        assert (rec[i] - ref).abs().max().item() < 2e-4, i
+    assert (z - g["final"]).abs().max().item() < 2e-4
+
+
+def test_ddim_inversion_oracle_matches_reference_loops(tiny_sd):
+    from oracle import pipeline_oracle as po
+    g = torch.load(os.path.join(GOLDEN, "ddim_inversion_tiny.pt"), weights_only=True)
+    traj_c, _, _ = po.synthetic_inputs(g["seed"], g["F"], g["hw"], 50)
+    fn = _tiny_unet_fn(tiny_sd)
+    lat = po.ddim_loop(fn, traj_c[0], g["emb"], g["n"])
+    assert (torch.stack(lat[1:]) - g["ddim_loop"]).abs().max().item() < 1e-4
+    lat = po.ddim_loop(fn, traj_c[0], g["emb"], g["n"], plus=True)
+    assert (torch.stack(lat[1:]) - g["ddim_loop_plus"]).abs().max().item() < 1e-4
+    assert (g["ddim_loop"] - g["ddim_loop_plus"]).abs().max() > 1e-3  # the Easy-Inv blend is live on steps 3..9
+    # file side effects of the reference loop (names are part of the inter-stage contract)
+    assert [f for f in g["files"] if f.startswith("ddim_latents_")] == sorted(f"ddim_latents_{k}.pt" for k in range(11))
+    assert "inversion_feature_map_2_block_301_step.pt" in g["files"]
+    assert tuple(g["feature"].shape) == (g["F"], g["hw"], g["hw"], 128)
+
+
+def test_load_mask_wraparound_semantics():
+    """uint8 * 255 wraps: every non-zero grey level (anti-aliased rims included) becomes 1 (src/util.py:138-143)."""
+    import numpy as np
+    from oracle import pipeline_oracle as po
+    px = np.array([[[0, 1, 2, 127, 128, 254, 255]]], dtype=np.uint8)
+    assert po.load_mask_values(px).flatten().tolist() == [0, 1, 1, 1, 1, 1, 1]
+
+
+def test_scheduler_mirror_matches_oracle():
+    from oracle import pipeline_oracle as po
+    from univst_b200.scheduler import DDIMScheduler
+    a, b = DDIMScheduler(), po.DDIMOracle()
+    for n in (50, 10):
+        a.set_timesteps(n), b.set_timesteps(n)
+        assert [int(t) for t in a.timesteps] == b.timesteps
+        for t in b.timesteps:
+            at, ap = a.step_alphas(t)
+            assert at == pytest.approx(float(b.alpha(t))) and ap == pytest.approx(float(b.alpha(t - 1000 // n)))
+            ac, an = a.inversion_alphas(t)
+            assert ac == pytest.approx(float(b.alpha(min(t - 1000 // n, 999)))) and an == pytest.approx(float(b.alpha(t)))
+    assert [int(t) for t in a.timesteps][:2] == [901, 801]
