@@ -36,6 +36,12 @@ static constexpr uint32_t kSlotCols = 128;  // TMEM columns per S slot
 static constexpr uint32_t kOBase = 256;     // TMEM column of the first O accumulator
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 before a forced rescale
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int NQ, int BKV>
 struct AttnSmem {
   static constexpr int kQChunkBytes = 128 * 128;      // [128 rows][64 halves]
@@ -192,27 +198,28 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       const int slot = i & 1;
       mbar_wait(&s_full[slot], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
-      float s[BKV];
+      // S tile -> registers: all loads in flight, one wait
+      uint32_t sraw[BKV];
       {
         const uint32_t sa = tmem_base + slot * kSlotCols + lane_off;
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) {
-          uint32_t t[32];
-          tmem_ld32(sa + c * 32, t);
-          tc_wait_ld();
-#pragma unroll
-          for (int x = 0; x < 32; ++x) s[c * 32 + x] = __uint_as_float(t[x]) * p.scale_log2;
-        }
+        for (int c = 0; c < BKV / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]));
+        tc_wait_ld();
       }
       const int valid = min(BKV, p.Nkv - (j % tps) * BKV);
       if (valid < BKV) {
 #pragma unroll
         for (int x = 0; x < BKV; ++x)
-          if (x >= valid) s[x] = -INFINITY;
+          if (x >= valid) sraw[x] = 0xff800000u;  // -inf
       }
-      float mx = s[0];
+      // row max of the raw scores: 8 independent chains (a single chain is 128 dependent FMNMX)
+      float mx8[8];
 #pragma unroll
-      for (int x = 1; x < BKV; ++x) mx = fmaxf(mx, s[x]);
+      for (int x = 0; x < 8; ++x) mx8[x] = __uint_as_float(sraw[x]);
+#pragma unroll
+      for (int x = 8; x < BKV; ++x) mx8[x & 7] = fmaxf(mx8[x & 7], __uint_as_float(sraw[x]));
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
       // previous P V of this query tile must have landed before O may be touched / P slot reused
       if (j > 0) {
         mbar_wait(&o_done[g], (uint32_t)((j - 1) & 1));
@@ -222,7 +229,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = fmaxf(m_used, mx);
         if (j > 0) {
-          const float alpha = exp2f(m_used - m_new);       // lanes that did not need it: alpha <= 1, harmless
+          const float alpha = ex2_approx(m_used - m_new);   // lanes that did not need it: alpha <= 1, harmless
           l *= alpha;
           for (uint32_t c = 0; c < opad; c += 16) {
             uint32_t t[16];
@@ -236,22 +243,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         m_used = m_new;
       }
-      // P = exp2(s - m_used), fp16, written as swizzled K-major chunks: chunk kc holds keys [64 kc, 64 kc + 64)
+      // P = 2^(s * scale - m_used): one FFMA + one MUFU.EX2 per element, fp16, written as swizzled K-major
+      // chunks (chunk kc holds keys [64 kc, 64 kc + 64)); the row sum runs in 4 independent chains
       uint8_t* prow = sP + slot * L::kPBytes + r * 128;
-      float lsum = 0.0f;
+      float ls4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+      const float neg_m = -m_used;
 #pragma unroll
       for (int c16 = 0; c16 < BKV / 8; ++c16) {
         uint32_t w[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-          const float e0 = exp2f(s[c16 * 8 + 2 * x] - m_used);
-          const float e1 = exp2f(s[c16 * 8 + 2 * x + 1] - m_used);
-          lsum += e0 + e1;
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x]), p.scale_log2, neg_m));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x + 1]), p.scale_log2, neg_m));
+          ls4[x] += e0 + e1;
           w[x] = pack_half2(e0, e1);
         }
         const int kc = c16 >> 3, cc = c16 & 7;
         *reinterpret_cast<uint4*>(prow + kc * (128 * 128) + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
+      const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       l += lsum;
       fence_proxy_async_smem();
       tc_fence_before();

@@ -48,6 +48,138 @@ struct GemmParams {
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, bool row_ok, const __half* rv,
+                                              const __half* res, __half* drow, int n0, int tile_n) {
+  if (!p.geglu) {
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      if (n0 + c0 >= p.N_out) break;  // warp-uniform
+      uint32_t acc[32];
+      tmem_ld32(taddr + c0, acc);
+      tc_wait_ld();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int n = n0 + c0 + g * 8;
+        if (n >= p.N_out) break;
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+        if (n + 8 <= p.N_out) {
+          if (p.bias) {
+            const uint4 b = *reinterpret_cast<const uint4*>(p.bias + n);
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = unpack_half2(bw[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          }
+          if (rv) {
+            const uint4 b = *reinterpret_cast<const uint4*>(rv + n);
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = unpack_half2(bw[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          }
+          if (res) {
+            const uint4 b = *reinterpret_cast<const uint4*>(res + n);
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = unpack_half2(bw[j]);
+              v[2 * j] += f.x;
+              v[2 * j + 1] += f.y;
+            }
+          }
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j] * p.out_scale, v[2 * j + 1] * p.out_scale);
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 y = unpack_half2(o[j]);
+              o[j] = pack_half2(y.x / (1.0f + __expf(-y.x)), y.y / (1.0f + __expf(-y.y)));
+            }
+          }
+          if (p.bias2) {
+            const uint4 b = *reinterpret_cast<const uint4*>(p.bias2 + n);
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = unpack_half2(bw[j]);
+              float2 y = unpack_half2(o[j]);
+              o[j] = pack_half2(y.x + f.x, y.y + f.y);
+            }
+          }
+          *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int j = 0; j < 8 && n + j < p.N_out; ++j) {
+            float x = v[j];
+            if (p.bias) x += __half2float(p.bias[n + j]);
+            if (rv) x += __half2float(rv[n + j]);
+            if (res) x += __half2float(res[n + j]);
+            __half y = __float2half_rn(x * p.out_scale);
+            if (p.act) {
+              const float yf = __half2float(y);
+              y = __float2half_rn(yf / (1.0f + __expf(-yf)));
+            }
+            if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(p.bias2[n + j]));
+            drow[n + j] = y;
+          }
+        }
+      }
+    }
+  } else {
+    // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates (weights packed that way).
+    const int half_bn = p.BN >> 1;
+    const int no0 = tile_n * half_bn;
+    for (int c0 = 0; c0 < half_bn; c0 += 32) {
+      if (no0 + c0 >= p.N_out) break;
+      uint32_t av[32], ag[32];
+      tmem_ld32(taddr + c0, av);
+      tmem_ld32(taddr + half_bn + c0, ag);
+      tc_wait_ld();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int c = c0 + g * 8;
+        const int n = no0 + c;
+        if (n >= p.N_out) break;
+        float v[8], gt[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          v[j] = __uint_as_float(av[g * 8 + j]);
+          gt[j] = __uint_as_float(ag[g * 8 + j]);
+          if (p.bias) {
+            v[j] += __half2float(p.bias[n0 + c + j]);
+            gt[j] += __half2float(p.bias[n0 + half_bn + c + j]);
+          }
+          // the reference rounds the projection to fp16 before h * gelu(gate)
+          v[j] = __half2float(__float2half_rn(v[j]));
+          gt[j] = __half2float(__float2half_rn(gt[j]));
+          v[j] = v[j] * __half2float(__float2half_rn(gelu_erf(gt[j])));
+        }
+        if (n + 8 <= p.N_out) {
+          uint32_t o[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j], v[2 * j + 1]);
+          *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+          for (int j = 0; j < 8 && n + j < p.N_out; ++j) drow[n + j] = __float2half_rn(v[j]);
+        }
+      }
+    }
+  }
+}
+
+// Persistent kernel: CTA c processes tiles c, c + gridDim.x, ... (tile = tile_m * tiles_n + tile_n, so the N tiles
+// of one A row-block run at the same time on neighbouring CTAs and share A through L2).  Two TMEM accumulators
+// alternate between consecutive tiles: the epilogue warps drain tile i while the MMA warp already accumulates
+// tile i + 1, and the TMA producer runs ahead across tile boundaries.
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -59,18 +191,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* empty_bar = full_bar + p.stages;
-  uint64_t* tmem_full_bar = empty_bar + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
-  const int tile_m = blockIdx.x;
-  const int tile_n = blockIdx.y;
-  const int m0 = tile_m * kBM;
-  const int n0 = tile_n * p.BN;
+  const int tiles_n = (p.N + p.BN - 1) / p.BN;
+  const int num_tiles = ((p.M + kBM - 1) / kBM) * tiles_n;
 
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.BN) tmem_cols <<= 1;
+  // accumulator stride: BN rounded up to a power of two >= 32 (TMEM allocations are powers of two)
+  uint32_t acc_cols = 32;
+  while ((int)acc_cols < p.BN) acc_cols <<= 1;
+  const uint32_t tmem_cols = acc_cols * 2;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -80,7 +213,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full_bar[a], 1);
+      mbar_init(&tmem_empty_bar[a], 128);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -95,41 +231,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   if (warp == 0) {
     if (lane == 0) {
       // ------------------------------------------------ TMA producer
-      int cn = 0, cy = 0;
-      if (p.mode == 1) {
-        cn = m0 / p.HW;
-        cy = (m0 % p.HW) / p.W;
-      }
       uint32_t phase = 0;
       int s = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty_bar[s], phase ^ 1);
-        uint8_t* sa = smem + (size_t)s * stage_bytes;
-        uint8_t* sb = sa + a_bytes;
-        mbar_expect_tx(&full_bar[s], stage_bytes);
-        int kw;  // K coordinate into the weight matrix
-        if (p.mode == 0) {
-          kw = kb * kBK;
-          if (kb < p.kb_split)
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * kBK, m0);
-          else
-            tma_load_2d(sa, &tmA2, &full_bar[s], kb * kBK - p.K1, m0);
-        } else {
-          const int tap = kb / p.cbs;
-          const int cb = kb - tap * p.cbs;
-          const int x = p.tap_dx[tap], y = cy + p.tap_dy[tap], n = cn + p.tap_plane[tap] * p.plane_stride;
-          if (cb < p.kb_split) {
-            kw = tap * p.Cin + cb * kBK;
-            tma_load_4d(sa, &tmA, &full_bar[s], cb * kBK, x, y, n);
-          } else {
-            kw = tap * p.Cin + p.K1 + (cb - p.kb_split) * kBK;
-            tma_load_4d(sa, &tmA2, &full_bar[s], (cb - p.kb_split) * kBK, x, y, n);
-          }
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * kBM;
+        const int n0 = (tile % tiles_n) * p.BN;
+        int cn = 0, cy = 0;
+        if (p.mode == 1) {
+          cn = m0 / p.HW;
+          cy = (m0 % p.HW) / p.W;
         }
-        tma_load_2d(sb, &tmB, &full_bar[s], kw, n0);
-        if (++s == p.stages) {
-          s = 0;
-          phase ^= 1;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[s], phase ^ 1);
+          uint8_t* sa = smem + (size_t)s * stage_bytes;
+          uint8_t* sb = sa + a_bytes;
+          mbar_expect_tx(&full_bar[s], stage_bytes);
+          int kw;  // K coordinate into the weight matrix
+          if (p.mode == 0) {
+            kw = kb * kBK;
+            if (kb < p.kb_split)
+              tma_load_2d(sa, &tmA, &full_bar[s], kb * kBK, m0);
+            else
+              tma_load_2d(sa, &tmA2, &full_bar[s], kb * kBK - p.K1, m0);
+          } else {
+            const int tap = kb / p.cbs;
+            const int cb = kb - tap * p.cbs;
+            const int x = p.tap_dx[tap], y = cy + p.tap_dy[tap], n = cn + p.tap_plane[tap] * p.plane_stride;
+            if (cb < p.kb_split) {
+              kw = tap * p.Cin + cb * kBK;
+              tma_load_4d(sa, &tmA, &full_bar[s], cb * kBK, x, y, n);
+            } else {
+              kw = tap * p.Cin + p.K1 + (cb - p.kb_split) * kBK;
+              tma_load_4d(sa, &tmA2, &full_bar[s], (cb - p.kb_split) * kBK, x, y, n);
+            }
+          }
+          tma_load_2d(sb, &tmB, &full_bar[s], kw, n0);
+          if (++s == p.stages) {
+            s = 0;
+            phase ^= 1;
+          }
         }
       }
     }
@@ -139,161 +279,55 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t idesc = make_idesc_f16(kBM, (uint32_t)p.BN, 0, 0);
       uint32_t phase = 0;
       int s = 0;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&full_bar[s], phase);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int a = it & 1;
+        // wait until the epilogue has drained this accumulator (its (it / 2)-th use)
+        mbar_wait(&tmem_empty_bar[a], (uint32_t)(((it >> 1) & 1) ^ 1));
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-        const uint32_t sb = sa + a_bytes;
-        const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-        const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+        const uint32_t acc = tmem_base + a * acc_cols;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[s], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
+          const uint32_t sb = sa + a_bytes;
+          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
 #pragma unroll
-        for (int k = 0; k < kBK / 16; ++k) {
-          // advance 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_f16_ss(tmem_base, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          for (int k = 0; k < kBK / 16; ++k) {
+            // advance 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+            umma_f16_ss(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+          }
+          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+          if (++s == p.stages) {
+            s = 0;
+            phase ^= 1;
+          }
         }
-        tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
-        if (++s == p.stages) {
-          s = 0;
-          phase ^= 1;
-        }
+        tc_commit(&tmem_full_bar[a]);
       }
-      tc_commit(tmem_full_bar);
     }
   } else {
     // -------------------------------------------------- epilogue warps 2..5 (TMEM lane quadrant = warp % 4)
     const uint32_t q = warp & 3;
-    const int row = m0 + (int)(q * 32 + lane);
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + ((q * 32) << 16);
-    const bool row_ok = row < p.M;
-    const __half* rv = (p.rowvec && row_ok) ? p.rowvec + (size_t)(row / p.rows_per_group) * p.rowvec_ld : nullptr;
-    const __half* res = (p.residual && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
-    __half* drow = p.D + (size_t)row * p.ldd;
-
-    if (!p.geglu) {
-      for (int c0 = 0; c0 < p.BN; c0 += 32) {
-        if (n0 + c0 >= p.N_out) break;  // warp-uniform
-        uint32_t acc[32];
-        tmem_ld32(taddr + c0, acc);
-        tc_wait_ld();
-        if (!row_ok) continue;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int n = n0 + c0 + g * 8;
-          if (n >= p.N_out) break;
-          float v[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-          if (n + 8 <= p.N_out) {
-            if (p.bias) {
-              const uint4 b = *reinterpret_cast<const uint4*>(p.bias + n);
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_half2(bw[j]);
-                v[2 * j] += f.x;
-                v[2 * j + 1] += f.y;
-              }
-            }
-            if (rv) {
-              const uint4 b = *reinterpret_cast<const uint4*>(rv + n);
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_half2(bw[j]);
-                v[2 * j] += f.x;
-                v[2 * j + 1] += f.y;
-              }
-            }
-            if (res) {
-              const uint4 b = *reinterpret_cast<const uint4*>(res + n);
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_half2(bw[j]);
-                v[2 * j] += f.x;
-                v[2 * j + 1] += f.y;
-              }
-            }
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j] * p.out_scale, v[2 * j + 1] * p.out_scale);
-            if (p.act) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 y = unpack_half2(o[j]);
-                o[j] = pack_half2(y.x / (1.0f + __expf(-y.x)), y.y / (1.0f + __expf(-y.y)));
-              }
-            }
-            if (p.bias2) {
-              const uint4 b = *reinterpret_cast<const uint4*>(p.bias2 + n);
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_half2(bw[j]);
-                float2 y = unpack_half2(o[j]);
-                o[j] = pack_half2(y.x + f.x, y.y + f.y);
-              }
-            }
-            *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
-          } else {
-            for (int j = 0; j < 8 && n + j < p.N_out; ++j) {
-              float x = v[j];
-              if (p.bias) x += __half2float(p.bias[n + j]);
-              if (rv) x += __half2float(rv[n + j]);
-              if (res) x += __half2float(res[n + j]);
-              __half y = __float2half_rn(x * p.out_scale);
-              if (p.act) {
-                const float yf = __half2float(y);
-                y = __float2half_rn(yf / (1.0f + __expf(-yf)));
-              }
-              if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(p.bias2[n + j]));
-              drow[n + j] = y;
-            }
-          }
-        }
-      }
-    } else {
-      // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates (weights packed that way).
-      const int half_bn = p.BN >> 1;
-      const int no0 = tile_n * half_bn;
-      for (int c0 = 0; c0 < half_bn; c0 += 32) {
-        if (no0 + c0 >= p.N_out) break;
-        uint32_t av[32], ag[32];
-        tmem_ld32(taddr + c0, av);
-        tmem_ld32(taddr + half_bn + c0, ag);
-        tc_wait_ld();
-        if (!row_ok) continue;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          const int c = c0 + g * 8;
-          const int n = no0 + c;
-          if (n >= p.N_out) break;
-          float v[8], gt[8];
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            v[j] = __uint_as_float(av[g * 8 + j]);
-            gt[j] = __uint_as_float(ag[g * 8 + j]);
-            if (p.bias) {
-              v[j] += __half2float(p.bias[n0 + c + j]);
-              gt[j] += __half2float(p.bias[n0 + half_bn + c + j]);
-            }
-            // the reference rounds the projection to fp16 before h * gelu(gate)
-            v[j] = __half2float(__float2half_rn(v[j]));
-            gt[j] = __half2float(__float2half_rn(gt[j]));
-            v[j] = v[j] * __half2float(__float2half_rn(gelu_erf(gt[j])));
-          }
-          if (n + 8 <= p.N_out) {
-            uint32_t o[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j], v[2 * j + 1]);
-            *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
-          } else {
-            for (int j = 0; j < 8 && n + j < p.N_out; ++j) drow[n + j] = __float2half_rn(v[j]);
-          }
-        }
-      }
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      const int tile_n = tile % tiles_n;
+      const int m0 = (tile / tiles_n) * kBM;
+      const int n0 = tile_n * p.BN;
+      const int row = m0 + (int)(q * 32 + lane);
+      mbar_wait(&tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + a * acc_cols + ((q * 32) << 16);
+      const bool row_ok = row < p.M;
+      const __half* rv = (p.rowvec && row_ok) ? p.rowvec + (size_t)(row / p.rows_per_group) * p.rowvec_ld : nullptr;
+      const __half* res = (p.residual && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
+      __half* drow = p.D + (size_t)row * p.ldd;
+      epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n);
+      // accumulator drained: hand it back to the MMA warp
+      tc_fence_before();
+      mbar_arrive(&tmem_empty_bar[a]);
     }
   }
 
@@ -323,20 +357,20 @@ static int pick_bn(int N, int geglu) {
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, GemmParams& p,
                   cudaStream_t stream) {
   const uint32_t stage_bytes = kBM * kBK * 2 + (uint32_t)p.BN * kBK * 2;
-  // up to two co-resident CTAs per SM when the tile is narrow, so one CTA's epilogue hides behind the other's MMAs
-  const uint32_t budget = (p.BN <= 160) ? 108 * 1024 : 200 * 1024;
+  // one persistent CTA per SM: the smem ring is as deep as fits so that the producer prefetches across tiles
+  const uint32_t budget = 200 * 1024;
   int stages = (int)(budget / stage_bytes);
   if (stages > 8) stages = 8;
-  if (stages > p.num_kb) stages = p.num_kb;
-  if (stages < 1) stages = 1;
+  if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 1) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
-  dim3 grid((p.M + kBM - 1) / kBM, (p.N + p.BN - 1) / p.BN);
+  const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
+  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
   gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
