@@ -47,3 +47,21 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / iters
 print(f"UNet 3x{F}x64x64 forward: {ms:.2f} ms  ({(ops.launch_count - n0) // iters} launches)  "
       f"{3 * F * 0.9751 / ms:.1f} TFLOP/s live  mem {torch.cuda.max_memory_allocated() / 2**30:.1f} GiB")
+
+if "--shapes" in sys.argv:
+    import collections
+    ops.profile_start({"gemm", "conv3x3", "sc_attention"})
+    unet(x, 981, encoder_hidden_states=ctx)
+    prof = ops.profile_stop()
+    for name, recs in prof.items():
+        agg = collections.defaultdict(lambda: [0, 0.0])
+        for ms_, meta in recs:
+            agg[meta][0] += 1
+            agg[meta][1] += ms_
+        print(f"== {name}: {sum(v[1] for v in agg.values()):.2f} ms")
+        for meta, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
+            if name == "sc_attention":
+                fl = 4.0 * meta[3] * meta[4] * meta[1] * meta[2] * meta[0]
+            else:
+                fl = 2.0 * meta[0] * meta[1] * meta[2]
+            print(f"  {t:8.3f} ms n={n:3d} avg={t / n * 1e3:8.1f} us {fl / (t / n) / 1e9:8.1f} TF/s  {meta}")

@@ -24,35 +24,44 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, const __half* x
 // grid (nchunks, NB); block = nvec * rows_par threads.  partial[b][chunk][group][2] = (sum, sumsq)
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, int C1, int C2, int rows,
                                 int groups, int nvec, int rows_par, int rows_per_chunk, float* __restrict__ partial) {
-  extern __shared__ float sh[];  // [groups][2]
+  extern __shared__ float sh[];  // [threads][8] per-thread pair sums, then [groups][2]
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int C = C1 + C2, cpg = C / groups;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) sh[i] = 0.0f;
-  __syncthreads();
   const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
   const int r_begin = chunk * rows_per_chunk, r_end = min(rows, r_begin + rows_per_chunk);
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  if (rl < rows_par) {
-    for (int r = r_begin + rl; r < r_end; r += rows_par) {
-      const uint4 u = __ldg(gn_src(x1, x2, C1, C2, (size_t)b * rows + r, v));
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_half2(w[j]);
-        s[j] += f.x + f.y;
-        q[j] += f.x * f.x + f.y * f.y;
-      }
-    }
+  for (int r = r_begin + rl; r < r_end; r += rows_par) {
+    const uint4 u = __ldg(gn_src(x1, x2, C1, C2, (size_t)b * rows + r, v));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int g = (v * 8 + j * 2) / cpg;  // cpg is even: a channel pair never straddles two groups
-      atomicAdd(&sh[g * 2], s[j]);
-      atomicAdd(&sh[g * 2 + 1], q[j]);
+      const float2 f = unpack_half2(w[j]);
+      s[j] += f.x + f.y;
+      q[j] += f.x * f.x + f.y * f.y;
     }
+  }
+  // deterministic fold (no float atomics): thread (rl, v) parks its four channel-pair sums, then thread g adds up the
+  // pairs of group g in a fixed order (cpg is even: a channel pair never straddles two groups)
+  float* mine = sh + (size_t)threadIdx.x * 8;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    mine[j] = s[j];
+    mine[4 + j] = q[j];
   }
   __syncthreads();
   float* out = partial + ((size_t)b * gridDim.x + chunk) * groups * 2;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) out[i] = sh[i];
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    float gs = 0.0f, gq = 0.0f;
+    const int p0 = g * (cpg / 2), p1 = p0 + cpg / 2;  // channel-pair range of the group
+    for (int o = 0; o < rows_par; ++o)
+      for (int pr = p0; pr < p1; ++pr) {
+        const float* e = sh + ((size_t)o * nvec + (pr >> 2)) * 8;
+        gs += e[pr & 3];
+        gq += e[4 + (pr & 3)];
+      }
+    out[g * 2] = gs;
+    out[g * 2 + 1] = gq;
+  }
 }
 
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
@@ -188,7 +197,7 @@ extern "C" int univst_groupnorm_f16(const void* X1, const void* X2, int32_t C1, 
   if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
   const int rows_per_chunk = (rows + nchunks - 1) / nchunks;
   cudaStream_t st = (cudaStream_t)stream;
-  gn_stats_kernel<<<dim3(nchunks, NB), threads, groups * 2 * sizeof(float), st>>>(
+  gn_stats_kernel<<<dim3(nchunks, NB), threads, threads * 8 * sizeof(float), st>>>(
       (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, rows_par, rows_per_chunk, (float*)workspace);
   UV_CHECK_CUDA(cudaGetLastError());
   // apply: ~32 KiB of activations per block
