@@ -3,7 +3,7 @@
 //   D[M, N_out] = epilogue( A[M, K] * W[N, K]^T )        fp16 operands, fp32 accumulation in TMEM
 //
 // One CTA owns one 128 x BN output tile.  Warp roles: warp 0 = TMA producer (one lane), warp 1 = TMEM
-// allocator + tcgen05.mma issuer (one lane), warps 2..5 = epilogue (TMEM -> registers -> global).
+// allocator + tcgen05.mma issuer (one lane), warps 2..9 = epilogue (TMEM -> registers -> global).
 // Operand tiles are 128B-swizzled K-major [rows][64 halves]; the A tile of the convolution is a 4-D TMA
 // box over the NHWC activation shifted by the filter tap, with out-of-bounds zero fill standing in for
 // the padding -- no im2col buffer exists.  The skip-connection concat of the UNet up blocks is a second
@@ -17,7 +17,8 @@ namespace uv {
 
 static constexpr int kBM = 128;   // rows per tile (UMMA_M, cta_group::1)
 static constexpr int kBK = 64;    // halves per k-block = one 128-byte swizzle row
-static constexpr int kThreads = 192;
+static constexpr int kEpiWarps = 8;  // two per TMEM lane quadrant, each draining every other 32-column chunk
+static constexpr int kThreads = 64 + 32 * kEpiWarps;
 
 struct GemmParams {
   int M, N, N_out, BN;
@@ -46,12 +47,24 @@ struct GemmParams {
   int ldd;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// Exact-form (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 rounding of
+// the result): one MUFU.RCP + one MUFU.EX2 + a degree-5 Horner chain instead of libdevice's branchy erff.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = __expf(-z * z);
+  const float erf_abs = fmaf(-poly * t, e, 1.0f);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
+}
 
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, bool row_ok, const __half* rv,
-                                              const __half* res, __half* drow, int n0, int tile_n) {
+                                              const __half* res, __half* drow, int n0, int tile_n, int chunk0) {
   if (!p.geglu) {
-    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+    for (int c0 = chunk0 * 32; c0 < p.BN; c0 += 64) {
       if (n0 + c0 >= p.N_out) break;  // warp-uniform
       uint32_t acc[32];
       tmem_ld32(taddr + c0, acc);
@@ -137,7 +150,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
     // GEGLU: tile columns [0, BN/2) are values, [BN/2, BN) the matching gates (weights packed that way).
     const int half_bn = p.BN >> 1;
     const int no0 = tile_n * half_bn;
-    for (int c0 = 0; c0 < half_bn; c0 += 32) {
+    for (int c0 = chunk0 * 32; c0 < half_bn; c0 += 64) {
       if (no0 + c0 >= p.N_out) break;
       uint32_t av[32], ag[32];
       tmem_ld32(taddr + c0, av);
@@ -215,7 +228,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
-      mbar_init(&tmem_empty_bar[a], 128);
+      mbar_init(&tmem_empty_bar[a], 32 * kEpiWarps);
     }
     fence_barrier_init();
   }
@@ -308,8 +321,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else {
-    // -------------------------------------------------- epilogue warps 2..5 (TMEM lane quadrant = warp % 4)
+    // -------------------------------------------------- epilogue warps 2..9 (TMEM lane quadrant = warp % 4)
     const uint32_t q = warp & 3;
+    const int chunk0 = (int)((warp - 2) >> 2);  // which half of the 32-column chunks this warp drains
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int a = it & 1;
@@ -324,7 +338,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const __half* rv = (p.rowvec && row_ok) ? p.rowvec + (size_t)(row / p.rows_per_group) * p.rowvec_ld : nullptr;
       const __half* res = (p.residual && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
       __half* drow = p.D + (size_t)row * p.ldd;
-      epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n);
+      epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0);
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[a]);
