@@ -127,6 +127,28 @@ int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t ld, int32_
                          int32_t HW, float alpha_t, float alpha_prev, void* z_out, void* x0_out, void* stream);
 int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n, void* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Point-matching mask propagation (src/mask_propagation.py:72-83): aff = exp(<tar_n, src_m> / T) on L2-normalised
+ * features; per target point keep the entries >= its topk-th largest (ties kept), normalise, transport the labels.
+ * feat_tar [N, C], feat_src [C, M] (the reference's layouts), segs [Ccls, M] -> segs_tar [Ccls, N]; all fp32 device
+ * pointers.  thresholds (optional, [N]) receives the per-target kept threshold (for index-set parity tests).
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t univst_maskprop_workspace_bytes(int32_t N, int32_t C, int32_t M);
+int univst_maskprop_f32(const float* feat_tar, const float* feat_src, const float* segs, int32_t N, int32_t C, int32_t M,
+                        int32_t Ccls, float temperature, int32_t topk, float* segs_tar, float* thresholds,
+                        void* workspace, void* stream);
+
+/* Sliding-window flow-warp smoothing, one key frame (src/cal_optica_flow.py:20-46; window loop of
+ * pipelines/stable_diffusion.py:725-751).  frames: [F, H, W, 3] uint8, updated IN PLACE at `key`; for each of the
+ * n <= 4 neighbours: fwd = flow(key -> neighbour), bwd = flow(neighbour -> key), [H, W, 2] fp32 device pointers
+ * (neighbour_idx, fwd_flows, bwd_flows are HOST arrays).  Bit-exact with NumPy + cv2.remap(INTER_LINEAR, constant 0).
+ * univst_mask_select_u8: out = keep_mask ? orig : est per pixel (stable_diffusion.py:751). */
+int univst_flow_warp_key_u8(void* frames, int32_t F, int32_t H, int32_t W, int32_t key, int32_t n_neighbours,
+                            const int32_t* neighbour_idx, const void* const* fwd_flows, const void* const* bwd_flows,
+                            float threshold, void* stream);
+int univst_mask_select_u8(const uint8_t* keep_mask, const void* orig, const void* est, int64_t npix, void* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -92,3 +92,22 @@ def sliding_window_smooth(frames, flow_of, keep_mask=None, r=2):
         m = keep_mask[..., None].astype(np.float64)
         est = (frames * m + (1 - m) * est).astype(np.uint8)
     return est
+
+
+def synthetic_flow(h, w, seed, backward_of=None):
+    """Deterministic test flows: a translation + smooth sinusoidal field, with exact-integer and half-pixel displacement
+    patches (exercise the 1/32-px rounding) and vectors that leave the image.  ``backward_of``: build the backward flow
+    of a given forward flow (= -fwd) except for a patch that violates consistency (-> occluded)."""
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float32)
+    if backward_of is not None:
+        f = (-backward_of).astype(np.float32)
+        f[h // 4:h // 2, w // 4:w // 2] += np.float32(4.0)
+        f[::9, ::7] += np.float32(1.4)   # borderline consistency errors around the 1.5 px threshold
+        return f
+    rng = np.random.default_rng(seed)
+    f = np.stack([2.5 + 1.5 * np.sin(yy / 9.0) + 0.3 * rng.standard_normal((h, w)),
+                  -1.25 + 1.5 * np.cos(xx / 7.0) + 0.3 * rng.standard_normal((h, w))], axis=-1).astype(np.float32)
+    f[:16, :16] = np.round(f[:16, :16])
+    f[16:32, :16] = np.round(f[16:32, :16] * 2) / 2
+    f[-8:, -8:] += np.float32(40.0)
+    return f

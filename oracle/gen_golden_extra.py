@@ -82,6 +82,43 @@ def gen_inversion(save):
     save("ddim_inversion_tiny.pt", out)
 
 
+def gen_maskprop(save):
+    """Reference mask_propogation (src/mask_propagation.py:72-99) on synthetic features, CPU fp32."""
+    import src.mask_propagation as mp
+    from oracle import maskprop_oracle as mo
+    out = {}
+    for name, sep, h in (("smooth", False, 16), ("separated", True, 16)):
+        feats = mo.synthetic_features(11, 3, h, h, 64, separated=sep)
+        feat_src = torch.cat([feats[0].reshape(h * h, -1).T, feats[1].reshape(h * h, -1).T[:, ::3]], dim=-1).contiguous()
+        feat_tar = feats[2].reshape(h * h, -1).contiguous()
+        g = torch.Generator().manual_seed(3)
+        labels = (torch.rand(feat_src.shape[1], generator=g) > 0.6).long()
+        segs = torch.stack([(labels == 0).float(), (labels == 1).float()])
+        args = types.SimpleNamespace(temperature=0.2, topk=15, sample_ratio=0.3)
+        torch.manual_seed(0)
+        segs_tar, feat_s, segs_s = mp.mask_propogation(feat_src, feat_tar, segs, args)
+        out[name] = {"segs_tar": segs_tar, "n_sample": feat_s.shape[1], "seed": 11, "h": h, "C": 64, "sep": sep,
+                     "feat_sample": feat_s, "segs_sample": segs_s}
+    save("maskprop.pt", out)
+
+
+def gen_flow_warp(save):
+    """Reference warp helpers (src/cal_optica_flow.py:20-46, cv2.remap inside) on real example frames + analytic flows."""
+    import cv2
+    import src.cal_optica_flow as cf
+    from oracle import flowwarp_oracle as fo
+    frames = np.stack([cv2.cvtColor(cv2.imread(f"/root/reference/examples/contents/mallard-fly/{i:05d}.png"), cv2.COLOR_BGR2RGB)
+                       [128:256, 192:320] for i in range(4)])
+    fwd, bwd = fo.synthetic_flow(128, 128, 0), fo.synthetic_flow(128, 128, 1, backward_of=fo.synthetic_flow(128, 128, 0))
+    occ = cf.compute_occlusion_mask(fwd, bwd, threshold=1.5)
+    warped = cf.warp_image_with_flow(frames[1], fwd)
+    masked = cf.apply_mask(warped, occ, frames[0])
+    save("flow_warp.pt", {"frames": torch.from_numpy(frames), "occ": torch.from_numpy(occ), "warped": torch.from_numpy(warped),
+                          "masked": torch.from_numpy(masked)})
+
+
 def main(save):
     gen_style_transfer(save)
     gen_inversion(save)
+    gen_maskprop(save)
+    gen_flow_warp(save)

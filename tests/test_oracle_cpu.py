@@ -141,3 +141,71 @@ def test_scheduler_mirror_matches_oracle():
             ac, an = a.inversion_alphas(t)
             assert ac == pytest.approx(float(b.alpha(min(t - 1000 // n, 999)))) and an == pytest.approx(float(b.alpha(t)))
     assert [int(t) for t in a.timesteps][:2] == [901, 801]
+
+
+# ------------------------------------------------------------------------------------------------ mask propagation / flow warp
+def _maskprop_inputs(entry):
+    from oracle import maskprop_oracle as mo
+    h = entry["h"]
+    feats = mo.synthetic_features(entry["seed"], 3, h, h, entry["C"], separated=entry["sep"])
+    feat_src = torch.cat([feats[0].reshape(h * h, -1).T, feats[1].reshape(h * h, -1).T[:, ::3]], dim=-1).contiguous()
+    feat_tar = feats[2].reshape(h * h, -1).contiguous()
+    g = torch.Generator().manual_seed(3)
+    labels = (torch.rand(feat_src.shape[1], generator=g) > 0.6).long()
+    segs = torch.stack([(labels == 0).float(), (labels == 1).float()])
+    return feat_src, feat_tar, segs
+
+
+@pytest.mark.parametrize("name", ["smooth", "separated"])
+def test_maskprop_oracle_matches_reference(name):
+    from oracle import maskprop_oracle as mo
+    g = torch.load(os.path.join(GOLDEN, "maskprop.pt"), weights_only=True)[name]
+    feat_src, feat_tar, segs = _maskprop_inputs(g)
+    segs_tar, aff, thr = mo.mask_propogation_core(feat_src, feat_tar, segs)
+    assert torch.allclose(segs_tar, g["segs_tar"], atol=1e-6)
+    assert ((aff > 0).sum(0) >= 15).all()  # at least topk kept per target (ties are kept)
+    assert torch.allclose(segs_tar.sum(0), torch.ones(segs_tar.shape[1]), atol=1e-5)  # columns of aff sum to 1
+
+
+def test_flowwarp_oracle_matches_reference_and_cv2():
+    """The NumPy restatement of cv2.remap's fixed-point bilinear path is bit-exact against the reference helpers'
+    outputs (golden) and -- when cv2 is importable -- against cv2.remap itself on fresh random flows."""
+    import numpy as np
+    from oracle import flowwarp_oracle as fo
+    g = torch.load(os.path.join(GOLDEN, "flow_warp.pt"), weights_only=True)
+    frames = g["frames"].numpy()
+    fwd = fo.synthetic_flow(128, 128, 0)
+    bwd = fo.synthetic_flow(128, 128, 1, backward_of=fwd)
+    occ = fo.compute_occlusion_mask(fwd, bwd, threshold=1.5)
+    assert np.array_equal(occ, g["occ"].numpy()) and 0.02 < (occ > 0).mean() < 0.9
+    warped = fo.warp_image_with_flow(frames[1], fwd)
+    assert np.array_equal(warped, g["warped"].numpy())
+    assert np.array_equal(fo.apply_mask(warped, occ, frames[0]), g["masked"].numpy())
+    try:
+        import cv2
+    except ImportError:
+        return
+    rng = np.random.default_rng(1)
+    flow = (rng.standard_normal((128, 128, 2)) * 30).astype(np.float32)
+    gx, gy = np.meshgrid(np.arange(128), np.arange(128))
+    mx, my = (gx + flow[..., 0]).astype(np.float32), (gy + flow[..., 1]).astype(np.float32)
+    ref = cv2.remap(frames[2], mx, my, interpolation=cv2.INTER_LINEAR, borderMode=cv2.BORDER_CONSTANT)
+    assert np.array_equal(fo.remap_bilinear_u8(frames[2], mx, my), ref)
+
+
+def test_sliding_window_is_gauss_seidel_and_truncates():
+    """Window mean with zero flow: frame k becomes trunc(mean of itself and its +-2 neighbours), earlier frames
+    already updated (stable_diffusion.py:731-747)."""
+    import numpy as np
+    from oracle import flowwarp_oracle as fo
+    frames = np.zeros((4, 8, 8, 3), np.uint8)
+    for f in range(4):
+        frames[f] = 10 * f + 1
+    zero = np.zeros((8, 8, 2), np.float32)
+    out = fo.sliding_window_smooth(frames, lambda k, n: (zero, zero))
+    # key 0: (1 + 11 + 21) / 3 = 11; key 1: (11 + 11 + 21 + 31) / 4 = 18.5 -> 18; key 2: (11 + 18 + 21 + 31) / 4 = 20.25 -> 20
+    assert out[0, 0, 0, 0] == 11 and out[1, 0, 0, 0] == 18 and out[2, 0, 0, 0] == 20 and out[3, 0, 0, 0] == (18 + 20 + 31) // 3
+    keep = np.zeros((4, 8, 8), np.uint8)
+    keep[:, :4] = 1
+    out2 = fo.sliding_window_smooth(frames, lambda k, n: (zero, zero), keep_mask=keep)
+    assert (out2[:, :4] == frames[:, :4]).all() and (out2[:, 4:] == out[:, 4:]).all()

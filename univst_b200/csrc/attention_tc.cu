@@ -8,11 +8,12 @@
 // Structure (FlashAttention-4 style, one CTA per (q-tile group, head, image)):
 //   warp 0        TMA producer: Q tiles once, K and V tiles through two 2-deep rings
 //   warp 1        tcgen05.mma issuer: S = Q K^T into a TMEM slot, O += P V with P read from shared memory
-//   warps 2..     softmax groups of 256 threads, two threads per query row (half of the score columns each):
-//                 TMEM -> registers, running max with lazy (thresholded) rescale of the TMEM-resident O, exp2,
-//                 fp16 P tile written 128B-swizzled
+//   warps 2..     softmax groups of 128 threads, one thread per query row: TMEM -> registers, running max with
+//                 lazy (thresholded) rescale of the TMEM-resident O, exp2, fp16 P tile written 128B-swizzled
 //   NQ = 2: two query tiles per CTA ping-pong on the tensor pipe (slot = q tile);
 //   NQ = 1: one query tile, the two S slots alternate between consecutive KV tiles.
+//   An S slot is released as soon as its tile sits in registers, so the next Q K^T of that query tile runs under the
+//   current tile's exponentials (the MUFU pipe, not the tensor pipe, bounds d = 40).
 // Head dims that are not multiples of 64 (SD-1.5: 40 / 80 / 160) are zero-filled by TMA out-of-bounds
 // handling; nothing is padded in global memory.
 #include "host_util.h"
@@ -51,7 +52,7 @@ struct AttnSmem {
 };
 
 template <int NQ, int BKV>
-__global__ void __launch_bounds__(64 + 256 * NQ, 1)
+__global__ void __launch_bounds__(64 + 128 * NQ, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using L = AttnSmem<NQ, BKV>;
@@ -75,8 +76,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* s_full = bars + 9;        // 2
   uint64_t* p_full = bars + 11;       // 2
   uint64_t* o_done = bars + 13;       // NQ (<= 2)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
-  float* xchg = reinterpret_cast<float*>(bars + 16);  // [NQ][2 parities][2 halves][128] row-pair exchange
+  uint64_t* s_free = bars + 15;       // 2
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -98,7 +99,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 256);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&s_free[s], 128);
       mbar_init(&o_done[s], 1);
     }
     fence_barrier_init();
@@ -162,11 +164,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (q == NQ - 1) tc_commit(&k_empty[ks]);
         tc_commit(&s_full[slot]);
       };
-      mbar_wait(q_full, 0);
-      tc_fence_after();
-      issue_s(0);
-      for (int i = 0; i < I; ++i) {
-        if (i + 1 < I) issue_s(i + 1);
+      auto issue_pv = [&](int i) {
         const int q = i % NQ, j = i / NQ, vs = j & 1, slot = i & 1;
         // P of item i is the (i/2)-th use of its slot
         mbar_wait(&p_full[slot], (uint32_t)((i >> 1) & 1));
@@ -184,72 +182,76 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         if (q == NQ - 1) tc_commit(&v_empty[vs]);
         tc_commit(&o_done[q]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      // Both S slots are filled up front; afterwards a slot is refilled with the scores of the next item that maps to
+      // it as soon as the softmax group has pulled the current tile into registers (s_free), i.e. *during* that
+      // tile's exponentials -- a group never waits for the tensor pipe between two tiles.
+      issue_s(0);
+      if (I > 1) issue_s(1);
+      for (int j = 0; j < T; ++j) {
+        for (int q = 0; q < NQ; ++q) {
+          const int i = j * NQ + q;
+          if (i + 2 < I) {
+            mbar_wait(&s_free[i & 1], (uint32_t)((i >> 1) & 1));
+            tc_fence_after();
+            issue_s(i + 2);
+          }
+        }
+        for (int q = 0; q < NQ; ++q) issue_pv(j * NQ + q);
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax groups
-    // A group = 8 warps = 256 threads on one 128-row query tile: two threads per row, each owning half of the BKV
-    // score columns (warps 2..5 / 10..13: first half, warps 6..9 / 14..17: second half; TMEM lane quadrant =
-    // warp % 4).  Four softmax warps per scheduler keep the MUFU pipe fed while their siblings wait on TMEM.
-    constexpr int HB = BKV / 2;                          // score columns per thread
-    const int wi = (int)(warp - 2);
-    const int g = wi >> 3;                               // group index (== q tile when NQ == 2)
-    const int half = (wi >> 2) & 1;                      // which half of the columns
-    const uint32_t quad = warp & 3;                      // TMEM lane quadrant this warp may touch
-    const uint32_t r = quad * 32 + lane;                 // row inside the 128-row tile
+    const int g = (int)(warp - 2) >> 2;                 // group index (== q tile when NQ == 2)
+    const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
+    const uint32_t r = quad * 32 + lane;                // row inside the 128-row tile
     const uint32_t lane_off = (quad * 32) << 16;
     const uint32_t o_addr = tmem_base + kOBase + g * opad + lane_off;
-    // O columns are split between the two threads of a row in units of 16
-    const uint32_t o_split = ((opad / 16 + 1) / 2) * 16;
-    const uint32_t oc0 = half ? o_split : 0, oc1 = half ? opad : o_split;
-    float* xrow = xchg + (size_t)g * 2 * 2 * 128;        // [parity][half][128]
-    const uint32_t bar_id = 1 + g;
-    float m_used = -INFINITY;   // max baked into O and l (identical in both threads of a row)
-    float l = 0.0f;             // partial row sum over this thread's columns
+    float m_used = -INFINITY;   // max baked into O and l
+    float l = 0.0f;
     for (int j = 0; j < T; ++j) {
       const int i = j * NQ + g;
       const int slot = i & 1;
       mbar_wait(&s_full[slot], (uint32_t)((i >> 1) & 1));
       tc_fence_after();
-      // S half-row -> registers: all loads in flight, one wait
-      uint32_t sraw[HB];
+      // S tile -> registers: all loads in flight, one wait
+      uint32_t sraw[BKV];
       {
-        const uint32_t sa = tmem_base + slot * kSlotCols + lane_off + half * HB;
+        const uint32_t sa = tmem_base + slot * kSlotCols + lane_off;
 #pragma unroll
-        for (int c = 0; c < HB / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]));
+        for (int c = 0; c < BKV / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]));
         tc_wait_ld();
       }
-      const int valid = min(BKV, p.Nkv - (j % tps) * BKV) - half * HB;   // valid columns of this half
-      if (valid < HB) {
+      tc_fence_before();
+      mbar_arrive(&s_free[slot]);  // the slot may be overwritten with the next scores from here on
+      const int valid = min(BKV, p.Nkv - (j % tps) * BKV);
+      if (valid < BKV) {
 #pragma unroll
-        for (int x = 0; x < HB; ++x)
+        for (int x = 0; x < BKV; ++x)
           if (x >= valid) sraw[x] = 0xff800000u;  // -inf
       }
-      // max of the raw scores over this half: 8 independent chains
+      // row max of the raw scores: 8 independent chains (a single chain is 128 dependent FMNMX)
       float mx8[8];
 #pragma unroll
       for (int x = 0; x < 8; ++x) mx8[x] = __uint_as_float(sraw[x]);
 #pragma unroll
-      for (int x = 8; x < HB; ++x) mx8[x & 7] = fmaxf(mx8[x & 7], __uint_as_float(sraw[x]));
-      const float mxh = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                              fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7])));
-      // exchange the half maxima inside the row pair (double-buffered by tile parity; one named barrier per tile)
-      float* xb = xrow + (j & 1) * 256;
-      xb[half * 128 + r] = mxh;
-      asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-      const float mx = fmaxf(mxh, xb[(half ^ 1) * 128 + r]) * p.scale_log2;
+      for (int x = 8; x < BKV; ++x) mx8[x & 7] = fmaxf(mx8[x & 7], __uint_as_float(sraw[x]));
+      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
+                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
       // previous P V of this query tile must have landed before O may be touched / P slot reused
       if (j > 0) {
         mbar_wait(&o_done[g], (uint32_t)((j - 1) & 1));
         tc_fence_after();
       }
       const bool need = mx > m_used + kRescaleThreshold;   // first tile: m_used = -inf -> always true
-      if (__any_sync(0xffffffffu, need)) {                 // same rows -> same decision in the sibling warp
+      if (__any_sync(0xffffffffu, need)) {
         const float m_new = fmaxf(m_used, mx);
         if (j > 0) {
           const float alpha = ex2_approx(m_used - m_new);   // lanes that did not need it: alpha <= 1, harmless
           l *= alpha;
-          for (uint32_t c = oc0; c < oc1; c += 16) {
+          for (uint32_t c = 0; c < opad; c += 16) {
             uint32_t t[16];
             tmem_ld16(o_addr + c, t);
             tc_wait_ld();
@@ -267,37 +269,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       float ls4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       const float neg_m = -m_used;
 #pragma unroll
-      for (int c8 = 0; c8 < HB / 8; ++c8) {
+      for (int c16 = 0; c16 < BKV / 8; ++c16) {
         uint32_t w[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[c8 * 8 + 2 * x]), p.scale_log2, neg_m));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[c8 * 8 + 2 * x + 1]), p.scale_log2, neg_m));
+          const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x]), p.scale_log2, neg_m));
+          const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x + 1]), p.scale_log2, neg_m));
           ls4[x] += e0 + e1;
           w[x] = pack_half2(e0, e1);
         }
-        const int c16 = half * (HB / 8) + c8;              // 16-byte chunk index inside the BKV-wide row
         const int kc = c16 >> 3, cc = c16 & 7;
         *reinterpret_cast<uint4*>(prow + kc * (128 * 128) + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
+      l += lsum;
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[slot]);
     }
     // ------------------------------------------------------------------ epilogue: O / l -> global
-    // total row sum = sum of the two partial sums (exchanged through the same buffer, parity T & 1)
-    float* xb = xrow + (T & 1) * 256;
-    xb[half * 128 + r] = l;
-    asm volatile("bar.sync %0, 256;" ::"r"(bar_id) : "memory");
-    l += xb[(half ^ 1) * 128 + r];
     mbar_wait(&o_done[g], (uint32_t)((T - 1) & 1));
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int qrow = (qt0 + g) * 128 + (int)r;
     const bool row_ok = qrow < p.N;
     __half* orow = p.O + ((size_t)img * p.N + qrow) * p.ldo + head * p.d;
-    for (uint32_t c = oc0; c < oc1; c += 16) {
+    for (uint32_t c = 0; c < opad; c += 16) {
       uint32_t t[16];
       tmem_ld16(o_addr + c, t);
       tc_wait_ld();
@@ -330,7 +327,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   using L = AttnSmem<NQ, BKV>;
   const int dch = (p.d + 63) / 64;
   const size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes + 2 * L::kPBytes +
-                      16 * sizeof(uint64_t) + NQ * 2 * 2 * 128 * sizeof(float) + 1024;
+                      18 * sizeof(uint64_t) + 1024;
   UV_REQUIRE(smem <= 227 * 1024, "attention: tile configuration needs %zu bytes of shared memory", smem);
   static bool configured = false;
   if (!configured) {
@@ -339,7 +336,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.N + 128 * NQ - 1) / (128 * NQ), p.H, p.NI);
-  attention_tc_kernel<NQ, BKV><<<grid, 64 + 256 * NQ, smem, stream>>>(tq, tk, tv, p);
+  attention_tc_kernel<NQ, BKV><<<grid, 64 + 128 * NQ, smem, stream>>>(tq, tk, tv, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

@@ -31,13 +31,17 @@ _lib.register("univst_latent_blend_f16", [_vp, _vp, _vp, _i32, _i32, _i32, _vp, 
 _lib.register("univst_latent_adain_f16", [_vp, _vp, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp])
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
+_lib.register("univst_maskprop_workspace_bytes", [_i32, _i32, _i32], _i64)
+_lib.register("univst_maskprop_f32", [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp])
+_lib.register("univst_flow_warp_key_u8", [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp), _f32, _vp])
+_lib.register("univst_mask_select_u8", [_vp, _vp, _vp, _i64, _vp, _vp])
 
 # number of kernels launched through this module (bench.py reports it as ``gpu_launches``)
 launch_count = 0
 _LAUNCHES = {
     "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 2, "layernorm": 1, "upsample2x": 1,
     "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
-    "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1,
+    "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
 
 
@@ -342,4 +346,53 @@ def axpby(a, b, wa: float, wb: float, out=None):
     check(_lib.lib().univst_axpby_f16(a.data_ptr(), b.data_ptr(), wa, wb, a.numel(), out.data_ptr(), _stream()),
           "univst_axpby_f16")
     _count("axpby")
+    return out
+
+
+def maskprop(feat_tar, feat_src, segs, temperature: float = 0.2, topk: int = 15, return_thresholds: bool = False):
+    """feat_tar [N, C], feat_src [C, M], segs [Ccls, M] fp32 CUDA -> segs_tar [Ccls, N] (mask_propagation.py:75-83)."""
+    _lib.require_device()
+    for t, n in ((feat_tar, "feat_tar"), (feat_src, "feat_src"), (segs, "segs")):
+        _chk(t, n, torch.float32)
+    N, C_ = feat_tar.shape
+    M = feat_src.shape[1]
+    Ccls = segs.shape[0]
+    assert feat_src.shape[0] == C_ and segs.shape[1] == M
+    out = torch.empty((Ccls, N), dtype=torch.float32, device=feat_tar.device)
+    thr = torch.empty((N,), dtype=torch.float32, device=feat_tar.device) if return_thresholds else None
+    ws = _workspace(_lib.lib().univst_maskprop_workspace_bytes(N, C_, M), feat_tar.device)
+    check(_lib.lib().univst_maskprop_f32(feat_tar.data_ptr(), feat_src.data_ptr(), segs.data_ptr(), N, C_, M, Ccls,
+                                         temperature, topk, out.data_ptr(), _ptr(thr), ws.data_ptr(), _stream()),
+          "univst_maskprop_f32")
+    _count("maskprop")
+    return (out, thr) if return_thresholds else out
+
+
+def flow_warp_key_(frames, key: int, neighbours, fwd_flows, bwd_flows, threshold: float = 1.5):
+    """In-place smoothing of frames[key] ([F, H, W, 3] uint8 CUDA) from its neighbours (stable_diffusion.py:731-747)."""
+    _lib.require_device()
+    _chk(frames, "frames", torch.uint8)
+    F, H, W, ch = frames.shape
+    assert ch == 3 and len(neighbours) == len(fwd_flows) == len(bwd_flows) <= 4
+    for f in list(fwd_flows) + list(bwd_flows):
+        _chk(f, "flow", torch.float32)
+        assert tuple(f.shape) == (H, W, 2)
+    n = len(neighbours)
+    idx = (_i32 * max(n, 1))(*neighbours)
+    fw = (_vp * max(n, 1))(*[f.data_ptr() for f in fwd_flows])
+    bw = (_vp * max(n, 1))(*[f.data_ptr() for f in bwd_flows])
+    check(_lib.lib().univst_flow_warp_key_u8(frames.data_ptr(), F, H, W, key, n, idx, fw, bw, threshold, _stream()),
+          "univst_flow_warp_key_u8")
+    _count("flow_warp_key")
+    return frames
+
+
+def mask_select(keep_mask, orig, est):
+    """keep_mask [.., H, W] uint8 (non-zero = keep ``orig``), orig / est [.., H, W, 3] uint8."""
+    _lib.require_device()
+    _chk(keep_mask, "keep_mask", torch.uint8), _chk(orig, "orig", torch.uint8), _chk(est, "est", torch.uint8)
+    out = torch.empty_like(est)
+    check(_lib.lib().univst_mask_select_u8(keep_mask.data_ptr(), orig.data_ptr(), est.data_ptr(), keep_mask.numel(),
+                                           out.data_ptr(), _stream()), "univst_mask_select_u8")
+    _count("mask_select")
     return out

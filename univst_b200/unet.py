@@ -338,4 +338,5 @@ class UNetPseudo3DConditionModel:
         out = ops.unpack_latents(self.last_eps_rows, B, cfg["out_channels"], F, h, w)
         return UNetPseudo3DConditionOutput(sample=out)
 
-    __call__ = forward
+    def __call__(self, *args, **kwargs):
+        return self.forward(*args, **kwargs)
