@@ -131,12 +131,13 @@ int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n
  * Point-matching mask propagation (src/mask_propagation.py:72-83): aff = exp(<tar_n, src_m> / T) on L2-normalised
  * features; per target point keep the entries >= its topk-th largest (ties kept), normalise, transport the labels.
  * feat_tar [N, C], feat_src [C, M] (the reference's layouts), segs [Ccls, M] -> segs_tar [Ccls, N]; all fp32 device
- * pointers.  thresholds (optional, [N]) receives the per-target kept threshold (for index-set parity tests).
+ * pointers.  Optional outputs for index-set parity tests: thresholds [N] (the per-target kept threshold) and
+ * kept_idx [N, kept_cap] (the kept source indices in ascending order, -1 padded).
  * ---------------------------------------------------------------------------------------------------------- */
 int64_t univst_maskprop_workspace_bytes(int32_t N, int32_t C, int32_t M);
 int univst_maskprop_f32(const float* feat_tar, const float* feat_src, const float* segs, int32_t N, int32_t C, int32_t M,
                         int32_t Ccls, float temperature, int32_t topk, float* segs_tar, float* thresholds,
-                        void* workspace, void* stream);
+                        int32_t* kept_idx, int32_t kept_cap, void* workspace, void* stream);
 
 /* Sliding-window flow-warp smoothing, one key frame (src/cal_optica_flow.py:20-46; window loop of
  * pipelines/stable_diffusion.py:725-751).  frames: [F, H, W, 3] uint8, updated IN PLACE at `key`; for each of the

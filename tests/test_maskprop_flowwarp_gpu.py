@@ -31,21 +31,27 @@ def test_maskprop_kernel(cuda_lib, h, C, sep):
     from univst_b200 import ops
     feat_src, feat_tar, segs = _inputs(11, h, C, sep)
     ref, aff, thr_ref = mo.mask_propogation_core(feat_src, feat_tar, segs)
-    out, thr = ops.maskprop(feat_tar.cuda(), feat_src.cuda(), segs.cuda(), 0.2, 15, return_thresholds=True)
-    out, thr = out.cpu(), thr.cpu()
-    # kept index set implied by the kernel's thresholds, evaluated on the oracle's affinity values
+    out, thr, kept = ops.maskprop(feat_tar.cuda(), feat_src.cuda(), segs.cuda(), 0.2, 15, return_kept=32)
+    out, kept = out.cpu(), kept.cpu()
+    N, M = feat_tar.shape[0], feat_src.shape[1]
+    kept_ours = torch.zeros(M, N, dtype=torch.bool)
+    cols = torch.arange(N)[:, None].expand(-1, 32)
+    valid = kept >= 0
+    kept_ours[kept[valid].long(), cols[valid]] = True
+    kept_ref = aff > 0
+    diff = kept_ref != kept_ours
+    # relative gap to the threshold of every entry on which the two kept sets disagree (oracle affinity values)
     src = torch.nn.functional.normalize(feat_src, dim=0)
     tar = torch.nn.functional.normalize(feat_tar, dim=1)
     a = torch.exp(tar @ src / 0.2).T
-    kept_ref, kept_ours = a >= thr_ref, a >= thr
-    diff = kept_ref != kept_ours
     rel_gap = ((a - thr_ref).abs() / thr_ref)[diff]
     print(f"h={h} C={C} sep={sep}: kept entries {int(kept_ref.sum())}, differing {int(diff.sum())}, "
           f"max |segs_tar err| {(out - ref).abs().max().item():.2e}")
+    assert (valid.sum(1) >= 15).all()
     if sep:
         assert int(diff.sum()) == 0, "kept index set must be bit-exact on well-separated features"
     else:
-        assert diff.sum() <= 1e-4 * kept_ref.sum() + 2 and (rel_gap < 1e-5).all()
+        assert diff.sum() <= 1e-3 * kept_ref.sum() + 2 and (rel_gap < 1e-5).all()
     ok = ~diff.any(0)
     assert (out - ref)[:, ok].abs().max().item() < 1e-5
 

@@ -44,6 +44,19 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// 2^x on the FMA / ALU pipes (Cody-Waite split + degree-3 minimax polynomial, max relative error 7.5e-5 -- below the
+// half-ulp of the fp16 P it feeds): a quarter of the exponentials take this path so that the MUFU pipe, which bounds
+// attention at head dim 40, is relieved (the FlashAttention-4 trick).
+__device__ __forceinline__ float ex2_poly(float x) {
+  x = fmaxf(x, -126.0f);
+  const float t = x + 12582912.0f;          // 1.5 * 2^23: nearest integer of x lands in the low mantissa bits
+  const float f = x - (t - 12582912.0f);    // fractional part in [-0.5, 0.5]
+  float p = fmaf(0.0551716574f, f, 0.2426111251f);
+  p = fmaf(p, f, 0.6932609677f);
+  p = fmaf(p, f, 0.9999280572f);
+  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
 template <int NQ, int BKV>
 struct AttnSmem {
   static constexpr int kQChunkBytes = 128 * 128;      // [128 rows][64 halves]
@@ -52,7 +65,7 @@ struct AttnSmem {
 };
 
 template <int NQ, int BKV>
-__global__ void __launch_bounds__(64 + 128 * NQ, 1)
+__global__ void __launch_bounds__(64 + 128 * NQ + 32 * (NQ - 1), 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
   using L = AttnSmem<NQ, BKV>;
@@ -95,9 +108,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
+      mbar_init(&k_empty[s], NQ);   // one tcgen05.commit per MMA issuer
       mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
+      mbar_init(&v_empty[s], NQ);
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
       mbar_init(&s_free[s], 128);
@@ -139,17 +152,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (s == 1) phase ^= 1;
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 1 || warp == 2 + 4 * NQ) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer
+      // ---------------------------------------------------------------- MMA issuer(s)
+      // NQ == 2: one issuing thread per query tile (warp 1 -> tile 0, last warp -> tile 1), so the two softmax groups
+      // are decoupled: neither ever waits behind the other's barriers.  NQ == 1: warp 1 alternates the two S slots.
+      const int mq = (warp == 1) ? 0 : 1;
       const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
       const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
       auto issue_s = [&](int i) {
         const int q = i % NQ, j = i / NQ, ks = j & 1, slot = i & 1;
-        if (q == 0) {
-          mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
-          tc_fence_after();
-        }
+        mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
         const uint32_t qa = smem_u32(sQ + q * q_bytes);
         const uint32_t ka = smem_u32(sK + ks * kv_bytes);
         int step = 0;
@@ -161,14 +175,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             umma_f16_ss(tmem_base + slot * kSlotCols, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s,
                         step ? 1u : 0u);
         }
-        if (q == NQ - 1) tc_commit(&k_empty[ks]);
+        tc_commit(&k_empty[ks]);
         tc_commit(&s_full[slot]);
       };
       auto issue_pv = [&](int i) {
         const int q = i % NQ, j = i / NQ, vs = j & 1, slot = i & 1;
         // P of item i is the (i/2)-th use of its slot
         mbar_wait(&p_full[slot], (uint32_t)((i >> 1) & 1));
-        if (q == 0) mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
+        mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
         const uint32_t pa = smem_u32(sP + slot * L::kPBytes);
         const uint32_t va = smem_u32(sV + vs * kv_bytes);
@@ -180,7 +194,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint64_t db = make_smem_desc_sw128(va + k * 2048, L::kKVChunkBytes, 1024);
           umma_f16_ss(tmem_base + kOBase + q * opad, da, db, idesc_o, (j | k) ? 1u : 0u);
         }
-        if (q == NQ - 1) tc_commit(&v_empty[vs]);
+        tc_commit(&v_empty[vs]);
         tc_commit(&o_done[q]);
       };
       mbar_wait(q_full, 0);
@@ -188,21 +202,31 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // Both S slots are filled up front; afterwards a slot is refilled with the scores of the next item that maps to
       // it as soon as the softmax group has pulled the current tile into registers (s_free), i.e. *during* that
       // tile's exponentials -- a group never waits for the tensor pipe between two tiles.
-      issue_s(0);
-      if (I > 1) issue_s(1);
-      for (int j = 0; j < T; ++j) {
-        for (int q = 0; q < NQ; ++q) {
-          const int i = j * NQ + q;
+      if constexpr (NQ == 2) {
+        // items of this issuer: (mq, j), slot = mq; item index i = 2 j + mq
+        issue_s(mq);
+        for (int j = 0; j < T; ++j) {
+          if (j + 1 < T) {
+            mbar_wait(&s_free[mq], (uint32_t)(j & 1));
+            tc_fence_after();
+            issue_s(2 * (j + 1) + mq);
+          }
+          issue_pv(2 * j + mq);
+        }
+      } else {
+        issue_s(0);
+        if (I > 1) issue_s(1);
+        for (int i = 0; i < I; ++i) {
           if (i + 2 < I) {
             mbar_wait(&s_free[i & 1], (uint32_t)((i >> 1) & 1));
             tc_fence_after();
             issue_s(i + 2);
           }
+          issue_pv(i);
         }
-        for (int q = 0; q < NQ; ++q) issue_pv(j * NQ + q);
       }
     }
-  } else {
+  } else if (warp < 2 + 4 * NQ) {
     // ------------------------------------------------------------------ softmax groups
     const int g = (int)(warp - 2) >> 2;                 // group index (== q tile when NQ == 2)
     const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
@@ -273,8 +297,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint32_t w[4];
 #pragma unroll
         for (int x = 0; x < 4; ++x) {
-          const float e0 = ex2_approx(fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x]), p.scale_log2, neg_m));
-          const float e1 = ex2_approx(fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x + 1]), p.scale_log2, neg_m));
+          const float a0 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x]), p.scale_log2, neg_m);
+          const float a1 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x + 1]), p.scale_log2, neg_m);
+          const float e0 = ex2_approx(a0);
+          const float e1 = (x & 1) ? ex2_poly(a1) : ex2_approx(a1);   // every 4th element off the MUFU pipe
           ls4[x] += e0 + e1;
           w[x] = pack_half2(e0, e1);
         }
@@ -336,7 +362,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.N + 128 * NQ - 1) / (128 * NQ), p.H, p.NI);
-  attention_tc_kernel<NQ, BKV><<<grid, 64 + 128 * NQ, smem, stream>>>(tq, tk, tv, p);
+  attention_tc_kernel<NQ, BKV><<<grid, 64 + 128 * NQ + 32 * (NQ - 1), smem, stream>>>(tq, tk, tv, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

@@ -106,7 +106,8 @@ __device__ __forceinline__ void aff_tile(const float* __restrict__ tar, const fl
 
 __global__ void __launch_bounds__(256)
 maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, const float* __restrict__ segs, int N, int C,
-                int M, int Ccls, float temperature, int topk, float* __restrict__ out, float* __restrict__ thr_out) {
+                int M, int Ccls, float temperature, int topk, float* __restrict__ out, float* __restrict__ thr_out,
+                int* __restrict__ kept_idx, int kept_cap) {
   __shared__ float At[kKC][kTR + 1];
   __shared__ float Bs[kKC][kSC + 4];
   __shared__ float S[kTR][kSC + 1];
@@ -153,6 +154,7 @@ maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, co
 
   // ---- pass 2: same scores again; kept entries (aff >= threshold) accumulated in ascending source order
   float num[4][kMaxClassRegs], den[4];
+  int cnt[4] = {0, 0, 0, 0};
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) {
     den[rr] = 0.0f;
@@ -174,6 +176,8 @@ maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, co
           const float a = __shfl_sync(0xffffffffu, v, srcl);
           const int m = chunk * kSC + t * 32 + srcl;
           den[rr] += a;
+          if (kept_idx && lane == 0 && n0 + row < N && cnt[rr] < kept_cap) kept_idx[(size_t)(n0 + row) * kept_cap + cnt[rr]] = m;
+          ++cnt[rr];
 #pragma unroll
           for (int u = 0; u < kMaxClassRegs; ++u) {
             const int c = lane + 32 * u;
@@ -194,6 +198,8 @@ maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, co
       if (c < Ccls) out[(size_t)c * N + n] = num[rr][u] / den[rr];
     }
     if (thr_out && lane == 0) thr_out[n] = thr4[rr];
+    if (kept_idx && lane == 0)
+      for (int e = cnt[rr]; e < kept_cap; ++e) kept_idx[(size_t)n * kept_cap + e] = -1;
   }
 }
 
@@ -207,7 +213,8 @@ extern "C" int64_t univst_maskprop_workspace_bytes(int32_t N, int32_t C, int32_t
 
 extern "C" int univst_maskprop_f32(const float* feat_tar, const float* feat_src, const float* segs, int32_t N, int32_t C,
                                    int32_t M, int32_t Ccls, float temperature, int32_t topk, float* segs_tar,
-                                   float* thresholds, void* workspace, void* stream) {
+                                   float* thresholds, int32_t* kept_idx, int32_t kept_cap, void* workspace,
+                                   void* stream) {
   UV_REQUIRE(feat_tar && feat_src && segs && segs_tar && workspace, "maskprop: null pointer");
   UV_REQUIRE(N > 0 && C > 0 && M >= topk && topk >= 1 && topk <= 32, "maskprop: need 1 <= topk <= 32 <= M");
   UV_REQUIRE(Ccls >= 1 && Ccls <= 32 * kMaxClassRegs, "maskprop: at most 256 classes");
@@ -220,7 +227,7 @@ extern "C" int univst_maskprop_f32(const float* feat_tar, const float* feat_src,
   normalize_cols_t_kernel<<<(M + 31) / 32, 256, 0, st>>>(feat_src, C, M, src_n);
   UV_CHECK_CUDA(cudaGetLastError());
   maskprop_kernel<<<(N + kTR - 1) / kTR, 256, 0, st>>>(tar_n, src_n, segs, N, C, M, Ccls, temperature, topk, segs_tar,
-                                                     thresholds);
+                                                     thresholds, kept_idx, kept_cap);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

@@ -32,7 +32,7 @@ _lib.register("univst_latent_adain_f16", [_vp, _vp, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp])
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
 _lib.register("univst_maskprop_workspace_bytes", [_i32, _i32, _i32], _i64)
-_lib.register("univst_maskprop_f32", [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _vp])
+_lib.register("univst_maskprop_f32", [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp])
 _lib.register("univst_flow_warp_key_u8", [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp), _f32, _vp])
 _lib.register("univst_mask_select_u8", [_vp, _vp, _vp, _i64, _vp, _vp])
 
@@ -349,7 +349,7 @@ def axpby(a, b, wa: float, wb: float, out=None):
     return out
 
 
-def maskprop(feat_tar, feat_src, segs, temperature: float = 0.2, topk: int = 15, return_thresholds: bool = False):
+def maskprop(feat_tar, feat_src, segs, temperature: float = 0.2, topk: int = 15, return_kept: int = 0):
     """feat_tar [N, C], feat_src [C, M], segs [Ccls, M] fp32 CUDA -> segs_tar [Ccls, N] (mask_propagation.py:75-83)."""
     _lib.require_device()
     for t, n in ((feat_tar, "feat_tar"), (feat_src, "feat_src"), (segs, "segs")):
@@ -359,13 +359,15 @@ def maskprop(feat_tar, feat_src, segs, temperature: float = 0.2, topk: int = 15,
     Ccls = segs.shape[0]
     assert feat_src.shape[0] == C_ and segs.shape[1] == M
     out = torch.empty((Ccls, N), dtype=torch.float32, device=feat_tar.device)
-    thr = torch.empty((N,), dtype=torch.float32, device=feat_tar.device) if return_thresholds else None
+    thr = torch.empty((N,), dtype=torch.float32, device=feat_tar.device) if return_kept else None
+    kept = torch.empty((N, return_kept), dtype=torch.int32, device=feat_tar.device) if return_kept else None
     ws = _workspace(_lib.lib().univst_maskprop_workspace_bytes(N, C_, M), feat_tar.device)
     check(_lib.lib().univst_maskprop_f32(feat_tar.data_ptr(), feat_src.data_ptr(), segs.data_ptr(), N, C_, M, Ccls,
-                                         temperature, topk, out.data_ptr(), _ptr(thr), ws.data_ptr(), _stream()),
+                                         temperature, topk, out.data_ptr(), _ptr(thr), _ptr(kept), return_kept,
+                                         ws.data_ptr(), _stream()),
           "univst_maskprop_f32")
     _count("maskprop")
-    return (out, thr) if return_thresholds else out
+    return (out, thr, kept) if return_kept else out
 
 
 def flow_warp_key_(frames, key: int, neighbours, fwd_flows, bwd_flows, threshold: float = 1.5):
