@@ -7,15 +7,18 @@
 //
 // Structure (FlashAttention-4 style, one CTA per (q-tile group, head, image)):
 //   warp 0        TMA producer: Q tiles once, K and V tiles through two 2-deep rings
-//   warp 1        tcgen05.mma issuer: S = Q K^T into a TMEM slot, O += P V with P read from shared memory
+//   warp 1 (+ one extra warp per additional query tile)  tcgen05.mma issuers, one per query tile:
+//                 S = Q K^T into a TMEM slot, O += P V with P read from shared memory
 //   warps 2..     softmax groups of 128 threads, one thread per query row: TMEM -> registers, running max with
 //                 lazy (thresholded) rescale of the TMEM-resident O, exp2, fp16 P tile written 128B-swizzled
-//   NQ = 2: two query tiles per CTA ping-pong on the tensor pipe (slot = q tile);
-//   NQ = 1: one query tile, the two S slots alternate between consecutive KV tiles.
+//   NQ = 2 / 4: that many query tiles per CTA share the K/V ring and keep 2 / 4 softmax warps per scheduler;
+//   NQ = 1: one query tile whose two S slots alternate between consecutive KV tiles.
 //   An S slot is released as soon as its tile sits in registers, so the next Q K^T of that query tile runs under the
 //   current tile's exponentials (the MUFU pipe, not the tensor pipe, bounds d = 40).
 // Head dims that are not multiples of 64 (SD-1.5: 40 / 80 / 160) are zero-filled by TMA out-of-bounds
 // handling; nothing is padded in global memory.
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -34,9 +37,9 @@ struct AttnParams {
   float scale_log2;  // d^-0.5 * log2(e)
 };
 
-static constexpr uint32_t kSlotCols = 128;  // TMEM columns per S slot
 static constexpr uint32_t kOBase = 256;     // TMEM column of the first O accumulator
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 before a forced rescale
+static constexpr int kDefaultVariant = 0;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -58,17 +61,26 @@ __device__ __forceinline__ float ex2_poly(float x) {
 }
 
 template <int NQ, int BKV>
-struct AttnSmem {
-  static constexpr int kQChunkBytes = 128 * 128;      // [128 rows][64 halves]
-  static constexpr int kKVChunkBytes = BKV * 128;     // [BKV rows][64 halves]
-  static constexpr int kPBytes = 128 * BKV * 2;       // [128 rows][BKV halves] as BKV/64 swizzled chunks
+struct AttnCfg {
+  static constexpr int kDepth = (NQ == 1) ? 2 : 1;      // S / P slots per query tile
+  static constexpr int kSlots = NQ * kDepth;
+  static constexpr int kThreads = 64 + 128 * NQ + 32 * (NQ - 1);
+  static constexpr int kQChunkBytes = 128 * 128;        // [128 rows][64 halves]
+  static constexpr int kKVChunkBytes = BKV * 128;       // [BKV rows][64 halves]
+  static constexpr int kPBytes = 128 * BKV * 2;         // [128 rows][BKV halves] as BKV/64 swizzled chunks
+  static constexpr int kBarriers = 32;
+  static_assert(kSlots * BKV <= 256, "S slots must fit below the O accumulators");
 };
 
-template <int NQ, int BKV>
-__global__ void __launch_bounds__(64 + 128 * NQ + 32 * (NQ - 1), 1)
+// Work decomposition: query tile q of the CTA streams KV tiles j = 0..T-1.  Tile (q, j) uses S/P slot
+// q * kDepth + j % kDepth for the (j / kDepth)-th time.  Every query tile has its own MMA-issuing thread and its own
+// softmax group, so the tiles only meet at the K/V ring.
+template <int NQ, int BKV, bool POLY>
+__global__ void __launch_bounds__(AttnCfg<NQ, BKV>::kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-  using L = AttnSmem<NQ, BKV>;
+  using L = AttnCfg<NQ, BKV>;
+  constexpr int D = L::kDepth, NS = L::kSlots;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
 
@@ -79,18 +91,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;                                  // [NQ][dch][128][64]
   uint8_t* sK = sQ + NQ * q_bytes;                     // [2][dch][BKV][64]
   uint8_t* sV = sK + 2 * kv_bytes;                     // [2][dch][BKV][64]
-  uint8_t* sP = sV + 2 * kv_bytes;                     // [2][BKV/64][128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * L::kPBytes);
+  uint8_t* sP = sV + 2 * kv_bytes;                     // [NS][BKV/64][128][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NS * L::kPBytes);
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // 2
   uint64_t* k_empty = bars + 3;       // 2
   uint64_t* v_full = bars + 5;        // 2
   uint64_t* v_empty = bars + 7;       // 2
-  uint64_t* s_full = bars + 9;        // 2
-  uint64_t* p_full = bars + 11;       // 2
-  uint64_t* o_done = bars + 13;       // NQ (<= 2)
-  uint64_t* s_free = bars + 15;       // 2
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* s_full = bars + 9;        // NS (<= 4)
+  uint64_t* p_full = bars + 13;       // NS
+  uint64_t* s_free = bars + 17;       // NS
+  uint64_t* o_done = bars + 21;       // NQ
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -99,7 +111,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int img = blockIdx.z;
   const int tps = (p.Nkv + BKV - 1) / BKV;   // KV tiles per source
   const int T = p.nsrc * tps;                // KV tiles in total
-  const int I = T * NQ;                      // work items (q, j), q fastest
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -111,11 +122,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       mbar_init(&k_empty[s], NQ);   // one tcgen05.commit per MMA issuer
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], NQ);
+    }
+    for (int s = 0; s < NS; ++s) {
       mbar_init(&s_full[s], 1);
       mbar_init(&p_full[s], 128);
       mbar_init(&s_free[s], 128);
-      mbar_init(&o_done[s], 1);
     }
+    for (int q = 0; q < NQ; ++q) mbar_init(&o_done[q], 1);
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -127,6 +140,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t opad = (uint32_t)dpad;
+  const bool is_mma = (warp == 1) || (warp >= 2 + 4 * NQ);
 
   if (warp == 0) {
     if (lane == 0) {
@@ -152,16 +166,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (s == 1) phase ^= 1;
       }
     }
-  } else if (warp == 1 || warp == 2 + 4 * NQ) {
+  } else if (is_mma) {
     if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer(s)
-      // NQ == 2: one issuing thread per query tile (warp 1 -> tile 0, last warp -> tile 1), so the two softmax groups
-      // are decoupled: neither ever waits behind the other's barriers.  NQ == 1: warp 1 alternates the two S slots.
-      const int mq = (warp == 1) ? 0 : 1;
+      // ---------------------------------------------------------------- MMA issuer of query tile q
+      const int q = (warp == 1) ? 0 : (int)(warp - (2 + 4 * NQ)) + 1;
       const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
       const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
-      auto issue_s = [&](int i) {
-        const int q = i % NQ, j = i / NQ, ks = j & 1, slot = i & 1;
+      auto issue_s = [&](int j) {
+        const int ks = j & 1, slot = q * D + j % D;
         mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
         const uint32_t qa = smem_u32(sQ + q * q_bytes);
@@ -172,16 +184,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const uint64_t da = make_smem_desc_sw128(qa + c * L::kQChunkBytes, 16, 1024);
           const uint64_t db = make_smem_desc_sw128(ka + c * L::kKVChunkBytes, 16, 1024);
           for (int k = 0; k < nk; ++k, ++step)
-            umma_f16_ss(tmem_base + slot * kSlotCols, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s,
-                        step ? 1u : 0u);
+            umma_f16_ss(tmem_base + slot * BKV, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, step ? 1u : 0u);
         }
         tc_commit(&k_empty[ks]);
         tc_commit(&s_full[slot]);
       };
-      auto issue_pv = [&](int i) {
-        const int q = i % NQ, j = i / NQ, vs = j & 1, slot = i & 1;
-        // P of item i is the (i/2)-th use of its slot
-        mbar_wait(&p_full[slot], (uint32_t)((i >> 1) & 1));
+      auto issue_pv = [&](int j) {
+        const int vs = j & 1, slot = q * D + j % D;
+        mbar_wait(&p_full[slot], (uint32_t)((j / D) & 1));
         mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
         const uint32_t pa = smem_u32(sP + slot * L::kPBytes);
@@ -199,36 +209,22 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
-      // Both S slots are filled up front; afterwards a slot is refilled with the scores of the next item that maps to
-      // it as soon as the softmax group has pulled the current tile into registers (s_free), i.e. *during* that
-      // tile's exponentials -- a group never waits for the tensor pipe between two tiles.
-      if constexpr (NQ == 2) {
-        // items of this issuer: (mq, j), slot = mq; item index i = 2 j + mq
-        issue_s(mq);
-        for (int j = 0; j < T; ++j) {
-          if (j + 1 < T) {
-            mbar_wait(&s_free[mq], (uint32_t)(j & 1));
-            tc_fence_after();
-            issue_s(2 * (j + 1) + mq);
-          }
-          issue_pv(2 * j + mq);
+      // The tile's slots are filled up front; afterwards a slot is refilled with the next scores that map to it as
+      // soon as the softmax group has pulled the current tile into registers (s_free), i.e. *during* that tile's
+      // exponentials -- a group never waits for the tensor pipe between two tiles.
+      for (int j = 0; j < D && j < T; ++j) issue_s(j);
+      for (int j = 0; j < T; ++j) {
+        if (j + D < T) {
+          mbar_wait(&s_free[q * D + j % D], (uint32_t)((j / D) & 1));
+          tc_fence_after();
+          issue_s(j + D);
         }
-      } else {
-        issue_s(0);
-        if (I > 1) issue_s(1);
-        for (int i = 0; i < I; ++i) {
-          if (i + 2 < I) {
-            mbar_wait(&s_free[i & 1], (uint32_t)((i >> 1) & 1));
-            tc_fence_after();
-            issue_s(i + 2);
-          }
-          issue_pv(i);
-        }
+        issue_pv(j);
       }
     }
-  } else if (warp < 2 + 4 * NQ) {
-    // ------------------------------------------------------------------ softmax groups
-    const int g = (int)(warp - 2) >> 2;                 // group index (== q tile when NQ == 2)
+  } else {
+    // ------------------------------------------------------------------ softmax group g = query tile g
+    const int g = (int)(warp - 2) >> 2;
     const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
     const uint32_t r = quad * 32 + lane;                // row inside the 128-row tile
     const uint32_t lane_off = (quad * 32) << 16;
@@ -236,14 +232,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     float m_used = -INFINITY;   // max baked into O and l
     float l = 0.0f;
     for (int j = 0; j < T; ++j) {
-      const int i = j * NQ + g;
-      const int slot = i & 1;
-      mbar_wait(&s_full[slot], (uint32_t)((i >> 1) & 1));
+      const int slot = g * D + j % D;
+      mbar_wait(&s_full[slot], (uint32_t)((j / D) & 1));
       tc_fence_after();
       // S tile -> registers: all loads in flight, one wait
       uint32_t sraw[BKV];
       {
-        const uint32_t sa = tmem_base + slot * kSlotCols + lane_off;
+        const uint32_t sa = tmem_base + slot * BKV + lane_off;
 #pragma unroll
         for (int c = 0; c < BKV / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]));
         tc_wait_ld();
@@ -256,7 +251,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int x = 0; x < BKV; ++x)
           if (x >= valid) sraw[x] = 0xff800000u;  // -inf
       }
-      // row max of the raw scores: 8 independent chains (a single chain is 128 dependent FMNMX)
+      // row max of the raw scores: 8 independent chains (a single chain is BKV dependent FMNMX)
       float mx8[8];
 #pragma unroll
       for (int x = 0; x < 8; ++x) mx8[x] = __uint_as_float(sraw[x]);
@@ -264,7 +259,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int x = 8; x < BKV; ++x) mx8[x & 7] = fmaxf(mx8[x & 7], __uint_as_float(sraw[x]));
       const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                              fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
-      // previous P V of this query tile must have landed before O may be touched / P slot reused
+      // previous P V of this query tile must have landed before O may be touched / the P slot reused
       if (j > 0) {
         mbar_wait(&o_done[g], (uint32_t)((j - 1) & 1));
         tc_fence_after();
@@ -300,15 +295,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float a0 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x]), p.scale_log2, neg_m);
           const float a1 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x + 1]), p.scale_log2, neg_m);
           const float e0 = ex2_approx(a0);
-          const float e1 = (x & 1) ? ex2_poly(a1) : ex2_approx(a1);   // every 4th element off the MUFU pipe
+          const float e1 = (POLY && (x & 1)) ? ex2_poly(a1) : ex2_approx(a1);   // POLY: every 4th element off the MUFU pipe
           ls4[x] += e0 + e1;
           w[x] = pack_half2(e0, e1);
         }
         const int kc = c16 >> 3, cc = c16 & 7;
         *reinterpret_cast<uint4*>(prow + kc * (128 * 128) + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
       }
-      const float lsum = (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-      l += lsum;
+      l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[slot]);
@@ -347,22 +341,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <int NQ, int BKV>
+template <int NQ, int BKV, bool POLY>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t stream) {
-  using L = AttnSmem<NQ, BKV>;
+  using L = AttnCfg<NQ, BKV>;
   const int dch = (p.d + 63) / 64;
-  const size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes + 2 * L::kPBytes +
-                      18 * sizeof(uint64_t) + 1024;
+  const size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes +
+                      (size_t)L::kSlots * L::kPBytes + L::kBarriers * sizeof(uint64_t) + 1024;
   UV_REQUIRE(smem <= 227 * 1024, "attention: tile configuration needs %zu bytes of shared memory", smem);
+  UV_REQUIRE(256 + NQ * ((p.d + 15) & ~15) <= 512, "attention: O accumulators do not fit into TMEM");
   static bool configured = false;
   if (!configured) {
-    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     configured = true;
   }
   dim3 grid((p.N + 128 * NQ - 1) / (128 * NQ), p.H, p.NI);
-  attention_tc_kernel<NQ, BKV><<<grid, 64 + 128 * NQ + 32 * (NQ - 1), smem, stream>>>(tq, tk, tv, p);
+  attention_tc_kernel<NQ, BKV, POLY><<<grid, L::kThreads, smem, stream>>>(tq, tk, tv, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
@@ -391,7 +386,15 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   p.ldo = ldo;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
 
-  const int bkv = (d <= 64) ? 128 : 64;
+  // tile configuration: d <= 64 -> variant from UNIVST_ATTN_VARIANT (0: 2 query tiles x 128 keys, 1: + polynomial exp2,
+  // 2: 4 query tiles x 64 keys, 3: + polynomial exp2); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
+  static int variant = -1;
+  if (variant < 0) {
+    const char* e = getenv("UNIVST_ATTN_VARIANT");
+    variant = e ? atoi(e) : kDefaultVariant;
+    if (variant < 0 || variant > 3) variant = kDefaultVariant;
+  }
+  const int bkv = (d <= 64 && variant < 2) ? 128 : 64;
   CUtensorMap tq, tk, tv;
   {
     uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)N, (uint64_t)NI};
@@ -410,7 +413,14 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
     if (r) return r;
   }
   cudaStream_t st = (cudaStream_t)stream;
-  if (d <= 64) return launch_attn<2, 128>(tq, tk, tv, p, st);
-  if (d <= 128) return launch_attn<2, 64>(tq, tk, tv, p, st);
-  return launch_attn<1, 64>(tq, tk, tv, p, st);
+  if (d <= 64) {
+    switch (variant) {
+      case 0: return launch_attn<2, 128, false>(tq, tk, tv, p, st);
+      case 1: return launch_attn<2, 128, true>(tq, tk, tv, p, st);
+      case 2: return launch_attn<4, 64, false>(tq, tk, tv, p, st);
+      default: return launch_attn<4, 64, true>(tq, tk, tv, p, st);
+    }
+  }
+  if (d <= 128) return launch_attn<2, 64, false>(tq, tk, tv, p, st);
+  return launch_attn<1, 64, false>(tq, tk, tv, p, st);
 }
