@@ -63,12 +63,13 @@ __device__ __forceinline__ float ex2_poly(float x) {
 template <int NQ, int BKV>
 struct AttnCfg {
   static constexpr int kDepth = (NQ == 1) ? 2 : 1;      // S / P slots per query tile
-  static constexpr int kSlots = NQ * kDepth;
+  static constexpr int kSlots = NQ * kDepth;              // S slots
+  static constexpr int kPSlots = NQ * 2;                  // P tiles are double-buffered per query tile
   static constexpr int kThreads = 64 + 128 * NQ + 32 * (NQ - 1);
   static constexpr int kQChunkBytes = 128 * 128;        // [128 rows][64 halves]
   static constexpr int kKVChunkBytes = BKV * 128;       // [BKV rows][64 halves]
   static constexpr int kPBytes = 128 * BKV * 2;         // [128 rows][BKV halves] as BKV/64 swizzled chunks
-  static constexpr int kBarriers = 32;
+  static constexpr int kBarriers = 40;
   static_assert(kSlots * BKV <= 256, "S slots must fit below the O accumulators");
 };
 
@@ -91,18 +92,18 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sQ = smem;                                  // [NQ][dch][128][64]
   uint8_t* sK = sQ + NQ * q_bytes;                     // [2][dch][BKV][64]
   uint8_t* sV = sK + 2 * kv_bytes;                     // [2][dch][BKV][64]
-  uint8_t* sP = sV + 2 * kv_bytes;                     // [NS][BKV/64][128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + NS * L::kPBytes);
+  uint8_t* sP = sV + 2 * kv_bytes;                     // [NQ * 2][BKV/64][128][64]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + L::kPSlots * L::kPBytes);
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // 2
   uint64_t* k_empty = bars + 3;       // 2
   uint64_t* v_full = bars + 5;        // 2
   uint64_t* v_empty = bars + 7;       // 2
   uint64_t* s_full = bars + 9;        // NS (<= 4)
-  uint64_t* p_full = bars + 13;       // NS
-  uint64_t* s_free = bars + 17;       // NS
-  uint64_t* o_done = bars + 21;       // NQ
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
+  uint64_t* s_free = bars + 13;       // NS
+  uint64_t* p_full = bars + 17;       // NQ * 2 (<= 8)
+  uint64_t* o_done = bars + 25;       // NQ * 2: P V of tile (q, j) commits to o_done[2 q + (j & 1)]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -125,10 +126,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     }
     for (int s = 0; s < NS; ++s) {
       mbar_init(&s_full[s], 1);
-      mbar_init(&p_full[s], 128);
       mbar_init(&s_free[s], 128);
     }
-    for (int q = 0; q < NQ; ++q) mbar_init(&o_done[q], 1);
+    for (int s = 0; s < L::kPSlots; ++s) {
+      mbar_init(&p_full[s], 128);
+      mbar_init(&o_done[s], 1);
+    }
     fence_barrier_init();
   }
   if (warp == 1) {
@@ -190,8 +193,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tc_commit(&s_full[slot]);
       };
       auto issue_pv = [&](int j) {
-        const int vs = j & 1, slot = q * D + j % D;
-        mbar_wait(&p_full[slot], (uint32_t)((j / D) & 1));
+        const int vs = j & 1, slot = q * 2 + (j & 1);        // P slot, used for the (j / 2)-th time
+        mbar_wait(&p_full[slot], (uint32_t)((j >> 1) & 1));
         mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
         const uint32_t pa = smem_u32(sP + slot * L::kPBytes);
@@ -205,7 +208,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           umma_f16_ss(tmem_base + kOBase + q * opad, da, db, idesc_o, (j | k) ? 1u : 0u);
         }
         tc_commit(&v_empty[vs]);
-        tc_commit(&o_done[q]);
+        tc_commit(&o_done[slot]);
       };
       mbar_wait(q_full, 0);
       tc_fence_after();
@@ -259,15 +262,13 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int x = 8; x < BKV; ++x) mx8[x & 7] = fmaxf(mx8[x & 7], __uint_as_float(sraw[x]));
       const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
                              fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
-      // previous P V of this query tile must have landed before O may be touched / the P slot reused
-      if (j > 0) {
-        mbar_wait(&o_done[g], (uint32_t)((j - 1) & 1));
-        tc_fence_after();
-      }
       const bool need = mx > m_used + kRescaleThreshold;   // first tile: m_used = -inf -> always true
       if (__any_sync(0xffffffffu, need)) {
         const float m_new = fmaxf(m_used, mx);
         if (j > 0) {
+          // rare path: O is rescaled in TMEM, so the previous P V of this query tile must have landed
+          mbar_wait(&o_done[g * 2 + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+          tc_fence_after();
           const float alpha = ex2_approx(m_used - m_new);   // lanes that did not need it: alpha <= 1, harmless
           l *= alpha;
           for (uint32_t c = 0; c < opad; c += 16) {
@@ -284,7 +285,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       // P = 2^(s * scale - m_used): one FFMA + one MUFU.EX2 per element, fp16, written as swizzled K-major
       // chunks (chunk kc holds keys [64 kc, 64 kc + 64)); the row sum runs in 4 independent chains
-      uint8_t* prow = sP + slot * L::kPBytes + r * 128;
+      const int pslot = g * 2 + (j & 1);
+      if (j >= 2) {  // the P buffer was last read by the P V of tile j - 2: long done, the wait is (almost) free
+        mbar_wait(&o_done[pslot], (uint32_t)(((j - 2) >> 1) & 1));
+      }
+      uint8_t* prow = sP + pslot * L::kPBytes + r * 128;
       float ls4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       const float neg_m = -m_used;
 #pragma unroll
@@ -305,10 +310,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       fence_proxy_async_smem();
       tc_fence_before();
-      mbar_arrive(&p_full[slot]);
+      mbar_arrive(&p_full[pslot]);
     }
     // ------------------------------------------------------------------ epilogue: O / l -> global
-    mbar_wait(&o_done[g], (uint32_t)((T - 1) & 1));
+    if (T >= 2) mbar_wait(&o_done[g * 2 + ((T - 2) & 1)], (uint32_t)(((T - 2) >> 1) & 1));
+    mbar_wait(&o_done[g * 2 + ((T - 1) & 1)], (uint32_t)(((T - 1) >> 1) & 1));
     tc_fence_after();
     const float inv_l = 1.0f / l;
     const int qrow = (qt0 + g) * 128 + (int)r;
@@ -347,7 +353,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   using L = AttnCfg<NQ, BKV>;
   const int dch = (p.d + 63) / 64;
   const size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes +
-                      (size_t)L::kSlots * L::kPBytes + L::kBarriers * sizeof(uint64_t) + 1024;
+                      (size_t)L::kPSlots * L::kPBytes + L::kBarriers * sizeof(uint64_t) + 1024;
   UV_REQUIRE(smem <= 227 * 1024, "attention: tile configuration needs %zu bytes of shared memory", smem);
   UV_REQUIRE(256 + NQ * ((p.d + 15) & ~15) <= 512, "attention: O accumulators do not fit into TMEM");
   static bool configured = false;

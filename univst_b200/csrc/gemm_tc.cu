@@ -48,15 +48,16 @@ struct GemmParams {
 };
 
 // Exact-form (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below the fp16 rounding of
-// the result): one MUFU.RCP + one MUFU.EX2 + a degree-5 Horner chain instead of libdevice's branchy erff.
+// the result): MUFU.RCP + MUFU.EX2 + a degree-5 Horner chain instead of libdevice's branchy erff.
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = __expf(-z * z);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
   const float erf_abs = fmaf(-poly * t, e, 1.0f);
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
@@ -162,19 +163,21 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
         const int c = c0 + g * 8;
         const int n = no0 + c;
         if (n >= p.N_out) break;
-        float v[8], gt[8];
+        // fp32 all the way: value * gelu(gate) with one rounding at the end (the reference rounds the projection
+        // and the GELU to fp16 first; skipping that is both cheaper and closer to the fp32 oracle)
+        uint4 bv = make_uint4(0, 0, 0, 0), bg = make_uint4(0, 0, 0, 0);
+        if (p.bias) {
+          bv = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + c));
+          bg = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + half_bn + c));
+        }
+        const uint32_t bvw[4] = {bv.x, bv.y, bv.z, bv.w}, bgw[4] = {bg.x, bg.y, bg.z, bg.w};
+        float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          v[j] = __uint_as_float(av[g * 8 + j]);
-          gt[j] = __uint_as_float(ag[g * 8 + j]);
-          if (p.bias) {
-            v[j] += __half2float(p.bias[n0 + c + j]);
-            gt[j] += __half2float(p.bias[n0 + half_bn + c + j]);
-          }
-          // the reference rounds the projection to fp16 before h * gelu(gate)
-          v[j] = __half2float(__float2half_rn(v[j]));
-          gt[j] = __half2float(__float2half_rn(gt[j]));
-          v[j] = v[j] * __half2float(__float2half_rn(gelu_erf(gt[j])));
+        for (int j = 0; j < 4; ++j) {
+          const float2 fv = unpack_half2(bvw[j]), fg = unpack_half2(bgw[j]);
+          v[2 * j] = (__uint_as_float(av[g * 8 + 2 * j]) + fv.x) * gelu_erf(__uint_as_float(ag[g * 8 + 2 * j]) + fg.x);
+          v[2 * j + 1] =
+              (__uint_as_float(av[g * 8 + 2 * j + 1]) + fv.y) * gelu_erf(__uint_as_float(ag[g * 8 + 2 * j + 1]) + fg.y);
         }
         if (n + 8 <= p.N_out) {
           uint32_t o[4];

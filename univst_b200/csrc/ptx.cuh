@@ -69,7 +69,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 26)) {
+    if (spins > 64) __nanosleep(32);  // long waits (producer / epilogue roles) back off instead of burning issue slots
+    if (++spins > (1u << 24)) {
       printf("univst_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
       __trap();
     }
