@@ -188,11 +188,11 @@ def run_ours(args):
                 "traj_s": [t.to(dev, non_blocking=True) for t in clip["traj_s"]],
                 "mask": clip["mask"].to(dev, non_blocking=True), "ctx": clip["ctx"].to(dev, non_blocking=True)}
 
-    def stylize(c):
+    def stylize(c, skip=None):
         z_T = ops.latent_adain(c["traj_c"][STEPS_DDIM], c["traj_s"][STEPS_DDIM])  # run_video_style_transfer_sd.py:57
         return pipe.video_style_transfer("", num_inference_steps=STEPS_DDIM, latents=z_T, content_inv_path=c["traj_c"],
                                          style_inv_path=c["traj_s"], mask_path=c["mask"], prompt_embeds=c["ctx"],
-                                         skip_dead_branches=args.skip_dead_branches).latents
+                                         skip_dead_branches=args.skip_dead_branches if skip is None else skip).latents
 
     def barrier():
         if world > 1:
@@ -230,10 +230,20 @@ def run_ours(args):
     barrier()
     ms_e2e = e0.elapsed_time(e1)
 
-    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    # ---- extra (not the headline): exact dead-branch skipping (content / style branches only while the shift is live)
+    barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    out_skip = stylize(resident, skip=True)
+    s1.record()
+    barrier()
+    ms_skip = s0.elapsed_time(s1)
+    skip_identical = bool(torch.equal(out_skip, out)) if not args.skip_dead_branches else True
+
+    t = torch.tensor([ms, ms_e2e, ms_skip], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = t.tolist()
+    ms, ms_e2e, ms_skip = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -263,7 +273,9 @@ def run_ours(args):
                    "weights": "random init (seed 33), SD-1.5 UNet shapes", "l2": "working set per UNet call ~5 GiB >> 126 MB L2",
                    "skip_dead_branches": bool(args.skip_dead_branches), "parallelism": f"clip-parallel x{world}",
                    "whole_loop_tensor_frac": (fps / world / F_FRAMES) * FLOP_PER_CLIP / 1e12 / pk["tflops"],
-                   "sc_attention_ms_per_clip": attn_ms},
+                   "sc_attention_ms_per_clip": attn_ms,
+                   "with_exact_dead_branch_skipping": {"frames_per_s": world * F_FRAMES / (ms_skip / 1e3),
+                                                       "edit_latents_bit_identical": skip_identical}},
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes(clip), "d2h_bytes_per_step": host_out.numel() * 2},
         "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
     }

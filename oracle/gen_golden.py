@@ -54,6 +54,25 @@ def gen_unet():
             out["cases"][f"patched_idx{idx}_t{t}"] = m(x, torch.tensor(t), encoder_hidden_states=ctx).sample.clone()
     save("unet_tiny.pt", out)
 
+    # SD-2.1 layout (use_linear_projection, per-level head counts, head dim 64)
+    cfg = uo.TINY_SD21_CONFIG
+    m = UNetPseudo3DConditionModel(block_out_channels=cfg["block_out_channels"], attention_head_dim=cfg["attention_head_dim"],
+                                   cross_attention_dim=cfg["cross_attention_dim"], use_linear_projection=True,
+                                   sample_size=16).eval()
+    shapes = uo.unet_param_shapes(cfg)
+    ref_sd = m.state_dict()
+    assert set(shapes) == set(ref_sd) and all(tuple(ref_sd[k].shape) == shapes[k] for k in shapes)
+    m.load_state_dict(uo.seeded_state_dict(cfg, seed=21))
+    ctx = torch.randn(1, 77, cfg["cross_attention_dim"], generator=g).repeat(3, 1, 1)
+    out = {"x": x, "ctx": ctx, "seed": 21, "cases": {}}
+    with torch.no_grad():
+        out["cases"]["stock_t501"] = m(x, torch.tensor(501), encoder_hidden_states=ctx).sample.clone()
+        pipe = types.SimpleNamespace(unet=m)
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        pnp_utils.register_time(pipe, 10)
+        out["cases"]["patched_idx10_t781"] = m(x, torch.tensor(781), encoder_hidden_states=ctx).sample.clone()
+    save("unet_tiny_sd21.pt", out)
+
 
 def gen_pnp():
     from backbones.video_diffusion_sd import pnp_utils

@@ -24,6 +24,8 @@ SD15_CONFIG = dict(block_out_channels=(320, 640, 1280, 1280), attention_head_dim
                    use_linear_projection=False)
 SD21_CONFIG = dict(SD15_CONFIG, attention_head_dim=(5, 10, 20, 20), cross_attention_dim=1024, use_linear_projection=True)
 TINY_CONFIG = dict(SD15_CONFIG, block_out_channels=(64, 128, 128, 128), attention_head_dim=4, cross_attention_dim=64)
+# SD-2.1 layout in miniature: head dim 64 on every level (heads 1/2/2/2), Linear proj_in / proj_out
+TINY_SD21_CONFIG = dict(TINY_CONFIG, attention_head_dim=(1, 2, 2, 2), use_linear_projection=True, cross_attention_dim=128)
 
 # layers whose attn1.forward is replaced by register_spatial_attention_pnp (pnp_utils.py:104-111)
 PATCHED = {(1, 1), (1, 2), (2, 0), (2, 1), (2, 2), (3, 0), (3, 1), (3, 2)}

@@ -35,6 +35,18 @@ def test_unet_oracle_matches_reference_module(unet_golden, tiny_sd, case):
     assert (y - ref).abs().max().item() < 5e-5
 
 
+@pytest.mark.parametrize("case", ["stock_t501", "patched_idx10_t781"])
+def test_unet_oracle_sd21_layout(case):
+    """SD-2.1 layout: Linear proj_in / proj_out, per-level head counts (head dim 64)."""
+    g = torch.load(os.path.join(GOLDEN, "unet_tiny_sd21.pt"), weights_only=True)
+    sd = uo.seeded_state_dict(uo.TINY_SD21_CONFIG, seed=g["seed"])
+    patched = case.startswith("patched")
+    with torch.no_grad():
+        y = uo.unet_forward(sd, uo.TINY_SD21_CONFIG, g["x"], int(case.split("_t")[-1]), g["ctx"], patched=patched,
+                            idx=10 if patched else None)
+    assert (y - g["cases"][case]).abs().max().item() < 5e-5
+
+
 def test_shift_is_live_in_the_goldens(unet_golden):
     """idx 25 (shift on, beta = 0.1) and idx 26 (shift off) differ: the goldens really exercise the patch window."""
     c = unet_golden["cases"]

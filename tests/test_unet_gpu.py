@@ -60,6 +60,24 @@ def test_unet_forward_matches_oracle(setup, case):
     assert rel <= 2.0 * rel16 + 1e-3
 
 
+@pytest.mark.parametrize("case", ["stock_t501", "patched_idx10_t781"])
+def test_unet_forward_sd21_layout(cuda_lib, case):
+    """BASELINE.json configs[2] backbone layout (SD-2.1: head dim 64, Linear projections) on the tiny golden."""
+    from types import SimpleNamespace
+    from univst_b200 import pnp_utils
+    from univst_b200.unet import UNetPseudo3DConditionModel
+    g = torch.load(os.path.join(GOLDEN, "unet_tiny_sd21.pt"), weights_only=True)
+    unet = UNetPseudo3DConditionModel(uo.seeded_state_dict(uo.TINY_SD21_CONFIG, seed=g["seed"]), uo.TINY_SD21_CONFIG)
+    if case.startswith("patched"):
+        pipe = SimpleNamespace(unet=unet)
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        pnp_utils.register_time(pipe, 10)
+    y = unet(g["x"].cuda().half(), int(case.split("_t")[-1]), encoder_hidden_states=g["ctx"].cuda().half()).sample
+    rel, mx = _errs(y, g["cases"][case])
+    print(f"sd21 {case}: rel={rel:.3e} max={mx:.3e}")
+    assert rel <= 1e-2 and mx <= 0.06
+
+
 def test_reference_patch_protocol_is_honoured(setup):
     """An instance-level ``forward`` override (what the reference's register_spatial_attention_pnp installs) marks the
     layer as patched; unpatched layers ignore idx."""
