@@ -99,6 +99,14 @@ int64_t univst_groupnorm_workspace_bytes(int32_t NB, int32_t groups);
 int univst_groupnorm_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
                          int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu, void* Y,
                          void* workspace, void* stream);
+/* Split form for frame-sharded execution (the reference's GroupNorm statistics span all frames, resnet.py:338): local
+ * (sum, sum of squares) per (batch, group) into sums[NB, groups, 2]; the caller all-reduces them over the ranks and
+ * applies with stat_rows = the global row count. */
+int univst_groupnorm_stats_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
+                               int32_t groups, float* sums, void* workspace, void* stream);
+int univst_groupnorm_apply_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
+                               int32_t groups, const float* sums, int64_t stat_rows, const void* gamma, const void* beta,
+                               float eps, int32_t silu, void* Y, void* stream);
 /* LayerNorm over the last axis of [rows, C] (attention.py:290,312,329). */
 int univst_layernorm_f16(const void* X, int32_t rows, int32_t C, const void* gamma, const void* beta, float eps, void* Y,
                          void* stream);

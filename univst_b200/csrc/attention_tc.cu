@@ -76,7 +76,7 @@ struct AttnCfg {
 // Work decomposition: query tile q of the CTA streams KV tiles j = 0..T-1.  Tile (q, j) uses S/P slot
 // q * kDepth + j % kDepth for the (j / kDepth)-th time.  Every query tile has its own MMA-issuing thread and its own
 // softmax group, so the tiles only meet at the K/V ring.
-template <int NQ, int BKV, bool POLY>
+template <int NQ, int BKV, int POLY>
 __global__ void __launch_bounds__(AttnCfg<NQ, BKV>::kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -300,7 +300,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const float a0 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x]), p.scale_log2, neg_m);
           const float a1 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x + 1]), p.scale_log2, neg_m);
           const float e0 = ex2_approx(a0);
-          const float e1 = (POLY && (x & 1)) ? ex2_poly(a1) : ex2_approx(a1);   // POLY: every 4th element off the MUFU pipe
+          // POLY = 1: every 4th exponential off the MUFU pipe; POLY = 2: every 2nd
+          const float e1 = (POLY == 2 || (POLY == 1 && (x & 1))) ? ex2_poly(a1) : ex2_approx(a1);
           ls4[x] += e0 + e1;
           w[x] = pack_half2(e0, e1);
         }
@@ -347,7 +348,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <int NQ, int BKV, bool POLY>
+template <int NQ, int BKV, int POLY>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t stream) {
   using L = AttnCfg<NQ, BKV>;
@@ -393,12 +394,12 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
 
   // tile configuration: d <= 64 -> variant from UNIVST_ATTN_VARIANT (0: 2 query tiles x 128 keys, 1: + polynomial exp2,
-  // 2: 4 query tiles x 64 keys, 3: + polynomial exp2); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
+  // 2: 4 query tiles x 64 keys, 3: + polynomial exp2, 4: 2 x 128 with half of the exp2 polynomial); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("UNIVST_ATTN_VARIANT");
     variant = e ? atoi(e) : kDefaultVariant;
-    if (variant < 0 || variant > 3) variant = kDefaultVariant;
+    if (variant < 0 || variant > 4) variant = kDefaultVariant;
   }
   const int bkv = (d <= 64 && variant < 2) ? 128 : 64;
   CUtensorMap tq, tk, tv;
@@ -421,12 +422,13 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   cudaStream_t st = (cudaStream_t)stream;
   if (d <= 64) {
     switch (variant) {
-      case 0: return launch_attn<2, 128, false>(tq, tk, tv, p, st);
-      case 1: return launch_attn<2, 128, true>(tq, tk, tv, p, st);
-      case 2: return launch_attn<4, 64, false>(tq, tk, tv, p, st);
-      default: return launch_attn<4, 64, true>(tq, tk, tv, p, st);
+      case 0: return launch_attn<2, 128, 0>(tq, tk, tv, p, st);
+      case 1: return launch_attn<2, 128, 1>(tq, tk, tv, p, st);
+      case 2: return launch_attn<4, 64, 0>(tq, tk, tv, p, st);
+      case 3: return launch_attn<4, 64, 1>(tq, tk, tv, p, st);
+      default: return launch_attn<2, 128, 2>(tq, tk, tv, p, st);
     }
   }
-  if (d <= 128) return launch_attn<2, 64, false>(tq, tk, tv, p, st);
-  return launch_attn<1, 64, false>(tq, tk, tv, p, st);
+  if (d <= 128) return launch_attn<2, 64, 0>(tq, tk, tv, p, st);
+  return launch_attn<1, 64, 0>(tq, tk, tv, p, st);
 }

@@ -70,7 +70,7 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 __global__ void gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, int C1, int C2, int rows,
                                 int groups, int nvec, int nchunks, const float* __restrict__ partial,
                                 const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps, int silu,
-                                int rows_per_block, __half* __restrict__ y) {
+                                int rows_per_block, int stat_rows, __half* __restrict__ y) {
   extern __shared__ float sh[];  // [groups][2] = (mean, rstd)
   const int b = blockIdx.y;
   const int C = C1 + C2, cpg = C / groups;
@@ -81,7 +81,7 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, const __half* __r
       s += pp[(size_t)c * groups * 2];
       q += pp[(size_t)c * groups * 2 + 1];
     }
-    const float n = (float)rows * (float)cpg;
+    const float n = (float)stat_rows * (float)cpg;  // rows the statistics were taken over (all ranks when sharded)
     const float mean = s / n;
     const float var = fmaxf(q / n - mean * mean, 0.0f);
     sh[g * 2] = mean;
@@ -206,7 +206,61 @@ extern "C" int univst_groupnorm_f16(const void* X1, const void* X2, int32_t C1, 
   const int row_blocks = (rows + rows_per_block - 1) / rows_per_block;
   gn_apply_kernel<<<dim3(row_blocks, NB), 256, groups * 2 * sizeof(float), st>>>(
       (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, nchunks, (const float*)workspace,
-      (const __half*)gamma, (const __half*)beta, eps, silu, rows_per_block, (__half*)Y);
+      (const __half*)gamma, (const __half*)beta, eps, silu, rows_per_block, rows, (__half*)Y);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+namespace uv {
+// sums[b][g][2] = sum over the chunk partials (fixed order)
+__global__ void gn_fold_kernel(const float* __restrict__ partial, int nchunks, int groups, float* __restrict__ sums) {
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
+    float s = 0.0f;
+    for (int c = 0; c < nchunks; ++c) s += partial[((size_t)b * nchunks + c) * groups * 2 + i];
+    sums[(size_t)b * groups * 2 + i] = s;
+  }
+}
+}  // namespace uv
+
+// Split form for frame-sharded execution: local (sum, sum of squares) per (batch, group) -> [all-reduce over ranks by
+// the caller] -> apply with the global row count.
+extern "C" int univst_groupnorm_stats_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
+                                          int32_t groups, float* sums, void* workspace, void* stream) {
+  UV_REQUIRE(X1 && sums && workspace, "groupnorm_stats: null pointer");
+  if (!X2) C2 = 0;
+  const int C = C1 + C2;
+  UV_REQUIRE(NB > 0 && rows > 0 && groups > 0 && C % groups == 0, "groupnorm_stats: bad shape");
+  UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && (C / groups) % 2 == 0 && C / 8 <= 1024, "groupnorm_stats: bad channels");
+  const int nvec = C / 8;
+  const int rows_par = nvec >= 256 ? 1 : 256 / nvec;
+  const int threads = nvec * rows_par;
+  int nchunks = (rows + 63) / 64;
+  if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
+  const int rows_per_chunk = (rows + nchunks - 1) / nchunks;
+  cudaStream_t st = (cudaStream_t)stream;
+  gn_stats_kernel<<<dim3(nchunks, NB), threads, threads * 8 * sizeof(float), st>>>(
+      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, rows_par, rows_per_chunk, (float*)workspace);
+  UV_CHECK_CUDA(cudaGetLastError());
+  gn_fold_kernel<<<NB, 64, 0, st>>>((const float*)workspace, nchunks, groups, sums);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_groupnorm_apply_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
+                                          int32_t groups, const float* sums, int64_t stat_rows, const void* gamma,
+                                          const void* beta, float eps, int32_t silu, void* Y, void* stream) {
+  UV_REQUIRE(X1 && Y && gamma && beta && sums, "groupnorm_apply: null pointer");
+  if (!X2) C2 = 0;
+  const int C = C1 + C2;
+  UV_REQUIRE(NB > 0 && rows > 0 && groups > 0 && C % groups == 0 && stat_rows >= rows, "groupnorm_apply: bad shape");
+  const int nvec = C / 8;
+  int rows_per_block = (16384 + C - 1) / C;
+  if (rows_per_block < 1) rows_per_block = 1;
+  const int row_blocks = (rows + rows_per_block - 1) / rows_per_block;
+  gn_apply_kernel<<<dim3(row_blocks, NB), 256, groups * 2 * sizeof(float), (cudaStream_t)stream>>>(
+      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, 1, sums, (const __half*)gamma,
+      (const __half*)beta, eps, silu, rows_per_block, (int)stat_rows, (__half*)Y);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

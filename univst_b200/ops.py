@@ -20,6 +20,8 @@ _lib.register("univst_attn_shift_workspace_bytes", [_i32, _i32], _i64)
 _lib.register("univst_attn_shift_f16", [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp])
 _lib.register("univst_groupnorm_workspace_bytes", [_i32, _i32], _i64)
 _lib.register("univst_groupnorm_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp])
+_lib.register("univst_groupnorm_stats_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _vp])
+_lib.register("univst_groupnorm_apply_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i64, _vp, _vp, _f32, _i32, _vp, _vp])
 _lib.register("univst_layernorm_f16", [_vp, _i32, _i32, _vp, _vp, _f32, _vp, _vp])
 _lib.register("univst_upsample2x_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_space_to_depth2_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _vp])
@@ -39,7 +41,7 @@ _lib.register("univst_mask_select_u8", [_vp, _vp, _vp, _i64, _vp, _vp])
 # number of kernels launched through this module (bench.py reports it as ``gpu_launches``)
 launch_count = 0
 _LAUNCHES = {
-    "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 2, "layernorm": 1, "upsample2x": 1,
+    "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 2, "layernorm": 1, "upsample2x": 1,
     "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
@@ -216,6 +218,28 @@ def groupnorm(x1: torch.Tensor, gamma, beta, *, NB: int, rows: int, groups: int 
                                           beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
                                           _stream()), "univst_groupnorm_f16")
     _count("groupnorm")
+    return out
+
+
+def groupnorm_sharded(x1, gamma, beta, *, NB, rows, group, world, groups=32, eps=1e-5, silu=False, x2=None):
+    """GroupNorm whose statistics span the rows of ALL ranks of ``group`` (frame-sharded UNet): local sums ->
+    all-reduce of NB x groups x 2 floats -> apply with the global row count."""
+    import torch.distributed as dist
+    _lib.require_device()
+    _chk(x1, "x1")
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    sums = torch.empty((NB, groups, 2), dtype=torch.float32, device=x1.device)
+    ws = _workspace(_lib.lib().univst_groupnorm_workspace_bytes(NB, groups), x1.device)
+    check(_lib.lib().univst_groupnorm_stats_f16(x1.data_ptr(), _ptr(x2), C1, C2, NB, rows, groups, sums.data_ptr(),
+                                                ws.data_ptr(), _stream()), "univst_groupnorm_stats_f16")
+    _count("groupnorm_stats")
+    dist.all_reduce(sums, group=group)
+    out = torch.empty((NB * rows, C1 + C2), dtype=torch.float16, device=x1.device)
+    check(_lib.lib().univst_groupnorm_apply_f16(x1.data_ptr(), _ptr(x2), C1, C2, NB, rows, groups, sums.data_ptr(),
+                                                rows * world, gamma.data_ptr(), beta.data_ptr(), eps, 1 if silu else 0,
+                                                out.data_ptr(), _stream()), "univst_groupnorm_apply_f16")
+    _count("groupnorm_apply")
     return out
 
 

@@ -52,6 +52,22 @@ def kv_source_table(B: int, F: int, mode: str) -> torch.Tensor:
     return torch.tensor(rows, dtype=torch.int32)
 
 
+def kv_source_table_sharded(B: int, Fl: int, mode: str, rank: int) -> torch.Tensor:
+    """Source table of a frame shard (local frames [rank * Fl, (rank + 1) * Fl) of every branch).  Local images are
+    0 .. B*Fl-1; two halo banks follow in the K/V buffer: B*Fl + b = last frame of the previous rank (branch b),
+    B*Fl + B + b = frame 0 of the clip (owned by rank 0).  Rank 0 needs neither (frame -1 clips to frame 0)."""
+    NI = B * Fl
+    rows = []
+    for b in range(B):
+        for fl in range(Fl):
+            me = b * Fl + fl
+            prev = me - 1 if fl > 0 else (NI + b if rank > 0 else me)
+            first = b * Fl if rank == 0 else NI + B + b
+            rows.append({"prev_first": [prev, first], "prev_self_first": [prev, me, first], "self": [me],
+                         "branch": [b]}[mode])
+    return torch.tensor(rows, dtype=torch.int32)
+
+
 class UNetPseudo3DConditionOutput(dict):
     """Attribute *and* item access, like diffusers' BaseOutput (ddim_inversion.py:209-211 uses ``["sample"]``)."""
 
@@ -109,6 +125,7 @@ class UNetPseudo3DConditionModel:
         self.nlev = len(boc)
         self._tables = {}
         self._ctx_cache = None
+        self._shard = None  # (process group, rank, world) when frames are sharded over GPUs
         self._build_tree()
         self._pack(state_dict)
 
@@ -119,6 +136,19 @@ class UNetPseudo3DConditionModel:
         c = module.config
         cfg = {k: c[k] for k in SD15_CONFIG if k in c}
         return cls(module.state_dict(), cfg, device=device)
+
+    def set_frame_sharding(self, group=None):
+        """Shard the frames of every clip over the ranks of ``group`` (default: the world group): rank r evaluates
+        frames [r F/P, (r+1) F/P) of all branches.  Per attn1 layer the boundary frame's K/V goes to the next rank and
+        frame 0's K/V is broadcast from rank 0 (NCCL over NVLink); every cross-frame GroupNorm all-reduces
+        B x 32 x 2 floats; the predicted noise is all-gathered at the end.  ``None`` world size 1 -> no-op."""
+        import torch.distributed as dist
+        if group is None and not dist.is_initialized():
+            self._shard = None
+            return
+        world = dist.get_world_size(group)
+        self._shard = (group, dist.get_rank(group), world) if world > 1 else None
+        self._tables = {}
 
     def _heads(self, level):
         h = self.config["attention_head_dim"]
@@ -196,21 +226,52 @@ class UNetPseudo3DConditionModel:
     def _table(self, B, F, mode):
         key = (B, F, mode)
         if key not in self._tables:
-            self._tables[key] = kv_source_table(B, F, mode).to(self.device)
+            if self._shard is None or mode == "branch":
+                t = kv_source_table(B, F, mode)
+            else:
+                t = kv_source_table_sharded(B, F, mode, self._shard[1])
+            self._tables[key] = t.to(self.device)
         return self._tables[key]
+
+    def _gn(self, x, gamma, beta, *, NB, rows, eps, silu, x2=None):
+        """GroupNorm whose statistics span all frames of a branch (all ranks when the frames are sharded)."""
+        g = self.config["norm_num_groups"]
+        if self._shard is None:
+            return ops.groupnorm(x, gamma, beta, NB=NB, rows=rows, groups=g, eps=eps, silu=silu, x2=x2)
+        return ops.groupnorm_sharded(x, gamma, beta, NB=NB, rows=rows, group=self._shard[0], world=self._shard[2],
+                                     groups=g, eps=eps, silu=silu, x2=x2)
+
+    def _exchange_kv_halo(self, qkv, B, F, N):
+        """Frame-sharded attn1: qkv is [(B*F + 2B) * N, 3C]; fill the two halo banks (see kv_source_table_sharded)."""
+        import torch.distributed as dist
+        group, rank, world = self._shard
+        NI = B * F
+        v = qkv[: NI * N].view(B, F, N, -1)
+        halo_prev = qkv[NI * N: (NI + B) * N].view(B, N, -1)
+        halo_first = qkv[(NI + B) * N: (NI + 2 * B) * N].view(B, N, -1)
+        ops_ = []
+        if rank + 1 < world:
+            ops_.append(dist.P2POp(dist.isend, v[:, F - 1].contiguous(), dist.get_global_rank(group, rank + 1) if group else rank + 1, group))
+        if rank > 0:
+            ops_.append(dist.P2POp(dist.irecv, halo_prev, dist.get_global_rank(group, rank - 1) if group else rank - 1, group))
+        if rank == 0:
+            halo_first.copy_(v[:, 0])
+        if ops_:
+            for w in dist.batch_isend_irecv(ops_):
+                w.wait()
+        dist.broadcast(halo_first, src=dist.get_global_rank(group, 0) if group else 0, group=group)
 
     # ------------------------------------------------------------------------------------------ building blocks
     def _resnet(self, pre, x, skip, temb_all, B, F, H, Wd):
         """ResnetBlockPseudo3D.forward (resnet.py:335-394).  x: [M, C1], skip: [M, C2] or None."""
         W, cfg = self.W, self.config
         NI, rows = B * F, F * H * Wd
-        g, eps = cfg["norm_num_groups"], cfg["norm_eps"]
-        h = ops.groupnorm(x, W[pre + "norm1.weight"], W[pre + "norm1.bias"], NB=B, rows=rows, groups=g, eps=eps,
-                          silu=True, x2=skip)
+        eps = cfg["norm_eps"]
+        h = self._gn(x, W[pre + "norm1.weight"], W[pre + "norm1.bias"], NB=B, rows=rows, eps=eps, silu=True, x2=skip)
         off, cout = self._temb_slices[pre]
         h = ops.conv3x3(h.view(NI, H, Wd, -1), W[pre + "conv1.weight"], bias=W[pre + "conv1.bias"],
                         rowvec=temb_all[:, off:off + cout], rows_per_group=rows)
-        h = ops.groupnorm(h, W[pre + "norm2.weight"], W[pre + "norm2.bias"], NB=B, rows=rows, groups=g, eps=eps, silu=True)
+        h = self._gn(h, W[pre + "norm2.weight"], W[pre + "norm2.bias"], NB=B, rows=rows, eps=eps, silu=True)
         if pre + "conv_shortcut.weight" in W:
             sc = ops.gemm(x, W[pre + "conv_shortcut.weight"], a2=skip, bias=W[pre + "conv_shortcut.bias"])
         else:
@@ -230,7 +291,13 @@ class UNetPseudo3DConditionModel:
         y = ops.gemm(y, W[pre + "proj_in.weight"], bias=W[pre + "proj_in.bias"])
         # 1. sparse-causal self-attention (stock or patched)
         n1 = ops.layernorm(y, W[b + "norm1.weight"], W[b + "norm1.bias"])
-        qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"])
+        NIkv = NI
+        if self._shard is None:
+            qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"])
+        else:  # two halo banks of B images each behind the local images
+            NIkv = NI + 2 * B
+            qkv_all = torch.empty((NIkv * N, 3 * C), dtype=torch.float16, device=x.device)
+            qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"], out=qkv_all[: NI * N])
         a1 = tr.transformer_blocks[0].attn1
         mode = "prev_self_first"
         if a1.patched:
@@ -242,7 +309,12 @@ class UNetPseudo3DConditionModel:
                     raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
                 beta = (0.9 - 0.1) / (a1.eta1 * 50 - a1.eta2 * 50) * (a1.idx - a1.eta2 * 50) + 0.1
                 ops.attn_shift_(qkv, F, N, C, 0.65, beta, 3.0)
-        o = ops.sc_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], self._table(B, F, mode), NI=NI, NIkv=NI, H=heads,
+        if self._shard is not None:
+            self._exchange_kv_halo(qkv_all, B, F, N)
+            kv = qkv_all
+        else:
+            kv = qkv
+        o = ops.sc_attention(qkv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], self._table(B, F, mode), NI=NI, NIkv=NIkv, H=heads,
                              d=d, N=N, Nkv=N)
         y = ops.gemm(o, W[b + "attn1.to_out.0.weight"], bias=W[b + "attn1.to_out.0.bias"], residual=y)
         # 2. cross-attention over the (per-branch) context
@@ -272,6 +344,15 @@ class UNetPseudo3DConditionModel:
             raise ValueError("latent height / width must be powers of two (64x64 for 512x512 frames)")
         boc = cfg["block_out_channels"]
         sample = sample.to(device=dev, dtype=torch.float16).contiguous()
+        F_total = F
+        if self._shard is not None:
+            _, rank, world = self._shard
+            if F % world:
+                raise ValueError(f"{F} frames do not shard evenly over {world} ranks")
+            if ft_path is not None:
+                raise NotImplementedError("feature dumps are not available under frame sharding")
+            F = F // world
+            sample = sample[:, :, rank * F:(rank + 1) * F].contiguous()
         x = ops.pack_latents([sample[b] for b in range(B)], Cpad=CIN_PAD)
 
         # time embedding: sinusoid -> Linear -> SiLU -> Linear; every ResNet consumes silu(emb) (resnet.py:355), so
@@ -331,10 +412,18 @@ class UNetPseudo3DConditionModel:
                     path = os.path.join(ft_path, f"inversion_feature_map_{i}_block_{timestep}_step.pt")
                     torch.save(x[: F * h * w].view(F, h, w, -1).clone(), path)
                     print(f"save feature map at: {path}")
-        y = ops.groupnorm(x, W["conv_norm_out.weight"], W["conv_norm_out.bias"], NB=B, rows=F * h * w,
-                          groups=cfg["norm_num_groups"], eps=cfg["norm_eps"], silu=True)
-        self.last_eps_rows = ops.conv3x3(y.view(B * F, h, w, -1), W["conv_out.weight"], bias=W["conv_out.bias"],
-                                         out=torch.empty((B * F * h * w, 8), dtype=torch.float16, device=dev))
+        y = self._gn(x, W["conv_norm_out.weight"], W["conv_norm_out.bias"], NB=B, rows=F * h * w, eps=cfg["norm_eps"],
+                     silu=True)
+        eps_rows = ops.conv3x3(y.view(B * F, h, w, -1), W["conv_out.weight"], bias=W["conv_out.bias"],
+                               out=torch.empty((B * F * h * w, 8), dtype=torch.float16, device=dev))
+        if self._shard is not None:  # all-gather the (tiny) noise prediction: [P][B][Fl] -> [B][P Fl]
+            import torch.distributed as dist
+            group, rank, world = self._shard
+            gathered = torch.empty((world, B, F, h * w, 8), dtype=torch.float16, device=dev)
+            dist.all_gather_into_tensor(gathered, eps_rows.view(B, F, h * w, 8), group=group)
+            eps_rows = gathered.permute(1, 0, 2, 3, 4).reshape(B * F_total * h * w, 8).contiguous()
+            F = F_total
+        self.last_eps_rows = eps_rows
         out = ops.unpack_latents(self.last_eps_rows, B, cfg["out_channels"], F, h, w)
         return UNetPseudo3DConditionOutput(sample=out)
 
