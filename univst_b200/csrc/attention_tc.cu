@@ -19,6 +19,8 @@
 // handling; nothing is padded in global memory.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -35,11 +37,12 @@ struct AttnParams {
   __half* O;     // [NI*N][ldo]
   int ldo;
   float scale_log2;  // d^-0.5 * log2(e)
+  int stagger;       // start offset between the softmax groups of a CTA, clocks
 };
 
 static constexpr uint32_t kOBase = 256;     // TMEM column of the first O accumulator
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 before a forced rescale
-static constexpr int kDefaultVariant = 0;
+static constexpr int kDefaultVariant = 1;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -62,7 +65,7 @@ __device__ __forceinline__ float ex2_poly(float x) {
 
 template <int NQ, int BKV>
 struct AttnCfg {
-  static constexpr int kDepth = (NQ == 1) ? 2 : 1;      // S / P slots per query tile
+  static constexpr int kDepth = (NQ == 1) ? 2 : 1;      // S slots per query tile
   static constexpr int kSlots = NQ * kDepth;              // S slots
   static constexpr int kPSlots = NQ * 2;                  // P tiles are double-buffered per query tile
   static constexpr int kThreads = 64 + 128 * NQ + 32 * (NQ - 1);
@@ -70,6 +73,7 @@ struct AttnCfg {
   static constexpr int kKVChunkBytes = BKV * 128;       // [BKV rows][64 halves]
   static constexpr int kPBytes = 128 * BKV * 2;         // [128 rows][BKV halves] as BKV/64 swizzled chunks
   static constexpr int kBarriers = 40;
+  static constexpr bool kConvergentIssue = BKV == 64;   // see the MMA issuer
   static_assert(kSlots * BKV <= 256, "S slots must fit below the O accumulators");
 };
 
@@ -153,160 +157,316 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int c = 0; c < dch; ++c)
           tma_load_4d(sQ + q * q_bytes + c * L::kQChunkBytes, &tmQ, q_full, c * 64, head, (qt0 + q) * 128, img);
       const int* src = p.kv_src + (size_t)img * p.nsrc;
-      uint32_t phase = 0;
-      for (int j = 0; j < T; ++j) {
-        const int s = j & 1;
-        const int simg = src[j / tps];
-        const int row0 = (j % tps) * BKV;
-        mbar_wait(&k_empty[s], phase ^ 1);
-        mbar_expect_tx(&k_full[s], kv_bytes);
-        for (int c = 0; c < dch; ++c)
-          tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &tmK, &k_full[s], c * 64, head, row0, simg);
-        mbar_wait(&v_empty[s], phase ^ 1);
-        mbar_expect_tx(&v_full[s], kv_bytes);
-        for (int c = 0; c < dch; ++c)
-          tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &tmV, &v_full[s], c * 64, head, row0, simg);
-        if (s == 1) phase ^= 1;
+      // K and V rings are fed independently (non-blocking polls): a K slot frees as soon as the Q K^T that read it has
+      // run, a V slot only after the P V one softmax later, so a single in-order K, V, K, V ... stream would hold every
+      // K load back behind the wait for a V slot and leave the score MMA starved by the TMA latency.
+      int jk = 0, sik = 0, jtk = 0;   // next K tile, its source index and tile inside the source
+      int jv = 0, siv = 0, jtv = 0;
+      while (jk < T || jv < T) {
+        bool progress = false;
+        if (jk < T && (jk < 2 || mbar_test_wait(&k_empty[jk & 1], (uint32_t)(((jk >> 1) & 1) ^ 1)))) {
+          const int s = jk & 1;
+          mbar_expect_tx(&k_full[s], kv_bytes);
+          for (int c = 0; c < dch; ++c)
+            tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &tmK, &k_full[s], c * 64, head, jtk * BKV, src[sik]);
+          if (++jtk == tps) {
+            jtk = 0;
+            ++sik;
+          }
+          ++jk;
+          progress = true;
+        }
+        if (jv < T && (jv < 2 || mbar_test_wait(&v_empty[jv & 1], (uint32_t)(((jv >> 1) & 1) ^ 1)))) {
+          const int s = jv & 1;
+          mbar_expect_tx(&v_full[s], kv_bytes);
+          for (int c = 0; c < dch; ++c)
+            tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &tmV, &v_full[s], c * 64, head, jtv * BKV, src[siv]);
+          if (++jtv == tps) {
+            jtv = 0;
+            ++siv;
+          }
+          ++jv;
+          progress = true;
+        }
+        if (!progress) __nanosleep(64);
       }
     }
   } else if (is_mma) {
-    if (lane == 0) {
-      // ---------------------------------------------------------------- MMA issuer of query tile q
-      const int q = (warp == 1) ? 0 : (int)(warp - (2 + 4 * NQ)) + 1;
-      const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
-      const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
-      auto issue_s = [&](int j) {
-        const int ks = j & 1, slot = q * D + j % D;
-        mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
-        tc_fence_after();
-        const uint32_t qa = smem_u32(sQ + q * q_bytes);
-        const uint32_t ka = smem_u32(sK + ks * kv_bytes);
-        int step = 0;
-        for (int c = 0; c < dch; ++c) {
-          const int nk = min(64, dpad - c * 64) >> 4;
-          const uint64_t da = make_smem_desc_sw128(qa + c * L::kQChunkBytes, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(ka + c * L::kKVChunkBytes, 16, 1024);
-          for (int k = 0; k < nk; ++k, ++step)
-            umma_f16_ss(tmem_base + slot * BKV, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, step ? 1u : 0u);
-        }
-        tc_commit(&k_empty[ks]);
-        tc_commit(&s_full[slot]);
-      };
-      auto issue_pv = [&](int j) {
-        const int vs = j & 1, slot = q * 2 + (j & 1);        // P slot, used for the (j / 2)-th time
-        mbar_wait(&p_full[slot], (uint32_t)((j >> 1) & 1));
-        mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
-        tc_fence_after();
-        const uint32_t pa = smem_u32(sP + slot * L::kPBytes);
-        const uint32_t va = smem_u32(sV + vs * kv_bytes);
-#pragma unroll
-        for (int k = 0; k < BKV / 16; ++k) {
-          // A: P chunk (k / 4), 32-byte step inside the swizzle row.  B: V, 16 keys = 2 KiB further down;
-          // the next 64 head-dim columns are a whole chunk away (LBO).
-          const uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(va + k * 2048, L::kKVChunkBytes, 1024);
-          umma_f16_ss(tmem_base + kOBase + q * opad, da, db, idesc_o, (j | k) ? 1u : 0u);
-        }
-        tc_commit(&v_empty[vs]);
-        tc_commit(&o_done[slot]);
-      };
-      mbar_wait(q_full, 0);
+    // ---------------------------------------------------------------- MMA issuer of query tile q
+    // Two issue styles (AttnCfg::kConvergentIssue), chosen by measurement.  Convergent (below): the whole warp runs the
+    // loop, lane 0 probes the barriers (voted) and an elected lane issues each tcgen05 instruction -- the shortest
+    // turn-around from "scores consumed" to "next scores issued", which is what bounds the 64-key tiles (head dims
+    // 80 / 160: 442 -> 416 us and 124 -> 105 us per layer).  Single lane (further down): only lane 0 runs the loop;
+    // measured faster for the MUFU-bound 128-key tiles of head dim 40 (4.9 vs 6.0-6.5 ms per layer).
+    static_assert(NQ <= 2, "one MMA-issuing warp per query tile: warp 1 and warp 2 + 4 NQ");
+    auto mma_role = [&](auto qc) {
+    constexpr int q = decltype(qc)::value;   // compile-time: everything derived from it stays in uniform registers
+    const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
+    const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
+    const uint32_t tmem_o = tmem_base + kOBase + q * opad;
+    // Descriptor words are built once; per UMMA only the 14-bit start-address field of the low word moves (it cannot
+    // carry out of the field: shared addresses are below 256 KiB).  The loop over KV tiles is unrolled by two so that
+    // the ring stage / P buffer of a tile is a compile-time constant.
+    const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + q * q_bytes), 16, 1024);
+    const uint64_t kd0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+    const uint64_t vd0 = make_smem_desc_sw128(smem_u32(sV), L::kKVChunkBytes, 1024);
+    const uint64_t pd0 = make_smem_desc_sw128(smem_u32(sP + (q * 2) * L::kPBytes), 16, 1024);
+    const uint32_t kv16 = kv_bytes >> 4;
+    auto issue_s = [&](int j, auto parc) {
+      constexpr int par = decltype(parc)::value;          // j & 1
+      const int slot = q * D + (D == 2 ? par : 0);
+      mbar_wait_warp(&k_full[par], (uint32_t)((j >> 1) & 1));
       tc_fence_after();
-      // The tile's slots are filled up front; afterwards a slot is refilled with the next scores that map to it as
-      // soon as the softmax group has pulled the current tile into registers (s_free), i.e. *during* that tile's
-      // exponentials -- a group never waits for the tensor pipe between two tiles.
-      for (int j = 0; j < D && j < T; ++j) issue_s(j);
-      for (int j = 0; j < T; ++j) {
-        if (j + D < T) {
-          mbar_wait(&s_free[q * D + j % D], (uint32_t)((j / D) & 1));
+      const uint64_t kd = desc_advance(kd0, par * kv16);
+      const uint32_t tmem_s = tmem_base + slot * BKV;
+      int step = 0;
+      for (int c = 0; c < dch; ++c) {
+        const int nk = min(64, dpad - c * 64) >> 4;
+        for (int k = 0; k < nk; ++k, ++step)
+          umma_f16_ss_elect(tmem_s, desc_advance(qd, (c * L::kQChunkBytes + k * 32) >> 4),
+                            desc_advance(kd, (c * L::kKVChunkBytes + k * 32) >> 4), idesc_s, step ? 1u : 0u);
+      }
+      tc_commit_elect(&k_empty[par]);
+      tc_commit_elect(&s_full[slot]);
+    };
+    auto issue_pv = [&](int j, auto parc) {
+      constexpr int par = decltype(parc)::value;          // j & 1: V ring stage and P buffer
+      constexpr int slot = q * 2 + par;
+      mbar_wait_warp(&p_full[slot], (uint32_t)((j >> 1) & 1));
+      mbar_wait_warp(&v_full[par], (uint32_t)((j >> 1) & 1));
+      tc_fence_after();
+      const uint64_t pd = desc_advance(pd0, par * (L::kPBytes >> 4));
+      const uint64_t vd = desc_advance(vd0, par * kv16);
+#pragma unroll
+      for (int k = 0; k < BKV / 16; ++k) {
+        // A: P chunk (k / 4), 32-byte step inside the swizzle row.  B: V, 16 keys = 2 KiB further down;
+        // the next 64 head-dim columns are a whole chunk away (LBO).
+        umma_f16_ss_elect(tmem_o, desc_advance(pd, ((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4),
+                          desc_advance(vd, (k * 2048) >> 4), idesc_o, (j | k) ? 1u : 0u);
+      }
+      tc_commit_elect(&v_empty[par]);
+      tc_commit_elect(&o_done[slot]);
+    };
+    using P0 = std::integral_constant<int, 0>;
+    using P1 = std::integral_constant<int, 1>;
+    mbar_wait_warp(q_full, 0);
+    tc_fence_after();
+    // The tile's slots are filled up front; afterwards a slot is refilled with the next scores that map to it as
+    // soon as the softmax group has pulled the current tile into registers (s_free), i.e. *during* that tile's
+    // exponentials -- a group never waits for the tensor pipe between two tiles.
+    issue_s(0, P0{});
+    if (D == 2 && T > 1) issue_s(1, P1{});
+    auto step = [&](int j, auto parc) {
+      constexpr int par = decltype(parc)::value;
+      if (j + D < T) {
+        mbar_wait_warp(&s_free[q * D + (D == 2 ? par : 0)], (uint32_t)((j / D) & 1));
+        tc_fence_after();
+        if constexpr (D == 2) issue_s(j + 2, parc);
+        else issue_s(j + 1, std::integral_constant<int, 1 - par>{});
+      }
+      issue_pv(j, parc);
+    };
+    for (int j = 0; j < T; j += 2) {
+      step(j, P0{});
+      if (j + 1 < T) step(j + 1, P1{});
+    }
+    };
+    if constexpr (L::kConvergentIssue) {
+      if (warp == 1) {
+        mma_role(std::integral_constant<int, 0>{});
+      } else {
+        if constexpr (NQ > 1) mma_role(std::integral_constant<int, 1>{});
+      }
+    } else {
+      if (lane == 0) {
+        // ---------------------------------------------------------------- MMA issuer of query tile q
+        const int q = (warp == 1) ? 0 : (int)(warp - (2 + 4 * NQ)) + 1;
+        const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
+        const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
+        auto issue_s = [&](int j) {
+          const int ks = j & 1, slot = q * D + j % D;
+          mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
           tc_fence_after();
-          issue_s(j + D);
+          const uint32_t qa = smem_u32(sQ + q * q_bytes);
+          const uint32_t ka = smem_u32(sK + ks * kv_bytes);
+          int step = 0;
+          for (int c = 0; c < dch; ++c) {
+            const int nk = min(64, dpad - c * 64) >> 4;
+            const uint64_t da = make_smem_desc_sw128(qa + c * L::kQChunkBytes, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(ka + c * L::kKVChunkBytes, 16, 1024);
+            for (int k = 0; k < nk; ++k, ++step)
+              umma_f16_ss(tmem_base + slot * BKV, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, step ? 1u : 0u);
+          }
+          tc_commit(&k_empty[ks]);
+          tc_commit(&s_full[slot]);
+        };
+        auto issue_pv = [&](int j) {
+          const int vs = j & 1, slot = q * 2 + (j & 1);        // P slot, used for the (j / 2)-th time
+          mbar_wait(&p_full[slot], (uint32_t)((j >> 1) & 1));
+          mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
+          tc_fence_after();
+          const uint32_t pa = smem_u32(sP + slot * L::kPBytes);
+          const uint32_t va = smem_u32(sV + vs * kv_bytes);
+  #pragma unroll
+          for (int k = 0; k < BKV / 16; ++k) {
+            // A: P chunk (k / 4), 32-byte step inside the swizzle row.  B: V, 16 keys = 2 KiB further down;
+            // the next 64 head-dim columns are a whole chunk away (LBO).
+            const uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
+            const uint64_t db = make_smem_desc_sw128(va + k * 2048, L::kKVChunkBytes, 1024);
+            umma_f16_ss(tmem_base + kOBase + q * opad, da, db, idesc_o, (j | k) ? 1u : 0u);
+          }
+          tc_commit(&v_empty[vs]);
+          tc_commit(&o_done[slot]);
+        };
+        mbar_wait(q_full, 0);
+        tc_fence_after();
+        // The tile's slots are filled up front; afterwards a slot is refilled with the next scores that map to it as
+        // soon as the softmax group has pulled the current tile into registers (s_free), i.e. *during* that tile's
+        // exponentials -- a group never waits for the tensor pipe between two tiles.
+        for (int j = 0; j < D && j < T; ++j) issue_s(j);
+        for (int j = 0; j < T; ++j) {
+          if (j + D < T) {
+            mbar_wait(&s_free[q * D + j % D], (uint32_t)((j / D) & 1));
+            tc_fence_after();
+            issue_s(j + D);
+          }
+          issue_pv(j);
         }
-        issue_pv(j);
       }
     }
   } else {
     // ------------------------------------------------------------------ softmax group g = query tile g
+    // One thread per query row.  The S tile is pulled into registers in one go and its TMEM slot released at once
+    // (the next Q K^T of this query tile runs under this tile's exponentials).  The tile is then consumed in 32-column
+    // chunks: the max of chunk c + 1 is computed in the same basic block as the exponentials of chunk c, so FMNMX and
+    // MUFU work are mixed instead of alternating in long phases, and a chunk is checked against the running (lazily
+    // updated) reference maximum right before its exponentials.
+    // The softmax groups of a CTA start staggered by about half a tile (p.stagger clocks): two warps of a scheduler
+    // that run in lockstep leave the MUFU pipe idle whenever both are between their exponentials; out of phase, one
+    // warp's loads / max / barrier work hides under the other's exponentials.
     const int g = (int)(warp - 2) >> 2;
     const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
     const uint32_t r = quad * 32 + lane;                // row inside the 128-row tile
     const uint32_t lane_off = (quad * 32) << 16;
     const uint32_t o_addr = tmem_base + kOBase + g * opad + lane_off;
+    const uint32_t prow0 = smem_u32(sP) + r * 128;
+    const uint32_t swz = r & 7;
+    constexpr int NC = BKV / 32;
     float m_used = -INFINITY;   // max baked into O and l
     float l = 0.0f;
+    int jt = 0;                 // tile index inside the current source image
     for (int j = 0; j < T; ++j) {
       const int slot = g * D + j % D;
+      const int pslot = g * 2 + (j & 1);
+      const uint32_t prow = prow0 + pslot * L::kPBytes;
       mbar_wait(&s_full[slot], (uint32_t)((j / D) & 1));
+      if (j == 0 && g > 0 && p.stagger > 0) {   // counted from the arrival of the first scores, not from the launch
+        const long long t0 = clock64();
+        while (clock64() - t0 < (long long)g * p.stagger) {
+        }
+      }
       tc_fence_after();
       // S tile -> registers: all loads in flight, one wait
       uint32_t sraw[BKV];
       {
         const uint32_t sa = tmem_base + slot * BKV + lane_off;
 #pragma unroll
-        for (int c = 0; c < BKV / 32; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]));
+        for (int c = 0; c < NC; ++c) tmem_ld32(sa + c * 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[c * 32]));
         tc_wait_ld();
       }
       tc_fence_before();
       mbar_arrive(&s_free[slot]);  // the slot may be overwritten with the next scores from here on
-      const int valid = min(BKV, p.Nkv - (j % tps) * BKV);
+      const int valid = p.Nkv - jt * BKV;   // >= BKV except on the ragged last tile of a source
+      if (++jt == tps) jt = 0;
       if (valid < BKV) {
 #pragma unroll
         for (int x = 0; x < BKV; ++x)
           if (x >= valid) sraw[x] = 0xff800000u;  // -inf
       }
-      // row max of the raw scores: 8 independent chains (a single chain is BKV dependent FMNMX)
-      float mx8[8];
-#pragma unroll
-      for (int x = 0; x < 8; ++x) mx8[x] = __uint_as_float(sraw[x]);
-#pragma unroll
-      for (int x = 8; x < BKV; ++x) mx8[x & 7] = fmaxf(mx8[x & 7], __uint_as_float(sraw[x]));
-      const float mx = fmaxf(fmaxf(fmaxf(mx8[0], mx8[1]), fmaxf(mx8[2], mx8[3])),
-                             fmaxf(fmaxf(mx8[4], mx8[5]), fmaxf(mx8[6], mx8[7]))) * p.scale_log2;
-      const bool need = mx > m_used + kRescaleThreshold;   // first tile: m_used = -inf -> always true
-      if (__any_sync(0xffffffffu, need)) {
-        const float m_new = fmaxf(m_used, mx);
-        if (j > 0) {
-          // rare path: O is rescaled in TMEM, so the previous P V of this query tile must have landed
-          mbar_wait(&o_done[g * 2 + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
-          tc_fence_after();
-          const float alpha = ex2_approx(m_used - m_new);   // lanes that did not need it: alpha <= 1, harmless
-          l *= alpha;
-          for (uint32_t c = 0; c < opad; c += 16) {
-            uint32_t t[16];
-            tmem_ld16(o_addr + c, t);
-            tc_wait_ld();
-#pragma unroll
-            for (int x = 0; x < 16; ++x) t[x] = __float_as_uint(__uint_as_float(t[x]) * alpha);
-            tmem_st16(o_addr + c, t);
-          }
-          tc_wait_st();
-        }
-        m_used = m_new;
-      }
-      // P = 2^(s * scale - m_used): one FFMA + one MUFU.EX2 per element, fp16, written as swizzled K-major
-      // chunks (chunk kc holds keys [64 kc, 64 kc + 64)); the row sum runs in 4 independent chains
-      const int pslot = g * 2 + (j & 1);
       if (j >= 2) {  // the P buffer was last read by the P V of tile j - 2: long done, the wait is (almost) free
         mbar_wait(&o_done[pslot], (uint32_t)(((j - 2) >> 1) & 1));
       }
-      uint8_t* prow = sP + pslot * L::kPBytes + r * 128;
+      auto chunk_max = [&](int c) {
+        float mx4[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) mx4[x] = __uint_as_float(sraw[c * 32 + x]);
+#pragma unroll
+        for (int x = 4; x < 32; ++x) mx4[x & 3] = fmaxf(mx4[x & 3], __uint_as_float(sraw[c * 32 + x]));
+        return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+      };
       float ls4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-      const float neg_m = -m_used;
+      float mx_next = chunk_max(0);
 #pragma unroll
-      for (int c16 = 0; c16 < BKV / 8; ++c16) {
-        uint32_t w[4];
+      for (int c = 0; c < NC; ++c) {
+        const float mx = mx_next;
+        const bool need = mx > m_used + kRescaleThreshold;   // very first chunk: m_used = -inf -> always true
+        if (__any_sync(0xffffffffu, need)) {
+          // rare path: move the reference maximum.  Everything already scaled by 2^-m_used follows: the row sum, the
+          // P chunks of this tile that sit in shared memory, and the O accumulator in TMEM (for which the previous
+          // P V of this query tile must have landed).
+          const float m_new = fmaxf(m_used, mx);
+          const float alpha = (m_new == m_used) ? 1.0f : ex2_approx(m_used - m_new);
+          l *= alpha;
 #pragma unroll
-        for (int x = 0; x < 4; ++x) {
-          const float a0 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x]), p.scale_log2, neg_m);
-          const float a1 = fmaf(__uint_as_float(sraw[c16 * 8 + 2 * x + 1]), p.scale_log2, neg_m);
-          const float e0 = ex2_approx(a0);
-          // POLY = 1: every 4th exponential off the MUFU pipe; POLY = 2: every 2nd
-          const float e1 = (POLY == 2 || (POLY == 1 && (x & 1))) ? ex2_poly(a1) : ex2_approx(a1);
-          ls4[x] += e0 + e1;
-          w[x] = pack_half2(e0, e1);
+          for (int x = 0; x < 4; ++x) ls4[x] *= alpha;
+          if (c > 0) {
+            const __half2 a2 = __float2half2_rn(alpha);
+#pragma unroll 1
+            for (int pc = 0; pc < c * 4; ++pc) {
+              const uint32_t addr = prow + (pc >> 3) * (128 * 128) + ((((uint32_t)pc & 7) ^ swz) << 4);
+              uint32_t w[4];
+              ld_shared_v4(addr, w);
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                __half2 h = __hmul2(*reinterpret_cast<__half2*>(&w[x]), a2);
+                w[x] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              st_shared_v4(addr, w[0], w[1], w[2], w[3]);
+            }
+          }
+          if (j > 0) {
+            mbar_wait(&o_done[g * 2 + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t oc = 0; oc < opad; oc += 16) {
+              uint32_t t[16];
+              tmem_ld16(o_addr + oc, t);
+              tc_wait_ld();
+#pragma unroll
+              for (int x = 0; x < 16; ++x) t[x] = __float_as_uint(__uint_as_float(t[x]) * alpha);
+              tmem_st16(o_addr + oc, t);
+            }
+            tc_wait_st();
+          }
+          m_used = m_new;
         }
-        const int kc = c16 >> 3, cc = c16 & 7;
-        *reinterpret_cast<uint4*>(prow + kc * (128 * 128) + ((cc ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+        // P = 2^(s * scale - m_used): one FFMA + one MUFU.EX2 per element, fp16, written as swizzled K-major
+        // chunks (chunk kc holds keys [64 kc, 64 kc + 64)); the row sum runs in 4 independent chains
+        const float neg_m = -m_used;
+        if (c + 1 < NC) mx_next = chunk_max(c + 1);
+        // (all 32 exponentials of the chunk are issued back to back before the first one is consumed: the MUFU
+        // latency is then paid once per chunk instead of once per few elements, which is what lets two warps keep
+        // the pipe busy)
+        float e[32];
+#pragma unroll
+        for (int x = 0; x < 32; ++x) e[x] = fmaf(__uint_as_float(sraw[c * 32 + x]), p.scale_log2, neg_m);
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          // POLY = 1: every 4th exponential off the MUFU pipe; POLY = 2: every 2nd; 3: all (experiments: 9 = none at all)
+          const bool poly = POLY == 3 || (POLY == 2 && (x & 1)) || (POLY == 1 && (x & 3) == 3);
+          e[x] = POLY == 9 ? e[x] : (poly ? ex2_poly(e[x]) : ex2_approx(e[x]));
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            ls4[x] += e[q8 * 8 + 2 * x] + e[q8 * 8 + 2 * x + 1];
+            w[x] = pack_half2(e[q8 * 8 + 2 * x], e[q8 * 8 + 2 * x + 1]);
+          }
+          const int pc = c * 4 + q8;   // 16-byte piece of the P row
+          st_shared_v4(prow + (pc >> 3) * (128 * 128) + ((((uint32_t)pc & 7) ^ swz) << 4), w[0], w[1], w[2], w[3]);
+        }
       }
       l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
       fence_proxy_async_smem();
@@ -393,15 +553,22 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   p.ldo = ldo;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
 
-  // tile configuration: d <= 64 -> variant from UNIVST_ATTN_VARIANT (0: 2 query tiles x 128 keys, 1: + polynomial exp2,
-  // 2: 4 query tiles x 64 keys, 3: + polynomial exp2, 4: 2 x 128 with half of the exp2 polynomial); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
+  // tile configuration: d <= 64 -> variant from UNIVST_ATTN_VARIANT (0: 2 query tiles x 128 keys, 1: + a quarter of the
+  // exp2 as polynomials, 2: 2 query tiles x 64 keys with two S slots each, 3: + polynomial exp2, 4: 2 x 128 with half
+  // of the exp2 polynomial); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
   static int variant = -1;
   if (variant < 0) {
     const char* e = getenv("UNIVST_ATTN_VARIANT");
     variant = e ? atoi(e) : kDefaultVariant;
-    if (variant < 0 || variant > 4) variant = kDefaultVariant;
+    if (variant < 0 || variant > 6) variant = kDefaultVariant;
   }
-  const int bkv = (d <= 64 && variant < 2) ? 128 : 64;
+  const int bkv = (d <= 64 && (variant < 2 || variant >= 4)) ? 128 : 64;
+  static int stagger = -2;
+  if (stagger == -2) {
+    const char* e = getenv("UNIVST_ATTN_STAGGER");
+    stagger = e ? atoi(e) : -1;
+  }
+  p.stagger = stagger >= 0 ? stagger : 0;   // measured neutral (0 .. 2500 clocks): off by default
   CUtensorMap tq, tk, tv;
   {
     uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)N, (uint64_t)NI};
@@ -424,9 +591,11 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
     switch (variant) {
       case 0: return launch_attn<2, 128, 0>(tq, tk, tv, p, st);
       case 1: return launch_attn<2, 128, 1>(tq, tk, tv, p, st);
-      case 2: return launch_attn<4, 64, 0>(tq, tk, tv, p, st);
-      case 3: return launch_attn<4, 64, 1>(tq, tk, tv, p, st);
-      default: return launch_attn<2, 128, 2>(tq, tk, tv, p, st);
+      case 2: return launch_attn<2, 64, 0>(tq, tk, tv, p, st);
+      case 3: return launch_attn<2, 64, 1>(tq, tk, tv, p, st);
+      case 4: return launch_attn<2, 128, 2>(tq, tk, tv, p, st);
+      case 5: return launch_attn<2, 128, 3>(tq, tk, tv, p, st);   // experiment: all exponentials as polynomials
+      default: return launch_attn<2, 128, 9>(tq, tk, tv, p, st);  // experiment: no exponentials (wrong results)
     }
   }
   if (d <= 128) return launch_attn<2, 64, 0>(tq, tk, tv, p, st);

@@ -31,6 +31,16 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4(uint32_t saddr, uint32_t (&w)[4]) {
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3])
+               : "r"(saddr)
+               : "memory");
+}
+
 // ------------------------------------------------------------------------------------------
 // mbarrier
 // ------------------------------------------------------------------------------------------
@@ -64,6 +74,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Non-blocking probe of a phase (for threads that poll several barriers).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
 // Bounded wait: a protocol bug traps (-> cudaErrorLaunchFailure) instead of hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
@@ -72,6 +96,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (spins > 64) __nanosleep(32);  // long waits (producer / epilogue roles) back off instead of burning issue slots
     if (++spins > (1u << 24)) {
       printf("univst_b200: mbarrier wait timed out (block %d thread %d)\n", (int)blockIdx.x, (int)threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// Warp-convergent wait: lane 0 probes (32 lanes probing would be 32 shared-memory transactions per try) and the
+// outcome is voted, so the warp never diverges.
+__device__ __forceinline__ void mbar_wait_warp(uint64_t* bar, uint32_t parity) {
+  const bool prober = lane_id() == 0;
+  uint32_t spins = 0;
+  while (true) {
+    uint32_t ok = 0;
+    if (prober) ok = mbar_try_wait(bar, parity) ? 1u : 0u;
+    if (__any_sync(0xffffffffu, ok != 0)) break;
+    if (spins > 16) __nanosleep(32);   // long waits back off: the probes share the MIO queue with the softmax warps' MUFU work
+    if (++spins > (1u << 24)) {
+      if (prober) printf("univst_b200: mbarrier wait timed out (block %d warp %d)\n", (int)blockIdx.x, (int)(threadIdx.x >> 5));
       __trap();
     }
   }
@@ -144,6 +185,17 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// Warp-convergent forms: every lane calls, one elected lane issues.  Keeping the surrounding control flow convergent
+// lets the compiler hold descriptors / addresses in uniform registers instead of paying an ELECT + R2UR sequence per
+// instruction (which is what a whole `if (lane == 0)` region costs).
+__device__ __forceinline__ void umma_f16_ss_elect(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  if (elect_one()) umma_f16_ss(tmem_d, desc_a, desc_b, idesc, accumulate);
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+  if (elect_one()) tc_commit(bar);
+}
+
 // Instruction descriptor for kind::f16: fp16 A/B, fp32 accumulate (bit layout: cute/arch/mma_sm100_desc.hpp).
 //   [4,6) c_format=1 (F32)  [7,10) a_format=0 (F16)  [10,13) b_format=0 (F16)
 //   [15] a_major (0=K)  [16] b_major (0=K, 1=MN)  [17,23) N>>3  [24,29) M>>4
@@ -165,6 +217,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr, uint32_
   d |= (uint64_t)1 << 46;  // version
   d |= (uint64_t)2 << 61;  // SWIZZLE_128B
   return d;
+}
+
+// Move the start address of a descriptor by `units16` 16-byte units (no carry out of the 14-bit field by construction).
+__device__ __forceinline__ uint64_t desc_advance(uint64_t desc, uint32_t units16) {
+  return (desc & 0xffffffff00000000ull) | (uint64_t)((uint32_t)desc + units16);
 }
 
 // TMEM -> registers, 32 lanes x 32 bit, 16 / 32 consecutive columns. Lane i of the warp reads TMEM lane
