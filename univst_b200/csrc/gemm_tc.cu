@@ -62,88 +62,158 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// Per-warp staging tile in shared memory: 32 rows x 32 halves (64 B per row), the 16-byte piece index XOR-swizzled with
+// (row >> 1) & 3 so that both access patterns below are bank-conflict free:
+//   "own row"   : thread r touches row r, pieces 0..3 (the TMEM layout: one accumulator row per thread)
+//   "coalesced" : lane l touches row (l >> 2) + 8 i, piece l & 3 -- one instruction covers 8 rows x 64 contiguous bytes
+//                 of global memory instead of 32 rows x 16 bytes
+static constexpr int kStageTileBytes = 32 * 64;
+__device__ __forceinline__ uint32_t stage_addr(uint32_t base, uint32_t row, uint32_t piece) {
+  return base + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4);
+}
+
+struct EpiCtx {
+  uint32_t stg;        // this warp's staging tile (shared address)
+  uint32_t lane;
+  int row0;            // first row of the warp's 32-row slab
+  int M;
+};
+
+// coalesced residual fetch of one 32-column chunk: 4 x 16 B per lane (zeros where out of range)
+__device__ __forceinline__ void residual_fetch(const GemmParams& p, const EpiCtx& e, int n, uint4 (&r)[4]) {
+  const int col = n + (int)(e.lane & 3) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = e.row0 + (int)(e.lane >> 2) + 8 * i;
+    r[i] = make_uint4(0, 0, 0, 0);
+    if (row < e.M && col < p.N_out) r[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + (size_t)row * p.ldr + col));
+  }
+}
+
+// own-row results (4 x 16 B) -> staging -> coalesced global stores
+__device__ __forceinline__ void staged_store(const GemmParams& p, const EpiCtx& e, int n, const uint32_t (&o)[16]) {
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    st_shared_v4(stage_addr(e.stg, e.lane, g), o[g * 4], o[g * 4 + 1], o[g * 4 + 2], o[g * 4 + 3]);
+  __syncwarp();
+  const int col = n + (int)(e.lane & 3) * 8;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const uint32_t rl = (e.lane >> 2) + 8 * i;
+    const int row = e.row0 + (int)rl;
+    uint32_t w[4];
+    ld_shared_v4(stage_addr(e.stg, rl, e.lane & 3), w);
+    if (row < e.M && col < p.N_out)
+      *reinterpret_cast<uint4*>(p.D + (size_t)row * p.ldd + col) = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  __syncwarp();   // the tile is rewritten by the next chunk
+}
+
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, bool row_ok, const __half* rv,
-                                              const __half* res, __half* drow, int n0, int tile_n, int chunk0) {
+                                              const __half* res, __half* drow, int n0, int tile_n, int chunk0,
+                                              const EpiCtx& e, uint64_t* acc_full, uint32_t acc_parity) {
+  const bool staged = (p.N_out & 7) == 0;   // whole 8-column groups only: every 16-byte piece is all in or all out
+  uint4 rnext[4];
+  // the first residual chunk is requested before the accumulator is even complete
+  if (!p.geglu && staged && p.residual && n0 + chunk0 * 32 < p.N_out) residual_fetch(p, e, n0 + chunk0 * 32, rnext);
+  mbar_wait(acc_full, acc_parity);
+  tc_fence_after();
   if (!p.geglu) {
     for (int c0 = chunk0 * 32; c0 < p.BN; c0 += 64) {
       if (n0 + c0 >= p.N_out) break;  // warp-uniform
       uint32_t acc[32];
       tmem_ld32(taddr + c0, acc);
+      uint32_t rw[16];
+      if (staged && p.residual) {
+        // residual: coalesced loads (issued one chunk ahead) -> staging -> own row
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          st_shared_v4(stage_addr(e.stg, (e.lane >> 2) + 8 * i, e.lane & 3), rnext[i].x, rnext[i].y, rnext[i].z, rnext[i].w);
+        __syncwarp();
+#pragma unroll
+        for (int g = 0; g < 4; ++g) ld_shared_v4(stage_addr(e.stg, e.lane, g), *reinterpret_cast<uint32_t(*)[4]>(&rw[g * 4]));
+        if (c0 + 64 < p.BN && n0 + c0 + 64 < p.N_out) residual_fetch(p, e, n0 + c0 + 64, rnext);
+      }
       tc_wait_ld();
+      if (staged) {
+        uint32_t o[16];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          const int n = n0 + c0 + g * 8;
+          float v[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
+          if (n < p.N_out) {
+            if (p.bias) {
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(bw[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (rv) {
+              const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + n));
+              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(bw[j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+            if (p.residual) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(rw[g * 4 + j]);
+                v[2 * j] += f.x;
+                v[2 * j + 1] += f.y;
+              }
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) o[g * 4 + j] = pack_half2(v[2 * j] * p.out_scale, v[2 * j + 1] * p.out_scale);
+          if (p.act) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 y = unpack_half2(o[g * 4 + j]);
+              o[g * 4 + j] = pack_half2(y.x / (1.0f + __expf(-y.x)), y.y / (1.0f + __expf(-y.y)));
+            }
+          }
+          if (p.bias2 && n < p.N_out) {
+            const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias2 + n));
+            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 f = unpack_half2(bw[j]);
+              float2 y = unpack_half2(o[g * 4 + j]);
+              o[g * 4 + j] = pack_half2(y.x + f.x, y.y + f.y);
+            }
+          }
+        }
+        staged_store(p, e, n0 + c0, o);
+        continue;
+      }
+      // ragged N_out (conv_out: 4 channels): one thread per row, scalar tail
       if (!row_ok) continue;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int n = n0 + c0 + g * 8;
         if (n >= p.N_out) break;
-        float v[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
-        if (n + 8 <= p.N_out) {
-          if (p.bias) {
-            const uint4 b = *reinterpret_cast<const uint4*>(p.bias + n);
-            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f = unpack_half2(bw[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
-            }
-          }
-          if (rv) {
-            const uint4 b = *reinterpret_cast<const uint4*>(rv + n);
-            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f = unpack_half2(bw[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
-            }
-          }
-          if (res) {
-            const uint4 b = *reinterpret_cast<const uint4*>(res + n);
-            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f = unpack_half2(bw[j]);
-              v[2 * j] += f.x;
-              v[2 * j + 1] += f.y;
-            }
-          }
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j] * p.out_scale, v[2 * j + 1] * p.out_scale);
+        for (int j = 0; j < 8 && n + j < p.N_out; ++j) {
+          float x = __uint_as_float(acc[g * 8 + j]);
+          if (p.bias) x += __half2float(p.bias[n + j]);
+          if (rv) x += __half2float(rv[n + j]);
+          if (res) x += __half2float(res[n + j]);
+          __half y = __float2half_rn(x * p.out_scale);
           if (p.act) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 y = unpack_half2(o[j]);
-              o[j] = pack_half2(y.x / (1.0f + __expf(-y.x)), y.y / (1.0f + __expf(-y.y)));
-            }
+            const float yf = __half2float(y);
+            y = __float2half_rn(yf / (1.0f + __expf(-yf)));
           }
-          if (p.bias2) {
-            const uint4 b = *reinterpret_cast<const uint4*>(p.bias2 + n);
-            const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float2 f = unpack_half2(bw[j]);
-              float2 y = unpack_half2(o[j]);
-              o[j] = pack_half2(y.x + f.x, y.y + f.y);
-            }
-          }
-          *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-          for (int j = 0; j < 8 && n + j < p.N_out; ++j) {
-            float x = v[j];
-            if (p.bias) x += __half2float(p.bias[n + j]);
-            if (rv) x += __half2float(rv[n + j]);
-            if (res) x += __half2float(res[n + j]);
-            __half y = __float2half_rn(x * p.out_scale);
-            if (p.act) {
-              const float yf = __half2float(y);
-              y = __float2half_rn(yf / (1.0f + __expf(-yf)));
-            }
-            if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(p.bias2[n + j]));
-            drow[n + j] = y;
-          }
+          if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(p.bias2[n + j]));
+          drow[n + j] = y;
         }
       }
     }
@@ -157,37 +227,28 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
       tmem_ld32(taddr + c0, av);
       tmem_ld32(taddr + half_bn + c0, ag);
       tc_wait_ld();
-      if (!row_ok) continue;
+      uint32_t o[16];
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         const int c = c0 + g * 8;
-        const int n = no0 + c;
-        if (n >= p.N_out) break;
         // fp32 all the way: value * gelu(gate) with one rounding at the end (the reference rounds the projection
         // and the GELU to fp16 first; skipping that is both cheaper and closer to the fp32 oracle)
         uint4 bv = make_uint4(0, 0, 0, 0), bg = make_uint4(0, 0, 0, 0);
-        if (p.bias) {
+        if (p.bias && no0 + c < p.N_out) {
           bv = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + c));
           bg = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + half_bn + c));
         }
         const uint32_t bvw[4] = {bv.x, bv.y, bv.z, bv.w}, bgw[4] = {bg.x, bg.y, bg.z, bg.w};
-        float v[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const float2 fv = unpack_half2(bvw[j]), fg = unpack_half2(bgw[j]);
-          v[2 * j] = (__uint_as_float(av[g * 8 + 2 * j]) + fv.x) * gelu_erf(__uint_as_float(ag[g * 8 + 2 * j]) + fg.x);
-          v[2 * j + 1] =
+          const float v0 = (__uint_as_float(av[g * 8 + 2 * j]) + fv.x) * gelu_erf(__uint_as_float(ag[g * 8 + 2 * j]) + fg.x);
+          const float v1 =
               (__uint_as_float(av[g * 8 + 2 * j + 1]) + fv.y) * gelu_erf(__uint_as_float(ag[g * 8 + 2 * j + 1]) + fg.y);
-        }
-        if (n + 8 <= p.N_out) {
-          uint32_t o[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) o[j] = pack_half2(v[2 * j], v[2 * j + 1]);
-          *reinterpret_cast<uint4*>(drow + n) = make_uint4(o[0], o[1], o[2], o[3]);
-        } else {
-          for (int j = 0; j < 8 && n + j < p.N_out; ++j) drow[n + j] = __float2half_rn(v[j]);
+          o[g * 4 + j] = pack_half2(v0, v1);
         }
       }
+      staged_store(p, e, no0 + c0, o);   // GEGLU outputs are whole 8-column groups (N % 128 == 0)
     }
   }
 }
@@ -205,7 +266,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t a_bytes = kBM * kBK * 2;
   const uint32_t b_bytes = (uint32_t)p.BN * kBK * 2;
   const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint8_t* stg = smem + (size_t)p.stages * stage_bytes;   // [kEpiWarps] staging tiles of the epilogue
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg + kEpiWarps * kStageTileBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full_bar = empty_bar + p.stages;   // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;     // [2]
@@ -290,38 +352,40 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      // ------------------------------------------------ MMA issuer
-      const uint32_t idesc = make_idesc_f16(kBM, (uint32_t)p.BN, 0, 0);
-      uint32_t phase = 0;
-      int s = 0;
-      int it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int a = it & 1;
-        // wait until the epilogue has drained this accumulator (its (it / 2)-th use)
-        mbar_wait(&tmem_empty_bar[a], (uint32_t)(((it >> 1) & 1) ^ 1));
+    // ------------------------------------------------ MMA issuer
+    // The whole warp runs the loop convergently; lane 0 probes the barriers (voted) and an elected lane issues each
+    // tcgen05 instruction, so stage addresses and descriptors stay in uniform registers.  (A plain `if (lane == 0)`
+    // region costs an ELECT / R2UR sequence of ~15 dependent instructions per UMMA -- more than a 128 x 160 x 16 MMA
+    // takes -- which made every BN < 256 tile issue-bound.)
+    const uint32_t idesc = make_idesc_f16(kBM, (uint32_t)p.BN, 0, 0);
+    const uint32_t smem0 = smem_u32(smem);
+    uint32_t phase = 0;
+    int s = 0;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int a = it & 1;
+      // wait until the epilogue has drained this accumulator (its (it / 2)-th use)
+      mbar_wait_warp(&tmem_empty_bar[a], (uint32_t)(((it >> 1) & 1) ^ 1));
+      tc_fence_after();
+      const uint32_t acc = tmem_base + a * acc_cols;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait_warp(&full_bar[s], phase);
         tc_fence_after();
-        const uint32_t acc = tmem_base + a * acc_cols;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[s], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes);
-          const uint32_t sb = sa + a_bytes;
-          const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(sb, 16, 1024);
+        const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
+        const uint64_t da = make_smem_desc_sw128(sa, 16, 1024);
+        const uint64_t db = make_smem_desc_sw128(sa + a_bytes, 16, 1024);
 #pragma unroll
-          for (int k = 0; k < kBK / 16; ++k) {
-            // advance 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-            umma_f16_ss(acc, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-          }
-          tc_commit(&empty_bar[s]);  // frees the smem stage once these MMAs retire
-          if (++s == p.stages) {
-            s = 0;
-            phase ^= 1;
-          }
+        for (int k = 0; k < kBK / 16; ++k) {
+          // advance 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+          umma_f16_ss_elect(acc, desc_advance(da, k * 2), desc_advance(db, k * 2), idesc, (kb | k) ? 1u : 0u);
         }
-        tc_commit(&tmem_full_bar[a]);
+        tc_commit_elect(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        if (++s == p.stages) {
+          s = 0;
+          phase ^= 1;
+        }
       }
+      tc_commit_elect(&tmem_full_bar[a]);
     }
   } else {
     // -------------------------------------------------- epilogue warps 2..9 (TMEM lane quadrant = warp % 4)
@@ -334,14 +398,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int m0 = (tile / tiles_n) * kBM;
       const int n0 = tile_n * p.BN;
       const int row = m0 + (int)(q * 32 + lane);
-      mbar_wait(&tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
-      tc_fence_after();
       const uint32_t taddr = tmem_base + a * acc_cols + ((q * 32) << 16);
       const bool row_ok = row < p.M;
       const __half* rv = (p.rowvec && row_ok) ? p.rowvec + (size_t)(row / p.rows_per_group) * p.rowvec_ld : nullptr;
       const __half* res = (p.residual && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
       __half* drow = p.D + (size_t)row * p.ldd;
-      epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0);
+      EpiCtx e;
+      e.stg = smem_u32(stg) + (warp - 2) * kStageTileBytes;
+      e.lane = lane;
+      e.row0 = m0 + (int)(q * 32);
+      e.M = p.M;
+      epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[a]);
@@ -380,7 +447,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + (2 * stages + 4) * sizeof(uint64_t) + 16 + 1024;
+  const size_t smem = (size_t)stages * stage_bytes + kEpiWarps * kStageTileBytes + (2 * stages + 4) * sizeof(uint64_t) +
+                      16 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
     UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -12,7 +12,8 @@
 
 namespace uv {
 
-static constexpr int kGnMaxChunks = 64;
+static constexpr int kGnMaxChunks = 512;
+static constexpr int kGnUnroll = 4;   // rows in flight per thread
 
 __device__ __forceinline__ const uint4* gn_src(const __half* x1, const __half* x2, int C1, int C2, size_t row, int v) {
   // v-th 8-channel vector of the concatenated row
@@ -21,7 +22,11 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, const __half* x
                   : reinterpret_cast<const uint4*>(x2 + row * C2 + (c - C1));
 }
 
-// grid (nchunks, NB); block = nvec * rows_par threads.  partial[b][chunk][group][2] = (sum, sumsq)
+// Thread mapping shared by the statistics and the apply kernel: block = nvec * rows_par threads, thread (rl, v) owns
+// the v-th 8-channel vector of rows rl, rl + rows_par, ... of its row range -- a warp reads whole contiguous rows, the
+// per-channel constants of a thread never change, and kGnUnroll independent 16-byte loads are in flight per thread.
+
+// grid (nchunks, NB).  partial[b][chunk][group][2] = (sum, sumsq)
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, int C1, int C2, int rows,
                                 int groups, int nvec, int rows_par, int rows_per_chunk, float* __restrict__ partial) {
   extern __shared__ float sh[];  // [threads][8] per-thread pair sums, then [groups][2]
@@ -29,15 +34,26 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __r
   const int C = C1 + C2, cpg = C / groups;
   const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
   const int r_begin = chunk * rows_per_chunk, r_end = min(rows, r_begin + rows_per_chunk);
+  const uint4* src = gn_src(x1, x2, C1, C2, (size_t)b * rows, v);
+  const size_t rstride = (size_t)((v * 8 < C1) ? C1 : C2) / 8;   // uint4 per row of the source this thread reads
   float s[4] = {0, 0, 0, 0}, q[4] = {0, 0, 0, 0};
-  for (int r = r_begin + rl; r < r_end; r += rows_par) {
-    const uint4 u = __ldg(gn_src(x1, x2, C1, C2, (size_t)b * rows + r, v));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int r = r_begin + rl; r < r_end; r += rows_par * kGnUnroll) {
+    uint4 u[kGnUnroll];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const float2 f = unpack_half2(w[j]);
-      s[j] += f.x + f.y;
-      q[j] += f.x * f.x + f.y * f.y;
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const int rr = r + k * rows_par;
+      u[k] = make_uint4(0, 0, 0, 0);
+      if (rr < r_end) u[k] = __ldg(src + (size_t)rr * rstride);
+    }
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_half2(w[j]);
+        s[j] += f.x + f.y;
+        q[j] = fmaf(f.x, f.x, fmaf(f.y, f.y, q[j]));
+      }
     }
   }
   // deterministic fold (no float atomics): thread (rl, v) parks its four channel-pair sums, then thread g adds up the
@@ -64,98 +80,126 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __r
   }
 }
 
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
-
-// grid (row blocks, NB); each block first folds the chunk partials of its batch into mean / rstd.
-__global__ void gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, int C1, int C2, int rows,
-                                int groups, int nvec, int nchunks, const float* __restrict__ partial,
-                                const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps, int silu,
-                                int rows_per_block, int stat_rows, __half* __restrict__ y) {
-  extern __shared__ float sh[];  // [groups][2] = (mean, rstd)
-  const int b = blockIdx.y;
-  const int C = C1 + C2, cpg = C / groups;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float s = 0.0f, q = 0.0f;
-    const float* pp = partial + (size_t)b * nchunks * groups * 2 + g * 2;
-    for (int c = 0; c < nchunks; ++c) {
-      s += pp[(size_t)c * groups * 2];
-      q += pp[(size_t)c * groups * 2 + 1];
-    }
-    const float n = (float)stat_rows * (float)cpg;  // rows the statistics were taken over (all ranks when sharded)
-    const float mean = s / n;
-    const float var = fmaxf(q / n - mean * mean, 0.0f);
-    sh[g * 2] = mean;
-    sh[g * 2 + 1] = rsqrtf(var + eps);
-  }
-  __syncthreads();
-  const int r_begin = blockIdx.x * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
-  const int total = (r_end - r_begin) * nvec;
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int r = r_begin + idx / nvec, v = idx % nvec;
-    const size_t row = (size_t)b * rows + r;
-    const uint4 u = __ldg(gn_src(x1, x2, C1, C2, row, v));
-    const uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
-    const uint4 bt = __ldg(reinterpret_cast<const uint4*>(beta + v * 8));
-    const uint32_t w[4] = {u.x, u.y, u.z, u.w}, gw[4] = {gm.x, gm.y, gm.z, gm.w}, bw[4] = {bt.x, bt.y, bt.z, bt.w};
-    uint32_t o[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int g = (v * 8 + j * 2) / cpg;
-      const float mean = sh[g * 2], rstd = sh[g * 2 + 1];
-      const float2 f = unpack_half2(w[j]), ga = unpack_half2(gw[j]), be = unpack_half2(bw[j]);
-      float a = (f.x - mean) * rstd * ga.x + be.x;
-      float c = (f.y - mean) * rstd * ga.y + be.y;
-      if (silu) {
-        // the reference rounds the GroupNorm output to fp16 before the activation
-        a = silu_f(__half2float(__float2half_rn(a)));
-        c = silu_f(__half2float(__float2half_rn(c)));
-      }
-      o[j] = pack_half2(a, c);
-    }
-    *reinterpret_cast<uint4*>(y + row * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+// sums[b][g][2] = sum over the chunk partials in a fixed order: 4 interleaved quarter sums per entry, then combined.
+// grid NB, block 4 * 64.
+__global__ void gn_fold_kernel(const float* __restrict__ partial, int nchunks, int groups, float* __restrict__ sums) {
+  __shared__ float sh[4][128];
+  const int b = blockIdx.x;
+  const int part = threadIdx.x >> 6, t = threadIdx.x & 63;
+  for (int i0 = 0; i0 < groups * 2; i0 += 64) {
+    const int i = i0 + t;
+    float acc = 0.0f;
+    if (i < groups * 2)
+      for (int c = part; c < nchunks; c += 4) acc += partial[((size_t)b * nchunks + c) * groups * 2 + i];
+    sh[part][t] = acc;
+    __syncthreads();
+    if (part == 0 && i < groups * 2) sums[(size_t)b * groups * 2 + i] = (sh[0][t] + sh[1][t]) + (sh[2][t] + sh[3][t]);
+    __syncthreads();
   }
 }
 
-// one warp per token row
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+// grid (row blocks, NB), block = nvec * rows_par.  y = x * a + b with a = rstd * gamma, b = beta - mean * a held in
+// registers for the thread's 8 channels.
+__global__ void gn_apply_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, int C1, int C2, int rows,
+                                int groups, int nvec, int rows_par, const float* __restrict__ sums,
+                                const __half* __restrict__ gamma, const __half* __restrict__ beta, float eps, int silu,
+                                int rows_per_block, float stat_rows, __half* __restrict__ y) {
+  const int b = blockIdx.y;
+  const int C = C1 + C2, cpg = C / groups;
+  const int v = threadIdx.x % nvec, rl = threadIdx.x / nvec;
+  float ca[8], cb[8];
+  {
+    const uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
+    const uint4 bt = __ldg(reinterpret_cast<const uint4*>(beta + v * 8));
+    const uint32_t gw[4] = {gm.x, gm.y, gm.z, gm.w}, bw[4] = {bt.x, bt.y, bt.z, bt.w};
+    const float n = stat_rows * (float)cpg;  // elements the statistics were taken over (all ranks when sharded)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int g = (v * 8 + j * 2) / cpg;   // cpg is even: a channel pair never straddles two groups
+      const float sm = __ldg(sums + ((size_t)b * groups + g) * 2), sq = __ldg(sums + ((size_t)b * groups + g) * 2 + 1);
+      const float mean = sm / n;
+      const float rstd = rsqrtf(fmaxf(sq / n - mean * mean, 0.0f) + eps);
+      const float2 ga = unpack_half2(gw[j]), be = unpack_half2(bw[j]);
+      ca[2 * j] = rstd * ga.x;
+      ca[2 * j + 1] = rstd * ga.y;
+      cb[2 * j] = fmaf(-mean, ca[2 * j], be.x);
+      cb[2 * j + 1] = fmaf(-mean, ca[2 * j + 1], be.y);
+    }
+  }
+  const int r_begin = blockIdx.x * rows_per_block, r_end = min(rows, r_begin + rows_per_block);
+  const uint4* src = gn_src(x1, x2, C1, C2, (size_t)b * rows, v);
+  const size_t rstride = (size_t)((v * 8 < C1) ? C1 : C2) / 8;
+  uint4* dst = reinterpret_cast<uint4*>(y + (size_t)b * rows * C) + v;
+  const size_t dstride = (size_t)C / 8;
+  for (int r = r_begin + rl; r < r_end; r += rows_par * kGnUnroll) {
+    uint4 u[kGnUnroll];
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const int rr = r + k * rows_par;
+      if (rr < r_end) u[k] = __ldg(src + (size_t)rr * rstride);
+    }
+#pragma unroll
+    for (int k = 0; k < kGnUnroll; ++k) {
+      const int rr = r + k * rows_par;
+      if (rr >= r_end) break;
+      const uint32_t w[4] = {u[k].x, u[k].y, u[k].z, u[k].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float2 f = unpack_half2(w[j]);
+        float a = fmaf(f.x, ca[2 * j], cb[2 * j]);
+        float c = fmaf(f.y, ca[2 * j + 1], cb[2 * j + 1]);
+        if (silu) {
+          // the reference rounds the GroupNorm output to fp16 before the activation
+          const float2 h = unpack_half2(pack_half2(a, c));
+          a = silu_f(h.x);
+          c = silu_f(h.y);
+        }
+        o[j] = pack_half2(a, c);
+      }
+      dst[(size_t)rr * dstride] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+// One warp per token row, NV = ceil(C / 256) 16-byte vectors per lane; single pass over registers: sum and sum of
+// squares share one shuffle tree.
+template <int NV>
 __global__ void layernorm_kernel(const __half* __restrict__ x, int rows, int C, const __half* __restrict__ gamma,
                                  const __half* __restrict__ beta, float eps, __half* __restrict__ y) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
-  constexpr int kMaxV = 8;  // C <= 2048
-  uint4 buf[kMaxV];
-  float s = 0.0f;
+  uint4 buf[NV];
+  float s = 0.0f, q = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
-    if (v < nvec) {
-      buf[i] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * C + v * 8));
-      const uint32_t w[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
+    buf[i] = make_uint4(0, 0, 0, 0);
+    if (v < nvec) buf[i] = __ldg(reinterpret_cast<const uint4*>(x + (size_t)row * C + v * 8));
+  }
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_half2(w[j]);
-        s += f.x + f.y;
-      }
+  for (int i = 0; i < NV; ++i) {
+    const uint32_t w[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 f = unpack_half2(w[j]);
+      s += f.x + f.y;
+      q = fmaf(f.x, f.x, fmaf(f.y, f.y, q));
     }
   }
-  const float mean = warp_sum(s) / (float)C;
-  float q = 0.0f;
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      const uint32_t w[4] = {buf[i].x, buf[i].y, buf[i].z, buf[i].w};
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const float2 f = unpack_half2(w[j]);
-        q += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-      }
-    }
+  for (int o = 16; o > 0; o >>= 1) {
+    s += __shfl_xor_sync(0xffffffffu, s, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+  const float mean = s / (float)C;
+  const float rstd = rsqrtf(fmaxf(q / (float)C - mean * mean, 0.0f) + eps);
 #pragma unroll
-  for (int i = 0; i < kMaxV; ++i) {
+  for (int i = 0; i < NV; ++i) {
     const int v = lane + i * 32;
     if (v < nvec) {
       const uint4 gm = __ldg(reinterpret_cast<const uint4*>(gamma + v * 8));
@@ -173,96 +217,95 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int rows, int C, 
   }
 }
 
+struct GnPlan {
+  int nvec, rows_par, threads, nchunks, rows_per_chunk, rows_per_block, row_blocks;
+};
+static GnPlan gn_plan(int C, int rows) {
+  GnPlan g;
+  g.nvec = C / 8;
+  g.rows_par = g.nvec >= 256 ? 1 : 256 / g.nvec;
+  g.threads = g.nvec * g.rows_par;
+  // statistics: about 32 row-steps of kGnUnroll rows per thread and chunk
+  g.nchunks = (rows + g.rows_par * kGnUnroll * 8 - 1) / (g.rows_par * kGnUnroll * 8);
+  if (g.nchunks > kGnMaxChunks) g.nchunks = kGnMaxChunks;
+  if (g.nchunks < 1) g.nchunks = 1;
+  g.rows_per_chunk = (rows + g.nchunks - 1) / g.nchunks;
+  // apply: a few unrolled steps per thread and block
+  g.rows_per_block = g.rows_par * kGnUnroll * 4;
+  g.row_blocks = (rows + g.rows_per_block - 1) / g.rows_per_block;
+  return g;
+}
+
+static int gn_launch_stats(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, float* sums,
+                           void* workspace, cudaStream_t st) {
+  const GnPlan g = gn_plan(C1 + C2, rows);
+  gn_stats_kernel<<<dim3(g.nchunks, NB), g.threads, g.threads * 8 * sizeof(float), st>>>(
+      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace);
+  UV_CHECK_CUDA(cudaGetLastError());
+  gn_fold_kernel<<<NB, 256, 0, st>>>((const float*)workspace, g.nchunks, groups, sums);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+static int gn_launch_apply(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, const float* sums,
+                           int64_t stat_rows, const void* gamma, const void* beta, float eps, int silu, void* Y,
+                           cudaStream_t st) {
+  const GnPlan g = gn_plan(C1 + C2, rows);
+  gn_apply_kernel<<<dim3(g.row_blocks, NB), g.threads, 0, st>>>(
+      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, sums, (const __half*)gamma,
+      (const __half*)beta, eps, silu, g.rows_per_block, (float)stat_rows, (__half*)Y);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
 }  // namespace uv
 
 using namespace uv;
 
+// workspace: [NB][kGnMaxChunks][groups][2] chunk partials followed by [NB][groups][2] folded sums
 extern "C" int64_t univst_groupnorm_workspace_bytes(int32_t NB, int32_t groups) {
-  return (int64_t)NB * kGnMaxChunks * groups * 2 * sizeof(float);
+  return (int64_t)NB * (kGnMaxChunks + 1) * groups * 2 * sizeof(float);
+}
+
+static int gn_check(const void* X1, const void* X2, int32_t& C1, int32_t& C2, int32_t NB, int32_t rows, int32_t groups) {
+  if (!X2) C2 = 0;
+  const int C = C1 + C2;
+  UV_REQUIRE(NB > 0 && rows > 0 && groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: bad shape");
+  UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && (C / groups) % 2 == 0, "groupnorm: channels %% 8, channels per group even");
+  UV_REQUIRE(C / 8 <= 1024, "groupnorm: at most 8192 channels");
+  return UNIVST_OK;
 }
 
 extern "C" int univst_groupnorm_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
                                     int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu,
                                     void* Y, void* workspace, void* stream) {
   UV_REQUIRE(X1 && Y && gamma && beta && workspace, "groupnorm: null pointer");
-  if (!X2) C2 = 0;
-  const int C = C1 + C2;
-  UV_REQUIRE(NB > 0 && rows > 0 && groups > 0 && C % groups == 0, "groupnorm: bad shape");
-  UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && (C / groups) % 2 == 0, "groupnorm: channels %% 8, channels per group even");
-  UV_REQUIRE(C / 8 <= 1024, "groupnorm: at most 8192 channels");
-  const int nvec = C / 8;
-  const int rows_par = nvec >= 256 ? 1 : 256 / nvec;
-  const int threads = nvec * rows_par;
-  int nchunks = (rows + 63) / 64;
-  if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
-  const int rows_per_chunk = (rows + nchunks - 1) / nchunks;
-  cudaStream_t st = (cudaStream_t)stream;
-  gn_stats_kernel<<<dim3(nchunks, NB), threads, threads * 8 * sizeof(float), st>>>(
-      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, rows_par, rows_per_chunk, (float*)workspace);
-  UV_CHECK_CUDA(cudaGetLastError());
-  // apply: ~32 KiB of activations per block
-  int rows_per_block = (16384 + C - 1) / C;
-  if (rows_per_block < 1) rows_per_block = 1;
-  const int row_blocks = (rows + rows_per_block - 1) / rows_per_block;
-  gn_apply_kernel<<<dim3(row_blocks, NB), 256, groups * 2 * sizeof(float), st>>>(
-      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, nchunks, (const float*)workspace,
-      (const __half*)gamma, (const __half*)beta, eps, silu, rows_per_block, rows, (__half*)Y);
-  UV_CHECK_CUDA(cudaGetLastError());
-  return UNIVST_OK;
+  int r = gn_check(X1, X2, C1, C2, NB, rows, groups);
+  if (r) return r;
+  float* sums = (float*)workspace + (size_t)NB * kGnMaxChunks * groups * 2;
+  r = gn_launch_stats(X1, X2, C1, C2, NB, rows, groups, sums, workspace, (cudaStream_t)stream);
+  if (r) return r;
+  return gn_launch_apply(X1, X2, C1, C2, NB, rows, groups, sums, rows, gamma, beta, eps, silu, Y, (cudaStream_t)stream);
 }
-
-namespace uv {
-// sums[b][g][2] = sum over the chunk partials (fixed order)
-__global__ void gn_fold_kernel(const float* __restrict__ partial, int nchunks, int groups, float* __restrict__ sums) {
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < groups * 2; i += blockDim.x) {
-    float s = 0.0f;
-    for (int c = 0; c < nchunks; ++c) s += partial[((size_t)b * nchunks + c) * groups * 2 + i];
-    sums[(size_t)b * groups * 2 + i] = s;
-  }
-}
-}  // namespace uv
 
 // Split form for frame-sharded execution: local (sum, sum of squares) per (batch, group) -> [all-reduce over ranks by
 // the caller] -> apply with the global row count.
 extern "C" int univst_groupnorm_stats_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
                                           int32_t groups, float* sums, void* workspace, void* stream) {
   UV_REQUIRE(X1 && sums && workspace, "groupnorm_stats: null pointer");
-  if (!X2) C2 = 0;
-  const int C = C1 + C2;
-  UV_REQUIRE(NB > 0 && rows > 0 && groups > 0 && C % groups == 0, "groupnorm_stats: bad shape");
-  UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && (C / groups) % 2 == 0 && C / 8 <= 1024, "groupnorm_stats: bad channels");
-  const int nvec = C / 8;
-  const int rows_par = nvec >= 256 ? 1 : 256 / nvec;
-  const int threads = nvec * rows_par;
-  int nchunks = (rows + 63) / 64;
-  if (nchunks > kGnMaxChunks) nchunks = kGnMaxChunks;
-  const int rows_per_chunk = (rows + nchunks - 1) / nchunks;
-  cudaStream_t st = (cudaStream_t)stream;
-  gn_stats_kernel<<<dim3(nchunks, NB), threads, threads * 8 * sizeof(float), st>>>(
-      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, rows_par, rows_per_chunk, (float*)workspace);
-  UV_CHECK_CUDA(cudaGetLastError());
-  gn_fold_kernel<<<NB, 64, 0, st>>>((const float*)workspace, nchunks, groups, sums);
-  UV_CHECK_CUDA(cudaGetLastError());
-  return UNIVST_OK;
+  int r = gn_check(X1, X2, C1, C2, NB, rows, groups);
+  if (r) return r;
+  return gn_launch_stats(X1, X2, C1, C2, NB, rows, groups, sums, workspace, (cudaStream_t)stream);
 }
 
 extern "C" int univst_groupnorm_apply_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
                                           int32_t groups, const float* sums, int64_t stat_rows, const void* gamma,
                                           const void* beta, float eps, int32_t silu, void* Y, void* stream) {
   UV_REQUIRE(X1 && Y && gamma && beta && sums, "groupnorm_apply: null pointer");
-  if (!X2) C2 = 0;
-  const int C = C1 + C2;
-  UV_REQUIRE(NB > 0 && rows > 0 && groups > 0 && C % groups == 0 && stat_rows >= rows, "groupnorm_apply: bad shape");
-  const int nvec = C / 8;
-  int rows_per_block = (16384 + C - 1) / C;
-  if (rows_per_block < 1) rows_per_block = 1;
-  const int row_blocks = (rows + rows_per_block - 1) / rows_per_block;
-  gn_apply_kernel<<<dim3(row_blocks, NB), 256, groups * 2 * sizeof(float), (cudaStream_t)stream>>>(
-      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, nvec, 1, sums, (const __half*)gamma,
-      (const __half*)beta, eps, silu, rows_per_block, (int)stat_rows, (__half*)Y);
-  UV_CHECK_CUDA(cudaGetLastError());
-  return UNIVST_OK;
+  int r = gn_check(X1, X2, C1, C2, NB, rows, groups);
+  if (r) return r;
+  UV_REQUIRE(stat_rows >= rows, "groupnorm_apply: stat_rows < rows");
+  return gn_launch_apply(X1, X2, C1, C2, NB, rows, groups, sums, stat_rows, gamma, beta, eps, silu, Y, (cudaStream_t)stream);
 }
 
 extern "C" int univst_layernorm_f16(const void* X, int32_t rows, int32_t C, const void* gamma, const void* beta,
@@ -270,8 +313,18 @@ extern "C" int univst_layernorm_f16(const void* X, int32_t rows, int32_t C, cons
   UV_REQUIRE(X && Y && gamma && beta, "layernorm: null pointer");
   UV_REQUIRE(rows > 0 && C % 8 == 0 && C <= 2048, "layernorm: C must be a multiple of 8, at most 2048");
   const int warps = 8;
-  layernorm_kernel<<<(rows + warps - 1) / warps, warps * 32, 0, (cudaStream_t)stream>>>(
-      (const __half*)X, rows, C, (const __half*)gamma, (const __half*)beta, eps, (__half*)Y);
+  const dim3 grid((rows + warps - 1) / warps);
+  const __half *x = (const __half*)X, *g = (const __half*)gamma, *b = (const __half*)beta;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int nv = (C / 8 + 31) / 32;
+  switch (nv) {
+    case 1: layernorm_kernel<1><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
+    case 2: layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
+    case 3: layernorm_kernel<3><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
+    case 4: layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
+    case 5: layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
+    default: layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
+  }
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

@@ -41,7 +41,7 @@ _lib.register("univst_mask_select_u8", [_vp, _vp, _vp, _i64, _vp, _vp])
 # number of kernels launched through this module (bench.py reports it as ``gpu_launches``)
 launch_count = 0
 _LAUNCHES = {
-    "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 2, "layernorm": 1, "upsample2x": 1,
+    "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 3, "layernorm": 1, "upsample2x": 1,
     "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
