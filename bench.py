@@ -240,10 +240,32 @@ def run_ours(args):
     ms_skip = s0.elapsed_time(s1)
     skip_identical = bool(torch.equal(out_skip, out)) if not args.skip_dead_branches else True
 
-    t = torch.tensor([ms, ms_e2e, ms_skip], device=dev, dtype=torch.float64)
+    # ---- extra (N > 1, not the headline): ONE clip with its frames sharded over the ranks (strong scaling): per attn1
+    # layer the boundary frame's K/V goes to the next rank and frame 0's K/V is broadcast (NCCL over NVLink), every
+    # cross-frame GroupNorm all-reduces 3 x 32 x 2 floats, the predicted noise is all-gathered
+    ms_fs, fs_rel = 0.0, None
+    if world > 1 and F_FRAMES % world == 0:
+        shared = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in resident.items()}
+        for v in shared.values():
+            for t in (v if isinstance(v, list) else [v]):
+                dist.broadcast(t, src=0)
+        ref0 = stylize(shared)           # rank-local evaluation of rank 0's clip
+        unet.set_frame_sharding()
+        stylize(shared)                  # warm-up (NCCL channels, halo buffers)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        out_fs = stylize(shared)
+        f1.record()
+        barrier()
+        ms_fs = f0.elapsed_time(f1)
+        unet.set_frame_sharding_off()
+        fs_rel = float((out_fs.float() - ref0.float()).norm() / ref0.float().norm())
+
+    t = torch.tensor([ms, ms_e2e, ms_skip, ms_fs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_skip = t.tolist()
+    ms, ms_e2e, ms_skip, ms_fs = t.tolist()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -261,8 +283,18 @@ def run_ours(args):
         flops = 4.0 * N * Nkv * H * d * NI
         avg_ms = sum(m_ for m_, _ in dom) / len(dom)
         ach = flops / (avg_ms * 1e-3) / 1e12
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "attention_traffic.json")) as f:
+                traffic = json.load(f)["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        clk = clocks.summary()["sm_mhz"] or 1900.0
+        # secondary limit of this kernel: one exponential per (query, key, head) on the MUFU pipe, 16 / clock / SM,
+        # 4 d = 160 useful FLOP per exponential at head dim 40
+        mufu_bound = 16 * 148 * clk * 1e6 * 4 * d / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                "traffic": None, "kernel": "attention_tc_kernel<2,128> (N=4096, Nkv=8192, H=8, d=40, 48 images)",
+                "traffic": traffic, "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": ach / mufu_bound, "kernel": "attention_tc_kernel<2,128> (N=4096, Nkv=8192, H=8, d=40, 48 images)",
                 "launches_timed": len(dom), "avg_ms": avg_ms, "peak_source": pk["src"] + " (sustained bf16 dense)"}
     attn_ms = sum(m_ for m_, _ in prof["sc_attention"]) / args.steps
     line = {
@@ -279,6 +311,10 @@ def run_ours(args):
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes(clip), "d2h_bytes_per_step": host_out.numel() * 2},
         "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
     }
+    if ms_fs > 0:
+        line["config"]["one_clip_frame_sharded"] = {"frames_per_s": F_FRAMES / (ms_fs / 1e3), "scaling": "strong",
+                                                    "ms_per_clip": ms_fs, "rel_l2_vs_single_gpu": fs_rel,
+                                                    "collectives": "K/V halo send/recv + frame-0 broadcast per attn1, GroupNorm stat all-reduce, eps all-gather (NCCL)"}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         step = cpu_reference_step(2, threads)

@@ -1,0 +1,27 @@
+"""Frame-sharded UNet forward over 2 GPUs == single-GPU forward (needs 2 visible GPUs; skipped otherwise)."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.gpu
+def test_frame_sharded_forward_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29631",
+                          os.path.join(ROOT, "tools", "check_frame_sharding.py"), "4", "32"],
+                         capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    # Identical arithmetic except for the order in which the GroupNorm partial sums are added across ranks; the last-bit
+    # differences in the statistics re-round fp16 activations and settle at the fp16 noise floor of the network
+    # (measured 1.9e-3, the same as the single-GPU path against the fp32 oracle).
+    for key in ("idx5", "idx30"):
+        assert res[key]["rel_l2"] < 5e-3, res

@@ -46,3 +46,66 @@ def test_reference_arm_other_ranks_exit_quietly():
     out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                          capture_output=True, text=True, env=env, timeout=120)
     assert out.returncode == 0 and out.stdout.strip() == ""
+
+
+def test_sharded_source_tables_match_global_table():
+    """A frame shard's K/V source table (local images + two halo banks) names the same frames as the global one."""
+    from univst_b200.unet import kv_source_table, kv_source_table_sharded
+    B, F = 3, 8
+    for P in (2, 4, 8):
+        Fl = F // P
+        NI = B * Fl
+        for mode in ("prev_first", "prev_self_first", "self"):
+            g = kv_source_table(B, F, mode)
+            for r in range(P):
+                t = kv_source_table_sharded(B, Fl, mode, r)
+
+                def glob(i):
+                    if i < NI:
+                        b, fl = divmod(i, Fl)
+                        return b * F + r * Fl + fl
+                    i -= NI
+                    if i < B:
+                        return i * F + r * Fl - 1      # halo bank 1: last frame of the previous rank
+                    return (i - B) * F                 # halo bank 2: frame 0 of the clip
+                for b in range(B):
+                    for fl in range(Fl):
+                        assert [glob(i) for i in t[b * Fl + fl].tolist()] == g[b * F + r * Fl + fl].tolist()
+
+
+def test_two_rank_gloo_kv_halo_exchange(tmp_path):
+    """The per-layer K/V halo exchange of the frame-sharded UNet (boundary frame to the next rank, frame 0 broadcast)."""
+    script = tmp_path / "h.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys, json, torch, torch.distributed as dist
+        from types import SimpleNamespace
+        sys.path.insert(0, {ROOT!r})
+        from univst_b200.unet import UNetPseudo3DConditionModel as U
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        B, Fl, N, C3 = 3, 2, 5, 6
+        NI = B * Fl
+        qkv = torch.zeros((NI + 2 * B) * N, C3)
+        # value of local image (b, fl) on rank r: 100 r + 10 b + fl
+        for b in range(B):
+            for fl in range(Fl):
+                qkv[(b * Fl + fl) * N:(b * Fl + fl + 1) * N] = 100 * r + 10 * b + fl
+        U._exchange_kv_halo(SimpleNamespace(_shard=(None, r, w)), qkv, B, Fl, N)
+        prev = [float(qkv[(NI + b) * N, 0]) for b in range(B)]
+        first = [float(qkv[(NI + B + b) * N, 0]) for b in range(B)]
+        out = [None] * w
+        dist.all_gather_object(out, {{"prev": prev, "first": first}})
+        if r == 0:
+            print(json.dumps(out))
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29617", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("[")][-1])
+    assert res[0]["first"] == [0.0, 10.0, 20.0] and res[1]["first"] == [0.0, 10.0, 20.0]   # frame 0 of rank 0
+    assert res[1]["prev"] == [1.0, 11.0, 21.0]                                             # last frame of rank 0
+    assert res[0]["prev"] == [0.0, 0.0, 0.0]                                               # rank 0 has no predecessor

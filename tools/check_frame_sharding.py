@@ -1,0 +1,75 @@
+"""Frame-sharded UNet forward (one clip over P GPUs) against the single-GPU forward of the same clip.
+Run: python -m torch.distributed.run --nnodes=1 --nproc-per-node=P --master-addr 127.0.0.1 tools/check_frame_sharding.py [F]
+Prints one JSON line on rank 0: max abs / rel-L2 difference, per-forward time of both modes (device events, max over ranks)."""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from types import SimpleNamespace
+from oracle import unet_oracle as uo
+from univst_b200.unet import UNetPseudo3DConditionModel
+from univst_b200 import pnp_utils
+
+
+def build_unet(cfg):
+    g = torch.Generator(device="cuda").manual_seed(33)
+    sd = {}
+    for k, s in uo.unet_param_shapes(cfg).items():
+        if "attn_temporal.to_out.0.weight" in k:
+            sd[k] = torch.zeros(s, device="cuda", dtype=torch.float16)
+        elif k.endswith("weight") and len(s) == 1:
+            sd[k] = torch.ones(s, device="cuda", dtype=torch.float16)
+        elif k.endswith("bias"):
+            sd[k] = (0.02 * torch.randn(s, device="cuda", generator=g)).half()
+        else:
+            fan = 1
+            for d in s[1:]:
+                fan *= d
+            sd[k] = (torch.randn(s, device="cuda", generator=g) * fan ** -0.5).half()
+    return UNetPseudo3DConditionModel(sd, cfg)
+
+
+def timed(fn, iters):
+    fn()
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / iters], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return out, float(t)
+
+
+def main():
+    F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+    hw = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
+    dist.init_process_group("nccl")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    unet = build_unet(uo.SD15_CONFIG)
+    pipe = SimpleNamespace(unet=unet)
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(3, 4, F, hw, hw, device="cuda", generator=g).half()
+    ctx = torch.randn(3, 77, 768, device="cuda", generator=g).half()
+    res = {"world": world, "frames": F, "latent": hw}
+    for idx, t in ((5, 881), (30, 381)):   # shift window open / closed
+        pnp_utils.register_time(pipe, idx)
+        unet.set_frame_sharding_off()
+        ref, t_single = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
+        unet.set_frame_sharding()
+        out, t_shard = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
+        diff = (out.float() - ref.float())
+        res[f"idx{idx}"] = {"max_abs": float(diff.abs().max()), "rel_l2": float(diff.norm() / ref.float().norm()),
+                            "ms_single": t_single, "ms_sharded": t_shard}
+    if rank == 0:
+        print(json.dumps(res))
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

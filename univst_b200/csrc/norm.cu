@@ -80,20 +80,29 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __r
   }
 }
 
-// sums[b][g][2] = sum over the chunk partials in a fixed order: 4 interleaved quarter sums per entry, then combined.
-// grid NB, block 4 * 64.
+// sums[b][g][2] = sum over the chunk partials in a fixed order: 16 interleaved partial sums per entry, combined by a
+// fixed tree.  grid NB, block 16 * 64.
 __global__ void gn_fold_kernel(const float* __restrict__ partial, int nchunks, int groups, float* __restrict__ sums) {
-  __shared__ float sh[4][128];
+  __shared__ float sh[16][64];
   const int b = blockIdx.x;
   const int part = threadIdx.x >> 6, t = threadIdx.x & 63;
   for (int i0 = 0; i0 < groups * 2; i0 += 64) {
     const int i = i0 + t;
     float acc = 0.0f;
     if (i < groups * 2)
-      for (int c = part; c < nchunks; c += 4) acc += partial[((size_t)b * nchunks + c) * groups * 2 + i];
+      for (int c = part; c < nchunks; c += 16) acc += partial[((size_t)b * nchunks + c) * groups * 2 + i];
     sh[part][t] = acc;
     __syncthreads();
-    if (part == 0 && i < groups * 2) sums[(size_t)b * groups * 2 + i] = (sh[0][t] + sh[1][t]) + (sh[2][t] + sh[3][t]);
+    if (part == 0 && i < groups * 2) {
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = sh[k][t];
+#pragma unroll
+      for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) v[k] += v[k + w];
+      sums[(size_t)b * groups * 2 + i] = v[0];
+    }
     __syncthreads();
   }
 }
@@ -242,7 +251,7 @@ static int gn_launch_stats(const void* X1, const void* X2, int C1, int C2, int N
   gn_stats_kernel<<<dim3(g.nchunks, NB), g.threads, g.threads * 8 * sizeof(float), st>>>(
       (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace);
   UV_CHECK_CUDA(cudaGetLastError());
-  gn_fold_kernel<<<NB, 256, 0, st>>>((const float*)workspace, g.nchunks, groups, sums);
+  gn_fold_kernel<<<NB, 1024, 0, st>>>((const float*)workspace, g.nchunks, groups, sums);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

@@ -150,6 +150,10 @@ class UNetPseudo3DConditionModel:
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
         self._tables = {}
 
+    def set_frame_sharding_off(self):
+        self._shard = None
+        self._tables = {}
+
     def _heads(self, level):
         h = self.config["attention_head_dim"]
         return h if isinstance(h, int) else h[level]
