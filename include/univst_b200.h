@@ -85,6 +85,10 @@ int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int
 int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
                             int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const int32_t* kv_src,
                             int32_t nsrc, void* O, int32_t ldo, void* stream);
+/* Tuning hook (no reference counterpart): tile / exp2 variant of the head-dim <= 64 kernel, collapsing of repeated
+ * K/V sources (exact: a source that occurs c times is streamed once with log2 c added to its scores) and the start
+ * stagger of the softmax groups.  Negative values restore the defaults (environment UNIVST_ATTN_*). */
+int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger);
 
 /* AdaIN-guided attention shift of the edit branch, in place on the fused [3 F N, ld] = [Q | K | V] buffer
  * (branch-major: 0 content, 1 style, 2 edit).  Replaces pnp_utils.py:47-57 + attention_adain :114-125. */

@@ -15,6 +15,7 @@ class Attention(nn.Module):
         self.group_norm = None
         self.added_kv_proj_dim = None
         self.upcast_attention = upcast_attention
+        self.upcast_softmax = False
         self.to_q = nn.Linear(query_dim, inner, bias=bias)
         self.to_k = nn.Linear(kv_dim, inner, bias=bias)
         self.to_v = nn.Linear(kv_dim, inner, bias=bias)
@@ -31,6 +32,35 @@ class Attention(nn.Module):
         o = F.scaled_dot_product_attention(q, k, v, attn_mask=attention_mask, dropout_p=0.0, is_causal=False)
         o = o.transpose(1, 2).reshape(b, -1, self.heads * d).to(q.dtype)
         return self.to_out[1](self.to_out[0](o))
+
+
+    # --- explicit-softmax helpers used by VersatileAttention.forward (backbones/animatediff/models/motion_module.py:
+    # 297-316); restated from the published diffusers 0.35.1 Attention methods of the same names
+    def head_to_batch_dim(self, tensor, out_dim=3):
+        b, n, dim = tensor.shape
+        tensor = tensor.reshape(b, n, self.heads, dim // self.heads).permute(0, 2, 1, 3)
+        if out_dim == 3:
+            tensor = tensor.reshape(b * self.heads, n, dim // self.heads)
+        return tensor
+
+    def batch_to_head_dim(self, tensor):
+        bh, n, d = tensor.shape
+        tensor = tensor.reshape(bh // self.heads, self.heads, n, d)
+        return tensor.permute(0, 2, 1, 3).reshape(bh // self.heads, n, d * self.heads)
+
+    def get_attention_scores(self, query, key, attention_mask=None):
+        dtype = query.dtype
+        if self.upcast_attention:
+            query, key = query.float(), key.float()
+        if attention_mask is None:
+            base = torch.empty(query.shape[0], query.shape[1], key.shape[1], dtype=query.dtype, device=query.device)
+            beta = 0
+        else:
+            base, beta = attention_mask, 1
+        scores = torch.baddbmm(base, query, key.transpose(-1, -2), beta=beta, alpha=self.scale)
+        if self.upcast_softmax:
+            scores = scores.float()
+        return scores.softmax(dim=-1).to(dtype)
 
 
 CrossAttention = Attention

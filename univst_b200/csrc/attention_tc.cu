@@ -15,6 +15,10 @@
 //   NQ = 1: one query tile whose two S slots alternate between consecutive KV tiles.
 //   An S slot is released as soon as its tile sits in registers, so the next Q K^T of that query tile runs under the
 //   current tile's exponentials (the MUFU pipe, not the tensor pipe, bounds d = 40).
+//   RS variants: the softmax row sums are computed by the tensor pipe (P times a block of ones into 16 extra accumulator
+//   columns) instead of 128 FADDs per thread and tile.
+//   Repeated K/V sources of an image (frame 0: [prev, self, first] = [0, 0, 0]) are streamed once with log2(count)
+//   added to their scores -- exact, and 1/16 fewer tiles per clip.
 // Head dims that are not multiples of 64 (SD-1.5: 40 / 80 / 160) are zero-filled by TMA out-of-bounds
 // handling; nothing is padded in global memory.
 #include <stdlib.h>
@@ -38,11 +42,67 @@ struct AttnParams {
   int ldo;
   float scale_log2;  // d^-0.5 * log2(e)
   int stagger;       // start offset between the softmax groups of a CTA, clocks
+  int dedupe;        // collapse repeated source images of a row into one pass with a log2(multiplicity) score bias
 };
+
+// Source list of one image with repeated entries collapsed.  softmax over [K_a, K_a, K_b] equals softmax over
+// [K_a, K_b] with the scores of K_a raised by ln 2, so a source that occurs c times is streamed once with log2(c)
+// added to its (log2-domain) scores: frame 0 of a clip ([prev, self, first] = [0, 0, 0]) costs one pass instead of
+// three, frame 1 two instead of three.  Every role of the CTA derives the same list from the table row.
+static constexpr int kMaxSrc = 4;
+struct SrcList {
+  int n;
+  int img[kMaxSrc];
+  float bias[kMaxSrc];
+};
+__device__ __forceinline__ SrcList load_sources(const AttnParams& p, int img) {
+  SrcList L;
+  const int* row = p.kv_src + (size_t)img * p.nsrc;
+  int cnt[kMaxSrc];
+  L.n = 0;
+#pragma unroll
+  for (int u = 0; u < kMaxSrc; ++u) {
+    L.img[u] = 0;
+    cnt[u] = 0;
+  }
+#pragma unroll
+  for (int s = 0; s < kMaxSrc; ++s) {
+    if (s < p.nsrc) {
+      const int v = row[s];
+      bool found = false;
+      if (p.dedupe) {
+#pragma unroll
+        for (int u = 0; u < kMaxSrc; ++u)
+          if (u < L.n && L.img[u] == v && !found) {
+            ++cnt[u];
+            found = true;
+          }
+      }
+      if (!found) {
+#pragma unroll
+        for (int u = 0; u < kMaxSrc; ++u)
+          if (u == L.n) {
+            L.img[u] = v;
+            cnt[u] = 1;
+          }
+        ++L.n;
+      }
+    }
+  }
+#pragma unroll
+  for (int u = 0; u < kMaxSrc; ++u) L.bias[u] = cnt[u] == 2 ? 1.0f : cnt[u] == 3 ? 1.5849625007f : cnt[u] == 4 ? 2.0f : 0.0f;
+  return L;
+}
+__device__ __forceinline__ int src_img(const SrcList& L, int i) {
+  return i == 0 ? L.img[0] : i == 1 ? L.img[1] : i == 2 ? L.img[2] : L.img[3];
+}
+__device__ __forceinline__ float src_bias(const SrcList& L, int i) {
+  return i == 0 ? L.bias[0] : i == 1 ? L.bias[1] : i == 2 ? L.bias[2] : L.bias[3];
+}
 
 static constexpr uint32_t kOBase = 256;     // TMEM column of the first O accumulator
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 before a forced rescale
-static constexpr int kDefaultVariant = 1;
+static constexpr int kDefaultVariant = 9;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -80,7 +140,7 @@ struct AttnCfg {
 // Work decomposition: query tile q of the CTA streams KV tiles j = 0..T-1.  Tile (q, j) uses S/P slot
 // q * kDepth + j % kDepth for the (j / kDepth)-th time.  Every query tile has its own MMA-issuing thread and its own
 // softmax group, so the tiles only meet at the K/V ring.
-template <int NQ, int BKV, int POLY>
+template <int NQ, int BKV, int POLY, int RS>
 __global__ void __launch_bounds__(AttnCfg<NQ, BKV>::kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -97,7 +157,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sK = sQ + NQ * q_bytes;                     // [2][dch][BKV][64]
   uint8_t* sV = sK + 2 * kv_bytes;                     // [2][dch][BKV][64]
   uint8_t* sP = sV + 2 * kv_bytes;                     // [NQ * 2][BKV/64][128][64]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sP + L::kPSlots * L::kPBytes);
+  // RS: the softmax row sums come out of the tensor pipe as P x 1 (a 16-key x 64-column block of fp16 ones, laid out
+  // like a V tile, multiplied into 16 extra accumulator columns behind O) instead of 128 FADDs per thread and tile
+  uint8_t* sOnes = sP + L::kPSlots * L::kPBytes;       // [16][64] ones (RS only)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (RS ? 2048 : 0));
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // 2
   uint64_t* k_empty = bars + 3;       // 2
@@ -108,6 +171,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint64_t* p_full = bars + 17;       // NQ * 2 (<= 8)
   uint64_t* o_done = bars + 25;       // NQ * 2: P V of tile (q, j) commits to o_done[2 q + (j & 1)]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 33);
+  if (RS && threadIdx.x == 0) {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if ((uint32_t)(reinterpret_cast<uint8_t*>(bars + L::kBarriers) - smem_raw) > dyn) {
+      printf("univst_b200: attention shared-memory window too small / misaligned\n");
+      __trap();
+    }
+  }
 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
@@ -115,7 +186,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const int tps = (p.Nkv + BKV - 1) / BKV;   // KV tiles per source
-  const int T = p.nsrc * tps;                // KV tiles in total
+  const SrcList SL = load_sources(p, img);
+  const int T = SL.n * tps;                  // KV tiles in total
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -142,11 +214,16 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     tmem_alloc(tmem_slot, 512);
     tmem_relinquish();
   }
+  if (RS && warp == 2) {
+    for (int i = lane; i < 2048 / 16; i += 32) st_shared_v4(smem_u32(sOnes) + i * 16, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+    fence_proxy_async_smem();
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t opad = (uint32_t)dpad;
+  const uint32_t ostride = opad + (RS ? 16u : 0u);     // TMEM columns per query tile: O, then the row sums
   const bool is_mma = (warp == 1) || (warp >= 2 + 4 * NQ);
 
   if (warp == 0) {
@@ -156,7 +233,6 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       for (int q = 0; q < NQ; ++q)
         for (int c = 0; c < dch; ++c)
           tma_load_4d(sQ + q * q_bytes + c * L::kQChunkBytes, &tmQ, q_full, c * 64, head, (qt0 + q) * 128, img);
-      const int* src = p.kv_src + (size_t)img * p.nsrc;
       // K and V rings are fed independently (non-blocking polls): a K slot frees as soon as the Q K^T that read it has
       // run, a V slot only after the P V one softmax later, so a single in-order K, V, K, V ... stream would hold every
       // K load back behind the wait for a V slot and leave the score MMA starved by the TMA latency.
@@ -168,7 +244,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int s = jk & 1;
           mbar_expect_tx(&k_full[s], kv_bytes);
           for (int c = 0; c < dch; ++c)
-            tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &tmK, &k_full[s], c * 64, head, jtk * BKV, src[sik]);
+            tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &tmK, &k_full[s], c * 64, head, jtk * BKV, src_img(SL, sik));
           if (++jtk == tps) {
             jtk = 0;
             ++sik;
@@ -180,7 +256,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           const int s = jv & 1;
           mbar_expect_tx(&v_full[s], kv_bytes);
           for (int c = 0; c < dch; ++c)
-            tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &tmV, &v_full[s], c * 64, head, jtv * BKV, src[siv]);
+            tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &tmV, &v_full[s], c * 64, head, jtv * BKV, src_img(SL, siv));
           if (++jtv == tps) {
             jtv = 0;
             ++siv;
@@ -203,7 +279,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     constexpr int q = decltype(qc)::value;   // compile-time: everything derived from it stays in uniform registers
     const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
     const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
-    const uint32_t tmem_o = tmem_base + kOBase + q * opad;
+    const uint32_t tmem_o = tmem_base + kOBase + q * ostride;
+    const uint32_t idesc_l = make_idesc_f16(128, 16, 0, 1);
+    const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
     // Descriptor words are built once; per UMMA only the 14-bit start-address field of the low word moves (it cannot
     // carry out of the field: shared addresses are below 256 KiB).  The loop over KV tiles is unrolled by two so that
     // the ring stage / P buffer of a tile is a compile-time constant.
@@ -243,6 +321,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // the next 64 head-dim columns are a whole chunk away (LBO).
         umma_f16_ss_elect(tmem_o, desc_advance(pd, ((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4),
                           desc_advance(vd, (k * 2048) >> 4), idesc_o, (j | k) ? 1u : 0u);
+        if constexpr (RS)
+          umma_f16_ss_elect(tmem_o + opad, desc_advance(pd, ((k >> 2) * (128 * 128) + (k & 3) * 32) >> 4), od, idesc_l,
+                            (j | k) ? 1u : 0u);
       }
       tc_commit_elect(&v_empty[par]);
       tc_commit_elect(&o_done[slot]);
@@ -283,6 +364,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         const int q = (warp == 1) ? 0 : (int)(warp - (2 + 4 * NQ)) + 1;
         const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
         const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
+        const uint32_t idesc_l = make_idesc_f16(128, 16, 0, 1);       // l += P 1
+        const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
         auto issue_s = [&](int j) {
           const int ks = j & 1, slot = q * D + j % D;
           mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
@@ -313,7 +396,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // the next 64 head-dim columns are a whole chunk away (LBO).
             const uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(va + k * 2048, L::kKVChunkBytes, 1024);
-            umma_f16_ss(tmem_base + kOBase + q * opad, da, db, idesc_o, (j | k) ? 1u : 0u);
+            umma_f16_ss(tmem_base + kOBase + q * ostride, da, db, idesc_o, (j | k) ? 1u : 0u);
+            if constexpr (RS) umma_f16_ss(tmem_base + kOBase + q * ostride + opad, da, od, idesc_l, (j | k) ? 1u : 0u);
           }
           tc_commit(&v_empty[vs]);
           tc_commit(&o_done[slot]);
@@ -348,13 +432,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
     const uint32_t r = quad * 32 + lane;                // row inside the 128-row tile
     const uint32_t lane_off = (quad * 32) << 16;
-    const uint32_t o_addr = tmem_base + kOBase + g * opad + lane_off;
+    const uint32_t o_addr = tmem_base + kOBase + g * ostride + lane_off;
     const uint32_t prow0 = smem_u32(sP) + r * 128;
     const uint32_t swz = r & 7;
     constexpr int NC = BKV / 32;
     float m_used = -INFINITY;   // max baked into O and l
     float l = 0.0f;
     int jt = 0;                 // tile index inside the current source image
+    int si = 0;                 // current source
+    float bias = SL.bias[0];    // log2 multiplicity of the current source
     for (int j = 0; j < T; ++j) {
       const int slot = g * D + j % D;
       const int pslot = g * 2 + (j & 1);
@@ -377,7 +463,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       tc_fence_before();
       mbar_arrive(&s_free[slot]);  // the slot may be overwritten with the next scores from here on
       const int valid = p.Nkv - jt * BKV;   // >= BKV except on the ragged last tile of a source
-      if (++jt == tps) jt = 0;
+      const float tbias = bias;
+      if (++jt == tps) {
+        jt = 0;
+        bias = src_bias(SL, ++si);
+      }
       if (valid < BKV) {
 #pragma unroll
         for (int x = 0; x < BKV; ++x)
@@ -392,7 +482,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int x = 0; x < 4; ++x) mx4[x] = __uint_as_float(sraw[c * 32 + x]);
 #pragma unroll
         for (int x = 4; x < 32; ++x) mx4[x & 3] = fmaxf(mx4[x & 3], __uint_as_float(sraw[c * 32 + x]));
-        return fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])) * p.scale_log2;
+        return fmaf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), p.scale_log2, tbias);
       };
       float ls4[4] = {0.0f, 0.0f, 0.0f, 0.0f};
       float mx_next = chunk_max(0);
@@ -406,9 +496,11 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           // P V of this query tile must have landed).
           const float m_new = fmaxf(m_used, mx);
           const float alpha = (m_new == m_used) ? 1.0f : ex2_approx(m_used - m_new);
-          l *= alpha;
+          if constexpr (!RS) {
+            l *= alpha;
 #pragma unroll
-          for (int x = 0; x < 4; ++x) ls4[x] *= alpha;
+            for (int x = 0; x < 4; ++x) ls4[x] *= alpha;
+          }
           if (c > 0) {
             const __half2 a2 = __float2half2_rn(alpha);
 #pragma unroll 1
@@ -428,7 +520,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_wait(&o_done[g * 2 + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
             tc_fence_after();
 #pragma unroll 1
-            for (uint32_t oc = 0; oc < opad; oc += 16) {
+            for (uint32_t oc = 0; oc < ostride; oc += 16) {   // O and (RS) the row sums behind it
               uint32_t t[16];
               tmem_ld16(o_addr + oc, t);
               tc_wait_ld();
@@ -442,7 +534,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         // P = 2^(s * scale - m_used): one FFMA + one MUFU.EX2 per element, fp16, written as swizzled K-major
         // chunks (chunk kc holds keys [64 kc, 64 kc + 64)); the row sum runs in 4 independent chains
-        const float neg_m = -m_used;
+        const float neg_m = tbias - m_used;
         if (c + 1 < NC) mx_next = chunk_max(c + 1);
         // (all 32 exponentials of the chunk are issued back to back before the first one is consumed: the MUFU
         // latency is then paid once per chunk instead of once per few elements, which is what lets two warps keep
@@ -453,7 +545,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           // POLY = 1: every 4th exponential off the MUFU pipe; POLY = 2: every 2nd; 3: all (experiments: 9 = none at all)
-          const bool poly = POLY == 3 || (POLY == 2 && (x & 1)) || (POLY == 1 && (x & 3) == 3);
+          const bool poly = POLY == 3 || (POLY == 2 && (x & 1)) || (POLY == 1 && (x & 3) == 3) ||
+                            (POLY == 4 && (x & 7) == 7) || (POLY == 5 && ((x & 7) == 2 || (x & 7) == 5 || (x & 7) == 7));
           e[x] = POLY == 9 ? e[x] : (poly ? ex2_poly(e[x]) : ex2_approx(e[x]));
         }
 #pragma unroll
@@ -461,7 +554,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           uint32_t w[4];
 #pragma unroll
           for (int x = 0; x < 4; ++x) {
-            ls4[x] += e[q8 * 8 + 2 * x] + e[q8 * 8 + 2 * x + 1];
+            if constexpr (!RS) ls4[x] += e[q8 * 8 + 2 * x] + e[q8 * 8 + 2 * x + 1];
             w[x] = pack_half2(e[q8 * 8 + 2 * x], e[q8 * 8 + 2 * x + 1]);
           }
           const int pc = c * 4 + q8;   // 16-byte piece of the P row
@@ -477,6 +570,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (T >= 2) mbar_wait(&o_done[g * 2 + ((T - 2) & 1)], (uint32_t)(((T - 2) >> 1) & 1));
     mbar_wait(&o_done[g * 2 + ((T - 1) & 1)], (uint32_t)(((T - 1) >> 1) & 1));
     tc_fence_after();
+    if constexpr (RS) {
+      uint32_t t[16];
+      tmem_ld16(o_addr + opad, t);
+      tc_wait_ld();
+      l = __uint_as_float(t[0]);
+    }
     const float inv_l = 1.0f / l;
     const int qrow = (qt0 + g) * 128 + (int)r;
     const bool row_ok = qrow < p.N;
@@ -508,23 +607,27 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
-template <int NQ, int BKV, int POLY>
+template <int NQ, int BKV, int POLY, int RS = 0>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t stream) {
   using L = AttnCfg<NQ, BKV>;
   const int dch = (p.d + 63) / 64;
-  const size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes +
-                      (size_t)L::kPSlots * L::kPBytes + L::kBarriers * sizeof(uint64_t) + 1024;
+  size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes +
+                      (size_t)L::kPSlots * L::kPBytes + (RS ? 2048 : 0) + L::kBarriers * sizeof(uint64_t) +
+                      1024;   // alignment slack
+  // RS at 2 x 128: 224 KiB of tiles + 2 KiB ones + barriers leave 704 B of slack; the kernel traps if the dynamic window
+  // turns out to be less aligned than that (it is 1 KiB aligned in practice)
+  if (RS && smem > 227 * 1024) smem = 227 * 1024;
   UV_REQUIRE(smem <= 227 * 1024, "attention: tile configuration needs %zu bytes of shared memory", smem);
-  UV_REQUIRE(256 + NQ * ((p.d + 15) & ~15) <= 512, "attention: O accumulators do not fit into TMEM");
+  UV_REQUIRE(256 + NQ * (((p.d + 15) & ~15) + (RS ? 16 : 0)) <= 512, "attention: O accumulators do not fit into TMEM");
   static bool configured = false;
   if (!configured) {
-    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV, POLY, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     configured = true;
   }
   dim3 grid((p.N + 128 * NQ - 1) / (128 * NQ), p.H, p.NI);
-  attention_tc_kernel<NQ, BKV, POLY><<<grid, L::kThreads, smem, stream>>>(tq, tk, tv, p);
+  attention_tc_kernel<NQ, BKV, POLY, RS><<<grid, L::kThreads, smem, stream>>>(tq, tk, tv, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
@@ -532,6 +635,15 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
 }  // namespace uv
 
 using namespace uv;
+
+static int g_variant = -1, g_dedupe = -1, g_stagger = -2;
+
+extern "C" int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger) {
+  g_variant = (variant < 0 || variant > 12) ? -1 : variant;   // -1: back to the environment / built-in default
+  g_dedupe = dedupe < 0 ? -1 : (dedupe != 0);
+  g_stagger = stagger < 0 ? -2 : stagger;
+  return UNIVST_OK;
+}
 
 extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv,
                                        int32_t NI, int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv,
@@ -553,17 +665,26 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   p.ldo = ldo;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
 
-  // tile configuration: d <= 64 -> variant from UNIVST_ATTN_VARIANT (0: 2 query tiles x 128 keys, 1: + a quarter of the
-  // exp2 as polynomials, 2: 2 query tiles x 64 keys with two S slots each, 3: + polynomial exp2, 4: 2 x 128 with half
-  // of the exp2 polynomial); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
-  static int variant = -1;
+  // tile configuration: d <= 64 -> variant from univst_attention_tune / UNIVST_ATTN_VARIANT (see the switch below; the
+  // default, 9, is 2 query tiles x 128 keys with the row sums on the tensor pipe and every exp2 on the MUFU pipe --
+  // measured 4.65 ms per 64x64 layer against 4.77 (variant 0), 5.27 (variant 1, a quarter of the exp2 as polynomials:
+  // the extra FMA / ALU instructions cost more issue slots than the MUFU relief returns) and 4.93 / 5.09 (an eighth
+  // polynomial, with / without tensor-pipe row sums)); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
+  int& variant = g_variant;
   if (variant < 0) {
     const char* e = getenv("UNIVST_ATTN_VARIANT");
     variant = e ? atoi(e) : kDefaultVariant;
-    if (variant < 0 || variant > 6) variant = kDefaultVariant;
+    if (variant < 0 || variant > 12) variant = kDefaultVariant;
   }
-  const int bkv = (d <= 64 && (variant < 2 || variant >= 4)) ? 128 : 64;
-  static int stagger = -2;
+  int& dedupe = g_dedupe;
+  if (dedupe < 0) {
+    const char* e = getenv("UNIVST_ATTN_DEDUPE");
+    dedupe = e ? (atoi(e) != 0) : 1;
+  }
+  UV_REQUIRE(nsrc <= kMaxSrc, "sc_attention: at most %d K/V sources per image", kMaxSrc);
+  p.dedupe = dedupe;
+  const int bkv = (d <= 64 && (variant < 2 || variant >= 4)) ? 128 : 64;   // must match the launch_attn<> picked below
+  int& stagger = g_stagger;
   if (stagger == -2) {
     const char* e = getenv("UNIVST_ATTN_STAGGER");
     stagger = e ? atoi(e) : -1;
@@ -587,6 +708,8 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
     if (r) return r;
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (d <= 64 && (int64_t)Nkv * nsrc <= 128 && variant == kDefaultVariant)   // one KV tile (cross-attention): the
+    return launch_attn<2, 128, 0>(tq, tk, tv, p, st);                        // row-sum MMA is pure overhead
   if (d <= 64) {
     switch (variant) {
       case 0: return launch_attn<2, 128, 0>(tq, tk, tv, p, st);
@@ -595,7 +718,13 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
       case 3: return launch_attn<2, 64, 1>(tq, tk, tv, p, st);
       case 4: return launch_attn<2, 128, 2>(tq, tk, tv, p, st);
       case 5: return launch_attn<2, 128, 3>(tq, tk, tv, p, st);   // experiment: all exponentials as polynomials
-      default: return launch_attn<2, 128, 9>(tq, tk, tv, p, st);  // experiment: no exponentials (wrong results)
+      case 6: return launch_attn<2, 128, 9>(tq, tk, tv, p, st);   // experiment: no exponentials (wrong results)
+      case 7: return launch_attn<2, 128, 1, 1>(tq, tk, tv, p, st);   // row sums on the tensor pipe
+      case 8: return launch_attn<2, 128, 2, 1>(tq, tk, tv, p, st);   // + half of the exp2 polynomial
+      case 9: return launch_attn<2, 128, 0, 1>(tq, tk, tv, p, st);   // row sums on the tensor pipe, all exp2 on MUFU
+      case 10: return launch_attn<2, 128, 4, 1>(tq, tk, tv, p, st);  // row sums on the tensor pipe, 1/8 polynomial
+      case 11: return launch_attn<2, 128, 5, 1>(tq, tk, tv, p, st);  // row sums on the tensor pipe, 3/8 polynomial
+      default: return launch_attn<2, 128, 4, 0>(tq, tk, tv, p, st);  // 1/8 polynomial
     }
   }
   if (d <= 128) return launch_attn<2, 64, 0>(tq, tk, tv, p, st);

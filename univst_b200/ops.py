@@ -16,6 +16,7 @@ from ._lib import Epilogue, check
 
 _vp, _i32, _f32, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 _lib.register("univst_sc_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp])
+_lib.register("univst_attention_tune", [_i32, _i32, _i32])
 _lib.register("univst_attn_shift_workspace_bytes", [_i32, _i32], _i64)
 _lib.register("univst_attn_shift_f16", [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp])
 _lib.register("univst_groupnorm_workspace_bytes", [_i32, _i32], _i64)
@@ -179,6 +180,11 @@ def sc_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: torc
                                                  out.stride(0), _stream()), "univst_sc_attention_f16")
     _count("sc_attention")
     return out
+
+
+def attention_tune(variant: int = -1, dedupe: int = -1, stagger: int = -1):
+    """Select the tile / exp2 variant of the fused attention kernel (tuning and A/B timing; -1 = default)."""
+    check(_lib.lib().univst_attention_tune(variant, dedupe, stagger), "univst_attention_tune")
 
 
 _workspaces = {}
