@@ -90,6 +90,13 @@ int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const voi
  * stagger of the softmax groups.  Negative values restore the defaults (environment UNIVST_ATTN_*). */
 int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger);
 
+/* Temporal self-attention of the AnimateDiff motion modules: for every (branch, pixel, head) softmax over the F
+ * frames.  QKV is the fused projection output [B F N, ld] (rows ordered branch, frame, pixel; Q at column 0, K at H d,
+ * V at 2 H d), O [B F N, ldo].  Replaces VersatileAttention.forward, backbones/animatediff/models/motion_module.py:
+ * 276-336 (including both "(b f) d c <-> (b d) f c" rearranges); F <= 32, d % 8 == 0. */
+int univst_temporal_attention_f16(const void* QKV, int32_t ld, int32_t B, int32_t F, int32_t N, int32_t H, int32_t d,
+                                  void* O, int32_t ldo, void* stream);
+
 /* AdaIN-guided attention shift of the edit branch, in place on the fused [3 F N, ld] = [Q | K | V] buffer
  * (branch-major: 0 content, 1 style, 2 edit).  Replaces pnp_utils.py:47-57 + attention_adain :114-125. */
 int64_t univst_attn_shift_workspace_bytes(int32_t F, int32_t C);

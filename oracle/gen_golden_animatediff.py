@@ -1,0 +1,60 @@
+"""Generate ``tests/golden/animatediff_tiny.pt`` by running the REFERENCE's own AnimateDiff backbone:
+``backbones/animatediff/models/unet.py`` ``UNet3DConditionModel`` constructed with the ``animatediff-v2.yaml`` kwargs
+(on the test-only diffusers shim, ``oracle/_shim``) and ``backbones/animatediff/pnp_utils.py``.  Build container
+only (needs ``/root/reference``).  Weights: ``animatediff_oracle.seeded_state_dict`` loaded with ``load_state_dict``
+(strict) -- the motion modules' ``proj_out`` is non-zero, as after loading ``mm_sd_v15_v2.ckpt``.
+
+    python oracle/gen_golden_animatediff.py
+"""
+import os
+import sys
+import types
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "oracle", "_shim"))
+sys.path.insert(0, "/root/reference")
+sys.path.insert(0, ROOT)
+OUT = os.path.join(ROOT, "tests", "golden")
+
+# backbones/animatediff/animatediff-v2.yaml:1-14
+UNET_ADDITIONAL_KWARGS = dict(
+    use_inflated_groupnorm=True, use_motion_module=True, motion_module_resolutions=[1, 2, 4, 8],
+    motion_module_mid_block=True, motion_module_type="Vanilla",
+    motion_module_kwargs=dict(num_attention_heads=8, num_transformer_block=1,
+                              attention_block_types=["Temporal_Self", "Temporal_Self"],
+                              temporal_position_encoding=True, temporal_attention_dim_div=1, zero_initialize=True))
+
+
+def main():
+    from backbones.animatediff import pnp_utils
+    from backbones.animatediff.models.unet import UNet3DConditionModel
+    from oracle import animatediff_oracle as ao
+
+    cfg = ao.AD_TINY_CONFIG
+    m = UNet3DConditionModel(block_out_channels=cfg["block_out_channels"], attention_head_dim=cfg["attention_head_dim"],
+                             cross_attention_dim=cfg["cross_attention_dim"], sample_size=16, **UNET_ADDITIONAL_KWARGS).eval()
+    ref_sd = m.state_dict()
+    shapes = ao.unet_param_shapes(cfg)
+    assert set(shapes) == set(ref_sd), (sorted(set(shapes) ^ set(ref_sd))[:10])
+    assert all(tuple(ref_sd[k].shape) == shapes[k] for k in shapes)
+    m.load_state_dict(ao.seeded_state_dict(cfg, seed=44))
+    g = torch.Generator().manual_seed(2025)
+    x = torch.randn(3, 4, 4, 16, 16, generator=g)
+    ctx = torch.randn(1, 77, cfg["cross_attention_dim"], generator=g).repeat(3, 1, 1)
+    out = {"x": x, "ctx": ctx, "seed": 44, "cases": {}}
+    with torch.no_grad():
+        out["cases"]["stock_t981"] = m(x, torch.tensor(981), encoder_hidden_states=ctx).sample.clone()
+        pipe = types.SimpleNamespace(unet=m)
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        for idx, t in ((0, 981), (13, 721), (24, 501), (25, 481)):   # 25: the window idx < eta2 * 50 has closed
+            pnp_utils.register_time(pipe, idx)
+            out["cases"][f"patched_idx{idx}_t{t}"] = m(x, torch.tensor(t), encoder_hidden_states=ctx).sample.clone()
+    os.makedirs(OUT, exist_ok=True)
+    torch.save(out, os.path.join(OUT, "animatediff_tiny.pt"))
+    print("wrote animatediff_tiny.pt", os.path.getsize(os.path.join(OUT, "animatediff_tiny.pt")) // 1024, "KiB")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,72 @@
+"""CPU: the AnimateDiff oracle against the golden vectors produced by the reference's own ``UNet3DConditionModel``
+(oracle/gen_golden_animatediff.py), and host-side properties of the B200 mirror that need no GPU."""
+import os
+
+import pytest
+import torch
+
+from oracle import animatediff_oracle as ao
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+CASES = ["stock_t981", "patched_idx0_t981", "patched_idx13_t721", "patched_idx24_t501", "patched_idx25_t481"]
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return torch.load(os.path.join(GOLDEN, "animatediff_tiny.pt"), weights_only=True)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_animatediff_oracle_matches_reference_module(golden, case):
+    sd = ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=golden["seed"])
+    patched = case.startswith("patched")
+    idx = int(case.split("idx")[1].split("_")[0]) if patched else None
+    with torch.no_grad():
+        y = ao.unet_forward(sd, ao.AD_TINY_CONFIG, golden["x"], int(case.split("_t")[-1]), golden["ctx"], patched=patched,
+                            idx=idx)
+    ref = golden["cases"][case]
+    rel = ((y - ref).norm() / ref.norm()).item()
+    assert y.shape == ref.shape and rel < 1e-4, rel   # fp32 vs fp32: summation-order noise only
+
+
+def test_shift_window_is_half_open(golden):
+    """backbones/animatediff/pnp_utils.py:45: ``idx < eta2 * 50`` -- idx 24 shifts, idx 25 does not (the SD backbone
+    still shifts at 25).  The goldens must tell the two apart, otherwise the cases above prove nothing about it."""
+    assert ao.shift_params(24)[0] and not ao.shift_params(25)[0]
+    sd = ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=golden["seed"])
+    with torch.no_grad():
+        on = ao.unet_forward(sd, ao.AD_TINY_CONFIG, golden["x"], 481, golden["ctx"], patched=True, idx=24)
+    off = golden["cases"]["patched_idx25_t481"]
+    assert ((on - off).norm() / off.norm()).item() > 1e-2
+
+
+def test_motion_modules_are_live_in_the_goldens(golden):
+    """With the motion modules removed the output must change: the goldens exercise temporal attention."""
+    sd = ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=golden["seed"])
+    dead = {k: (torch.zeros_like(v) if "temporal_transformer.proj_out" in k else v) for k, v in sd.items()}
+    with torch.no_grad():
+        y = ao.unet_forward(dead, ao.AD_TINY_CONFIG, golden["x"], 981, golden["ctx"])
+    ref = golden["cases"]["stock_t981"]
+    assert ((y - ref).norm() / ref.norm()).item() > 1e-2
+
+
+def test_positional_encoding_folds_through_the_projection():
+    """The identity the B200 mirror relies on: W (n + pe_f) = W n + W pe_f (to_q / to_k / to_v have no bias)."""
+    from univst_b200.animatediff import positional_encoding
+    torch.manual_seed(0)
+    C, F = 64, 5
+    pe = positional_encoding(C, 24)
+    assert torch.equal(pe, ao.positional_encoding(C, 24))
+    w, n = torch.randn(3 * C, C), torch.randn(F, 7, C)
+    lhs = torch.nn.functional.linear(n + pe[:F, None], w)
+    rhs = torch.nn.functional.linear(n, w) + (pe[:F] @ w.T)[:, None]
+    assert torch.allclose(lhs, rhs, atol=1e-4)
+
+
+def test_pipeline_flavour_matches_reference_conditions():
+    """pipeline_animation.py:505-506 (index 50 - i) and :515 (i >= 0.8 n) against stable_diffusion.py:683, :694."""
+    from univst_b200.animatediff import AnimationPipeline
+    from univst_b200.pipeline import SpatioTemporalStableDiffusionPipeline as SD
+    assert AnimationPipeline._traj_index(7, 50) == 43 and SD._traj_index(7, 50) == 43
+    assert AnimationPipeline._late_adain(40, 50) and not SD._late_adain(40, 50)
+    assert AnimationPipeline._late_adain(45, 50) and not AnimationPipeline._late_adain(46, 50)

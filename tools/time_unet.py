@@ -9,9 +9,16 @@ from types import SimpleNamespace
 
 F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 3
-cfg = uo.SD15_CONFIG
+AD = "--animatediff" in sys.argv
+if AD:
+    from oracle import animatediff_oracle as ao
+    from univst_b200.animatediff import UNet3DConditionModel as UNetPseudo3DConditionModel  # noqa: F811
+    cfg = ao.AD_SD15_CONFIG
+    shapes = ao.unet_param_shapes(cfg)
+else:
+    cfg = uo.SD15_CONFIG
+    shapes = uo.unet_param_shapes(cfg)
 t0 = time.time()
-shapes = uo.unet_param_shapes(cfg)
 g = torch.Generator(device="cuda").manual_seed(33)
 sd = {}
 for k, s in shapes.items():
@@ -50,7 +57,7 @@ print(f"UNet 3x{F}x64x64 forward: {ms:.2f} ms  ({(ops.launch_count - n0) // iter
 
 if "--shapes" in sys.argv:
     import collections
-    ops.profile_start({"gemm", "conv3x3", "sc_attention"})
+    ops.profile_start({"gemm", "conv3x3", "sc_attention", "temporal_attention"})
     unet(x, 981, encoder_hidden_states=ctx)
     prof = ops.profile_stop()
     for name, recs in prof.items():
@@ -62,6 +69,8 @@ if "--shapes" in sys.argv:
         for meta, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
             if name == "sc_attention":
                 fl = 4.0 * meta[3] * meta[4] * meta[1] * meta[2] * meta[0]
+            elif name == "temporal_attention":   # (B, F, N, H, d): report GB/s of Q/K/V + output traffic instead
+                fl = 4.0 * meta[0] * meta[1] * meta[2] * meta[3] * meta[4] * 2 * 1e3
             else:
                 fl = 2.0 * meta[0] * meta[1] * meta[2]
             print(f"  {t:8.3f} ms n={n:3d} avg={t / n * 1e3:8.1f} us {fl / (t / n) / 1e9:8.1f} TF/s  {meta}")

@@ -1,0 +1,146 @@
+"""B200 host-side mirror of the reference's AnimateDiff-v2 backbone (``backbones/animatediff``):
+``UNet3DConditionModel`` (models/unet.py:41, forward :322-466) with its ``VanillaTemporalModule`` motion modules
+(models/motion_module.py:52-337) and ``AnimationPipeline.video_style_transfer`` (pipelines/pipeline_animation.py:
+449-603).  Same ``state_dict`` key names, same patch protocol (``backbones/animatediff/pnp_utils.py`` sets ``idx`` /
+``eta1`` / ``eta2`` / an instance-level ``forward`` on ``up_blocks[r].attentions[b].transformer_blocks[0].attn1``).
+
+What differs from the SD "pseudo-3D" backbone (unet.py), all of it read off the reference:
+* GroupNorm statistics are per frame (``InflatedGroupNorm``, models/resnet.py:21-29);
+* attn1 is per-frame self-attention: the patched forward is called without ``clip_length`` (models/attention.py:333,
+  pnp_utils.py:57), so K/V = the frame itself; shift window ``eta1*50 <= idx < eta2*50``, alpha 0.8, gamma 2.0
+  (pnp_utils.py:45-49);
+* the transformer block has no (dead) temporal attention;
+* a motion module follows every (resnet, attention) pair: GroupNorm -> Linear -> 2 x [LayerNorm -> +positional
+  encoding -> attention over the F frames of each pixel -> +residual] -> GEGLU feed-forward -> Linear -> +residual.
+
+On the GPU the motion module is five tcgen05 GEMMs with fused epilogues plus the temporal-attention kernel
+(csrc/temporal_attn.cu).  The sinusoidal positional encoding is folded through the (bias-free) Q/K/V projection:
+``W (n + pe_f) = W n + W pe_f``, so ``W pe_f`` is computed once at pack time per attention block and added as a
+per-frame row vector in the epilogue of the fused QKV GEMM -- the "(b f) d c -> (b d) f c" rearrange and the
+elementwise add of the reference do not exist.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+
+from . import ops
+from .pack import pack_geglu
+from .pipeline import SpatioTemporalStableDiffusionPipeline
+from .unet import SD15_CONFIG, UNetPseudo3DConditionModel
+
+AD_SD15_CONFIG = dict(SD15_CONFIG, motion_heads=8, motion_max_len=24)  # animatediff-v2.yaml:8-14 + motion_module.py:60
+
+
+def positional_encoding(d_model: int, max_len: int) -> torch.Tensor:
+    """PositionalEncoding buffer of the reference (models/motion_module.py:232-243), fp32 (max_len, d_model)."""
+    position = torch.arange(max_len).unsqueeze(1)
+    div_term = torch.exp(torch.arange(0, d_model, 2) * (-math.log(10000.0) / d_model))
+    pe = torch.zeros(max_len, d_model)
+    pe[:, 0::2] = torch.sin(position * div_term)
+    pe[:, 1::2] = torch.cos(position * div_term)
+    return pe
+
+
+class UNet3DConditionModel(UNetPseudo3DConditionModel):
+    def __init__(self, state_dict: Dict[str, torch.Tensor], config: Optional[dict] = None, device="cuda"):
+        cfg = dict(AD_SD15_CONFIG)
+        cfg.update(config or {})
+        if cfg.get("use_linear_projection"):
+            raise NotImplementedError("AnimateDiff-v2 sits on SD-1.5 (1x1-conv proj_in / proj_out)")
+        self._pe_rows = {}
+        super().__init__(state_dict, cfg, device=device)
+
+    def set_frame_sharding(self, group=None):
+        import torch.distributed as dist
+        if (group is not None or dist.is_initialized()) and dist.get_world_size(group) > 1:
+            raise NotImplementedError("frame sharding of the AnimateDiff backbone needs a frames <-> pixels all-to-all per "
+                                      "motion module (SURVEY.md 8e); run clip-parallel replicas instead")
+        self._shard = None
+
+    # ------------------------------------------------------------------------------------------ flavour hooks
+    def _pack_extra(self):
+        W, cfg = self.W, self.config
+        self._motion_prefixes = sorted({k[: k.index("temporal_transformer.")] for k in W if "motion_modules" in k})
+        for pre in self._motion_prefixes:
+            b = pre + "temporal_transformer.transformer_blocks.0."
+            C = W[b + "norms.0.weight"].shape[0]
+            pe = positional_encoding(C, cfg["motion_max_len"]).to(self.device)
+            for i in range(2):
+                a = b + f"attention_blocks.{i}."
+                wqkv = torch.cat([W.pop(a + "to_q.weight"), W.pop(a + "to_k.weight"), W.pop(a + "to_v.weight")], 0)
+                W[a + "to_qkv.weight"] = wqkv.contiguous()
+                # W (n + pe_f) = W n + W pe_f: the positional term of every frame as an epilogue row vector
+                W[a + "pe_qkv"] = (pe @ wqkv.float().T).to(torch.float16).contiguous()
+            W[b + "ff.net.0.proj.weight"], W[b + "ff.net.0.proj.bias"] = pack_geglu(W[b + "ff.net.0.proj.weight"],
+                                                                                  W[b + "ff.net.0.proj.bias"])
+
+    def _gn_span(self, B, F, HW):
+        return B * F, HW   # InflatedGroupNorm: per-frame statistics (models/resnet.py:21-29)
+
+    def _gn(self, x, gamma, beta, *, NB, rows, eps, silu, x2=None):
+        return ops.groupnorm(x, gamma, beta, NB=NB, rows=rows, groups=self.config["norm_num_groups"], eps=eps, silu=silu,
+                             x2=x2)
+
+    def _attn1_plan(self, a1):
+        if not a1.patched:
+            return "self", None
+        if a1.idx is None:
+            raise RuntimeError("patched attn1 called before register_time() set .idx")
+        shift = None
+        if a1.idx >= a1.eta1 * 50 and a1.idx < a1.eta2 * 50:  # backbones/animatediff/pnp_utils.py:45
+            beta = (0.9 - 0.1) / (a1.eta1 * 50 - a1.eta2 * 50) * (a1.idx - a1.eta2 * 50) + 0.1
+            shift = (0.8, beta, 2.0)
+        return "self", shift
+
+    def _ff_out_bias2(self, b):
+        return None
+
+    def _pe_table(self, key, B, F):
+        """[B*F, 3C] row vectors for the QKV epilogue: image (b, f) takes row f of W pe."""
+        ck = (key, B, F)
+        if ck not in self._pe_rows:
+            t = self.W[key]
+            if F > t.shape[0]:
+                raise ValueError(f"{F} frames exceed the motion modules' positional-encoding length {t.shape[0]}")
+            self._pe_rows[ck] = t[:F].repeat(B, 1).contiguous()
+        return self._pe_rows[ck]
+
+    def _motion(self, prefix, x, B, F, H, Wd):
+        """VanillaTemporalModule.forward (models/motion_module.py:83-89 -> :138-163, :218-229).  x: [B*F*H*W, C]."""
+        W, cfg = self.W, self.config
+        t = prefix + "temporal_transformer."
+        if t + "norm.weight" not in W:
+            return x
+        NI, N, C = B * F, H * Wd, x.shape[1]
+        heads = cfg["motion_heads"]
+        y = ops.groupnorm(x, W[t + "norm.weight"], W[t + "norm.bias"], NB=NI, rows=N, groups=cfg["norm_num_groups"],
+                          eps=1e-6, silu=False)
+        y = ops.gemm(y, W[t + "proj_in.weight"], bias=W[t + "proj_in.bias"])
+        b = t + "transformer_blocks.0."
+        for i in range(2):
+            a = b + f"attention_blocks.{i}."
+            n = ops.layernorm(y, W[b + f"norms.{i}.weight"], W[b + f"norms.{i}.bias"])
+            qkv = ops.gemm(n, W[a + "to_qkv.weight"], rowvec=self._pe_table(a + "pe_qkv", B, F), rows_per_group=N)
+            o = ops.temporal_attention(qkv, B=B, F=F, N=N, H=heads, d=C // heads)
+            y = ops.gemm(o, W[a + "to_out.0.weight"], bias=W[a + "to_out.0.bias"], residual=y)
+        n = ops.layernorm(y, W[b + "ff_norm.weight"], W[b + "ff_norm.bias"])
+        g = ops.gemm(n, W[b + "ff.net.0.proj.weight"], bias=W[b + "ff.net.0.proj.bias"], geglu=True)
+        y = ops.gemm(g, W[b + "ff.net.2.weight"], bias=W[b + "ff.net.2.bias"], residual=y)
+        return ops.gemm(y, W[t + "proj_out.weight"], bias=W[t + "proj_out.bias"], residual=x)
+
+
+class AnimationPipeline(SpatioTemporalStableDiffusionPipeline):
+    """``AnimationPipeline.video_style_transfer`` (pipelines/pipeline_animation.py:449-603): the SD loop with the
+    late latent AdaIN starting one step earlier (``i >= 0.8 n``, :515) and the trajectory index hard-coded to
+    ``50 - i`` (:505-506)."""
+
+    @staticmethod
+    def _traj_index(i, n):
+        return 50 - i
+
+    @staticmethod
+    def _late_adain(i, n):
+        return i >= 0.8 * n and i <= 0.9 * n

@@ -17,6 +17,7 @@ from ._lib import Epilogue, check
 _vp, _i32, _f32, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 _lib.register("univst_sc_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp])
 _lib.register("univst_attention_tune", [_i32, _i32, _i32])
+_lib.register("univst_temporal_attention_f16", [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp])
 _lib.register("univst_attn_shift_workspace_bytes", [_i32, _i32], _i64)
 _lib.register("univst_attn_shift_f16", [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp])
 _lib.register("univst_groupnorm_workspace_bytes", [_i32, _i32], _i64)
@@ -43,7 +44,7 @@ _lib.register("univst_mask_select_u8", [_vp, _vp, _vp, _i64, _vp, _vp])
 launch_count = 0
 _LAUNCHES = {
     "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 3, "layernorm": 1, "upsample2x": 1,
-    "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
+    "temporal_attention": 1, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
 
@@ -179,6 +180,19 @@ def sc_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: torc
                                                  NIkv, H, d, N, Nkv, kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(),
                                                  out.stride(0), _stream()), "univst_sc_attention_f16")
     _count("sc_attention")
+    return out
+
+
+def temporal_attention(qkv: torch.Tensor, *, B: int, F: int, N: int, H: int, d: int, out: Optional[torch.Tensor] = None):
+    """Motion-module attention over the frames of every pixel.  ``qkv``: [B*F*N, 3*H*d] (rows: branch, frame, pixel)."""
+    _lib.require_device()
+    assert qkv.stride(1) == 1 and qkv.shape[0] == B * F * N and qkv.shape[1] >= 3 * H * d
+    if out is None:
+        out = torch.empty((B * F * N, H * d), dtype=torch.float16, device=qkv.device)
+    with _Timed("temporal_attention", (B, F, N, H, d)):
+        check(_lib.lib().univst_temporal_attention_f16(qkv.data_ptr(), qkv.stride(0), B, F, N, H, d, out.data_ptr(),
+                                                       out.stride(0), _stream()), "univst_temporal_attention_f16")
+    _count("temporal_attention")
     return out
 
 

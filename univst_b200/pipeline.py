@@ -57,6 +57,15 @@ class SpatioTemporalStableDiffusionPipeline:
         m = m.reshape(-1, m.shape[-2], m.shape[-1])
         return ops.mask_resize((m != 0).to(torch.uint8).to(self.device).contiguous(), h, w)
 
+    # ------------------------------------------------------------------------------------------ backbone flavour
+    @staticmethod
+    def _traj_index(i, n):
+        return n - i   # load_ddim_latents_at_t(num_inference_steps - i, ...), :683-684
+
+    @staticmethod
+    def _late_adain(i, n):
+        return i > 0.8 * n and i <= 0.9 * n   # :694
+
     # ------------------------------------------------------------------------------------------ hot loop
     @torch.no_grad()
     def video_style_transfer(self, prompt: Union[str, List[str]], num_inference_steps: int = 50, latents=None,
@@ -76,16 +85,15 @@ class SpatioTemporalStableDiffusionPipeline:
         zc_traj, zs_traj = self._trajectory(content_inv_path, n), self._trajectory(style_inv_path, n)
         m = self._mask(mask_path, F, h, w)
         for i, t in enumerate(timesteps):
-            zc, zs = zc_traj[n - i], zs_traj[n - i]
+            zc, zs = zc_traj[self._traj_index(i, n)], zs_traj[self._traj_index(i, n)]
             if m is not None and i <= 0.9 * n:  # localized latent blending, :687-692
                 z = ops.latent_blend(z, zc, m)
-            if i > 0.8 * n and i <= 0.9 * n:  # late latent AdaIN, :694-702
+            if self._late_adain(i, n):  # late latent AdaIN, :694-702
                 za = ops.latent_adain(z, zs)
                 z = ops.latent_blend(za, zc, m) if m is not None else za
             register_time(self, i)  # :707
             a1 = self.unet.up_blocks[1].attentions[1].transformer_blocks[0].attn1
-            shift_live = (not a1.patched) or (a1.idx >= a1.eta1 and a1.idx <= a1.eta2 * 50)
-            if skip_dead_branches and a1.patched and not shift_live:
+            if skip_dead_branches and not self.unet.shift_live(a1):
                 self.unet(z, t, encoder_hidden_states=ctx[2:3])
                 branch = 0
             else:

@@ -222,6 +222,38 @@ class UNetPseudo3DConditionModel:
             W[b + "ff.net.0.proj.weight"], W[b + "ff.net.0.proj.bias"] = pack_geglu(W[b + "ff.net.0.proj.weight"],
                                                                                   W[b + "ff.net.0.proj.bias"])
         self.W = W
+        self._pack_extra()
+
+    # ------------------------------------------------------------------------------------------ backbone flavour
+    # The SD "pseudo-3D" inflation is the default; backbones/animatediff overrides these (univst_b200/animatediff.py).
+    def _pack_extra(self):
+        pass
+
+    def _gn_span(self, B, F, HW):
+        """(groups of rows, rows per group) the ResNet GroupNorm statistics span: all frames of a branch (resnet.py:338)."""
+        return B, F * HW
+
+    def _attn1_plan(self, a1):
+        """K/V source mode of attn1 and, while the AdaIN-guided shift is active, its (alpha, beta, gamma)."""
+        if not a1.patched:
+            return "prev_self_first", None   # stock SparseCausalAttention, models/attention.py:356
+        if a1.idx is None:
+            raise RuntimeError("patched attn1 called before register_time() set .idx")
+        shift = None
+        if a1.idx >= a1.eta1 and a1.idx <= a1.eta2 * 50:  # pnp_utils.py:47
+            beta = (0.9 - 0.1) / (a1.eta1 * 50 - a1.eta2 * 50) * (a1.idx - a1.eta2 * 50) + 0.1
+            shift = (0.65, beta, 3.0)
+        return "prev_first", shift
+
+    def shift_live(self, a1) -> bool:
+        """False once the content / style branches can no longer influence the edit branch (patched, window closed)."""
+        return (not a1.patched) or self._attn1_plan(a1)[1] is not None
+
+    def _ff_out_bias2(self, b):
+        return self.W[b + "attn_temporal.to_out.0.bias"]   # the dead temporal attention (models/attention.py:331-346)
+
+    def _motion(self, prefix, x, B, F, H, Wd):
+        return x
 
     def _all_transformers(self):
         for blk in self.down_blocks + [self.mid_block] + self.up_blocks:
@@ -269,13 +301,14 @@ class UNetPseudo3DConditionModel:
     def _resnet(self, pre, x, skip, temb_all, B, F, H, Wd):
         """ResnetBlockPseudo3D.forward (resnet.py:335-394).  x: [M, C1], skip: [M, C2] or None."""
         W, cfg = self.W, self.config
-        NI, rows = B * F, F * H * Wd
+        NI = B * F
+        NBg, rows = self._gn_span(B, F, H * Wd)
         eps = cfg["norm_eps"]
-        h = self._gn(x, W[pre + "norm1.weight"], W[pre + "norm1.bias"], NB=B, rows=rows, eps=eps, silu=True, x2=skip)
+        h = self._gn(x, W[pre + "norm1.weight"], W[pre + "norm1.bias"], NB=NBg, rows=rows, eps=eps, silu=True, x2=skip)
         off, cout = self._temb_slices[pre]
         h = ops.conv3x3(h.view(NI, H, Wd, -1), W[pre + "conv1.weight"], bias=W[pre + "conv1.bias"],
-                        rowvec=temb_all[:, off:off + cout], rows_per_group=rows)
-        h = self._gn(h, W[pre + "norm2.weight"], W[pre + "norm2.bias"], NB=B, rows=rows, eps=eps, silu=True)
+                        rowvec=temb_all[:, off:off + cout], rows_per_group=F * H * Wd)
+        h = self._gn(h, W[pre + "norm2.weight"], W[pre + "norm2.bias"], NB=NBg, rows=rows, eps=eps, silu=True)
         if pre + "conv_shortcut.weight" in W:
             sc = ops.gemm(x, W[pre + "conv_shortcut.weight"], a2=skip, bias=W[pre + "conv_shortcut.bias"])
         else:
@@ -303,16 +336,11 @@ class UNetPseudo3DConditionModel:
             qkv_all = torch.empty((NIkv * N, 3 * C), dtype=torch.float16, device=x.device)
             qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"], out=qkv_all[: NI * N])
         a1 = tr.transformer_blocks[0].attn1
-        mode = "prev_self_first"
-        if a1.patched:
-            mode = "prev_first"
-            if a1.idx is None:
-                raise RuntimeError("patched attn1 called before register_time() set .idx")
-            if a1.idx >= a1.eta1 and a1.idx <= a1.eta2 * 50:  # pnp_utils.py:47
-                if B != 3:
-                    raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
-                beta = (0.9 - 0.1) / (a1.eta1 * 50 - a1.eta2 * 50) * (a1.idx - a1.eta2 * 50) + 0.1
-                ops.attn_shift_(qkv, F, N, C, 0.65, beta, 3.0)
+        mode, shift = self._attn1_plan(a1)
+        if shift is not None:
+            if B != 3:
+                raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
+            ops.attn_shift_(qkv, F, N, C, *shift)
         if self._shard is not None:
             self._exchange_kv_halo(qkv_all, B, F, N)
             kv = qkv_all
@@ -331,8 +359,7 @@ class UNetPseudo3DConditionModel:
         # 3. GEGLU feed-forward; the dead temporal attention (attention.py:331-346) is its bias, added in the epilogue
         n3 = ops.layernorm(y, W[b + "norm3.weight"], W[b + "norm3.bias"])
         g = ops.gemm(n3, W[b + "ff.net.0.proj.weight"], bias=W[b + "ff.net.0.proj.bias"], geglu=True)
-        y = ops.gemm(g, W[b + "ff.net.2.weight"], bias=W[b + "ff.net.2.bias"], residual=y,
-                     bias2=W[b + "attn_temporal.to_out.0.bias"])
+        y = ops.gemm(g, W[b + "ff.net.2.weight"], bias=W[b + "ff.net.2.bias"], residual=y, bias2=self._ff_out_bias2(b))
         return ops.gemm(y, W[pre + "proj_out.weight"], bias=W[pre + "proj_out.bias"], residual=x)
 
     # ------------------------------------------------------------------------------------------ forward
@@ -390,6 +417,7 @@ class UNetPseudo3DConditionModel:
                 x = self._resnet(blk.resnets[j], x, None, temb_all, B, F, h, w)
                 if blk.attentions:
                     x = self._transformer(blk.attentions[j], x, ctx_kv_of, B, F, h, w)
+                x = self._motion(f"down_blocks.{i}.motion_modules.{j}.", x, B, F, h, w)
                 skips.append(x)
             if i < n - 1:
                 planes = ops.space_to_depth2(x.view(B * F, h, w, -1))
@@ -399,12 +427,14 @@ class UNetPseudo3DConditionModel:
                 skips.append(x)
         x = self._resnet("mid_block.resnets.0.", x, None, temb_all, B, F, h, w)
         x = self._transformer(self.mid_block.attentions[0], x, ctx_kv_of, B, F, h, w)
+        x = self._motion("mid_block.motion_modules.0.", x, B, F, h, w)
         x = self._resnet("mid_block.resnets.1.", x, None, temb_all, B, F, h, w)
         for i, blk in enumerate(self.up_blocks):
             for j in range(lpb + 1):
                 x = self._resnet(blk.resnets[j], x, skips.pop(), temb_all, B, F, h, w)
                 if blk.attentions:
                     x = self._transformer(blk.attentions[j], x, ctx_kv_of, B, F, h, w)
+                x = self._motion(f"up_blocks.{i}.motion_modules.{j}.", x, B, F, h, w)
             if i < n - 1:
                 up = ops.upsample2x(x.view(B * F, h, w, -1))
                 h, w = h * 2, w * 2
@@ -416,7 +446,8 @@ class UNetPseudo3DConditionModel:
                     path = os.path.join(ft_path, f"inversion_feature_map_{i}_block_{timestep}_step.pt")
                     torch.save(x[: F * h * w].view(F, h, w, -1).clone(), path)
                     print(f"save feature map at: {path}")
-        y = self._gn(x, W["conv_norm_out.weight"], W["conv_norm_out.bias"], NB=B, rows=F * h * w, eps=cfg["norm_eps"],
+        NBg, rows = self._gn_span(B, F, h * w)
+        y = self._gn(x, W["conv_norm_out.weight"], W["conv_norm_out.bias"], NB=NBg, rows=rows, eps=cfg["norm_eps"],
                      silu=True)
         eps_rows = ops.conv3x3(y.view(B * F, h, w, -1), W["conv_out.weight"], bias=W["conv_out.bias"],
                                out=torch.empty((B * F * h * w, 8), dtype=torch.float16, device=dev))
