@@ -262,6 +262,31 @@ def run_ours(args):
         unet.set_frame_sharding_off()
         fs_rel = float((out_fs.float() - ref0.float()).norm() / ref0.float().norm())
 
+    # ---- extra (N = 1, not the headline): the same clip through the AnimateDiff-v2 backbone (BASELINE.json configs[3]
+    # architecture: per-frame self-attention + 21 motion modules), AnimationPipeline loop, one timed pass
+    ms_ad = 0.0
+    if world == 1 and not args.no_animatediff:
+        from univst_b200.animatediff import AD_SD15_CONFIG, AnimationPipeline, UNet3DConditionModel
+        from univst_b200.scheduler import DDIMScheduler
+        del unet, pipe
+        torch.cuda.empty_cache()
+        unet_ad = UNet3DConditionModel(random_state_dict(AD_SD15_CONFIG, seed=34, device=dev, animatediff=True), AD_SD15_CONFIG, device=dev)
+        pipe_ad = AnimationPipeline(unet_ad, DDIMScheduler(beta_schedule="linear"))
+        pnp_utils.register_spatial_attention_pnp(pipe_ad)
+
+        def stylize_ad(c):
+            z_T = ops.latent_adain(c["traj_c"][STEPS_DDIM], c["traj_s"][STEPS_DDIM])
+            return pipe_ad.video_style_transfer("", num_inference_steps=STEPS_DDIM, latents=z_T, content_inv_path=c["traj_c"],
+                                                style_inv_path=c["traj_s"], mask_path=c["mask"], prompt_embeds=c["ctx"]).latents
+        out_ad = stylize_ad(resident)   # warm-up
+        barrier()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        out_ad = stylize_ad(resident)
+        a1.record()
+        barrier()
+        ms_ad = a0.elapsed_time(a1) if bool(torch.isfinite(out_ad).all()) else -1.0
+
     t = torch.tensor([ms, ms_e2e, ms_skip, ms_fs], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,7 +319,7 @@ def run_ours(args):
         # 4 d = 160 useful FLOP per exponential at head dim 40
         mufu_bound = 16 * 148 * clk * 1e6 * 4 * d / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                "traffic": traffic, "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": ach / mufu_bound, "kernel": "attention_tc_kernel<2,128> (N=4096, Nkv=8192, H=8, d=40, 48 images)",
+                "traffic": traffic, "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": ach / mufu_bound, "kernel": "attention_tc_kernel<2,128,0,1> (N=4096, Nkv=8192, H=8, d=40, 48 images)",
                 "launches_timed": len(dom), "avg_ms": avg_ms, "peak_source": pk["src"] + " (sustained bf16 dense)"}
     attn_ms = sum(m_ for m_, _ in prof["sc_attention"]) / args.steps
     line = {
@@ -315,6 +340,10 @@ def run_ours(args):
         line["config"]["one_clip_frame_sharded"] = {"frames_per_s": F_FRAMES / (ms_fs / 1e3), "scaling": "strong",
                                                     "ms_per_clip": ms_fs, "rel_l2_vs_single_gpu": fs_rel,
                                                     "collectives": "K/V halo send/recv + frame-0 broadcast per attn1, GroupNorm stat all-reduce, eps all-gather (NCCL)"}
+    if ms_ad != 0.0:
+        line["config"]["animatediff_v2_backbone"] = {"frames_per_s": F_FRAMES / (ms_ad / 1e3) if ms_ad > 0 else None,
+                                                     "ms_per_clip": ms_ad, "note": "same clip and loop, AnimateDiff-v2 UNet "
+                                                     "(21 motion modules, per-frame attention), one timed pass, supplementary"}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         step = cpu_reference_step(2, threads)
@@ -334,6 +363,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--skip-dead-branches", dest="skip_dead_branches", action="store_true", default=False)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-animatediff", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -50,3 +50,12 @@ class _Unused:
 
 DPMSolverMultistepScheduler = EulerAncestralDiscreteScheduler = EulerDiscreteScheduler = _Unused
 LMSDiscreteScheduler = PNDMScheduler = DDPMScheduler = _Unused
+
+
+class _UnusedScheduler:  # names imported by backbones/animatediff/pipelines/pipeline_animation.py:23-30, never used
+    def __init__(self, *a, **k):
+        raise NotImplementedError("only DDIMScheduler is on the UniVST path")
+
+
+DPMSolverMultistepScheduler = EulerAncestralDiscreteScheduler = EulerDiscreteScheduler = _UnusedScheduler
+LMSDiscreteScheduler = PNDMScheduler = _UnusedScheduler

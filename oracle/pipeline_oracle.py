@@ -19,8 +19,11 @@ from . import unet_oracle as uo
 class DDIMOracle:
     """beta_schedule scaled_linear [0.00085, 0.012], T = 1000, set_alpha_to_one False, steps_offset 1, leading spacing."""
 
-    def __init__(self, T=1000, beta_start=0.00085, beta_end=0.012):
-        betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, T, dtype=torch.float32) ** 2
+    def __init__(self, T=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear"):
+        if beta_schedule == "scaled_linear":
+            betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, T, dtype=torch.float32) ** 2
+        else:  # "linear": backbones/animatediff/animatediff-v2.yaml:16-21
+            betas = torch.linspace(beta_start, beta_end, T, dtype=torch.float32)
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
         self.final_alpha_cumprod = self.alphas_cumprod[0]
         self.T = T
@@ -59,18 +62,21 @@ def resized_mask(mask_1fhw: torch.Tensor, h: int, w: int, dtype=torch.float32) -
     return F.interpolate(mask_1fhw.to(dtype), size=(h, w), mode="bilinear", align_corners=False)[None, :]
 
 
-def video_style_transfer(unet_fn, latents, traj_c, traj_s, mask_1fhw, ctx3, n=50, record=None):
+def video_style_transfer(unet_fn, latents, traj_c, traj_s, mask_1fhw, ctx3, n=50, record=None, animatediff=False):
     """stable_diffusion.py:681-766.  ``unet_fn(x, t, ctx, idx) -> eps`` evaluates the patched three-branch UNet;
-    ``traj_*[k]`` = inversion latent k (k = 1..n); ``mask_1fhw`` (1, F, H, W) in {0, 1} or None."""
-    sch = DDIMOracle()
+    ``traj_*[k]`` = inversion latent k (k = 1..n); ``mask_1fhw`` (1, F, H, W) in {0, 1} or None.
+    ``animatediff``: the AnimationPipeline flavour (backbones/animatediff/pipelines/pipeline_animation.py:501-584):
+    trajectory index hard-coded ``50 - i`` (:505-506), late AdaIN from ``i >= 0.8 n`` (:515), linear betas."""
+    sch = DDIMOracle(beta_schedule="linear" if animatediff else "scaled_linear")
     sch.set_timesteps(n)
     z = latents.clone()
     for i, t in enumerate(sch.timesteps):
-        zc, zs = traj_c[n - i], traj_s[n - i]
+        k = 50 - i if animatediff else n - i
+        zc, zs = traj_c[k], traj_s[k]
         if mask_1fhw is not None and i <= 0.9 * n:
             m = resized_mask(mask_1fhw, z.shape[-2], z.shape[-1], z.dtype)
             z = (1 - m) * z + m * zc
-        if i > 0.8 * n and i <= 0.9 * n:
+        if (i >= 0.8 * n if animatediff else i > 0.8 * n) and i <= 0.9 * n:
             m = resized_mask(mask_1fhw, z.shape[-2], z.shape[-1], z.dtype) if mask_1fhw is not None else 0.0
             z = (1.0 - m) * uo.latent_adain(z, zs) + m * zc
         eps = unet_fn(torch.cat([zc, zs, z]), t, ctx3, i)

@@ -70,3 +70,26 @@ def test_pipeline_flavour_matches_reference_conditions():
     assert AnimationPipeline._traj_index(7, 50) == 43 and SD._traj_index(7, 50) == 43
     assert AnimationPipeline._late_adain(40, 50) and not SD._late_adain(40, 50)
     assert AnimationPipeline._late_adain(45, 50) and not AnimationPipeline._late_adain(46, 50)
+
+
+def test_animation_pipeline_oracle_matches_reference_pipeline():
+    """The reference's own AnimationPipeline.video_style_transfer (50 steps, 16 frames, linear-beta DDIM, mask blend,
+    late AdaIN from step 40, shift window idx < 25) vs the oracle loop: fp32, 2e-4 absolute after 50 steps."""
+    from oracle import pipeline_oracle as po
+    from oracle import unet_oracle as uo
+    g = torch.load(os.path.join(GOLDEN, "style_transfer_animatediff_tiny.pt"), weights_only=True)
+    sd = ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=44)
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], g["n"])
+    z_T = uo.latent_adain(traj_c[g["n"]], traj_s[g["n"]])
+    assert torch.allclose(z_T, g["z_T"], atol=1e-6)
+
+    def unet_fn(x, t, ctx, idx):
+        with torch.no_grad():
+            return ao.unet_forward(sd, ao.AD_TINY_CONFIG, x, t, ctx, patched=idx is not None, idx=idx)
+
+    rec = {i: None for i in g["steps"]}
+    z = po.video_style_transfer(unet_fn, z_T, traj_c, traj_s, po.load_mask_values(mask_u8), g["emb"].repeat(3, 1, 1),
+                                g["n"], rec, animatediff=True)
+    for i, ref in g["steps"].items():
+        assert (rec[i] - ref).abs().max().item() < 2e-4, i
+    assert (z - g["final"]).abs().max().item() < 2e-4

@@ -94,3 +94,48 @@ def test_animatediff_dead_branch_skip_is_bit_identical(setup):
     y3 = unet(x, 381, encoder_hidden_states=ctx).sample[2:3].clone()
     y1 = unet(x[2:3].contiguous(), 381, encoder_hidden_states=ctx[2:3]).sample
     assert torch.equal(y3, y1)
+
+
+def test_animation_pipeline_matches_reference_golden(cuda_lib, tmp_path):
+    """Our AnimationPipeline.video_style_transfer (through the C ABI, fp16) against the latents of the reference's own
+    AnimationPipeline (fp32 golden): rel-L2 <= 3e-2 and PSNR >= 30 dB after 50 steps, as for the SD pipeline."""
+    from PIL import Image
+    from oracle import pipeline_oracle as po
+    from univst_b200 import pnp_utils
+    from univst_b200.animatediff import AnimationPipeline, UNet3DConditionModel
+    from univst_b200.scheduler import DDIMScheduler
+    g = torch.load(os.path.join(GOLDEN, "style_transfer_animatediff_tiny.pt"), weights_only=True)
+    n = g["n"]
+    unet = UNet3DConditionModel(ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=44), ao.AD_TINY_CONFIG)
+    pipe = AnimationPipeline(unet, DDIMScheduler(beta_schedule="linear"))   # animatediff-v2.yaml:16-21
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], n)
+    cdir, sdir, mdir = (tmp_path / d for d in ("c", "s", "m"))
+    for d in (cdir, sdir, mdir):
+        d.mkdir()
+    for k in range(1, n + 1):
+        torch.save(traj_c[k].half(), cdir / f"ddim_latents_{k}.pt")
+        torch.save(traj_s[k].half(), sdir / f"ddim_latents_{k}.pt")
+    for f in range(g["F"]):
+        Image.fromarray(mask_u8[f], mode="L").save(mdir / ("%05d.png" % f))
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    z_T = pnp_utils.latent_adain(traj_c[n].cuda().half(), traj_s[n].cuda().half())
+    rec = {}
+    out = pipe.video_style_transfer("", num_inference_steps=n, latents=z_T, content_inv_path=str(cdir),
+                                    style_inv_path=str(sdir), mask_path=str(mdir), prompt_embeds=g["emb"],
+                                    callback=lambda i, t, z: rec.__setitem__(i, z.clone()))
+    for i, ref in g["steps"].items():
+        print(f"animatediff step {i}: rel={_errs(rec[i], ref)[0]:.3e}")
+    a, b = out.latents.float().cpu(), g["final"].float()
+    rel = ((a - b).norm() / b.norm()).item()
+    psnr = (10 * torch.log10((b.max() - b.min()) ** 2 / ((a - b) ** 2).mean())).item()
+    print(f"animatediff final latents after {n} steps: rel={rel:.3e} psnr={psnr:.1f} dB")
+    assert torch.isfinite(out.latents).all() and rel <= 3e-2 and psnr >= 30.0
+    # exact dead-branch skipping: the window is idx < 25 here (25 three-branch calls, then the edit branch alone)
+    batches = []
+    fwd = pipe.unet.forward
+    pipe.unet.forward = lambda x, *a_, **k_: (batches.append(x.shape[0]), fwd(x, *a_, **k_))[1]
+    skip = pipe.video_style_transfer("", num_inference_steps=n, latents=z_T, content_inv_path=str(cdir),
+                                     style_inv_path=str(sdir), mask_path=str(mdir), prompt_embeds=g["emb"],
+                                     skip_dead_branches=True).latents
+    del pipe.unet.forward
+    assert torch.equal(skip, out.latents) and batches == [3] * 25 + [1] * 25

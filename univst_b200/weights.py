@@ -83,10 +83,43 @@ def unet_param_shapes(cfg) -> Dict[str, tuple]:
     return s
 
 
-def random_state_dict(cfg, seed: int = 33, device="cuda", dtype=torch.float16) -> Dict[str, torch.Tensor]:
+def animatediff_param_shapes(cfg) -> Dict[str, tuple]:
+    """Key -> shape of the reference AnimateDiff ``UNet3DConditionModel`` with the animatediff-v2.yaml kwargs
+    (backbones/animatediff/models/unet.py:41): the SD tree without ``*_temporal*`` keys plus one motion module
+    (models/motion_module.py:52) per (resnet, attention) pair -- 21 in all."""
+    s = {k: v for k, v in unet_param_shapes(cfg).items() if "_temporal" not in k}
+    boc, lpb, nlev = cfg["block_out_channels"], cfg["layers_per_block"], len(cfg["block_out_channels"])
+
+    def mm(pre, c):
+        t = pre + "temporal_transformer."
+        s[t + "norm.weight"], s[t + "norm.bias"] = (c,), (c,)
+        s[t + "proj_in.weight"], s[t + "proj_in.bias"] = (c, c), (c,)
+        s[t + "proj_out.weight"], s[t + "proj_out.bias"] = (c, c), (c,)
+        b = t + "transformer_blocks.0."
+        for i in range(2):
+            a = b + f"attention_blocks.{i}."
+            s[a + "to_q.weight"] = s[a + "to_k.weight"] = s[a + "to_v.weight"] = s[a + "to_out.0.weight"] = (c, c)
+            s[a + "to_out.0.bias"] = (c,)
+            s[b + f"norms.{i}.weight"], s[b + f"norms.{i}.bias"] = (c,), (c,)
+        s[b + "ff.net.0.proj.weight"], s[b + "ff.net.0.proj.bias"] = (8 * c, c), (8 * c,)
+        s[b + "ff.net.2.weight"], s[b + "ff.net.2.bias"] = (c, 4 * c), (c,)
+        s[b + "ff_norm.weight"], s[b + "ff_norm.bias"] = (c,), (c,)
+
+    for i in range(nlev):
+        for j in range(lpb):
+            mm(f"down_blocks.{i}.motion_modules.{j}.", boc[i])
+    mm("mid_block.motion_modules.0.", boc[-1])
+    rev = list(reversed(boc))
+    for i in range(nlev):
+        for j in range(lpb + 1):
+            mm(f"up_blocks.{i}.motion_modules.{j}.", rev[i])
+    return s
+
+
+def random_state_dict(cfg, seed: int = 33, device="cuda", dtype=torch.float16, animatediff: bool = False) -> Dict[str, torch.Tensor]:
     g = torch.Generator(device=device).manual_seed(seed)
     out = {}
-    for key, shape in unet_param_shapes(cfg).items():
+    for key, shape in (animatediff_param_shapes(cfg) if animatediff else unet_param_shapes(cfg)).items():
         if "conv_temporal.weight" in key:
             t = torch.zeros(shape, device=device)
             torch.nn.init.dirac_(t)
