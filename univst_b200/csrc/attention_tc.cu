@@ -102,7 +102,7 @@ __device__ __forceinline__ float src_bias(const SrcList& L, int i) {
 
 static constexpr uint32_t kOBase = 256;     // TMEM column of the first O accumulator
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 before a forced rescale
-static constexpr int kDefaultVariant = 9;
+static constexpr int kDefaultVariant = 17;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -540,8 +540,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         // latency is then paid once per chunk instead of once per few elements, which is what lets two warps keep
         // the pipe busy)
         float e[32];
+        if constexpr (POLY == 6) {   // packed FFMA2: two scores per issue slot
 #pragma unroll
-        for (int x = 0; x < 32; ++x) e[x] = fmaf(__uint_as_float(sraw[c * 32 + x]), p.scale_log2, neg_m);
+          for (int x = 0; x < 32; x += 2)
+            fma2_bcast(e[x], e[x + 1], __uint_as_float(sraw[c * 32 + x]), __uint_as_float(sraw[c * 32 + x + 1]), p.scale_log2, neg_m);
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) e[x] = fmaf(__uint_as_float(sraw[c * 32 + x]), p.scale_log2, neg_m);
+        }
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
           // POLY = 1: every 4th exponential off the MUFU pipe; POLY = 2: every 2nd; 3: all (experiments: 9 = none at all)
@@ -607,6 +613,364 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Split-row variant for head dims <= 48 (SD-1.5's 64 x 64 level, the layer that dominates the clip): two query tiles x
+// 128 keys as above, but every query row is shared by TWO softmax threads, each owning 64 of the 128 key columns of a
+// tile with its OWN running maximum, its own P chunk, and its own O / row-sum accumulator in TMEM (O_half += P_half
+// V_half).  The two halves are independent online softmaxes over disjoint key subsets and are merged once, in the
+// epilogue: O = (w_a O_a + w_b O_b) / (w_a l_a + w_b l_b), w_x = 2^(m_x - max(m_a, m_b)).  No per-tile exchange is needed, and
+// the CTA runs 16 softmax warps (4 per scheduler) instead of 8: with one row per thread the MUFU pipe sat idle ~40 % of
+// the time because two warps per scheduler cannot cover each other's TMEM loads, maxima, packs and barrier waits.
+// TMEM: S 2 x 128 columns, then 4 accumulators of (dpad + 16) columns: 256 + 4 x 64 = 512 at d = 40.
+template <int POLY>
+__global__ void __launch_bounds__(608, 1)   // 19 warps -> 96 registers (the allocation unit is 16 per thread: 104 does not fit)
+attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+  constexpr int NQ = 2, BKV = 128;
+  constexpr uint32_t kTile = 128 * 128;     // bytes of a [128][64]-half tile chunk
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int dpad = (p.d + 15) & ~15;
+  uint8_t* sQ = smem;                         // [2][128][64]
+  uint8_t* sK = sQ + NQ * kTile;              // [2][128][64]
+  uint8_t* sV = sK + 2 * kTile;               // [2][128][64]
+  uint8_t* sP = sV + 2 * kTile;               // [2 q][2 buffers][2 halves][128][64]
+  uint8_t* sOnes = sP + 8 * kTile;            // [16][64] ones
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + 2048);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* k_full = bars + 1;        // 2
+  uint64_t* k_empty = bars + 3;       // 2
+  uint64_t* v_full = bars + 5;        // 2
+  uint64_t* v_empty = bars + 7;       // 2
+  uint64_t* s_full = bars + 9;        // 2
+  uint64_t* s_free = bars + 11;       // 2
+  uint64_t* p_full = bars + 13;       // 4
+  uint64_t* o_done = bars + 17;       // 4
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 21);
+  if (threadIdx.x == 0) {
+    uint32_t dyn;
+    asm volatile("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn));
+    if ((uint32_t)(reinterpret_cast<uint8_t*>(bars + 24) - smem_raw) > dyn) {
+      printf("univst_b200: attention shared-memory window too small / misaligned\n");
+      __trap();
+    }
+  }
+  const uint32_t warp = warp_id();
+  const uint32_t lane = lane_id();
+  const int qt0 = blockIdx.x * NQ;
+  const int head = blockIdx.y;
+  const int img = blockIdx.z;
+  const int tps = (p.Nkv + BKV - 1) / BKV;
+  const SrcList SL = load_sources(p, img);
+  const int T = SL.n * tps;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmQ);
+    tma_prefetch_desc(&tmK);
+    tma_prefetch_desc(&tmV);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], NQ);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], NQ);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], 256);
+    }
+    for (int s = 0; s < 4; ++s) {
+      mbar_init(&p_full[s], 256);
+      mbar_init(&o_done[s], 1);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  if (warp == 2) {
+    for (int i = lane; i < 2048 / 16; i += 32) st_shared_v4(smem_u32(sOnes) + i * 16, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u, 0x3c003c00u);
+    fence_proxy_async_smem();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t opad = (uint32_t)dpad;
+  const uint32_t ostride = opad + 16u;          // O, then the row sums
+  const bool is_mma = (warp == 1) || (warp == 18);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA producer (K and V rings polled independently)
+      mbar_expect_tx(q_full, NQ * kTile);
+      for (int q = 0; q < NQ; ++q) tma_load_4d(sQ + q * kTile, &tmQ, q_full, 0, head, (qt0 + q) * 128, img);
+      int jk = 0, sik = 0, jtk = 0;
+      int jv = 0, siv = 0, jtv = 0;
+      while (jk < T || jv < T) {
+        bool progress = false;
+        if (jk < T && (jk < 2 || mbar_test_wait(&k_empty[jk & 1], (uint32_t)(((jk >> 1) & 1) ^ 1)))) {
+          const int s = jk & 1;
+          mbar_expect_tx(&k_full[s], kTile);
+          tma_load_4d(sK + s * kTile, &tmK, &k_full[s], 0, head, jtk * BKV, src_img(SL, sik));
+          if (++jtk == tps) {
+            jtk = 0;
+            ++sik;
+          }
+          ++jk;
+          progress = true;
+        }
+        if (jv < T && (jv < 2 || mbar_test_wait(&v_empty[jv & 1], (uint32_t)(((jv >> 1) & 1) ^ 1)))) {
+          const int s = jv & 1;
+          mbar_expect_tx(&v_full[s], kTile);
+          tma_load_4d(sV + s * kTile, &tmV, &v_full[s], 0, head, jtv * BKV, src_img(SL, siv));
+          if (++jtv == tps) {
+            jtv = 0;
+            ++siv;
+          }
+          ++jv;
+          progress = true;
+        }
+        if (!progress) __nanosleep(64);
+      }
+    }
+  } else if (is_mma) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- MMA issuer of query tile q
+      const int q = (warp == 1) ? 0 : 1;
+      const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
+      const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O_half += P_half V_half : V MN-major
+      const uint32_t idesc_l = make_idesc_f16(128, 16, 0, 1);       // l_half += P_half 1
+      const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
+      auto issue_s = [&](int j) {
+        const int ks = j & 1;
+        mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_sw128(smem_u32(sQ + q * kTile), 16, 1024);
+        const uint64_t db = make_smem_desc_sw128(smem_u32(sK + ks * kTile), 16, 1024);
+        const int nk = dpad >> 4;
+        for (int k = 0; k < nk; ++k)
+          umma_f16_ss(tmem_base + q * BKV, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
+        tc_commit(&k_empty[ks]);
+        tc_commit(&s_full[q]);
+      };
+      auto issue_pv = [&](int j) {
+        const int vs = j & 1, slot = q * 2 + (j & 1);
+        mbar_wait(&p_full[slot], (uint32_t)((j >> 1) & 1));
+        mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
+        tc_fence_after();
+        const uint32_t pa = smem_u32(sP + slot * 2 * kTile);
+        const uint32_t va = smem_u32(sV + vs * kTile);
+#pragma unroll
+        for (int k = 0; k < BKV / 16; ++k) {
+          const int hf = k >> 2;                                     // which half of the keys / which accumulator
+          const uint32_t acc = tmem_base + kOBase + (q * 2 + hf) * ostride;
+          const uint64_t da = make_smem_desc_sw128(pa + hf * kTile + (k & 3) * 32, 16, 1024);
+          const uint64_t db = make_smem_desc_sw128(va + k * 2048, kTile, 1024);
+          const uint32_t accum = (j | (k & 3)) ? 1u : 0u;
+          umma_f16_ss(acc, da, db, idesc_o, accum);
+          umma_f16_ss(acc + opad, da, od, idesc_l, accum);
+        }
+        tc_commit(&v_empty[vs]);
+        tc_commit(&o_done[slot]);
+      };
+      mbar_wait(q_full, 0);
+      tc_fence_after();
+      issue_s(0);
+      for (int j = 0; j < T; ++j) {
+        if (j + 1 < T) {
+          mbar_wait(&s_free[q], (uint32_t)(j & 1));
+          tc_fence_after();
+          issue_s(j + 1);
+        }
+        issue_pv(j);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax: group g = query tile, half hf = key half
+    const int sw = (int)warp - 2;                       // 0 .. 15
+    const int g = sw >> 3;
+    const int hf = (sw >> 2) & 1;
+    const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
+    const uint32_t r = quad * 32 + lane;                // row inside the 128-row tile
+    const uint32_t lane_off = (quad * 32) << 16;
+    const uint32_t acc_addr = tmem_base + kOBase + (g * 2 + hf) * ostride + lane_off;
+    const uint32_t prow0 = smem_u32(sP) + hf * kTile + r * 128;
+    const uint32_t swz = r & 7;
+    float m_used = -INFINITY;   // max baked into this half's O and l
+    int jt = 0, si = 0;
+    float bias = SL.bias[0];
+    for (int j = 0; j < T; ++j) {
+      const int pslot = g * 2 + (j & 1);
+      const uint32_t prow = prow0 + pslot * 2 * kTile;
+      mbar_wait(&s_full[g], (uint32_t)(j & 1));
+      tc_fence_after();
+      uint32_t sraw[64];
+      {
+        const uint32_t sa = tmem_base + g * BKV + hf * 64 + lane_off;
+        tmem_ld32(sa, *reinterpret_cast<uint32_t(*)[32]>(&sraw[0]));
+        tmem_ld32(sa + 32, *reinterpret_cast<uint32_t(*)[32]>(&sraw[32]));
+        tc_wait_ld();
+      }
+      tc_fence_before();
+      mbar_arrive(&s_free[g]);
+      const int valid = p.Nkv - jt * BKV - hf * 64;   // valid columns of this half (>= 64 except on a ragged last tile)
+      const float tbias = bias;
+      if (++jt == tps) {
+        jt = 0;
+        bias = src_bias(SL, ++si);
+      }
+      if (valid < 64) {
+#pragma unroll
+        for (int x = 0; x < 64; ++x)
+          if (x >= valid) sraw[x] = 0xff800000u;  // -inf
+      }
+      if (j >= 2) mbar_wait(&o_done[pslot], (uint32_t)(((j - 2) >> 1) & 1));   // P buffer free (P V of tile j - 2)
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float mx4[4];
+#pragma unroll
+        for (int x = 0; x < 4; ++x) mx4[x] = __uint_as_float(sraw[c * 32 + x]);
+#pragma unroll
+        for (int x = 4; x < 32; ++x) mx4[x & 3] = fmaxf(mx4[x & 3], __uint_as_float(sraw[c * 32 + x]));
+        const float mx = fmaf(fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3])), p.scale_log2, tbias);
+        const bool need = mx > m_used + kRescaleThreshold;
+        if (__any_sync(0xffffffffu, need)) {
+          // rare path: move this half's reference maximum; its P pieces of this tile and its accumulators follow
+          const float m_new = fmaxf(m_used, mx);
+          const float alpha = (m_new == m_used) ? 1.0f : ex2_approx(m_used - m_new);
+          if (c > 0) {
+            const __half2 a2 = __float2half2_rn(alpha);
+#pragma unroll 1
+            for (int pc = 0; pc < 4; ++pc) {
+              const uint32_t addr = prow + ((((uint32_t)pc & 7) ^ swz) << 4);
+              uint32_t w[4];
+              ld_shared_v4(addr, w);
+#pragma unroll
+              for (int x = 0; x < 4; ++x) {
+                __half2 h = __hmul2(*reinterpret_cast<__half2*>(&w[x]), a2);
+                w[x] = *reinterpret_cast<uint32_t*>(&h);
+              }
+              st_shared_v4(addr, w[0], w[1], w[2], w[3]);
+            }
+          }
+          if (j > 0) {
+            mbar_wait(&o_done[g * 2 + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+            tc_fence_after();
+#pragma unroll 1
+            for (uint32_t oc = 0; oc < ostride; oc += 16) {
+              uint32_t t[16];
+              tmem_ld16(acc_addr + oc, t);
+              tc_wait_ld();
+#pragma unroll
+              for (int x = 0; x < 16; ++x) t[x] = __float_as_uint(__uint_as_float(t[x]) * alpha);
+              tmem_st16(acc_addr + oc, t);
+            }
+            tc_wait_st();
+          }
+          m_used = m_new;
+        }
+        // a half with no valid key so far keeps m_used = -inf: its scores are all -inf and must map to P = 0, not NaN
+        const float neg_m = (m_used == -INFINITY) ? 0.0f : tbias - m_used;
+        float e[32];
+        if constexpr (POLY == 6) {
+#pragma unroll
+          for (int x = 0; x < 32; x += 2)
+            fma2_bcast(e[x], e[x + 1], __uint_as_float(sraw[c * 32 + x]), __uint_as_float(sraw[c * 32 + x + 1]), p.scale_log2, neg_m);
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) e[x] = fmaf(__uint_as_float(sraw[c * 32 + x]), p.scale_log2, neg_m);
+        }
+#pragma unroll
+        for (int x = 0; x < 32; ++x) {
+          const bool poly = (POLY == 1 && (x & 3) == 3) || (POLY == 4 && (x & 7) == 7);
+          e[x] = poly ? ex2_poly(e[x]) : ex2_approx(e[x]);
+        }
+#pragma unroll
+        for (int q8 = 0; q8 < 4; ++q8) {
+          uint32_t w[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) w[x] = pack_half2(e[q8 * 8 + 2 * x], e[q8 * 8 + 2 * x + 1]);
+          const int pc = c * 4 + q8;   // 16-byte piece of this half's 128-byte P row
+          st_shared_v4(prow + ((((uint32_t)pc & 7) ^ swz) << 4), w[0], w[1], w[2], w[3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(&p_full[pslot]);
+    }
+    // ------------------------------------------------------------------ epilogue: merge the halves, O / l -> global
+    if (T >= 2) mbar_wait(&o_done[g * 2 + ((T - 2) & 1)], (uint32_t)(((T - 2) >> 1) & 1));
+    mbar_wait(&o_done[g * 2 + ((T - 1) & 1)], (uint32_t)(((T - 1) >> 1) & 1));
+    tc_fence_after();
+    float l_own;
+    {
+      uint32_t t[16];
+      tmem_ld16(acc_addr + opad, t);
+      tc_wait_ld();
+      l_own = __uint_as_float(t[0]);
+    }
+    // exchange (m, l) with the thread that owns the other half of this row, through the (dead) Q tile of this group
+    float2* xch = reinterpret_cast<float2*>(sQ + g * kTile);          // [2 halves][128 rows]
+    xch[hf * 128 + r] = make_float2(m_used, l_own);
+    asm volatile("bar.sync %0, 256;" ::"r"(1 + g) : "memory");
+    const float2 other = xch[(1 - hf) * 128 + r];
+    const float m_all = fmaxf(m_used, other.x);
+    const float w_own = (m_used == -INFINITY) ? 0.0f : ex2_approx(m_used - m_all);
+    const float w_oth = (other.x == -INFINITY) ? 0.0f : ex2_approx(other.x - m_all);
+    const float inv_l = 1.0f / (w_own * l_own + w_oth * other.y);
+    const float s_own = w_own * inv_l, s_oth = w_oth * inv_l;
+    const uint32_t oth_addr = tmem_base + kOBase + (g * 2 + (1 - hf)) * ostride + lane_off;
+    const int qrow = (qt0 + g) * 128 + (int)r;
+    const bool row_ok = qrow < p.N;
+    __half* orow = p.O + ((size_t)img * p.N + qrow) * p.ldo + head * p.d;
+    // 16-column chunks alternate between the two threads of a row
+    for (uint32_t c = (uint32_t)hf * 16; c < opad; c += 32) {
+      uint32_t ta[16], tb[16];
+      tmem_ld16(acc_addr + c, ta);
+      tmem_ld16(oth_addr + c, tb);
+      tc_wait_ld();
+      if (!row_ok) continue;
+#pragma unroll
+      for (int h8 = 0; h8 < 2; ++h8) {
+        const int col = (int)c + h8 * 8;
+        if (col < p.d) {
+          uint32_t w[4];
+#pragma unroll
+          for (int x = 0; x < 4; ++x) {
+            const float v0 = __uint_as_float(ta[h8 * 8 + 2 * x]) * s_own + __uint_as_float(tb[h8 * 8 + 2 * x]) * s_oth;
+            const float v1 = __uint_as_float(ta[h8 * 8 + 2 * x + 1]) * s_own + __uint_as_float(tb[h8 * 8 + 2 * x + 1]) * s_oth;
+            w[x] = pack_half2(v0, v1);
+          }
+          *reinterpret_cast<uint4*>(orow + col) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int POLY>
+static int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
+                             cudaStream_t stream) {
+  UV_REQUIRE(p.d <= 48, "attention (split rows): head dim <= 48");
+  const size_t smem = 227 * 1024;   // 14 tiles of 16 KiB + ones + barriers: 704 B of slack for the 1 KiB alignment
+  static bool configured = false;
+  if (!configured) {
+    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    configured = true;
+  }
+  dim3 grid((p.N + 255) / 256, p.H, p.NI);
+  attention_tc_split_kernel<POLY><<<grid, 608, smem, stream>>>(tq, tk, tv, p);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
 template <int NQ, int BKV, int POLY, int RS = 0>
 static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
                        cudaStream_t stream) {
@@ -639,7 +1003,7 @@ using namespace uv;
 static int g_variant = -1, g_dedupe = -1, g_stagger = -2;
 
 extern "C" int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger) {
-  g_variant = (variant < 0 || variant > 12) ? -1 : variant;   // -1: back to the environment / built-in default
+  g_variant = (variant < 0 || variant > 17) ? -1 : variant;   // -1: back to the environment / built-in default
   g_dedupe = dedupe < 0 ? -1 : (dedupe != 0);
   g_stagger = stagger < 0 ? -2 : stagger;
   return UNIVST_OK;
@@ -665,16 +1029,19 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   p.ldo = ldo;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
 
-  // tile configuration: d <= 64 -> variant from univst_attention_tune / UNIVST_ATTN_VARIANT (see the switch below; the
-  // default, 9, is 2 query tiles x 128 keys with the row sums on the tensor pipe and every exp2 on the MUFU pipe --
-  // measured 4.65 ms per 64x64 layer against 4.77 (variant 0), 5.27 (variant 1, a quarter of the exp2 as polynomials:
-  // the extra FMA / ALU instructions cost more issue slots than the MUFU relief returns) and 4.93 / 5.09 (an eighth
-  // polynomial, with / without tensor-pipe row sums)); 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
+  // tile configuration: d <= 64 -> variant from univst_attention_tune / UNIVST_ATTN_VARIANT (see the switches below).
+  // Default 17: d <= 48 -> split rows (two softmax threads per query row, 16 softmax warps) with the row sums on the
+  // tensor pipe, packed FFMA2 score scaling and every exp2 on the MUFU pipe; 48 < d <= 64 -> the same without the row
+  // split (variant 16).  Measured per 64x64 layer, same run: 4.50 ms (17), 4.59 (16), 4.61 (13 = 17 without FFMA2),
+  // 4.70 (9 = 16 without FFMA2), 4.77 (0: row sums as FADDs), 5.27 (1: a quarter of the exp2 as polynomials -- the
+  // extra FMA / ALU instructions cost more issue slots than the MUFU relief returns).  The kernel is bound by issue
+  // slots around the MUFU work, so every instruction removed from the softmax loop shows.
+  // 64 < d <= 128 -> 2 x 64; d > 128 -> 1 x 64
   int& variant = g_variant;
   if (variant < 0) {
     const char* e = getenv("UNIVST_ATTN_VARIANT");
     variant = e ? atoi(e) : kDefaultVariant;
-    if (variant < 0 || variant > 12) variant = kDefaultVariant;
+    if (variant < 0 || variant > 17) variant = kDefaultVariant;
   }
   int& dedupe = g_dedupe;
   if (dedupe < 0) {
@@ -710,6 +1077,16 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   cudaStream_t st = (cudaStream_t)stream;
   if (d <= 64 && (int64_t)Nkv * nsrc <= 128 && variant == kDefaultVariant)   // one KV tile (cross-attention): the
     return launch_attn<2, 128, 0>(tq, tk, tv, p, st);                        // row-sum MMA is pure overhead
+  if ((variant == 16 || (variant >= 13 && d > 48)) && d <= 64)
+    return launch_attn<2, 128, 6, 1>(tq, tk, tv, p, st);   // variant 9 + packed FFMA2 score scaling
+  if (d <= 48 && variant >= 13) {   // split rows: two softmax threads per query row (head dim 40)
+    switch (variant) {
+      case 13: return launch_attn_split<0>(tq, tk, tv, p, st);
+      case 17: return launch_attn_split<6>(tq, tk, tv, p, st);   // + packed FFMA2 score scaling
+      case 14: return launch_attn_split<4>(tq, tk, tv, p, st);   // + 1/8 of the exp2 as polynomials
+      default: return launch_attn_split<1>(tq, tk, tv, p, st);   // + 1/4
+    }
+  }
   if (d <= 64) {
     switch (variant) {
       case 0: return launch_attn<2, 128, 0>(tq, tk, tv, p, st);
@@ -724,7 +1101,8 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
       case 9: return launch_attn<2, 128, 0, 1>(tq, tk, tv, p, st);   // row sums on the tensor pipe, all exp2 on MUFU
       case 10: return launch_attn<2, 128, 4, 1>(tq, tk, tv, p, st);  // row sums on the tensor pipe, 1/8 polynomial
       case 11: return launch_attn<2, 128, 5, 1>(tq, tk, tv, p, st);  // row sums on the tensor pipe, 3/8 polynomial
-      default: return launch_attn<2, 128, 4, 0>(tq, tk, tv, p, st);  // 1/8 polynomial
+      case 12: return launch_attn<2, 128, 4, 0>(tq, tk, tv, p, st);  // 1/8 polynomial
+      default: return launch_attn<2, 128, 0, 1>(tq, tk, tv, p, st);  // (13+ with 48 < d <= 64: no split-row kernel)
     }
   }
   if (d <= 128) return launch_attn<2, 64, 0>(tq, tk, tv, p, st);

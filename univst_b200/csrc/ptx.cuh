@@ -283,6 +283,15 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
   __half2 h = *reinterpret_cast<__half2*>(&u);
   return __half22float2(h);
 }
+// Packed fp32 FMA (sm_100: FFMA2): {a.x * b + c, a.y * b + c} in ONE issue slot.
+__device__ __forceinline__ void fma2_bcast(float& d0, float& d1, float a0, float a1, float b, float c) {
+  unsigned long long av, bv, cv, dv;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(av) : "f"(a0), "f"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(bv) : "f"(b), "f"(b));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(cv) : "f"(c), "f"(c));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dv) : "l"(av), "l"(bv), "l"(cv));
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dv));
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
