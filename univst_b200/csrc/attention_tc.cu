@@ -159,7 +159,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   uint8_t* sP = sV + 2 * kv_bytes;                     // [NQ * 2][BKV/64][128][64]
   // RS: the softmax row sums come out of the tensor pipe as P x 1 (a 16-key x 64-column block of fp16 ones, laid out
   // like a V tile, multiplied into 16 extra accumulator columns behind O) instead of 128 FADDs per thread and tile
-  uint8_t* sOnes = sP + L::kPSlots * L::kPBytes;       // [16][64] ones (RS only)
+  // RS == 2: P never touches shared memory -- the softmax threads store it to tensor memory (tcgen05.st) and P V reads
+  // its A operand from there (no st.shared, no proxy fence, a third of the shared-memory traffic of the kernel)
+  uint8_t* sOnes = sP + (RS == 2 ? 0 : L::kPSlots * L::kPBytes);   // [16][64] ones (RS only)
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + (RS ? 2048 : 0));
   uint64_t* q_full = bars;            // 1
   uint64_t* k_full = bars + 1;        // 2
@@ -224,6 +226,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t opad = (uint32_t)dpad;
   const uint32_t ostride = opad + (RS ? 16u : 0u);     // TMEM columns per query tile: O, then the row sums
+  // TMEM map: S slots from column 0; RS == 2: one fp16 P tile per query tile (BKV / 2 columns) at 256, accumulators behind
+  constexpr uint32_t kPT = 256;
+  const uint32_t obase = (RS == 2) ? kPT + NQ * (BKV / 2) : kOBase;
   const bool is_mma = (warp == 1) || (warp >= 2 + 4 * NQ);
 
   if (warp == 0) {
@@ -279,7 +284,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     constexpr int q = decltype(qc)::value;   // compile-time: everything derived from it stays in uniform registers
     const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
     const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O += P V  : P K-major, V MN-major
-    const uint32_t tmem_o = tmem_base + kOBase + q * ostride;
+    const uint32_t tmem_o = tmem_base + obase + q * ostride;
     const uint32_t idesc_l = make_idesc_f16(128, 16, 0, 1);
     const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
     // Descriptor words are built once; per UMMA only the 14-bit start-address field of the low word moves (it cannot
@@ -396,8 +401,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             // the next 64 head-dim columns are a whole chunk away (LBO).
             const uint64_t da = make_smem_desc_sw128(pa + (k >> 2) * (128 * 128) + (k & 3) * 32, 16, 1024);
             const uint64_t db = make_smem_desc_sw128(va + k * 2048, L::kKVChunkBytes, 1024);
-            umma_f16_ss(tmem_base + kOBase + q * ostride, da, db, idesc_o, (j | k) ? 1u : 0u);
-            if constexpr (RS) umma_f16_ss(tmem_base + kOBase + q * ostride + opad, da, od, idesc_l, (j | k) ? 1u : 0u);
+            if constexpr (RS == 2) {
+              const uint32_t ta = tmem_base + kPT + q * (BKV / 2) + k * 8;   // 16 keys = 8 packed columns
+              umma_f16_ts(tmem_base + obase + q * ostride, ta, db, idesc_o, (j | k) ? 1u : 0u);
+              umma_f16_ts(tmem_base + obase + q * ostride + opad, ta, od, idesc_l, (j | k) ? 1u : 0u);
+            } else {
+              umma_f16_ss(tmem_base + obase + q * ostride, da, db, idesc_o, (j | k) ? 1u : 0u);
+              if constexpr (RS) umma_f16_ss(tmem_base + obase + q * ostride + opad, da, od, idesc_l, (j | k) ? 1u : 0u);
+            }
           }
           tc_commit(&v_empty[vs]);
           tc_commit(&o_done[slot]);
@@ -432,7 +443,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const uint32_t quad = warp & 3;                     // TMEM lane quadrant this warp may touch
     const uint32_t r = quad * 32 + lane;                // row inside the 128-row tile
     const uint32_t lane_off = (quad * 32) << 16;
-    const uint32_t o_addr = tmem_base + kOBase + g * ostride + lane_off;
+    const uint32_t o_addr = tmem_base + obase + g * ostride + lane_off;
+    const uint32_t p_taddr = tmem_base + kPT + g * (BKV / 2) + lane_off;   // RS == 2: this row's P tile in TMEM
     const uint32_t prow0 = smem_u32(sP) + r * 128;
     const uint32_t swz = r & 7;
     constexpr int NC = BKV / 32;
@@ -473,7 +485,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         for (int x = 0; x < BKV; ++x)
           if (x >= valid) sraw[x] = 0xff800000u;  // -inf
       }
-      if (j >= 2) {  // the P buffer was last read by the P V of tile j - 2: long done, the wait is (almost) free
+      if (RS != 2 && j >= 2) {  // the P buffer was last read by the P V of tile j - 2: long done, the wait is (almost) free
         mbar_wait(&o_done[pslot], (uint32_t)(((j - 2) >> 1) & 1));
       }
       auto chunk_max = [&](int c) {
@@ -503,17 +515,33 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           }
           if (c > 0) {
             const __half2 a2 = __float2half2_rn(alpha);
+            if constexpr (RS == 2) {
+              tc_wait_st();   // this tile's earlier P stores must have landed before they are read back
 #pragma unroll 1
-            for (int pc = 0; pc < c * 4; ++pc) {
-              const uint32_t addr = prow + (pc >> 3) * (128 * 128) + ((((uint32_t)pc & 7) ^ swz) << 4);
-              uint32_t w[4];
-              ld_shared_v4(addr, w);
+              for (int pc = 0; pc < c; ++pc) {   // chunks of 32 keys = 16 packed columns already stored for this tile
+                uint32_t w[16];
+                tmem_ld16(p_taddr + pc * 16, w);
+                tc_wait_ld();
 #pragma unroll
-              for (int x = 0; x < 4; ++x) {
-                __half2 h = __hmul2(*reinterpret_cast<__half2*>(&w[x]), a2);
-                w[x] = *reinterpret_cast<uint32_t*>(&h);
+                for (int x = 0; x < 16; ++x) {
+                  __half2 h = __hmul2(*reinterpret_cast<__half2*>(&w[x]), a2);
+                  w[x] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                tmem_st16(p_taddr + pc * 16, w);
               }
-              st_shared_v4(addr, w[0], w[1], w[2], w[3]);
+            } else {
+#pragma unroll 1
+              for (int pc = 0; pc < c * 4; ++pc) {
+                const uint32_t addr = prow + (pc >> 3) * (128 * 128) + ((((uint32_t)pc & 7) ^ swz) << 4);
+                uint32_t w[4];
+                ld_shared_v4(addr, w);
+#pragma unroll
+                for (int x = 0; x < 4; ++x) {
+                  __half2 h = __hmul2(*reinterpret_cast<__half2*>(&w[x]), a2);
+                  w[x] = *reinterpret_cast<uint32_t*>(&h);
+                }
+                st_shared_v4(addr, w[0], w[1], w[2], w[3]);
+              }
             }
           }
           if (j > 0) {
@@ -555,20 +583,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                             (POLY == 4 && (x & 7) == 7) || (POLY == 5 && ((x & 7) == 2 || (x & 7) == 5 || (x & 7) == 7));
           e[x] = POLY == 9 ? e[x] : (poly ? ex2_poly(e[x]) : ex2_approx(e[x]));
         }
+        if constexpr (RS == 2) {
+          uint32_t w[16];
 #pragma unroll
-        for (int q8 = 0; q8 < 4; ++q8) {
-          uint32_t w[4];
-#pragma unroll
-          for (int x = 0; x < 4; ++x) {
-            if constexpr (!RS) ls4[x] += e[q8 * 8 + 2 * x] + e[q8 * 8 + 2 * x + 1];
-            w[x] = pack_half2(e[q8 * 8 + 2 * x], e[q8 * 8 + 2 * x + 1]);
+          for (int x = 0; x < 16; ++x) w[x] = pack_half2(e[2 * x], e[2 * x + 1]);
+          if (c == 0 && j >= 1) {   // the single P tile was last read by the P V of tile j - 1
+            mbar_wait(&o_done[g * 2 + ((j - 1) & 1)], (uint32_t)(((j - 1) >> 1) & 1));
+            tc_fence_after();
           }
-          const int pc = c * 4 + q8;   // 16-byte piece of the P row
-          st_shared_v4(prow + (pc >> 3) * (128 * 128) + ((((uint32_t)pc & 7) ^ swz) << 4), w[0], w[1], w[2], w[3]);
+          tmem_st16(p_taddr + c * 16, w);
+        } else {
+#pragma unroll
+          for (int q8 = 0; q8 < 4; ++q8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+              if constexpr (!RS) ls4[x] += e[q8 * 8 + 2 * x] + e[q8 * 8 + 2 * x + 1];
+              w[x] = pack_half2(e[q8 * 8 + 2 * x], e[q8 * 8 + 2 * x + 1]);
+            }
+            const int pc = c * 4 + q8;   // 16-byte piece of the P row
+            st_shared_v4(prow + (pc >> 3) * (128 * 128) + ((((uint32_t)pc & 7) ^ swz) << 4), w[0], w[1], w[2], w[3]);
+          }
         }
       }
       l += (ls4[0] + ls4[1]) + (ls4[2] + ls4[3]);
-      fence_proxy_async_smem();
+      if constexpr (RS == 2) tc_wait_st();
+      else fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(&p_full[pslot]);
     }
@@ -977,13 +1017,15 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
   using L = AttnCfg<NQ, BKV>;
   const int dch = (p.d + 63) / 64;
   size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes +
-                      (size_t)L::kPSlots * L::kPBytes + (RS ? 2048 : 0) + L::kBarriers * sizeof(uint64_t) +
+                      (RS == 2 ? 0 : (size_t)L::kPSlots * L::kPBytes) + (RS ? 2048 : 0) + L::kBarriers * sizeof(uint64_t) +
                       1024;   // alignment slack
   // RS at 2 x 128: 224 KiB of tiles + 2 KiB ones + barriers leave 704 B of slack; the kernel traps if the dynamic window
   // turns out to be less aligned than that (it is 1 KiB aligned in practice)
   if (RS && smem > 227 * 1024) smem = 227 * 1024;
   UV_REQUIRE(smem <= 227 * 1024, "attention: tile configuration needs %zu bytes of shared memory", smem);
-  UV_REQUIRE(256 + NQ * (((p.d + 15) & ~15) + (RS ? 16 : 0)) <= 512, "attention: O accumulators do not fit into TMEM");
+  UV_REQUIRE((RS == 2 ? 256 + NQ * (BKV / 2) : 256) + NQ * (((p.d + 15) & ~15) + (RS ? 16 : 0)) <= 512,
+             "attention: O accumulators do not fit into TMEM");
+  static_assert(RS != 2 || (NQ == 2 && BKV == 128), "P in TMEM: 2 query tiles x 128 keys only");
   static bool configured = false;
   if (!configured) {
     UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV, POLY, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1003,7 +1045,7 @@ using namespace uv;
 static int g_variant = -1, g_dedupe = -1, g_stagger = -2;
 
 extern "C" int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger) {
-  g_variant = (variant < 0 || variant > 17) ? -1 : variant;   // -1: back to the environment / built-in default
+  g_variant = (variant < 0 || variant > 18) ? -1 : variant;   // -1: back to the environment / built-in default
   g_dedupe = dedupe < 0 ? -1 : (dedupe != 0);
   g_stagger = stagger < 0 ? -2 : stagger;
   return UNIVST_OK;
@@ -1041,7 +1083,7 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   if (variant < 0) {
     const char* e = getenv("UNIVST_ATTN_VARIANT");
     variant = e ? atoi(e) : kDefaultVariant;
-    if (variant < 0 || variant > 17) variant = kDefaultVariant;
+    if (variant < 0 || variant > 18) variant = kDefaultVariant;
   }
   int& dedupe = g_dedupe;
   if (dedupe < 0) {
@@ -1077,6 +1119,7 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   cudaStream_t st = (cudaStream_t)stream;
   if (d <= 64 && (int64_t)Nkv * nsrc <= 128 && variant == kDefaultVariant)   // one KV tile (cross-attention): the
     return launch_attn<2, 128, 0>(tq, tk, tv, p, st);                        // row-sum MMA is pure overhead
+  if (variant == 18 && d <= 48) return launch_attn<2, 128, 6, 2>(tq, tk, tv, p, st);   // 16 + P through tensor memory
   if ((variant == 16 || (variant >= 13 && d > 48)) && d <= 64)
     return launch_attn<2, 128, 6, 1>(tq, tk, tv, p, st);   // variant 9 + packed FFMA2 score scaling
   if (d <= 48 && variant >= 13) {   // split rows: two softmax threads per query row (head dim 40)

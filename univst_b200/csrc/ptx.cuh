@@ -202,6 +202,20 @@ __device__ __forceinline__ void umma_f16_ss(uint32_t tmem_d, uint64_t desc_a, ui
       : "memory");
 }
 
+// D[tmem] (+)= A[tmem] * B[smem desc]: the A operand (M = 128 rows x 16 fp16 = 8 columns per instruction) is read from
+// tensor memory -- lane = row, two K elements per 32-bit column, exactly what tcgen05.st.32x32b of packed half2 lays down.
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // Warp-convergent forms: every lane calls, one elected lane issues.  Keeping the surrounding control flow convergent
 // lets the compiler hold descriptors / addresses in uniform registers instead of paying an ELECT + R2UR sequence per
 // instruction (which is what a whole `if (lane == 0)` region costs).
