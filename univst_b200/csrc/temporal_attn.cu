@@ -168,17 +168,40 @@ __global__ void __launch_bounds__(256) temporal_attention_mma_kernel(const TAttn
   const int b = blockIdx.x / p.N, pix = blockIdx.x % p.N;
   const size_t row0 = (size_t)b * F * p.N + pix;
 
-  // ---- cooperative load; frames >= F and channels >= d are zero (they enter the products as exact zeros)
+  // ---- cooperative load; frames >= F and channels >= d are zero (they enter the products as exact zeros).
+  // Thread (tx, ty): tx = 16-byte unit inside a frame row, ty = frame parity; the (q|k|v, head, unit) split of tx is
+  // worked out once, and the 8 frame loads of a thread are all in flight before the first shared-memory store (the
+  // first version interleaved one load with one store and three integer divisions each: 49 % ALU, long-scoreboard bound).
   {
-    const int row_units = 3 * p.H * pu;    // padded units per frame row
-    for (int v = threadIdx.x; v < 16 * row_units; v += blockDim.x) {
-      const int f = v / row_units, u = v - f * row_units;
-      const int which = u / (p.H * pu), hu = u - which * (p.H * pu);
-      const int h = hu / pu, cu = hu - h * pu;
-      uint4 val = make_uint4(0u, 0u, 0u, 0u);
-      if (f < F && cu < du)
-        val = *reinterpret_cast<const uint4*>(p.QKV + (row0 + (size_t)f * p.N) * p.ld + which * C + h * p.d + cu * 8);
-      sm[which * which_units + h * head_units + f * su + cu] = val;
+    const int real_units = 3 * C / 8;                 // 16-byte units of a [Q | K | V] row
+    const int tx = threadIdx.x & 127, ty = threadIdx.x >> 7;
+    for (int u0 = 0; u0 < real_units; u0 += 128) {
+      const int u = u0 + tx;
+      const bool active = u < real_units;
+      const int col = u * 8;
+      const int which = col / C, hc = col - which * C;
+      const int h = hc / p.d, c = hc - h * p.d;
+      uint4* dst = sm + which * which_units + h * head_units + (c >> 3);
+      const __half* src = p.QKV + row0 * p.ld + col;
+      uint4 val[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int f = 2 * i + ty;
+        val[i] = make_uint4(0u, 0u, 0u, 0u);
+        if (active && f < F) val[i] = *reinterpret_cast<const uint4*>(src + (size_t)f * p.N * p.ld);
+      }
+      if (active) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dst[(2 * i + ty) * su] = val[i];
+      }
+    }
+    // zero the padded units [du, pu) of every (which, head, frame) row
+    if (pu > du) {
+      const int pad = pu - du, rows = 3 * p.H * 16;
+      for (int v = threadIdx.x; v < rows * pad; v += blockDim.x) {
+        const int rw = v / pad, k = v - rw * pad;
+        sm[rw * su + du + k] = make_uint4(0u, 0u, 0u, 0u);
+      }
     }
   }
   __syncthreads();
@@ -308,12 +331,13 @@ extern "C" int univst_temporal_attention_f16(const void* QKV, int32_t ld, int32_
   if (F <= 16 && !force_scalar) {
     const int kc = (d + 15) / 16;
     switch (kc) {
-      case 1: return launch_tattn_mma<1>(p, grid, threads, st);
-      case 2: return launch_tattn_mma<2>(p, grid, threads, st);
-      case 3: return launch_tattn_mma<3>(p, grid, threads, st);   // d = 40
-      case 4: return launch_tattn_mma<4>(p, grid, threads, st);
-      case 5: return launch_tattn_mma<5>(p, grid, threads, st);   // d = 80
-      case 10: return launch_tattn_mma<10>(p, grid, threads, st); // d = 160
+      // (always 256 threads: the load phase maps threads to (unit, frame parity); idle warps skip the head loop)
+      case 1: return launch_tattn_mma<1>(p, grid, 256, st);
+      case 2: return launch_tattn_mma<2>(p, grid, 256, st);
+      case 3: return launch_tattn_mma<3>(p, grid, 256, st);   // d = 40
+      case 4: return launch_tattn_mma<4>(p, grid, 256, st);
+      case 5: return launch_tattn_mma<5>(p, grid, 256, st);   // d = 80
+      case 10: return launch_tattn_mma<10>(p, grid, 256, st); // d = 160
       default: break;                                             // other head dims: scalar kernel below
     }
   }
