@@ -10,6 +10,8 @@
 // tensor map consumed by the same K loop.
 //
 // Reference call sites replaced: see include/univst_b200.h (univst_gemm_f16 / univst_conv3x3_f16).
+#include <stdlib.h>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -134,6 +136,23 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
         for (int g = 0; g < 4; ++g) ld_shared_v4(stage_addr(e.stg, e.lane, g), *reinterpret_cast<uint32_t(*)[4]>(&rw[g * 4]));
         if (c0 + 64 < p.BN && n0 + c0 + 64 < p.N_out) residual_fetch(p, e, n0 + c0 + 64, rnext);
       }
+      // the chunk's bias (the same 4 x 8 columns in every lane) is requested before the TMEM load is awaited: issued
+      // right before use, each of these loads stalled the warp for an L1 / L2 round trip
+      uint4 bq[4], vq[4];
+      if (staged && p.bias) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          bq[g] = make_uint4(0, 0, 0, 0);
+          if (n0 + c0 + g * 8 < p.N_out) bq[g] = __ldg(reinterpret_cast<const uint4*>(p.bias + n0 + c0 + g * 8));
+        }
+      }
+      if (staged && rv) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          vq[g] = make_uint4(0, 0, 0, 0);
+          if (n0 + c0 + g * 8 < p.N_out) vq[g] = __ldg(reinterpret_cast<const uint4*>(rv + n0 + c0 + g * 8));
+        }
+      }
       tc_wait_ld();
       if (staged) {
         uint32_t o[16];
@@ -145,8 +164,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
           for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(acc[g * 8 + j]);
           if (n < p.N_out) {
             if (p.bias) {
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(p.bias + n));
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+              const uint32_t bw[4] = {bq[g].x, bq[g].y, bq[g].z, bq[g].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float2 f = unpack_half2(bw[j]);
@@ -155,8 +173,7 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
               }
             }
             if (rv) {
-              const uint4 b = __ldg(reinterpret_cast<const uint4*>(rv + n));
-              const uint32_t bw[4] = {b.x, b.y, b.z, b.w};
+              const uint32_t bw[4] = {vq[g].x, vq[g].y, vq[g].z, vq[g].w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 float2 f = unpack_half2(bw[j]);
@@ -427,15 +444,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // host side
 // ------------------------------------------------------------------------------------------------------------
 static int pick_bn(int N, int geglu) {
+  // experiments: UNIVST_BN_OVERRIDE="640:256,320:192" forces the tile width for a given N
+  if (const char* e = getenv("UNIVST_BN_OVERRIDE")) {
+    for (const char* q = e; *q;) {
+      char* end;
+      const long n = strtol(q, &end, 10);
+      if (*end != ':') break;
+      const long bn = strtol(end + 1, &end, 10);
+      if (n == N && bn >= 32 && bn <= 256 && bn % 32 == 0 && !geglu) return (int)bn;
+      q = (*end == ',') ? end + 1 : end;
+      if (*end != ',') break;
+    }
+  }
   if (geglu) return (N % 256 == 0) ? 256 : 128;
   if (N <= 32) return 32;
   if (N <= 64) return 64;
-  if (N % 256 == 0) return 256;
-  if (N % 160 == 0) return 160;
-  if (N % 128 == 0) return 128;
-  if (N % 96 == 0) return 96;
-  if (N % 64 == 0) return 64;
-  return 128;
+  if (N <= 256) return (N + 31) & ~31;
+  // Tile-width choice by a measured cost model: one 128 x BN tile costs about (BN + 375) units -- the A side of a tile
+  // (TMA fill + operand reads of the 128-row block) is a large fixed cost, so few wide tiles beat many exact ones even
+  // when the last tile is ragged.  Measured (profiles/r01_tile_width_sweep.txt): conv 640 -> 640 at 32 x 32: BN 160
+  // (4 exact tiles) 377 us, 224 (3 tiles, 5 % padding) 316 us, 256 326 us, 128 436 us; GEMM N = 960: 160 220 us, 192 199 us.
+  int best = 256;
+  long best_cost = -1;
+  for (int bn = 256; bn >= 128; bn -= 32) {   // multiples of 32: the epilogue drains whole 32-column chunks
+    const long tiles = (N + bn - 1) / bn;
+    const long cost = tiles * (bn + 375);
+    if (best_cost < 0 || cost < best_cost) {
+      best_cost = cost;
+      best = bn;
+    }
+  }
+  return best;
 }
 
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, GemmParams& p,
