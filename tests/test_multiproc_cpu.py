@@ -109,3 +109,40 @@ def test_two_rank_gloo_kv_halo_exchange(tmp_path):
     assert res[0]["first"] == [0.0, 10.0, 20.0] and res[1]["first"] == [0.0, 10.0, 20.0]   # frame 0 of rank 0
     assert res[1]["prev"] == [1.0, 11.0, 21.0]                                             # last frame of rank 0
     assert res[0]["prev"] == [0.0, 0.0, 0.0]                                               # rank 0 has no predecessor
+
+
+def test_two_rank_gloo_frames_pixels_all_to_all(tmp_path):
+    """The AnimateDiff motion-module exchange: frames <-> pixels all-to-all and its inverse, world size 2 on gloo."""
+    script = tmp_path / "a.py"
+    script.write_text(textwrap.dedent(f"""
+        import sys, json, torch, torch.distributed as dist
+        sys.path.insert(0, {ROOT!r})
+        from univst_b200.animatediff import frames_to_pixels, pixels_to_frames
+        dist.init_process_group("gloo")
+        r, w = dist.get_rank(), dist.get_world_size()
+        B, Fl, N, C = 3, 2, 6, 4
+        F = Fl * w
+        # global tensor value at (b, f, pix, c) = 1000 b + 100 f + 10 pix + c; this rank owns frames [r Fl, (r+1) Fl)
+        b, f, p, c = torch.meshgrid(torch.arange(B), torch.arange(F), torch.arange(N), torch.arange(C), indexing="ij")
+        glob = (1000 * b + 100 * f + 10 * p + c).float()
+        mine = glob[:, r * Fl:(r + 1) * Fl].reshape(B * Fl * N, C).contiguous()
+        got = frames_to_pixels(mine, B, Fl, N, w)
+        n = N // w
+        want = glob[:, :, r * n:(r + 1) * n].reshape(B * F * n, C)
+        ok1 = bool(torch.equal(got, want))
+        back = pixels_to_frames(got, B, Fl, N, w)
+        ok2 = bool(torch.equal(back, mine))
+        out = [None] * w
+        dist.all_gather_object(out, [ok1, ok2])
+        if r == 0:
+            print(json.dumps(out))
+        dist.destroy_process_group()
+    """))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29619", str(script)],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    import json
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("[")][-1])
+    assert res == [[True, True], [True, True]]

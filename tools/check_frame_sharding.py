@@ -11,10 +11,19 @@ from univst_b200.unet import UNetPseudo3DConditionModel
 from univst_b200 import pnp_utils
 
 
+AD = "--animatediff" in sys.argv
+
+
 def build_unet(cfg):
     g = torch.Generator(device="cuda").manual_seed(33)
     sd = {}
-    for k, s in uo.unet_param_shapes(cfg).items():
+    if AD:
+        from oracle import animatediff_oracle as ao
+        from univst_b200.animatediff import UNet3DConditionModel
+        shapes, cls = ao.unet_param_shapes(cfg), UNet3DConditionModel
+    else:
+        shapes, cls = uo.unet_param_shapes(cfg), UNetPseudo3DConditionModel
+    for k, s in shapes.items():
         if "attn_temporal.to_out.0.weight" in k:
             sd[k] = torch.zeros(s, device="cuda", dtype=torch.float16)
         elif k.endswith("weight") and len(s) == 1:
@@ -26,7 +35,7 @@ def build_unet(cfg):
             for d in s[1:]:
                 fan *= d
             sd[k] = (torch.randn(s, device="cuda", generator=g) * fan ** -0.5).half()
-    return UNetPseudo3DConditionModel(sd, cfg)
+    return cls(sd, cfg)
 
 
 def timed(fn, iters):
@@ -45,18 +54,23 @@ def timed(fn, iters):
 
 
 def main():
-    F = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-    hw = int(sys.argv[2]) if len(sys.argv) > 2 else 64
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    F = int(args[0]) if len(args) > 0 else 16
+    hw = int(args[1]) if len(args) > 1 else 64
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", 0)))
     dist.init_process_group("nccl")
     rank, world = dist.get_rank(), dist.get_world_size()
-    unet = build_unet(uo.SD15_CONFIG)
+    if AD:
+        from oracle import animatediff_oracle as ao
+        unet = build_unet(ao.AD_SD15_CONFIG)
+    else:
+        unet = build_unet(uo.SD15_CONFIG)
     pipe = SimpleNamespace(unet=unet)
     pnp_utils.register_spatial_attention_pnp(pipe)
     g = torch.Generator(device="cuda").manual_seed(7)
     x = torch.randn(3, 4, F, hw, hw, device="cuda", generator=g).half()
     ctx = torch.randn(3, 77, 768, device="cuda", generator=g).half()
-    res = {"world": world, "frames": F, "latent": hw}
+    res = {"world": world, "frames": F, "latent": hw, "backbone": "animatediff" if AD else "sd"}
     for idx, t in ((5, 881), (30, 381)):   # shift window open / closed
         pnp_utils.register_time(pipe, idx)
         unet.set_frame_sharding_off()

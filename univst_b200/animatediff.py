@@ -44,6 +44,29 @@ def positional_encoding(d_model: int, max_len: int) -> torch.Tensor:
     return pe
 
 
+def frames_to_pixels(x: torch.Tensor, B: int, Fl: int, N: int, P: int, group=None) -> torch.Tensor:
+    """Rows (b, local frame, pixel) of every rank -> rows (b, global frame, local pixel): rank r ends up with pixel
+    slice [r N/P, (r+1) N/P) of ALL P*Fl frames (frame order = rank order).  One all_to_all_single."""
+    import torch.distributed as dist
+    if N % P:
+        raise ValueError(f"{N} pixels do not split evenly over {P} ranks")
+    n, C = N // P, x.shape[1]
+    send = x.view(B, Fl, P, n, C).permute(2, 0, 1, 3, 4).contiguous()          # [dest rank, b, fl, pix, C]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)                           # [source rank, b, fl, pix, C]
+    return recv.permute(1, 0, 2, 3, 4).reshape(B * P * Fl * n, C)             # (b, (rank, fl) = global frame, pix)
+
+
+def pixels_to_frames(x: torch.Tensor, B: int, Fl: int, N: int, P: int, group=None) -> torch.Tensor:
+    """Inverse of :func:`frames_to_pixels`: rows (b, global frame, local pixel) -> rows (b, local frame, pixel)."""
+    import torch.distributed as dist
+    n, C = N // P, x.shape[1]
+    send = x.view(B, P, Fl, n, C).permute(1, 0, 2, 3, 4).contiguous()          # [frame owner, b, fl, pix, C]
+    recv = torch.empty_like(send)
+    dist.all_to_all_single(recv, send, group=group)                           # [pixel-slice owner, b, fl, pix, C]
+    return recv.permute(1, 2, 0, 3, 4).reshape(B * Fl * N, C)                 # (b, fl, (slice, pix) = pixel)
+
+
 class UNet3DConditionModel(UNetPseudo3DConditionModel):
     def __init__(self, state_dict: Dict[str, torch.Tensor], config: Optional[dict] = None, device="cuda"):
         cfg = dict(AD_SD15_CONFIG)
@@ -54,11 +77,16 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
         super().__init__(state_dict, cfg, device=device)
 
     def set_frame_sharding(self, group=None):
-        import torch.distributed as dist
-        if (group is not None or dist.is_initialized()) and dist.get_world_size(group) > 1:
-            raise NotImplementedError("frame sharding of the AnimateDiff backbone needs a frames <-> pixels all-to-all per "
-                                      "motion module (SURVEY.md 8e); run clip-parallel replicas instead")
-        self._shard = None
+        """Shard the frames of every clip over the ranks of ``group``.  Everything spatial is frame-local in this backbone
+        (per-frame GroupNorm, per-frame attn1); the only exchange is inside the motion modules, whose attention runs over
+        the frames of one pixel: an all-to-all turns "my frames, all pixels" into "all frames, my pixels" before the
+        temporal attention and back after it (2 x 2 all-to-alls per motion module over NVLink)."""
+        super().set_frame_sharding(group)
+        self._pe_rows = {}
+
+    def set_frame_sharding_off(self):
+        super().set_frame_sharding_off()
+        self._pe_rows = {}
 
     # ------------------------------------------------------------------------------------------ flavour hooks
     def _pack_extra(self):
@@ -99,14 +127,24 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
         return None
 
     def _pe_table(self, key, B, F):
-        """[B*F, 3C] row vectors for the QKV epilogue: image (b, f) takes row f of W pe."""
+        """[B*F, 3C] row vectors for the QKV epilogue: local image (b, f) takes row (first local frame + f) of W pe."""
         ck = (key, B, F)
         if ck not in self._pe_rows:
             t = self.W[key]
-            if F > t.shape[0]:
-                raise ValueError(f"{F} frames exceed the motion modules' positional-encoding length {t.shape[0]}")
-            self._pe_rows[ck] = t[:F].repeat(B, 1).contiguous()
+            f0, total = (0, F) if self._shard is None else (self._shard[1] * F, self._shard[2] * F)
+            if total > t.shape[0]:
+                raise ValueError(f"{total} frames exceed the motion modules' positional-encoding length {t.shape[0]}")
+            self._pe_rows[ck] = t[f0:f0 + F].repeat(B, 1).contiguous()
         return self._pe_rows[ck]
+
+    def _temporal_attention(self, qkv, B, F, N, heads, d):
+        """Attention over the frames of every pixel.  Frame-sharded: frames <-> pixels all-to-all around the kernel."""
+        if self._shard is None:
+            return ops.temporal_attention(qkv, B=B, F=F, N=N, H=heads, d=d)
+        group, _, P = self._shard
+        full = frames_to_pixels(qkv, B, F, N, P, group)                       # [B * (P F) * (N / P), 3C]
+        o = ops.temporal_attention(full, B=B, F=P * F, N=N // P, H=heads, d=d)
+        return pixels_to_frames(o, B, F, N, P, group)
 
     def _motion(self, prefix, x, B, F, H, Wd):
         """VanillaTemporalModule.forward (models/motion_module.py:83-89 -> :138-163, :218-229).  x: [B*F*H*W, C]."""
@@ -124,7 +162,7 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
             a = b + f"attention_blocks.{i}."
             n = ops.layernorm(y, W[b + f"norms.{i}.weight"], W[b + f"norms.{i}.bias"])
             qkv = ops.gemm(n, W[a + "to_qkv.weight"], rowvec=self._pe_table(a + "pe_qkv", B, F), rows_per_group=N)
-            o = ops.temporal_attention(qkv, B=B, F=F, N=N, H=heads, d=C // heads)
+            o = self._temporal_attention(qkv, B, F, N, heads, C // heads)
             y = ops.gemm(o, W[a + "to_out.0.weight"], bias=W[a + "to_out.0.bias"], residual=y)
         n = ops.layernorm(y, W[b + "ff_norm.weight"], W[b + "ff_norm.bias"])
         g = ops.gemm(n, W[b + "ff.net.0.proj.weight"], bias=W[b + "ff.net.0.proj.bias"], geglu=True)

@@ -329,19 +329,20 @@ class UNetPseudo3DConditionModel:
         # 1. sparse-causal self-attention (stock or patched)
         n1 = ops.layernorm(y, W[b + "norm1.weight"], W[b + "norm1.bias"])
         NIkv = NI
-        if self._shard is None:
+        a1 = tr.transformer_blocks[0].attn1
+        mode, shift = self._attn1_plan(a1)
+        halo = self._shard is not None and mode != "self"   # per-frame self-attention needs no neighbour K/V
+        if not halo:
             qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"])
         else:  # two halo banks of B images each behind the local images
             NIkv = NI + 2 * B
             qkv_all = torch.empty((NIkv * N, 3 * C), dtype=torch.float16, device=x.device)
             qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"], out=qkv_all[: NI * N])
-        a1 = tr.transformer_blocks[0].attn1
-        mode, shift = self._attn1_plan(a1)
         if shift is not None:
             if B != 3:
                 raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
             ops.attn_shift_(qkv, F, N, C, *shift)
-        if self._shard is not None:
+        if halo:
             self._exchange_kv_halo(qkv_all, B, F, N)
             kv = qkv_all
         else:
