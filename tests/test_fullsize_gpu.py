@@ -61,3 +61,18 @@ def test_full_size_patched_forward(cuda_lib, backbone, idx):
     assert torch.isfinite(y).all() and y.shape == truth.shape
     assert rel <= 1e-2 and rel <= 2.0 * rel16 + 1e-3
     assert edit <= 1e-2 and edit <= 2.0 * edit16 + 1e-3
+
+
+def test_full_size_aux_kernels(cuda_lib):
+    """Mask propagation (4096 x 15000 x 640) and the 16 x 512 x 512 flow-warp window pass against their oracles."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "aux_kernels_bench.py")], capture_output=True, text=True,
+                         timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    print(json.dumps(res, indent=1))
+    assert res["maskprop"]["max_abs_err_vs_oracle"] < 1e-4 and res["flow_warp_window"]["bit_exact_vs_oracle"]

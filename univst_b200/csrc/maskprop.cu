@@ -11,27 +11,44 @@
 namespace uv {
 
 static constexpr int kTR = 32;    // target rows per CTA
-static constexpr int kSC = 128;   // source columns per chunk
+static constexpr int kSC = 256;   // source columns per chunk
 static constexpr int kKC = 32;    // feature channels per smem step
 static constexpr int kMaxClassRegs = 8;  // classes <= 256
+static constexpr int kStageFloats = kKC * kTR + kKC * kSC;                       // one pipeline stage: At | Bs
+static constexpr int kSmemBytes = (2 * kStageFloats + kTR * (kSC + 1)) * 4;      // 2 stages + the affinity tile
 
-// rows: y[r, :] = x[r, :] / max(||x[r, :]||, 1e-12)   (F.normalize(dim=1))
-__global__ void normalize_rows_kernel(const float* __restrict__ x, int rows, int C, float* __restrict__ y) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int lane = threadIdx.x & 31;
-  float s = 0.0f;
-  for (int c = lane; c < C; c += 32) {
-    const float v = x[(size_t)row * C + c];
-    s += v * v;
+// Both operands are normalised once into K-MAJOR layouts ([C][ld], the point index contiguous), so that the tile loads
+// of the affinity GEMM are contiguous 16-byte copies (cp.async) in global AND conflict-free in shared memory.
+// rows of x[rows, C] -> y[C, ld] = normalised rows, transposed   (F.normalize(dim=1) of the target features)
+__global__ void normalize_rows_t_kernel(const float* __restrict__ x, int rows, int C, int ld, float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  __shared__ float inv_s[32];
+  const int r0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
+  // norms: warp ty handles rows ty, ty + 8, ...
+  for (int i = ty; i < 32; i += 8) {
+    float s = 0.0f;
+    if (r0 + i < rows)
+      for (int c = tx; c < C; c += 32) {
+        const float v = x[(size_t)(r0 + i) * C + c];
+        s += v * v;
+      }
+    s = warp_sum(s);
+    if (tx == 0) inv_s[i] = 1.0f / fmaxf(sqrtf(s), 1e-12f);
   }
-  const float inv = 1.0f / fmaxf(sqrtf(warp_sum(s)), 1e-12f);
-  for (int c = lane; c < C; c += 32) y[(size_t)row * C + c] = x[(size_t)row * C + c] * inv;
+  __syncthreads();
+  for (int c0 = 0; c0 < C; c0 += 32) {
+    for (int i = ty; i < 32; i += 8)
+      tile[i][tx] = (r0 + i < rows && c0 + tx < C) ? x[(size_t)(r0 + i) * C + c0 + tx] * inv_s[i] : 0.0f;
+    __syncthreads();
+    for (int i = ty; i < 32; i += 8)
+      if (c0 + i < C && r0 + tx < ld) y[(size_t)(c0 + i) * ld + r0 + tx] = (r0 + tx < rows) ? tile[tx][i] : 0.0f;
+    __syncthreads();
+  }
 }
 
-// columns of x[C, M] -> y[M, C] = normalised columns (F.normalize(dim=0)), transposed for coalesced dot products
-__global__ void normalize_cols_t_kernel(const float* __restrict__ x, int C, int M, float* __restrict__ y) {
-  __shared__ float tile[32][33];
+// columns of x[C, M] -> y[C, ld] = normalised columns, same orientation (F.normalize(dim=0) of the source features)
+__global__ void normalize_cols_kernel(const float* __restrict__ x, int C, int M, int ld, float* __restrict__ y) {
+  __shared__ float part[8][32];
   __shared__ float inv_s[32];
   const int m0 = blockIdx.x * 32, tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8 threads
   float s = 0.0f;
@@ -39,65 +56,93 @@ __global__ void normalize_cols_t_kernel(const float* __restrict__ x, int C, int 
     const float v = (m0 + tx < M) ? x[(size_t)c * M + m0 + tx] : 0.0f;
     s += v * v;
   }
-  tile[ty][tx] = s;
+  part[ty][tx] = s;
   __syncthreads();
   if (ty == 0) {
     float t = 0.0f;
-    for (int i = 0; i < 8; ++i) t += tile[i][tx];
+    for (int i = 0; i < 8; ++i) t += part[i][tx];
     inv_s[tx] = 1.0f / fmaxf(sqrtf(t), 1e-12f);
   }
   __syncthreads();
-  for (int c0 = 0; c0 < C; c0 += 32) {
-    for (int i = ty; i < 32; i += 8)
-      tile[i][tx] = (c0 + i < C && m0 + tx < M) ? x[(size_t)(c0 + i) * M + m0 + tx] * inv_s[tx] : 0.0f;
-    __syncthreads();
-    for (int i = ty; i < 32; i += 8)
-      if (m0 + i < M && c0 + tx < C) y[(size_t)(m0 + i) * C + c0 + tx] = tile[tx][i];
-    __syncthreads();
-  }
+  if (m0 + tx < ld)
+    for (int c = ty; c < C; c += 8) y[(size_t)c * ld + m0 + tx] = (m0 + tx < M) ? x[(size_t)c * M + m0 + tx] * inv_s[tx] : 0.0f;
 }
 
-// aff tile [kTR][kSC] of this CTA's targets against source chunk `chunk` -> smem S
-__device__ __forceinline__ void aff_tile(const float* __restrict__ tar, const float* __restrict__ src, int N, int C, int M,
-                                         int n0, int chunk, float inv_temp_unused, float temperature, float (*At)[kTR + 1],
-                                         float (*Bs)[kSC + 4], float (*S)[kSC + 1]) {
-  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;  // 4 cols x 4 rows per thread
-  float acc[4][4];
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// aff tile [kTR][kSC] of this CTA's targets against source chunk `chunk` -> smem S.
+// 256 threads, 4 x 8 outputs each (rows ty*4.., columns tx*4.. and 128 + tx*4..): per k one broadcast LDS.128 of the
+// targets, two conflict-free LDS.128 of the sources and 32 FFMAs; the K loop runs over a two-stage cp.async pipeline.
+// Every accumulator is the plain sequential fma over k = 0 .. C-1, so pass 2 reproduces pass 1 bit for bit.
+// tarT [C][ldn], srcT [C][ldm] (K-major, padded to multiples of 4 floats; rows beyond C do not exist -> C % 32 handled
+// by zero-filling), ldn / ldm multiples of 4 and the padding columns are zero.
+__device__ __forceinline__ void aff_tile(const float* __restrict__ tarT, const float* __restrict__ srcT, int N, int C, int M,
+                                         int ldn, int ldm, int n0, int chunk, float temperature, float* stage,
+                                         float (*S)[kSC + 1]) {
+  const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+  float acc[4][8];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
   const int m0 = chunk * kSC;
-  for (int k0 = 0; k0 < C; k0 += kKC) {
-    // At[k][r] = tar[n0 + r][k0 + k]; Bs[k][c] = src[m0 + c][k0 + k]
-    for (int e = tid; e < kTR * kKC; e += 256) {
-      const int r = e / kKC, k = e % kKC;
-      At[k][r] = (n0 + r < N && k0 + k < C) ? tar[(size_t)(n0 + r) * C + k0 + k] : 0.0f;
+  const int nsteps = (C + kKC - 1) / kKC;
+  auto load_stage = [&](int step, int buf) {
+    float* At = stage + buf * kStageFloats;          // [kKC][kTR]
+    float* Bs = At + kKC * kTR;                      // [kKC][kSC]
+    const int k0 = step * kKC;
+    {  // targets: 32 k x 8 float4
+      const int k = tid >> 3, r4 = (tid & 7) * 4;
+      float* dst = At + k * kTR + r4;
+      if (k0 + k < C && n0 + r4 < ldn) cp_async16(dst, tarT + (size_t)(k0 + k) * ldn + n0 + r4);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int e = tid; e < kSC * kKC; e += 256) {
-      const int c = e / kKC, k = e % kKC;
-      Bs[k][c] = (m0 + c < M && k0 + k < C) ? src[(size_t)(m0 + c) * C + k0 + k] : 0.0f;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {  // sources: 32 k x 64 float4
+      const int e = tid + 256 * it;
+      const int k = e >> 6, c4 = (e & 63) * 4;
+      float* dst = Bs + k * kSC + c4;
+      if (k0 + k < C && m0 + c4 < ldm) cp_async16(dst, srcT + (size_t)(k0 + k) * ldm + m0 + c4);
+      else *reinterpret_cast<float4*>(dst) = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    cp_async_commit();
+  };
+  load_stage(0, 0);
+  for (int step = 0; step < nsteps; ++step) {
+    const int buf = step & 1;
+    if (step + 1 < nsteps) {
+      load_stage(step + 1, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
+    const float* At = stage + buf * kStageFloats;
+    const float* Bs = At + kKC * kTR;
 #pragma unroll 8
     for (int k = 0; k < kKC; ++k) {
-      float a[4], b[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = At[k][ty * 4 + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[k][tx + 32 * j];
+      const float4 a = *reinterpret_cast<const float4*>(At + k * kTR + ty * 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(Bs + k * kSC + tx * 4);
+      const float4 b1 = *reinterpret_cast<const float4*>(Bs + k * kSC + 128 + tx * 4);
+      const float av[4] = {a.x, a.y, a.z, a.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
     }
-    __syncthreads();
+    __syncthreads();   // the buffer just read is refilled by the next iteration's load
   }
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int c = tx + 32 * j;
+    for (int j = 0; j < 8; ++j) {
+      const int c = (j < 4 ? 0 : 128) + tx * 4 + (j & 3);
       // out-of-range source columns can never be selected
       S[ty * 4 + i][c] = (m0 + c < M) ? expf(__fdiv_rn(acc[i][j], temperature)) : -1.0f;
     }
@@ -106,11 +151,11 @@ __device__ __forceinline__ void aff_tile(const float* __restrict__ tar, const fl
 
 __global__ void __launch_bounds__(256)
 maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, const float* __restrict__ segs, int N, int C,
-                int M, int Ccls, float temperature, int topk, float* __restrict__ out, float* __restrict__ thr_out,
-                int* __restrict__ kept_idx, int kept_cap) {
-  __shared__ float At[kKC][kTR + 1];
-  __shared__ float Bs[kKC][kSC + 4];
-  __shared__ float S[kTR][kSC + 1];
+                int M, int ldn, int ldm, int Ccls, float temperature, int topk, float* __restrict__ out,
+                float* __restrict__ thr_out, int* __restrict__ kept_idx, int kept_cap) {
+  extern __shared__ __align__(16) float mp_smem[];
+  float* stage = mp_smem;                                                       // 2 x (At | Bs)
+  float (*S)[kSC + 1] = reinterpret_cast<float (*)[kSC + 1]>(mp_smem + 2 * kStageFloats);
   const int n0 = blockIdx.x * kTR;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nchunks = (M + kSC - 1) / kSC;
@@ -120,7 +165,7 @@ maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, co
 #pragma unroll
   for (int rr = 0; rr < 4; ++rr) list[rr] = -INFINITY;
   for (int chunk = 0; chunk < nchunks; ++chunk) {
-    aff_tile(tar, src, N, C, M, n0, chunk, 0.0f, temperature, At, Bs, S);
+    aff_tile(tar, src, N, C, M, ldn, ldm, n0, chunk, temperature, stage, S);
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int row = warp * 4 + rr;
@@ -162,7 +207,7 @@ maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, co
     for (int u = 0; u < kMaxClassRegs; ++u) num[rr][u] = 0.0f;
   }
   for (int chunk = 0; chunk < nchunks; ++chunk) {
-    aff_tile(tar, src, N, C, M, n0, chunk, 0.0f, temperature, At, Bs, S);
+    aff_tile(tar, src, N, C, M, ldn, ldm, n0, chunk, temperature, stage, S);
 #pragma unroll
     for (int rr = 0; rr < 4; ++rr) {
       const int row = warp * 4 + rr;
@@ -207,8 +252,10 @@ maskprop_kernel(const float* __restrict__ tar, const float* __restrict__ src, co
 
 using namespace uv;
 
+static inline int64_t pad4(int64_t v) { return (v + 3) & ~int64_t(3); }
+
 extern "C" int64_t univst_maskprop_workspace_bytes(int32_t N, int32_t C, int32_t M) {
-  return ((int64_t)N * C + (int64_t)M * C) * sizeof(float);
+  return (pad4(N) * C + pad4(M) * C) * sizeof(float);
 }
 
 extern "C" int univst_maskprop_f32(const float* feat_tar, const float* feat_src, const float* segs, int32_t N, int32_t C,
@@ -220,14 +267,21 @@ extern "C" int univst_maskprop_f32(const float* feat_tar, const float* feat_src,
   UV_REQUIRE(Ccls >= 1 && Ccls <= 32 * kMaxClassRegs, "maskprop: at most 256 classes");
   UV_REQUIRE(temperature > 0.0f, "maskprop: temperature must be positive");
   cudaStream_t st = (cudaStream_t)stream;
-  float* tar_n = (float*)workspace;
-  float* src_n = tar_n + (size_t)N * C;
-  normalize_rows_kernel<<<(N + 7) / 8, 256, 0, st>>>(feat_tar, N, C, tar_n);
+  UV_REQUIRE(((uintptr_t)workspace & 15) == 0, "maskprop: workspace must be 16-byte aligned");
+  const int ldn = (int)pad4(N), ldm = (int)pad4(M);
+  float* tar_n = (float*)workspace;                 // [C][ldn], K-major
+  float* src_n = tar_n + (size_t)C * ldn;           // [C][ldm]
+  normalize_rows_t_kernel<<<(ldn + 31) / 32, 256, 0, st>>>(feat_tar, N, C, ldn, tar_n);
   UV_CHECK_CUDA(cudaGetLastError());
-  normalize_cols_t_kernel<<<(M + 31) / 32, 256, 0, st>>>(feat_src, C, M, src_n);
+  normalize_cols_kernel<<<(ldm + 31) / 32, 256, 0, st>>>(feat_src, C, M, ldm, src_n);
   UV_CHECK_CUDA(cudaGetLastError());
-  maskprop_kernel<<<(N + kTR - 1) / kTR, 256, 0, st>>>(tar_n, src_n, segs, N, C, M, Ccls, temperature, topk, segs_tar,
-                                                     thresholds, kept_idx, kept_cap);
+  static bool configured = false;
+  if (!configured) {
+    UV_CHECK_CUDA(cudaFuncSetAttribute(maskprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  maskprop_kernel<<<(N + kTR - 1) / kTR, 256, kSmemBytes, st>>>(tar_n, src_n, segs, N, C, M, ldn, ldm, Ccls, temperature,
+                                                               topk, segs_tar, thresholds, kept_idx, kept_cap);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
