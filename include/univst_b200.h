@@ -85,6 +85,17 @@ int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int
 int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
                             int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const int32_t* kv_src,
                             int32_t nsrc, void* O, int32_t ldo, void* stream);
+/* Frame-sharded form (one clip over several GPUs): the K/V sources "previous frame" of a shard's first
+ * frame and "first frame of the clip" live on other ranks.  Instead of exchanging them (NCCL send/recv + broadcast) the
+ * kernel's TMA producer reads those tiles straight from PEER memory over NVLink (the buffers must be P2P-mapped, e.g.
+ * torch symmetric memory) while the tensor pipe works on the previous tile -- the halo transfer is the attention
+ * kernel's own loads.  Source index NI + b names image b*Fl + Fl-1 of (K_prev, V_prev) = the previous rank's buffer,
+ * NI + B + b names image b*Fl of (K_first, V_first) = rank 0's buffer; all buffers share ldkv and the [NI*N, .] row
+ * layout.  The caller orders the launch after the peers' projections (a cross-rank barrier on the stream). */
+int univst_sc_attention_sharded_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
+                                    int32_t H, int32_t d, int32_t N, const int32_t* kv_src, int32_t nsrc, void* O,
+                                    int32_t ldo, const void* K_prev, const void* V_prev, const void* K_first,
+                                    const void* V_first, int32_t B, int32_t Fl, void* stream);
 /* Tuning hook (no reference counterpart): tile / exp2 variant of the head-dim <= 64 kernel, collapsing of repeated
  * K/V sources (exact: a source that occurs c times is streamed once with log2 c added to its scores) and the start
  * stagger of the softmax groups.  Negative values restore the defaults (environment UNIVST_ATTN_*). */

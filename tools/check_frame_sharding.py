@@ -80,6 +80,11 @@ def main():
         diff = (out.float() - ref.float())
         res[f"idx{idx}"] = {"max_abs": float(diff.abs().max()), "rel_l2": float(diff.norm() / ref.float().norm()),
                             "ms_single": t_single, "ms_sharded": t_shard}
+        if "--fused" in sys.argv and not AD:   # K/V halo read from peer memory by the attention kernel itself
+            unet.set_frame_sharding(fused_halo=True)
+            out_f, t_fused = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
+            res[f"idx{idx}"].update({"ms_sharded_fused_halo": t_fused,
+                                     "fused_vs_nccl_max_abs": float((out_f.float() - out.float()).abs().max())})
     if rank == 0:
         print(json.dumps(res))
     dist.destroy_process_group()

@@ -43,7 +43,28 @@ struct AttnParams {
   float scale_log2;  // d^-0.5 * log2(e)
   int stagger;       // start offset between the softmax groups of a CTA, clocks
   int dedupe;        // collapse repeated source images of a row into one pass with a log2(multiplicity) score bias
+  // frame-sharded execution: sources >= NI live in PEER memory (NVLink P2P, read tile by tile by the TMA producer --
+  // the K/V halo "exchange" is the attention kernel's own loads).  Source NI + (bank - 1) * bankB + b is image
+  // b * bankFl + (bank == 1 ? bankFl - 1 : 0) of bank 1 (previous rank's buffer) / bank 2 (rank 0's buffer).
+  int bankB;         // images per remote bank (branches); 0 = no remote banks
+  int bankFl;        // frames per branch in a peer's buffer
 };
+
+// K / V tensor maps: bank 0 = this rank's buffer, 1 = the previous rank's, 2 = rank 0's (same shape and strides)
+struct KVMaps {
+  CUtensorMap k[3];
+  CUtensorMap v[3];
+};
+
+__device__ __forceinline__ void resolve_source(const AttnParams& p, int src, int& bank, int& image) {
+  bank = 0;
+  image = src;
+  if (p.bankB > 0 && src >= p.NI) {
+    const int r = src - p.NI;
+    bank = 1 + r / p.bankB;
+    image = (r - (bank - 1) * p.bankB) * p.bankFl + (bank == 1 ? p.bankFl - 1 : 0);
+  }
+}
 
 // Source list of one image with repeated entries collapsed.  softmax over [K_a, K_a, K_b] equals softmax over
 // [K_a, K_b] with the scores of K_a raised by ln 2, so a source that occurs c times is streamed once with log2(c)
@@ -142,8 +163,7 @@ struct AttnCfg {
 // softmax group, so the tiles only meet at the K/V ring.
 template <int NQ, int BKV, int POLY, int RS>
 __global__ void __launch_bounds__(AttnCfg<NQ, BKV>::kThreads, 1)
-attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                    const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ KVMaps kvm, const AttnParams p) {
   using L = AttnCfg<NQ, BKV>;
   constexpr int D = L::kDepth, NS = L::kSlots;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -193,8 +213,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&kvm.k[0]);
+    tma_prefetch_desc(&kvm.v[0]);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
@@ -248,8 +268,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (jk < T && (jk < 2 || mbar_test_wait(&k_empty[jk & 1], (uint32_t)(((jk >> 1) & 1) ^ 1)))) {
           const int s = jk & 1;
           mbar_expect_tx(&k_full[s], kv_bytes);
+          int bank, image;
+          resolve_source(p, src_img(SL, sik), bank, image);
           for (int c = 0; c < dch; ++c)
-            tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &tmK, &k_full[s], c * 64, head, jtk * BKV, src_img(SL, sik));
+            tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &kvm.k[bank], &k_full[s], c * 64, head, jtk * BKV, image);
           if (++jtk == tps) {
             jtk = 0;
             ++sik;
@@ -260,8 +282,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         if (jv < T && (jv < 2 || mbar_test_wait(&v_empty[jv & 1], (uint32_t)(((jv >> 1) & 1) ^ 1)))) {
           const int s = jv & 1;
           mbar_expect_tx(&v_full[s], kv_bytes);
+          int bank, image;
+          resolve_source(p, src_img(SL, siv), bank, image);
           for (int c = 0; c < dch; ++c)
-            tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &tmV, &v_full[s], c * 64, head, jtv * BKV, src_img(SL, siv));
+            tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &kvm.v[bank], &v_full[s], c * 64, head, jtv * BKV, image);
           if (++jtv == tps) {
             jtv = 0;
             ++siv;
@@ -664,8 +688,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // TMEM: S 2 x 128 columns, then 4 accumulators of (dpad + 16) columns: 256 + 4 x 64 = 512 at d = 40.
 template <int POLY>
 __global__ void __launch_bounds__(608, 1)   // 19 warps -> 96 registers (the allocation unit is 16 per thread: 104 does not fit)
-attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                          const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
+attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ KVMaps kvm, const AttnParams p) {
   constexpr int NQ = 2, BKV = 128;
   constexpr uint32_t kTile = 128 * 128;     // bytes of a [128][64]-half tile chunk
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -706,8 +729,8 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
-    tma_prefetch_desc(&tmK);
-    tma_prefetch_desc(&tmV);
+    tma_prefetch_desc(&kvm.k[0]);
+    tma_prefetch_desc(&kvm.v[0]);
     mbar_init(q_full, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&k_full[s], 1);
@@ -751,7 +774,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         if (jk < T && (jk < 2 || mbar_test_wait(&k_empty[jk & 1], (uint32_t)(((jk >> 1) & 1) ^ 1)))) {
           const int s = jk & 1;
           mbar_expect_tx(&k_full[s], kTile);
-          tma_load_4d(sK + s * kTile, &tmK, &k_full[s], 0, head, jtk * BKV, src_img(SL, sik));
+          int bank, image;
+          resolve_source(p, src_img(SL, sik), bank, image);
+          tma_load_4d(sK + s * kTile, &kvm.k[bank], &k_full[s], 0, head, jtk * BKV, image);
           if (++jtk == tps) {
             jtk = 0;
             ++sik;
@@ -762,7 +787,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         if (jv < T && (jv < 2 || mbar_test_wait(&v_empty[jv & 1], (uint32_t)(((jv >> 1) & 1) ^ 1)))) {
           const int s = jv & 1;
           mbar_expect_tx(&v_full[s], kTile);
-          tma_load_4d(sV + s * kTile, &tmV, &v_full[s], 0, head, jtv * BKV, src_img(SL, siv));
+          int bank, image;
+          resolve_source(p, src_img(SL, siv), bank, image);
+          tma_load_4d(sV + s * kTile, &kvm.v[bank], &v_full[s], 0, head, jtv * BKV, image);
           if (++jtv == tps) {
             jtv = 0;
             ++siv;
@@ -996,8 +1023,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 }
 
 template <int POLY>
-static int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
-                             cudaStream_t stream) {
+static int launch_attn_split(const CUtensorMap& tq, const KVMaps& kvm, const AttnParams& p, cudaStream_t stream) {
   UV_REQUIRE(p.d <= 48, "attention (split rows): head dim <= 48");
   const size_t smem = 227 * 1024;   // 14 tiles of 16 KiB + ones + barriers: 704 B of slack for the 1 KiB alignment
   static bool configured = false;
@@ -1006,14 +1032,13 @@ static int launch_attn_split(const CUtensorMap& tq, const CUtensorMap& tk, const
     configured = true;
   }
   dim3 grid((p.N + 255) / 256, p.H, p.NI);
-  attention_tc_split_kernel<POLY><<<grid, 608, smem, stream>>>(tq, tk, tv, p);
+  attention_tc_split_kernel<POLY><<<grid, 608, smem, stream>>>(tq, kvm, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
 
 template <int NQ, int BKV, int POLY, int RS = 0>
-static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const AttnParams& p,
-                       cudaStream_t stream) {
+static int launch_attn(const CUtensorMap& tq, const KVMaps& kvm, const AttnParams& p, cudaStream_t stream) {
   using L = AttnCfg<NQ, BKV>;
   const int dch = (p.d + 63) / 64;
   size_t smem = (size_t)NQ * dch * L::kQChunkBytes + 4 * (size_t)dch * L::kKVChunkBytes +
@@ -1033,7 +1058,7 @@ static int launch_attn(const CUtensorMap& tq, const CUtensorMap& tk, const CUten
     configured = true;
   }
   dim3 grid((p.N + 128 * NQ - 1) / (128 * NQ), p.H, p.NI);
-  attention_tc_kernel<NQ, BKV, POLY, RS><<<grid, L::kThreads, smem, stream>>>(tq, tk, tv, p);
+  attention_tc_kernel<NQ, BKV, POLY, RS><<<grid, L::kThreads, smem, stream>>>(tq, kvm, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
@@ -1051,9 +1076,13 @@ extern "C" int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t st
   return UNIVST_OK;
 }
 
-extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv,
-                                       int32_t NI, int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv,
-                                       const int32_t* kv_src, int32_t nsrc, void* O, int32_t ldo, void* stream) {
+// Shared body of the two entry points.  Kb / Vb: K / V base pointers of bank 0 (local), 1 (previous rank), 2 (rank 0);
+// banks 1 and 2 may be null (no remote sources).
+static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, const void* const* Vb, int32_t ldkv,
+                             int32_t NI, int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const int32_t* kv_src,
+                             int32_t nsrc, void* O, int32_t ldo, int32_t bankB, int32_t bankFl, void* stream) {
+  const void* K = Kb[0];
+  const void* V = Vb[0];
   UV_REQUIRE(Q && K && V && O && kv_src, "sc_attention: null pointer");
   UV_REQUIRE(NI > 0 && NIkv > 0 && H > 0 && N > 0 && Nkv > 0 && nsrc > 0, "sc_attention: empty shape");
   UV_REQUIRE(d % 8 == 0 && d >= 8 && d <= 192, "sc_attention: head dim must be a multiple of 8 in [8, 192]");
@@ -1070,6 +1099,8 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
   p.O = (__half*)O;
   p.ldo = ldo;
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
+  p.bankB = bankB;
+  p.bankFl = bankFl;
 
   // tile configuration: d <= 64 -> variant from univst_attention_tune / UNIVST_ATTN_VARIANT (see the switches below).
   // Default 17: d <= 48 -> split rows (two softmax threads per query row, 16 softmax warps) with the row sums on the
@@ -1099,7 +1130,8 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
     stagger = e ? atoi(e) : -1;
   }
   p.stagger = stagger >= 0 ? stagger : 0;   // measured neutral (0 .. 2500 clocks): off by default
-  CUtensorMap tq, tk, tv;
+  CUtensorMap tq;
+  KVMaps kvm;
   {
     uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)N, (uint64_t)NI};
     uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ldq * 2, (uint64_t)N * ldq * 2};
@@ -1111,43 +1143,66 @@ extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K
     uint64_t dims[4] = {(uint64_t)d, (uint64_t)H, (uint64_t)Nkv, (uint64_t)NIkv};
     uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ldkv * 2, (uint64_t)Nkv * ldkv * 2};
     uint32_t box[4] = {64, 1, (uint32_t)bkv, 1};
-    int r = make_tmap_f16(&tk, K, 4, dims, str, box, true);
-    if (r) return r;
-    r = make_tmap_f16(&tv, V, 4, dims, str, box, true);
-    if (r) return r;
+    for (int b = 0; b < 3; ++b) {   // absent banks alias the local buffer (never addressed: bankB = 0 or the table has no such source)
+      int r = make_tmap_f16(&kvm.k[b], Kb[b] ? Kb[b] : K, 4, dims, str, box, true);
+      if (r) return r;
+      r = make_tmap_f16(&kvm.v[b], Vb[b] ? Vb[b] : V, 4, dims, str, box, true);
+      if (r) return r;
+    }
   }
   cudaStream_t st = (cudaStream_t)stream;
   if (d <= 64 && (int64_t)Nkv * nsrc <= 128 && variant == kDefaultVariant)   // one KV tile (cross-attention): the
-    return launch_attn<2, 128, 0>(tq, tk, tv, p, st);                        // row-sum MMA is pure overhead
-  if (variant == 18 && d <= 48) return launch_attn<2, 128, 6, 2>(tq, tk, tv, p, st);   // 16 + P through tensor memory
+    return launch_attn<2, 128, 0>(tq, kvm, p, st);                        // row-sum MMA is pure overhead
+  if (variant == 18 && d <= 48) return launch_attn<2, 128, 6, 2>(tq, kvm, p, st);   // 16 + P through tensor memory
   if ((variant == 16 || (variant >= 13 && d > 48)) && d <= 64)
-    return launch_attn<2, 128, 6, 1>(tq, tk, tv, p, st);   // variant 9 + packed FFMA2 score scaling
+    return launch_attn<2, 128, 6, 1>(tq, kvm, p, st);   // variant 9 + packed FFMA2 score scaling
   if (d <= 48 && variant >= 13) {   // split rows: two softmax threads per query row (head dim 40)
     switch (variant) {
-      case 13: return launch_attn_split<0>(tq, tk, tv, p, st);
-      case 17: return launch_attn_split<6>(tq, tk, tv, p, st);   // + packed FFMA2 score scaling
-      case 14: return launch_attn_split<4>(tq, tk, tv, p, st);   // + 1/8 of the exp2 as polynomials
-      default: return launch_attn_split<1>(tq, tk, tv, p, st);   // + 1/4
+      case 13: return launch_attn_split<0>(tq, kvm, p, st);
+      case 17: return launch_attn_split<6>(tq, kvm, p, st);   // + packed FFMA2 score scaling
+      case 14: return launch_attn_split<4>(tq, kvm, p, st);   // + 1/8 of the exp2 as polynomials
+      default: return launch_attn_split<1>(tq, kvm, p, st);   // + 1/4
     }
   }
   if (d <= 64) {
     switch (variant) {
-      case 0: return launch_attn<2, 128, 0>(tq, tk, tv, p, st);
-      case 1: return launch_attn<2, 128, 1>(tq, tk, tv, p, st);
-      case 2: return launch_attn<2, 64, 0>(tq, tk, tv, p, st);
-      case 3: return launch_attn<2, 64, 1>(tq, tk, tv, p, st);
-      case 4: return launch_attn<2, 128, 2>(tq, tk, tv, p, st);
-      case 5: return launch_attn<2, 128, 3>(tq, tk, tv, p, st);   // experiment: all exponentials as polynomials
-      case 6: return launch_attn<2, 128, 9>(tq, tk, tv, p, st);   // experiment: no exponentials (wrong results)
-      case 7: return launch_attn<2, 128, 1, 1>(tq, tk, tv, p, st);   // row sums on the tensor pipe
-      case 8: return launch_attn<2, 128, 2, 1>(tq, tk, tv, p, st);   // + half of the exp2 polynomial
-      case 9: return launch_attn<2, 128, 0, 1>(tq, tk, tv, p, st);   // row sums on the tensor pipe, all exp2 on MUFU
-      case 10: return launch_attn<2, 128, 4, 1>(tq, tk, tv, p, st);  // row sums on the tensor pipe, 1/8 polynomial
-      case 11: return launch_attn<2, 128, 5, 1>(tq, tk, tv, p, st);  // row sums on the tensor pipe, 3/8 polynomial
-      case 12: return launch_attn<2, 128, 4, 0>(tq, tk, tv, p, st);  // 1/8 polynomial
-      default: return launch_attn<2, 128, 0, 1>(tq, tk, tv, p, st);  // (13+ with 48 < d <= 64: no split-row kernel)
+      case 0: return launch_attn<2, 128, 0>(tq, kvm, p, st);
+      case 1: return launch_attn<2, 128, 1>(tq, kvm, p, st);
+      case 2: return launch_attn<2, 64, 0>(tq, kvm, p, st);
+      case 3: return launch_attn<2, 64, 1>(tq, kvm, p, st);
+      case 4: return launch_attn<2, 128, 2>(tq, kvm, p, st);
+      case 5: return launch_attn<2, 128, 3>(tq, kvm, p, st);   // experiment: all exponentials as polynomials
+      case 6: return launch_attn<2, 128, 9>(tq, kvm, p, st);   // experiment: no exponentials (wrong results)
+      case 7: return launch_attn<2, 128, 1, 1>(tq, kvm, p, st);   // row sums on the tensor pipe
+      case 8: return launch_attn<2, 128, 2, 1>(tq, kvm, p, st);   // + half of the exp2 polynomial
+      case 9: return launch_attn<2, 128, 0, 1>(tq, kvm, p, st);   // row sums on the tensor pipe, all exp2 on MUFU
+      case 10: return launch_attn<2, 128, 4, 1>(tq, kvm, p, st);  // row sums on the tensor pipe, 1/8 polynomial
+      case 11: return launch_attn<2, 128, 5, 1>(tq, kvm, p, st);  // row sums on the tensor pipe, 3/8 polynomial
+      case 12: return launch_attn<2, 128, 4, 0>(tq, kvm, p, st);  // 1/8 polynomial
+      default: return launch_attn<2, 128, 0, 1>(tq, kvm, p, st);  // (13+ with 48 < d <= 64: no split-row kernel)
     }
   }
-  if (d <= 128) return launch_attn<2, 64, 0>(tq, tk, tv, p, st);
-  return launch_attn<1, 64, 0>(tq, tk, tv, p, st);
+  if (d <= 128) return launch_attn<2, 64, 0>(tq, kvm, p, st);
+  return launch_attn<1, 64, 0>(tq, kvm, p, st);
+}
+
+extern "C" int univst_sc_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
+                                       int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const int32_t* kv_src,
+                                       int32_t nsrc, void* O, int32_t ldo, void* stream) {
+  const void* Kb[3] = {K, nullptr, nullptr};
+  const void* Vb[3] = {V, nullptr, nullptr};
+  return sc_attention_impl(Q, ldq, Kb, Vb, ldkv, NI, NIkv, H, d, N, Nkv, kv_src, nsrc, O, ldo, 0, 0, stream);
+}
+
+extern "C" int univst_sc_attention_sharded_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv,
+                                               int32_t NI, int32_t H, int32_t d, int32_t N, const int32_t* kv_src,
+                                               int32_t nsrc, void* O, int32_t ldo, const void* K_prev, const void* V_prev,
+                                               const void* K_first, const void* V_first, int32_t B, int32_t Fl,
+                                               void* stream) {
+  UV_REQUIRE(B > 0 && Fl > 0 && B * Fl == NI, "sc_attention_sharded: NI must be B * Fl");
+  UV_REQUIRE((((uintptr_t)K_prev | (uintptr_t)V_prev | (uintptr_t)K_first | (uintptr_t)V_first) % 16) == 0,
+             "sc_attention_sharded: 16-byte alignment");
+  const void* Kb[3] = {K, K_prev, K_first};
+  const void* Vb[3] = {V, V_prev, V_first};
+  return sc_attention_impl(Q, ldq, Kb, Vb, ldkv, NI, NI, H, d, N, N, kv_src, nsrc, O, ldo, B, Fl, stream);
 }

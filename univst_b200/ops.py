@@ -17,6 +17,7 @@ from ._lib import Epilogue, check
 _vp, _i32, _f32, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 _lib.register("univst_sc_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp])
 _lib.register("univst_attention_tune", [_i32, _i32, _i32])
+_lib.register("univst_sc_attention_sharded_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp])
 _lib.register("univst_temporal_attention_f16", [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp])
 _lib.register("univst_attn_shift_workspace_bytes", [_i32, _i32], _i64)
 _lib.register("univst_attn_shift_f16", [_vp, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp])
@@ -179,6 +180,31 @@ def sc_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: torc
         check(_lib.lib().univst_sc_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), NI,
                                                  NIkv, H, d, N, Nkv, kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(),
                                                  out.stride(0), _stream()), "univst_sc_attention_f16")
+    _count("sc_attention")
+    return out
+
+
+def sc_attention_sharded(qkv: torch.Tensor, qkv_prev: Optional[torch.Tensor], qkv_first: Optional[torch.Tensor],
+                         kv_src: torch.Tensor, *, B: int, Fl: int, H: int, d: int, N: int, out: Optional[torch.Tensor] = None):
+    """Frame-sharded attn1: ``qkv`` [B*Fl*N, 3C] is this rank's fused projection, ``qkv_prev`` / ``qkv_first`` the
+    previous rank's / rank 0's (peer-mapped views of the same shape, or None where the table never names them)."""
+    _lib.require_device()
+    C_ = H * d
+    NI = B * Fl
+    assert qkv.stride(1) == 1 and qkv.shape[0] == NI * N and kv_src.dtype == torch.int32 and kv_src.shape[0] == NI
+    if out is None:
+        out = torch.empty((NI * N, C_), dtype=torch.float16, device=qkv.device)
+    es = qkv.element_size()
+    kp = lambda t: t.data_ptr() + C_ * es if t is not None else None
+    vp = lambda t: t.data_ptr() + 2 * C_ * es if t is not None else None
+    for t in (qkv_prev, qkv_first):
+        assert t is None or (t.stride(0) == qkv.stride(0) and t.shape == qkv.shape)
+    with _Timed("sc_attention", (NI, H, d, N, N * kv_src.shape[1])):
+        check(_lib.lib().univst_sc_attention_sharded_f16(qkv.data_ptr(), qkv.stride(0), kp(qkv), vp(qkv), qkv.stride(0), NI, H,
+                                                         d, N, kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(),
+                                                         out.stride(0), kp(qkv_prev), vp(qkv_prev), kp(qkv_first),
+                                                         vp(qkv_first), B, Fl, _stream()),
+              "univst_sc_attention_sharded_f16")
     _count("sc_attention")
     return out
 

@@ -126,6 +126,7 @@ class UNetPseudo3DConditionModel:
         self._tables = {}
         self._ctx_cache = None
         self._shard = None  # (process group, rank, world) when frames are sharded over GPUs
+        self._fused_halo = False
         self._build_tree()
         self._pack(state_dict)
 
@@ -137,11 +138,16 @@ class UNetPseudo3DConditionModel:
         cfg = {k: c[k] for k in SD15_CONFIG if k in c}
         return cls(module.state_dict(), cfg, device=device)
 
-    def set_frame_sharding(self, group=None):
+    def set_frame_sharding(self, group=None, fused_halo: bool = False):
         """Shard the frames of every clip over the ranks of ``group`` (default: the world group): rank r evaluates
-        frames [r F/P, (r+1) F/P) of all branches.  Per attn1 layer the boundary frame's K/V goes to the next rank and
-        frame 0's K/V is broadcast from rank 0 (NCCL over NVLink); every cross-frame GroupNorm all-reduces
-        B x 32 x 2 floats; the predicted noise is all-gathered at the end.  ``None`` world size 1 -> no-op."""
+        frames [r F/P, (r+1) F/P) of all branches.  Every cross-frame GroupNorm all-reduces B x 32 x 2 floats; the
+        predicted noise is all-gathered at the end.  The K/V of the neighbouring frames that attn1 needs from other
+        ranks (last frame of the previous rank, frame 0 of the clip) arrive in one of two ways:
+        * ``fused_halo=False``: NCCL send/recv + broadcast into two halo banks behind the local images;
+        * ``fused_halo=True``: no exchange step at all -- the fused projection is written into torch symmetric memory
+          and the attention kernel's TMA producer reads the peers' K/V tiles straight over NVLink while the tensor pipe
+          works on the previous tile (``univst_sc_attention_sharded_f16``); one cross-rank barrier per layer orders
+          the reads after the peers' projections, double buffering makes a second barrier unnecessary."""
         import torch.distributed as dist
         if group is None and not dist.is_initialized():
             self._shard = None
@@ -149,9 +155,33 @@ class UNetPseudo3DConditionModel:
         world = dist.get_world_size(group)
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
         self._tables = {}
+        self._fused_halo = bool(fused_halo) and self._shard is not None
+        if not hasattr(self, "_symm"):
+            self._symm = {}
+
+    def _symm_qkv(self, rows, cols):
+        """Double-buffered symmetric-memory projection buffer of one UNet level: (local [rows, cols] view to write,
+        previous rank's view, rank 0's view, handle).  Allocation + rendezvous happen on first use (same order on
+        every rank); the parity flips per use so that a buffer is rewritten only two barriers after it was read."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group, rank, world = self._shard
+        key = (rows, cols)
+        if key not in self._symm:
+            t = symm_mem.empty(2, rows, cols, dtype=torch.float16, device=self.device)
+            hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+            peers = {r: hdl.get_buffer(r, (2, rows, cols), torch.float16) for r in {max(rank - 1, 0), 0} if r != rank}
+            self._symm[key] = [t, hdl, peers, 0]
+        ent = self._symm[key]
+        t, hdl, peers, par = ent
+        ent[3] = par ^ 1
+        prev = peers[rank - 1][par] if rank > 0 else None
+        first = peers[0][par] if rank > 0 else None
+        return t[par], prev, first, hdl
 
     def set_frame_sharding_off(self):
         self._shard = None
+        self._fused_halo = False
         self._tables = {}
 
     def _heads(self, level):
@@ -334,6 +364,9 @@ class UNetPseudo3DConditionModel:
         halo = self._shard is not None and mode != "self"   # per-frame self-attention needs no neighbour K/V
         if not halo:
             qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"])
+        elif self._fused_halo:  # projection into symmetric memory: the peers' attention kernels read it over NVLink
+            qkv_buf, qkv_prev, qkv_first, symm_hdl = self._symm_qkv(NI * N, 3 * C)
+            qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"], out=qkv_buf)
         else:  # two halo banks of B images each behind the local images
             NIkv = NI + 2 * B
             qkv_all = torch.empty((NIkv * N, 3 * C), dtype=torch.float16, device=x.device)
@@ -342,13 +375,17 @@ class UNetPseudo3DConditionModel:
             if B != 3:
                 raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
             ops.attn_shift_(qkv, F, N, C, *shift)
-        if halo:
-            self._exchange_kv_halo(qkv_all, B, F, N)
-            kv = qkv_all
+        if halo and self._fused_halo:
+            symm_hdl.barrier(channel=0)   # every rank's projection (and shift) of this layer is complete and visible
+            o = ops.sc_attention_sharded(qkv, qkv_prev, qkv_first, self._table(B, F, mode), B=B, Fl=F, H=heads, d=d, N=N)
         else:
-            kv = qkv
-        o = ops.sc_attention(qkv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], self._table(B, F, mode), NI=NI, NIkv=NIkv, H=heads,
-                             d=d, N=N, Nkv=N)
+            if halo:
+                self._exchange_kv_halo(qkv_all, B, F, N)
+                kv = qkv_all
+            else:
+                kv = qkv
+            o = ops.sc_attention(qkv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], self._table(B, F, mode), NI=NI, NIkv=NIkv,
+                                 H=heads, d=d, N=N, Nkv=N)
         y = ops.gemm(o, W[b + "attn1.to_out.0.weight"], bias=W[b + "attn1.to_out.0.bias"], residual=y)
         # 2. cross-attention over the (per-branch) context
         n2 = ops.layernorm(y, W[b + "norm2.weight"], W[b + "norm2.bias"])
