@@ -25,15 +25,15 @@ def _inputs():
     return x, ctx
 
 
-@pytest.mark.parametrize("backbone,idx", [("sd", 5), ("sd", 30), ("animatediff", 5)])
+@pytest.mark.parametrize("backbone,idx", [("sd", 5), ("sd", 30), ("animatediff", 5), ("sd21", 5)])
 def test_full_size_patched_forward(cuda_lib, backbone, idx):
     from univst_b200 import pnp_utils
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    if backbone == "sd":
+    if backbone in ("sd", "sd21"):
         from oracle import unet_oracle as orc
         from univst_b200.unet import UNetPseudo3DConditionModel as Net
-        cfg = orc.SD15_CONFIG
+        cfg = orc.SD15_CONFIG if backbone == "sd" else orc.SD21_CONFIG   # configs[2] backbone: head dim 64, ctx 1024
     else:
         from oracle import animatediff_oracle as orc
         from univst_b200.animatediff import UNet3DConditionModel as Net
@@ -44,6 +44,8 @@ def test_full_size_patched_forward(cuda_lib, backbone, idx):
     pnp_utils.register_spatial_attention_pnp(pipe)
     pnp_utils.register_time(pipe, idx)
     x, ctx = _inputs()
+    if cfg["cross_attention_dim"] != ctx.shape[-1]:
+        ctx = torch.randn(1, 77, cfg["cross_attention_dim"], generator=torch.Generator().manual_seed(8)).repeat(3, 1, 1).cuda()
     t = 981 - 20 * idx
     y = unet(x.half(), t, encoder_hidden_states=ctx.half()).sample
     torch.cuda.synchronize()

@@ -16,7 +16,7 @@ if AD:
     cfg = ao.AD_SD15_CONFIG
     shapes = ao.unet_param_shapes(cfg)
 else:
-    cfg = uo.SD15_CONFIG
+    cfg = uo.SD21_CONFIG if "--sd21" in sys.argv else uo.SD15_CONFIG
     shapes = uo.unet_param_shapes(cfg)
 t0 = time.time()
 g = torch.Generator(device="cuda").manual_seed(33)
@@ -39,7 +39,7 @@ pipe = SimpleNamespace(unet=unet)
 pnp_utils.register_spatial_attention_pnp(pipe)
 pnp_utils.register_time(pipe, 5)
 x = torch.randn(3, 4, F, 64, 64, device="cuda").half()
-ctx = torch.randn(3, 77, 768, device="cuda").half()
+ctx = torch.randn(3, 77, cfg["cross_attention_dim"], device="cuda").half()
 for _ in range(2):
     y = unet(x, 981, encoder_hidden_states=ctx).sample
 torch.cuda.synchronize()
