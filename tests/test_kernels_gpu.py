@@ -174,6 +174,42 @@ def test_sc_attention_large_logits(cuda_lib):
     _close(out, ref, 5e-3, 1e-2, "sc_attention peaked")
 
 
+@pytest.mark.parametrize("d", [40, 32, 64])
+def test_sc_attention_peaked_small_head_dim(cuda_lib, d):
+    """The split-row kernel (d <= 48) keeps one running maximum per half row: peaked scores force its rescale path
+    (P pieces already stored, both accumulators) and the merge of two halves with very different maxima."""
+    from univst_b200 import ops
+    from univst_b200.unet import kv_source_table
+    B, Fr, H, N = 1, 3, 2, 384
+    NI, C = B * Fr, H * d
+    qkv = _rand(NI * N, 3 * C, scale=2.5, seed=5)
+    qkv[:, C:2 * C][::7] *= 3.0          # a few keys dominate, scattered over both halves of the tiles
+    q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    src = kv_source_table(B, Fr, "prev_self_first").cuda()
+    out = ops.sc_attention(q, k, v, src, NI=NI, NIkv=NI, H=H, d=d, N=N, Nkv=N)
+    ref = _attn_ref(q.contiguous(), k.contiguous(), v.contiguous(), src, NI, H, d, N, N)
+    _close(out, ref, 5e-3, 1e-2, f"sc_attention peaked d{d}")
+
+
+@pytest.mark.parametrize("H,d,N,Nkv,nsrc", [(2, 40, 200, 330, 2), (2, 40, 128, 64, 3), (3, 16, 72, 136, 2), (2, 40, 256, 192, 1),
+                                            (2, 64, 200, 330, 2), (2, 80, 200, 330, 2)])
+def test_sc_attention_ragged(cuda_lib, H, d, N, Nkv, nsrc):
+    """Query / key counts that are not multiples of the 128-token tiles: partial query tiles, a ragged last KV tile
+    per source, and (Nkv = 64, 192) key halves of a tile that are entirely past the end (their half-row softmax must
+    contribute exactly nothing, not NaN)."""
+    from univst_b200 import ops
+    NI, NIkv, C = 4, 5, H * d
+    q = _rand(NI * N, C, seed=1)
+    kv = _rand(NIkv * Nkv, 2 * C, seed=2)
+    k, v = kv[:, :C], kv[:, C:]
+    g = torch.Generator().manual_seed(9)
+    src = torch.stack([torch.randperm(NIkv, generator=g)[:nsrc] for _ in range(NI)]).to(torch.int32).cuda()
+    out = ops.sc_attention(q, k, v, src, NI=NI, NIkv=NIkv, H=H, d=d, N=N, Nkv=Nkv)
+    ref = _attn_ref(q, k.contiguous(), v.contiguous(), src, NI, H, d, N, Nkv)
+    assert torch.isfinite(out).all()
+    _close(out, ref, 2e-3, 5e-3, f"sc_attention ragged H{H} d{d} N{N} Nkv{Nkv} x{nsrc}")
+
+
 @pytest.mark.parametrize("H,d,N", [(8, 40, 256), (8, 160, 64), (5, 64, 128)])
 def test_cross_attention_77_tokens(cuda_lib, H, d, N):
     from univst_b200 import ops

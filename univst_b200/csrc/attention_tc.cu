@@ -123,7 +123,7 @@ __device__ __forceinline__ float src_bias(const SrcList& L, int i) {
 
 static constexpr uint32_t kOBase = 256;     // TMEM column of the first O accumulator
 static constexpr float kRescaleThreshold = 8.0f;  // log2 units: P <= 2^8 before a forced rescale
-static constexpr int kDefaultVariant = 17;
+static constexpr int kDefaultVariant = 19;
 
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
@@ -686,7 +686,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // the CTA runs 16 softmax warps (4 per scheduler) instead of 8: with one row per thread the MUFU pipe sat idle ~40 % of
 // the time because two warps per scheduler cannot cover each other's TMEM loads, maxima, packs and barrier waits.
 // TMEM: S 2 x 128 columns, then 4 accumulators of (dpad + 16) columns: 256 + 4 x 64 = 512 at d = 40.
-template <int POLY>
+template <int POLY, int CI>
 __global__ void __launch_bounds__(608, 1)   // 19 warps -> 96 registers (the allocation unit is 16 per thread: 104 does not fit)
 attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ KVMaps kvm, const AttnParams p) {
   constexpr int NQ = 2, BKV = 128;
@@ -801,51 +801,69 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
     }
   } else if (is_mma) {
-    if (lane == 0) {
+    // CI = 1: the whole warp runs the role convergently (lane 0 probes the barriers, an elected lane issues), so that
+    // descriptors live in uniform registers; CI = 0: lane 0 alone.  The issuers share their schedulers with four softmax
+    // warps each, so their instruction count matters.
+    auto wait = [&](uint64_t* bar, uint32_t par) {
+      if constexpr (CI) mbar_wait_warp(bar, par);
+      else mbar_wait(bar, par);
+    };
+    auto mma = [&](uint32_t dt, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accum) {
+      if constexpr (CI) umma_f16_ss_elect(dt, da, db, idesc, accum);
+      else umma_f16_ss(dt, da, db, idesc, accum);
+    };
+    auto commit = [&](uint64_t* bar) {
+      if constexpr (CI) tc_commit_elect(bar);
+      else tc_commit(bar);
+    };
+    if (CI || lane == 0) {
       // ---------------------------------------------------------------- MMA issuer of query tile q
       const int q = (warp == 1) ? 0 : 1;
       const uint32_t idesc_s = make_idesc_f16(128, BKV, 0, 0);      // S = Q K^T : both K-major
       const uint32_t idesc_o = make_idesc_f16(128, opad, 0, 1);     // O_half += P_half V_half : V MN-major
       const uint32_t idesc_l = make_idesc_f16(128, 16, 0, 1);       // l_half += P_half 1
       const uint64_t od = make_smem_desc_sw128(smem_u32(sOnes), 16, 1024);
+      const uint64_t qd = make_smem_desc_sw128(smem_u32(sQ + q * kTile), 16, 1024);
+      const uint64_t kd0 = make_smem_desc_sw128(smem_u32(sK), 16, 1024);
+      const uint64_t vd0 = make_smem_desc_sw128(smem_u32(sV), kTile, 1024);
+      const uint64_t pd0 = make_smem_desc_sw128(smem_u32(sP + q * 4 * kTile), 16, 1024);
+      const int nk = dpad >> 4;
       auto issue_s = [&](int j) {
         const int ks = j & 1;
-        mbar_wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
+        wait(&k_full[ks], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
-        const uint64_t da = make_smem_desc_sw128(smem_u32(sQ + q * kTile), 16, 1024);
-        const uint64_t db = make_smem_desc_sw128(smem_u32(sK + ks * kTile), 16, 1024);
-        const int nk = dpad >> 4;
+        const uint64_t kd = desc_advance(kd0, ks * (kTile >> 4));
         for (int k = 0; k < nk; ++k)
-          umma_f16_ss(tmem_base + q * BKV, da + (uint64_t)(k * 2), db + (uint64_t)(k * 2), idesc_s, k ? 1u : 0u);
-        tc_commit(&k_empty[ks]);
-        tc_commit(&s_full[q]);
+          mma(tmem_base + q * BKV, desc_advance(qd, k * 2), desc_advance(kd, k * 2), idesc_s, k ? 1u : 0u);
+        commit(&k_empty[ks]);
+        commit(&s_full[q]);
       };
       auto issue_pv = [&](int j) {
         const int vs = j & 1, slot = q * 2 + (j & 1);
-        mbar_wait(&p_full[slot], (uint32_t)((j >> 1) & 1));
-        mbar_wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
+        wait(&p_full[slot], (uint32_t)((j >> 1) & 1));
+        wait(&v_full[vs], (uint32_t)((j >> 1) & 1));
         tc_fence_after();
-        const uint32_t pa = smem_u32(sP + slot * 2 * kTile);
-        const uint32_t va = smem_u32(sV + vs * kTile);
+        const uint64_t pd = desc_advance(pd0, (j & 1) * ((2 * kTile) >> 4));
+        const uint64_t vd = desc_advance(vd0, vs * (kTile >> 4));
 #pragma unroll
         for (int k = 0; k < BKV / 16; ++k) {
           const int hf = k >> 2;                                     // which half of the keys / which accumulator
           const uint32_t acc = tmem_base + kOBase + (q * 2 + hf) * ostride;
-          const uint64_t da = make_smem_desc_sw128(pa + hf * kTile + (k & 3) * 32, 16, 1024);
-          const uint64_t db = make_smem_desc_sw128(va + k * 2048, kTile, 1024);
+          const uint64_t da = desc_advance(pd, (hf * kTile + (k & 3) * 32) >> 4);
+          const uint64_t db = desc_advance(vd, (k * 2048) >> 4);
           const uint32_t accum = (j | (k & 3)) ? 1u : 0u;
-          umma_f16_ss(acc, da, db, idesc_o, accum);
-          umma_f16_ss(acc + opad, da, od, idesc_l, accum);
+          mma(acc, da, db, idesc_o, accum);
+          mma(acc + opad, da, od, idesc_l, accum);
         }
-        tc_commit(&v_empty[vs]);
-        tc_commit(&o_done[slot]);
+        commit(&v_empty[vs]);
+        commit(&o_done[slot]);
       };
-      mbar_wait(q_full, 0);
+      wait(q_full, 0);
       tc_fence_after();
       issue_s(0);
       for (int j = 0; j < T; ++j) {
         if (j + 1 < T) {
-          mbar_wait(&s_free[q], (uint32_t)(j & 1));
+          wait(&s_free[q], (uint32_t)(j & 1));
           tc_fence_after();
           issue_s(j + 1);
         }
@@ -1022,17 +1040,17 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   }
 }
 
-template <int POLY>
+template <int POLY, int CI = 0>
 static int launch_attn_split(const CUtensorMap& tq, const KVMaps& kvm, const AttnParams& p, cudaStream_t stream) {
   UV_REQUIRE(p.d <= 48, "attention (split rows): head dim <= 48");
   const size_t smem = 227 * 1024;   // 14 tiles of 16 KiB + ones + barriers: 704 B of slack for the 1 KiB alignment
   static bool configured = false;
   if (!configured) {
-    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_split_kernel<POLY, CI>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   dim3 grid((p.N + 255) / 256, p.H, p.NI);
-  attention_tc_split_kernel<POLY><<<grid, 608, smem, stream>>>(tq, kvm, p);
+  attention_tc_split_kernel<POLY, CI><<<grid, 608, smem, stream>>>(tq, kvm, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
@@ -1070,7 +1088,7 @@ using namespace uv;
 static int g_variant = -1, g_dedupe = -1, g_stagger = -2;
 
 extern "C" int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger) {
-  g_variant = (variant < 0 || variant > 18) ? -1 : variant;   // -1: back to the environment / built-in default
+  g_variant = (variant < 0 || variant > 19) ? -1 : variant;   // -1: back to the environment / built-in default
   g_dedupe = dedupe < 0 ? -1 : (dedupe != 0);
   g_stagger = stagger < 0 ? -2 : stagger;
   return UNIVST_OK;
@@ -1103,9 +1121,10 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
   p.bankFl = bankFl;
 
   // tile configuration: d <= 64 -> variant from univst_attention_tune / UNIVST_ATTN_VARIANT (see the switches below).
-  // Default 17: d <= 48 -> split rows (two softmax threads per query row, 16 softmax warps) with the row sums on the
-  // tensor pipe, packed FFMA2 score scaling and every exp2 on the MUFU pipe; 48 < d <= 64 -> the same without the row
-  // split (variant 16).  Measured per 64x64 layer, same run: 4.50 ms (17), 4.59 (16), 4.61 (13 = 17 without FFMA2),
+  // Default 19: d <= 48 -> split rows (two softmax threads per query row, 16 softmax warps) with the row sums on the
+  // tensor pipe, packed FFMA2 score scaling, every exp2 on the MUFU pipe and convergent (elected-lane) MMA issue;
+  // 48 < d <= 64 -> the same without the row split (variant 16).  Measured per 64x64 layer, same run: 4.36 ms (19),
+  // 4.41 (17 = 19 with single-lane MMA issue), 4.59 (16), 4.61 (13 = 17 without FFMA2),
   // 4.70 (9 = 16 without FFMA2), 4.77 (0: row sums as FADDs), 5.27 (1: a quarter of the exp2 as polynomials -- the
   // extra FMA / ALU instructions cost more issue slots than the MUFU relief returns).  The kernel is bound by issue
   // slots around the MUFU work, so every instruction removed from the softmax loop shows.
@@ -1114,7 +1133,7 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
   if (variant < 0) {
     const char* e = getenv("UNIVST_ATTN_VARIANT");
     variant = e ? atoi(e) : kDefaultVariant;
-    if (variant < 0 || variant > 18) variant = kDefaultVariant;
+    if (variant < 0 || variant > 19) variant = kDefaultVariant;
   }
   int& dedupe = g_dedupe;
   if (dedupe < 0) {
@@ -1160,6 +1179,7 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
     switch (variant) {
       case 13: return launch_attn_split<0>(tq, kvm, p, st);
       case 17: return launch_attn_split<6>(tq, kvm, p, st);   // + packed FFMA2 score scaling
+      case 19: return launch_attn_split<6, 1>(tq, kvm, p, st);   // + convergent (whole-warp, elected-lane) MMA issue
       case 14: return launch_attn_split<4>(tq, kvm, p, st);   // + 1/8 of the exp2 as polynomials
       default: return launch_attn_split<1>(tq, kvm, p, st);   // + 1/4
     }
