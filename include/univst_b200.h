@@ -101,6 +101,15 @@ int univst_sc_attention_sharded_f16(const void* Q, int32_t ldq, const void* K, c
  * stagger of the softmax groups.  Negative values restore the defaults (environment UNIVST_ATTN_*). */
 int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger);
 
+/* Cross-attention over a short context (<= 80 tokens: the 77 CLIP tokens), one K/V "image" per branch named by
+ * kv_src[NI].  Same math as univst_sc_attention_f16 with one source; a dedicated kernel because the context fits in a
+ * few KB of shared memory (diffusers Attention / AttnProcessor2_0 at models/attention.py:316-323).
+ * univst_cross_attention_supported(d, Nkv) tells whether the shape is covered (otherwise use univst_sc_attention_f16). */
+int univst_cross_attention_supported(int32_t d, int32_t Nkv);
+int univst_cross_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
+                               int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const int32_t* kv_src, void* O,
+                               int32_t ldo, void* stream);
+
 /* Temporal self-attention of the AnimateDiff motion modules: for every (branch, pixel, head) softmax over the F
  * frames.  QKV is the fused projection output [B F N, ld] (rows ordered branch, frame, pixel; Q at column 0, K at H d,
  * V at 2 H d), O [B F N, ldo].  Replaces VersatileAttention.forward, backbones/animatediff/models/motion_module.py:

@@ -222,6 +222,21 @@ def test_cross_attention_77_tokens(cuda_lib, H, d, N):
     _close(out, ref, 2e-3, 5e-3, f"cross attention H{H} d{d} N{N}")
 
 
+@pytest.mark.parametrize("H,d,N,Nkv,NIkv", [(8, 40, 256, 77, 3), (8, 160, 64, 77, 3), (5, 64, 200, 77, 2), (8, 80, 1024, 77, 3),
+                                             (4, 16, 72, 33, 1), (2, 8, 128, 80, 2), (2, 40, 130, 1, 1)])
+def test_cross_attention_kernel(cuda_lib, H, d, N, Nkv, NIkv):
+    """The dedicated short-context kernel (mma.sync fragments, K/V of a branch in shared memory) vs fp32 SDPA."""
+    from univst_b200 import ops
+    NI, C = 6, H * d
+    q, kv = _rand(NI * N, C, seed=1), _rand(NIkv * Nkv, 2 * C, seed=2)
+    k, v = kv[:, :C], kv[:, C:]
+    src = (torch.arange(NI, dtype=torch.int32) % NIkv).view(NI, 1).cuda()
+    out = ops.cross_attention(q, k, v, src, NI=NI, NIkv=NIkv, H=H, d=d, N=N, Nkv=Nkv)
+    ref = _attn_ref(q, k.contiguous(), v.contiguous(), src, NI, H, d, N, Nkv)
+    assert torch.isfinite(out).all()
+    _close(out, ref, 2e-3, 5e-3, f"cross_attention H{H} d{d} N{N} Nkv{Nkv}")
+
+
 # ------------------------------------------------------------------------------------------------ norms
 @pytest.mark.parametrize("NB,rows,C1,C2,silu", [(3, 1024, 320, 0, True), (3, 256, 1280, 640, True), (12, 64, 64, 0, False),
                                                 (2, 4096, 320, 0, False), (3, 100, 128, 64, True)])

@@ -57,7 +57,7 @@ print(f"UNet 3x{F}x64x64 forward: {ms:.2f} ms  ({(ops.launch_count - n0) // iter
 
 if "--shapes" in sys.argv:
     import collections
-    ops.profile_start({"gemm", "conv3x3", "sc_attention", "temporal_attention"})
+    ops.profile_start({"gemm", "conv3x3", "sc_attention", "temporal_attention", "cross_attention"})
     unet(x, 981, encoder_hidden_states=ctx)
     prof = ops.profile_stop()
     for name, recs in prof.items():
@@ -67,7 +67,7 @@ if "--shapes" in sys.argv:
             agg[meta][1] += ms_
         print(f"== {name}: {sum(v[1] for v in agg.values()):.2f} ms")
         for meta, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:30]:
-            if name == "sc_attention":
+            if name in ("sc_attention", "cross_attention"):
                 fl = 4.0 * meta[3] * meta[4] * meta[1] * meta[2] * meta[0]
             elif name == "temporal_attention":   # (B, F, N, H, d): report GB/s of Q/K/V + output traffic instead
                 fl = 4.0 * meta[0] * meta[1] * meta[2] * meta[3] * meta[4] * 2 * 1e3

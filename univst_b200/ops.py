@@ -17,6 +17,8 @@ from ._lib import Epilogue, check
 _vp, _i32, _f32, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 _lib.register("univst_sc_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp])
 _lib.register("univst_attention_tune", [_i32, _i32, _i32])
+_lib.register("univst_cross_attention_supported", [_i32, _i32])
+_lib.register("univst_cross_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp])
 _lib.register("univst_sc_attention_sharded_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp])
 _lib.register("univst_temporal_attention_f16", [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp])
 _lib.register("univst_attn_shift_workspace_bytes", [_i32, _i32], _i64)
@@ -45,7 +47,7 @@ _lib.register("univst_mask_select_u8", [_vp, _vp, _vp, _i64, _vp, _vp])
 launch_count = 0
 _LAUNCHES = {
     "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 3, "layernorm": 1, "upsample2x": 1,
-    "temporal_attention": 1, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
+    "temporal_attention": 1, "cross_attention": 1, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
 
@@ -181,6 +183,24 @@ def sc_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: torc
                                                  NIkv, H, d, N, Nkv, kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(),
                                                  out.stride(0), _stream()), "univst_sc_attention_f16")
     _count("sc_attention")
+    return out
+
+
+def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: torch.Tensor, *, NI: int, NIkv: int, H: int,
+                    d: int, N: int, Nkv: int, out: Optional[torch.Tensor] = None):
+    """attn2: every query image attends to the short context of its branch (``kv_src``: int32 [NI] or [NI, 1])."""
+    _lib.require_device()
+    if not _lib.lib().univst_cross_attention_supported(d, Nkv):   # long contexts / odd head dims: the general kernel
+        return sc_attention(q, k, v, kv_src.view(NI, 1), NI=NI, NIkv=NIkv, H=H, d=d, N=N, Nkv=Nkv, out=out)
+    assert q.stride(1) == 1 and k.stride(1) == 1 and v.stride(1) == 1 and k.stride(0) == v.stride(0)
+    assert kv_src.dtype == torch.int32 and kv_src.is_cuda and kv_src.is_contiguous() and kv_src.numel() == NI
+    if out is None:
+        out = torch.empty((NI * N, H * d), dtype=torch.float16, device=q.device)
+    with _Timed("cross_attention", (NI, H, d, N, Nkv)):
+        check(_lib.lib().univst_cross_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), NI,
+                                                    NIkv, H, d, N, Nkv, kv_src.data_ptr(), out.data_ptr(), out.stride(0),
+                                                    _stream()), "univst_cross_attention_f16")
+    _count("cross_attention")
     return out
 
 

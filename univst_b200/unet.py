@@ -391,8 +391,8 @@ class UNetPseudo3DConditionModel:
         n2 = ops.layernorm(y, W[b + "norm2.weight"], W[b + "norm2.bias"])
         q2 = ops.gemm(n2, W[b + "attn2.to_q.weight"])
         kv2, L = ctx_kv_of(b)
-        o2 = ops.sc_attention(q2, kv2[:, :C], kv2[:, C:], self._table(B, F, "branch"), NI=NI, NIkv=B, H=heads, d=d, N=N,
-                              Nkv=L)
+        o2 = ops.cross_attention(q2, kv2[:, :C], kv2[:, C:], self._table(B, F, "branch"), NI=NI, NIkv=B, H=heads, d=d, N=N,
+                                 Nkv=L)
         y = ops.gemm(o2, W[b + "attn2.to_out.0.weight"], bias=W[b + "attn2.to_out.0.bias"], residual=y)
         # 3. GEGLU feed-forward; the dead temporal attention (attention.py:331-346) is its bias, added in the epilogue
         n3 = ops.layernorm(y, W[b + "norm3.weight"], W[b + "norm3.bias"])
