@@ -319,7 +319,7 @@ def run_ours(args):
         # 4 d = 160 useful FLOP per exponential at head dim 40
         mufu_bound = 16 * 148 * clk * 1e6 * 4 * d / 1e12
         roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                "traffic": traffic, "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": ach / mufu_bound, "kernel": "attention_tc_split_kernel<6> (2 query tiles x 128 keys, two softmax threads per row; N=4096, Nkv=8192, H=8, d=40, 48 images)",
+                "traffic": traffic, "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": ach / mufu_bound, "kernel": "attention_tc_split_kernel<6,1> (2 query tiles x 128 keys, two softmax threads per row; N=4096, Nkv=8192, H=8, d=40, 48 images)",
                 "launches_timed": len(dom), "avg_ms": avg_ms, "peak_source": pk["src"] + " (sustained bf16 dense)"}
     attn_ms = sum(m_ for m_, _ in prof["sc_attention"]) / args.steps
     line = {

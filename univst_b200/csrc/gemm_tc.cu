@@ -34,6 +34,7 @@ struct GemmParams {
   int plane_stride;     // conv: images per parity plane (stride-2 input was rearranged into 4 planes)
   int8_t tap_dy[9], tap_dx[9], tap_plane[9];
   int stages;
+  int cluster;          // 2: CTA pairs share every weight tile (each loads half of it and multicasts), 1: independent CTAs
   // epilogue
   const __half* bias;
   const __half* rowvec;
@@ -274,6 +275,11 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
 // of one A row-block run at the same time on neighbouring CTAs and share A through L2).  Two TMEM accumulators
 // alternate between consecutive tiles: the epilogue warps drain tile i while the MMA warp already accumulates
 // tile i + 1, and the TMA producer runs ahead across tile boundaries.
+// CL = 2 (thread-block clusters of two): the pair works on two consecutive 128-row blocks of the SAME weight tile.  Each
+// CTA fetches half of every B k-block and multicasts it into both shared memories, so the weight traffic out of L2 --
+// the larger half of what these kernels pull through L2, which is what bounds the 128 x 160 / 224 tiles -- is halved.
+// A stage may be refilled only when both CTAs' MMAs have consumed it: the commit that frees a stage is multicast too.
+template <int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -293,7 +299,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
   const int tiles_n = (p.N + p.BN - 1) / p.BN;
-  const int num_tiles = ((p.M + kBM - 1) / kBM) * tiles_n;
+  const int tiles_m = (p.M + kBM - 1) / kBM;
+  // work items: CL = 1: tiles (m, n), n fastest, one per CTA; CL = 2: pairs of row blocks (2 mm, 2 mm + 1) x n per cluster
+  const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
+  const int num_tiles = (CL == 2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
+  const int tile_first = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int tile_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto tile_m0 = [&](int tile) { return ((tile / tiles_n) * CL + (int)crank) * kBM; };   // may be >= M for the odd tail
 
   // accumulator stride: BN rounded up to a power of two >= 32 (TMEM allocations are powers of two)
   uint32_t acc_cols = 32;
@@ -306,7 +318,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], CL);   // one commit per CTA of the cluster
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full_bar[a], 1);
@@ -320,6 +332,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();   // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -328,8 +341,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ------------------------------------------------ TMA producer
       uint32_t phase = 0;
       int s = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * kBM;
+      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+        const int m0 = tile_m0(tile);
         const int n0 = (tile % tiles_n) * p.BN;
         int cn = 0, cy = 0;
         if (p.mode == 1) {
@@ -360,7 +373,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               tma_load_4d(sa, &tmA2, &full_bar[s], (cb - p.kb_split) * kBK, x, y, n);
             }
           }
-          tma_load_2d(sb, &tmB, &full_bar[s], kw, n0);
+          if constexpr (CL == 2) {   // my half of the weight k-block, delivered to both CTAs
+            const int half = p.BN >> 1;
+            tma_load_2d_mcast(sb + (size_t)crank * half * (kBK * 2), &tmB, &full_bar[s], kw, n0 + (int)crank * half, 0x3);
+          } else {
+            tma_load_2d(sb, &tmB, &full_bar[s], kw, n0);
+          }
           if (++s == p.stages) {
             s = 0;
             phase ^= 1;
@@ -379,7 +397,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int s = 0;
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int a = it & 1;
       // wait until the epilogue has drained this accumulator (its (it / 2)-th use)
       mbar_wait_warp(&tmem_empty_bar[a], (uint32_t)(((it >> 1) & 1) ^ 1));
@@ -396,7 +414,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           // advance 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
           umma_f16_ss_elect(acc, desc_advance(da, k * 2), desc_advance(db, k * 2), idesc, (kb | k) ? 1u : 0u);
         }
-        tc_commit_elect(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        if constexpr (CL == 2) {
+          if (elect_one()) tc_commit_mcast(&empty_bar[s], 0x3);   // the stage is free when BOTH CTAs' MMAs have retired
+        } else {
+          tc_commit_elect(&empty_bar[s]);  // frees the smem stage once these MMAs retire
+        }
         if (++s == p.stages) {
           s = 0;
           phase ^= 1;
@@ -409,10 +431,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t q = warp & 3;
     const int chunk0 = (int)((warp - 2) >> 2);  // which half of the 32-column chunks this warp drains
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
       const int a = it & 1;
       const int tile_n = tile % tiles_n;
-      const int m0 = (tile / tiles_n) * kBM;
+      const int m0 = tile_m0(tile);
       const int n0 = tile_n * p.BN;
       const int row = m0 + (int)(q * 32 + lane);
       const uint32_t taddr = tmem_base + a * acc_cols + ((q * 32) << 16);
@@ -434,6 +456,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (CL == 2) cluster_sync_all();   // no CTA leaves while its peer may still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -477,6 +500,16 @@ static int pick_bn(int N, int geglu) {
   return best;
 }
 
+// CTA pairs with multicast weight tiles (UNIVST_GEMM_CLUSTER=1): at least two row blocks, tile width a multiple of 16
+static int pick_cluster(int M, int BN) {
+  static int enabled = -1;
+  if (enabled < 0) {
+    const char* e = getenv("UNIVST_GEMM_CLUSTER");
+    enabled = e ? atoi(e) : 0;
+  }
+  return (enabled && M > kBM && BN % 16 == 0) ? 2 : 1;
+}
+
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, GemmParams& p,
                   cudaStream_t stream) {
   const uint32_t stage_bytes = kBM * kBK * 2 + (uint32_t)p.BN * kBK * 2;
@@ -490,12 +523,32 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
                       16 + 1024;
   static size_t configured = 0;
   if (smem > configured) {
-    UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
-  const int num_tiles = ((p.M + kBM - 1) / kBM) * ((p.N + p.BN - 1) / p.BN);
+  const int tiles_m = (p.M + kBM - 1) / kBM, tiles_n = (p.N + p.BN - 1) / p.BN;
+  if (p.cluster == 2) {
+    const int pairs = ((tiles_m + 1) / 2) * tiles_n;
+    const int max_pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (pairs < max_pairs ? pairs : max_pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    UV_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gemm_tc_kernel<2>, tmA, tmA2, tmB, p));
+    return UNIVST_OK;
+  }
+  const int num_tiles = tiles_m * tiles_n;
   const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
-  gemm_tc_kernel<<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
+  gemm_tc_kernel<1><<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
@@ -565,9 +618,10 @@ extern "C" int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32
     tmA2 = tmA;
   }
   {
+    p.cluster = pick_cluster(M, p.BN);
     uint64_t dims[2] = {(uint64_t)K, (uint64_t)N};
     uint64_t str[1] = {(uint64_t)K * 2};
-    uint32_t box[2] = {kBK, (uint32_t)p.BN};
+    uint32_t box[2] = {kBK, (uint32_t)(p.BN / p.cluster)};   // cluster: each CTA fetches half of the tile's rows
     int r = make_tmap_f16(&tmB, W, 2, dims, str, box, true);
     if (r) return r;
   }
@@ -644,9 +698,10 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
     tmA2 = tmA;
   }
   {
+    p.cluster = pick_cluster(p.M, p.BN);
     uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
     uint64_t str[1] = {(uint64_t)9 * Cin * 2};
-    uint32_t box[2] = {kBK, (uint32_t)p.BN};
+    uint32_t box[2] = {kBK, (uint32_t)(p.BN / p.cluster)};
     int r = make_tmap_f16(&tmB, Wt, 2, dims, str, box, true);
     if (r) return r;
   }
