@@ -262,6 +262,26 @@ def run_ours(args):
         unet.set_frame_sharding_off()
         fs_rel = float((out_fs.float() - ref0.float()).norm() / ref0.float().norm())
 
+    # ---- extra (N = 1, not the headline): 50-step DDIM content inversion of the clip (the stage that produces the
+    # trajectories the loop consumes: stock sparse-causal attention in all 16 layers, one branch; inversion_tools/
+    # ddim_inversion.py:88-113) through the mirror of the reference API, latents kept in memory
+    ms_inv = 0.0
+    if world == 1 and not args.no_animatediff:
+        from univst_b200 import ddim_inversion as di
+        for tr in unet._all_transformers():   # inversion runs the UNPATCHED model (run_content_inversion_sd.py)
+            tr.transformer_blocks[0].attn1.__dict__.pop("_patched", None)
+        pipe.scheduler.set_timesteps(STEPS_DDIM)
+        z0 = resident["traj_c"][0]
+        di.ddim_inversion(pipe, pipe.scheduler, z0, 2, "", None, prompt_embeds=resident["ctx"])   # warm-up
+        barrier()
+        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        i0.record()
+        inv = di.ddim_inversion(pipe, pipe.scheduler, z0, STEPS_DDIM, "", None, prompt_embeds=resident["ctx"])
+        i1.record()
+        barrier()
+        ms_inv = i0.elapsed_time(i1) if bool(torch.isfinite(inv[-1]).all()) else -1.0
+        pnp_utils.register_spatial_attention_pnp(pipe)
+
     # ---- extra (N = 1, not the headline): the same clip through the AnimateDiff-v2 backbone (BASELINE.json configs[3]
     # architecture: per-frame self-attention + 21 motion modules), AnimationPipeline loop, one timed pass
     ms_ad = 0.0
@@ -340,6 +360,10 @@ def run_ours(args):
         line["config"]["one_clip_frame_sharded"] = {"frames_per_s": F_FRAMES / (ms_fs / 1e3), "scaling": "strong",
                                                     "ms_per_clip": ms_fs, "rel_l2_vs_single_gpu": fs_rel,
                                                     "collectives": "K/V halo send/recv + frame-0 broadcast per attn1, GroupNorm stat all-reduce, eps all-gather (NCCL)"}
+    if ms_inv != 0.0:
+        line["config"]["ddim_inversion_50_steps"] = {"frames_per_s": F_FRAMES / (ms_inv / 1e3) if ms_inv > 0 else None,
+                                                     "ms_per_clip": ms_inv, "note": "content inversion of the same clip, "
+                                                     "stock [prev, self, first] attention in all layers, supplementary"}
     if ms_ad != 0.0:
         line["config"]["animatediff_v2_backbone"] = {"frames_per_s": F_FRAMES / (ms_ad / 1e3) if ms_ad > 0 else None,
                                                      "ms_per_clip": ms_ad, "note": "same clip and loop, AnimateDiff-v2 UNet "
