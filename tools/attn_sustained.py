@@ -16,7 +16,7 @@ from univst_b200 import ops
 from univst_b200.unet import kv_source_table
 
 secs = float(sys.argv[1]) if len(sys.argv) > 1 else 8.0
-variants = [int(a) for a in sys.argv[2:]] or [1, 0, 9, 12]
+variants = [int(a) for a in sys.argv[2:]] or [0, 9, 16, 19]
 B, F, H, d, N = 3, 16, 8, 40, 4096
 C, NI = H * d, B * F
 torch.manual_seed(0)

@@ -1,7 +1,7 @@
 """A/B of the fused attention variants at the headline shape: each variant is checked against an fp32 torch softmax
 on a slice (so a wrong variant cannot win) and timed back to back with CUDA events.
 
-    python tools/attn_variants.py [variants ...]      # e.g. 1 7 8 9
+    python tools/attn_variants.py [variants ...]      # e.g. 0 9 16 17 19 (see the switch in attention_tc.cu)
 """
 import os
 import sys
@@ -12,7 +12,7 @@ import torch
 from univst_b200 import ops
 from univst_b200.unet import kv_source_table
 
-variants = [int(a) for a in sys.argv[1:]] or [1, 7, 8, 9]
+variants = [int(a) for a in sys.argv[1:]] or [0, 9, 16, 17, 19]
 B, F, H, d, N = 3, 16, 8, 40, 4096
 C = H * d
 NI = B * F

@@ -12,7 +12,7 @@ from univst_b200.pipeline import SpatioTemporalStableDiffusionPipeline
 from univst_b200.unet import SD15_CONFIG, UNetPseudo3DConditionModel
 from univst_b200.weights import random_state_dict
 
-variants = [int(a) for a in sys.argv[1:]] or [1, 0, 9]
+variants = [int(a) for a in sys.argv[1:]] or [9, 16, 19]
 dev = torch.device("cuda", 0)
 unet = UNetPseudo3DConditionModel(random_state_dict(SD15_CONFIG, seed=33, device=dev), SD15_CONFIG, device=dev)
 pipe = SpatioTemporalStableDiffusionPipeline(unet)

@@ -602,10 +602,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
 #pragma unroll
         for (int x = 0; x < 32; ++x) {
-          // POLY = 1: every 4th exponential off the MUFU pipe; POLY = 2: every 2nd; 3: all (experiments: 9 = none at all)
-          const bool poly = POLY == 3 || (POLY == 2 && (x & 1)) || (POLY == 1 && (x & 3) == 3) ||
-                            (POLY == 4 && (x & 7) == 7) || (POLY == 5 && ((x & 7) == 2 || (x & 7) == 5 || (x & 7) == 7));
-          e[x] = POLY == 9 ? e[x] : (poly ? ex2_poly(e[x]) : ex2_approx(e[x]));
+          // POLY = 1: every 4th exponential off the MUFU pipe; 4: every 8th; 0 / 6: none (6 = packed FFMA2 score scaling)
+          const bool poly = (POLY == 1 && (x & 3) == 3) || (POLY == 4 && (x & 7) == 7);
+          e[x] = poly ? ex2_poly(e[x]) : ex2_approx(e[x]);
         }
         if constexpr (RS == 2) {
           uint32_t w[16];
@@ -1142,7 +1141,7 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
   }
   UV_REQUIRE(nsrc <= kMaxSrc, "sc_attention: at most %d K/V sources per image", kMaxSrc);
   p.dedupe = dedupe;
-  const int bkv = (d <= 64 && (variant < 2 || variant >= 4)) ? 128 : 64;   // must match the launch_attn<> picked below
+  const int bkv = d <= 64 ? 128 : 64;   // must match the launch_attn<> picked below
   int& stagger = g_stagger;
   if (stagger == -2) {
     const char* e = getenv("UNIVST_ATTN_STAGGER");
@@ -1188,16 +1187,10 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
     switch (variant) {
       case 0: return launch_attn<2, 128, 0>(tq, kvm, p, st);
       case 1: return launch_attn<2, 128, 1>(tq, kvm, p, st);
-      case 2: return launch_attn<2, 64, 0>(tq, kvm, p, st);
-      case 3: return launch_attn<2, 64, 1>(tq, kvm, p, st);
-      case 4: return launch_attn<2, 128, 2>(tq, kvm, p, st);
-      case 5: return launch_attn<2, 128, 3>(tq, kvm, p, st);   // experiment: all exponentials as polynomials
-      case 6: return launch_attn<2, 128, 9>(tq, kvm, p, st);   // experiment: no exponentials (wrong results)
-      case 7: return launch_attn<2, 128, 1, 1>(tq, kvm, p, st);   // row sums on the tensor pipe
-      case 8: return launch_attn<2, 128, 2, 1>(tq, kvm, p, st);   // + half of the exp2 polynomial
+      // (2 - 6, 8, 11: retired experiments -- 64-key tiles for small head dims, 1/2, 3/8 and all-polynomial exp2; all slower)
+      case 7: return launch_attn<2, 128, 1, 1>(tq, kvm, p, st);   // row sums on the tensor pipe + 1/4 polynomial
       case 9: return launch_attn<2, 128, 0, 1>(tq, kvm, p, st);   // row sums on the tensor pipe, all exp2 on MUFU
       case 10: return launch_attn<2, 128, 4, 1>(tq, kvm, p, st);  // row sums on the tensor pipe, 1/8 polynomial
-      case 11: return launch_attn<2, 128, 5, 1>(tq, kvm, p, st);  // row sums on the tensor pipe, 3/8 polynomial
       case 12: return launch_attn<2, 128, 4, 0>(tq, kvm, p, st);  // 1/8 polynomial
       default: return launch_attn<2, 128, 0, 1>(tq, kvm, p, st);  // (13+ with 48 < d <= 64: no split-row kernel)
     }
