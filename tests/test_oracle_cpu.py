@@ -221,3 +221,27 @@ def test_sliding_window_is_gauss_seidel_and_truncates():
     keep[:, :4] = 1
     out2 = fo.sliding_window_smooth(frames, lambda k, n: (zero, zero), keep_mask=keep)
     assert (out2[:, :4] == frames[:, :4]).all() and (out2[:, 4:] == out[:, 4:]).all()
+
+
+# ------------------------------------------------------------------------------------------------ SD3 processors
+def test_sd3_processor_oracle_matches_reference():
+    """oracle/sd3_oracle.py vs the outputs of the reference's own CrossFrameProcessor / AttentionShiftProcessor."""
+    from oracle import sd3_oracle as so
+    g = torch.load(os.path.join(GOLDEN, "sd3_processors.pt"), weights_only=True)
+    heads = g["heads"]
+    w = so.seeded_attn_weights(heads * 64, heads, g["seed"])
+    hidden, enc = so.synthetic_inputs(g["input_seed"], g["N"], g["L"], heads * 64)
+    with torch.no_grad():
+        h, e = so.joint_attention(w, hidden[:16], enc[:16], heads)
+        assert torch.allclose(h, g["cases"]["cross_frame"][0], atol=1e-5) and torch.allclose(e, g["cases"]["cross_frame"][1], atol=1e-5)
+        outs = {}
+        for idx in (0, 15, 30, 31):
+            h, e = so.joint_attention(w, hidden, enc, heads, idx=idx)
+            rh, re = g["cases"][f"shift_idx{idx}"]
+            assert torch.allclose(h[g["keep"]], rh, atol=1e-5) and torch.allclose(e[g["keep"]], re, atol=1e-5), idx
+            outs[idx] = h
+        a = g["adain"]
+        assert torch.allclose(so.attention_adain(a["cnt"], a["sty"]), a["out"], atol=1e-6)
+    # the window is closed interval [0, 30]: idx 30 still shifts, 31 does not; only the edit branch ever changes
+    assert so.shift_params(30)[0] and not so.shift_params(31)[0]
+    assert torch.equal(outs[0][:32], outs[31][:32]) and not torch.allclose(outs[30][32:], outs[31][32:], atol=1e-3)
