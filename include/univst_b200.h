@@ -96,6 +96,26 @@ int univst_sc_attention_sharded_f16(const void* Q, int32_t ldq, const void* K, c
                                     int32_t H, int32_t d, int32_t N, const int32_t* kv_src, int32_t nsrc, void* O,
                                     int32_t ldo, const void* K_prev, const void* V_prev, const void* K_first,
                                     const void* V_first, int32_t B, int32_t Fl, void* stream);
+/* Joint attention of the SD3 / SD3.5 MMDiT processors (backbones/video_diffusion_sd3/pnp_utils.py:9-132, :135-271): the
+ * key / value sequence of an image is [K/V of source frames in the first tensor | the text tokens of a second tensor with
+ * its own token count] -- source indices >= NIkv name image (src - NIkv) of (K2, V2).  Called once with the image tokens
+ * as queries and once with the text tokens (the reference concatenates them into one query sequence, :100). */
+int univst_joint_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
+                               int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const void* K2, const void* V2,
+                               int32_t ldkv2, int32_t NIkv2, int32_t Nkv2, const int32_t* kv_src, int32_t nsrc, void* O,
+                               int32_t ldo, void* stream);
+/* Per-head RMS norm of the Q and K column blocks of a fused [rows, ld] = [Q | K | V] buffer, in place (attn.norm_q /
+ * norm_k / norm_added_q / norm_added_k, sd3/pnp_utils.py:46-49, :92-95; diffusers RMSNorm semantics).  wq / wk: fp16 [d]
+ * or NULL to skip that block. */
+int univst_rmsnorm_heads_f16(void* QKV, int32_t ld, int32_t rows, int32_t H, int32_t d, const void* wq, const void* wk,
+                             float eps, void* stream);
+/* AdaIN-guided shift of the edit branch in the SD3 layout (sd3/pnp_utils.py:180-193 + attention_adain :287-300), in
+ * place on the fused [3 F N, ld] buffer: style statistics per (frame, head, channel) over the tokens, content instance
+ * norm over (tokens, head_dim) per (frame, head). */
+int64_t univst_sd3_shift_workspace_bytes(int32_t F, int32_t C, int32_t d);
+int univst_sd3_attn_shift_f16(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t H, int32_t d, float alpha, float beta,
+                              float gamma, void* workspace, void* stream);
+
 /* Tuning hook (no reference counterpart): tile / exp2 variant of the head-dim <= 64 kernel, collapsing of repeated
  * K/V sources (exact: a source that occurs c times is streamed once with log2 c added to its scores) and the start
  * stagger of the softmax groups.  Negative values restore the defaults (environment UNIVST_ATTN_*). */

@@ -1,0 +1,87 @@
+"""GPU parity of the SD3 joint-attention processors (through the C ABI) against goldens produced by the reference's own
+``CrossFrameProcessor`` / ``AttentionShiftProcessor`` (oracle/gen_golden_sd3.py), plus the two new elementwise kernels
+against the oracle.  Tolerance: fp16 path vs fp32 golden, rel-L2 <= 5e-3."""
+import os
+
+import pytest
+import torch
+
+from oracle import sd3_oracle as so
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _rel(a, b):
+    a, b = a.float().cpu(), b.float().cpu()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def _attn_module(w, heads):
+    C = w["to_q.weight"].shape[0]
+    attn = torch.nn.Module()
+    for n in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_add_out"):
+        setattr(attn, n, torch.nn.Linear(C, C))
+    attn.to_out = torch.nn.ModuleList([torch.nn.Linear(C, C), torch.nn.Dropout(0.0)])
+
+    class _Norm(torch.nn.Module):
+        def __init__(self, dim):
+            super().__init__()
+            self.weight, self.eps = torch.nn.Parameter(torch.ones(dim)), 1e-6
+    for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+        setattr(attn, n, _Norm(C // heads))
+    attn.heads, attn.context_pre_only = heads, False
+    attn.load_state_dict(w)
+    return attn
+
+
+def test_rmsnorm_heads_kernel(cuda_lib):
+    from univst_b200 import ops
+    torch.manual_seed(0)
+    rows, H, d = 333, 3, 64
+    qkv = torch.randn(rows, 3 * H * d, device="cuda").half()
+    wq, wk = (1 + 0.2 * torch.randn(d, device="cuda")).half(), (1 + 0.2 * torch.randn(d, device="cuda")).half()
+    ref = qkv.float().clone()
+    ref[:, :H * d] = so.rms_norm(ref[:, :H * d].view(rows, H, d), wq.float()).view(rows, -1)
+    ref[:, H * d:2 * H * d] = so.rms_norm(ref[:, H * d:2 * H * d].view(rows, H, d), wk.float()).view(rows, -1)
+    ops.rmsnorm_heads_(qkv, H, d, wq, wk)
+    assert _rel(qkv, ref) < 1e-3 and torch.equal(qkv[:, 2 * H * d:].float(), ref[:, 2 * H * d:])
+
+
+def test_sd3_attn_shift_kernel(cuda_lib):
+    from univst_b200 import ops
+    torch.manual_seed(1)
+    Fr, N, H, d = 4, 96, 2, 64
+    C = H * d
+    qkv = (torch.randn(3 * Fr * N, 3 * C, device="cuda") * 1.2 + 0.1).half()
+    x = qkv.float().cpu().view(3, Fr, N, 3, H, d).permute(3, 0, 1, 4, 2, 5)     # (qkv, branch, F, H, N, d)
+    q, k, v = x[0].clone(), x[1].clone(), x[2].clone()
+    alpha, beta, gamma = 0.8, 0.42, 2.0
+    q[2] = gamma * (alpha * q[0] + (1 - alpha) * q[2])
+    k[2] = beta * so.attention_adain(k[2], k[1]) + (1 - beta) * k[1]
+    v[2] = beta * so.attention_adain(v[2], v[1]) + (1 - beta) * v[1]
+    ref = torch.stack([q, k, v]).permute(1, 2, 4, 0, 3, 5).reshape(3 * Fr * N, 3 * C)
+    ops.sd3_attn_shift_(qkv, Fr, N, H, d, alpha, beta, gamma)
+    assert _rel(qkv, ref) < 2e-3
+    assert torch.equal(qkv[:2 * Fr * N].float().cpu(), x.permute(1, 2, 4, 0, 3, 5).reshape(3 * Fr * N, 3 * C)[:2 * Fr * N])
+
+
+@pytest.mark.parametrize("case", ["cross_frame", "shift_idx0", "shift_idx15", "shift_idx30", "shift_idx31"])
+def test_sd3_processors_match_reference(cuda_lib, case):
+    from univst_b200 import sd3
+    g = torch.load(os.path.join(GOLDEN, "sd3_processors.pt"), weights_only=True)
+    heads = g["heads"]
+    C = heads * 64
+    attn = _attn_module(so.seeded_attn_weights(C, heads, g["seed"]), heads)
+    hidden, enc = so.synthetic_inputs(g["input_seed"], g["N"], g["L"], C)
+    if case == "cross_frame":
+        h, e = sd3.CrossFrameProcessor()(attn, hidden[:16].cuda().half(), enc[:16].cuda().half())
+        rh, re = g["cases"][case]
+    else:
+        idx = int(case.split("idx")[1])
+        h, e = sd3.AttentionShiftProcessor(0.0, 0.6)(attn, hidden.cuda().half(), enc.cuda().half(), idx=idx)
+        h, e = h[g["keep"]], e[g["keep"]]
+        rh, re = g["cases"][case]
+    print(f"sd3 {case}: hidden rel={_rel(h, rh):.3e} text rel={_rel(e, re):.3e}")
+    assert torch.isfinite(h).all() and torch.isfinite(e).all()
+    assert _rel(h, rh) < 5e-3 and _rel(e, re) < 5e-3

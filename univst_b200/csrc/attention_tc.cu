@@ -48,6 +48,10 @@ struct AttnParams {
   // b * bankFl + (bank == 1 ? bankFl - 1 : 0) of bank 1 (previous rank's buffer) / bank 2 (rank 0's buffer).
   int bankB;         // images per remote bank (branches); 0 = no remote banks
   int bankFl;        // frames per branch in a peer's buffer
+  // joint attention (SD3): sources >= NIkv name image (src - NIkv) of a SECOND K/V tensor (bank 1) with its own token
+  // count -- the text tokens appended to the image keys (video_diffusion_sd3/pnp_utils.py:100-102)
+  int NIkv;          // images in the first K/V tensor
+  int Nkv2;          // tokens per image of the second tensor; 0 = no second tensor
 };
 
 // K / V tensor maps: bank 0 = this rank's buffer, 1 = the previous rank's, 2 = rank 0's (same shape and strides)
@@ -59,7 +63,12 @@ struct KVMaps {
 __device__ __forceinline__ void resolve_source(const AttnParams& p, int src, int& bank, int& image) {
   bank = 0;
   image = src;
-  if (p.bankB > 0 && src >= p.NI) {
+  if (p.Nkv2 > 0) {
+    if (src >= p.NIkv) {
+      bank = 1;
+      image = src - p.NIkv;
+    }
+  } else if (p.bankB > 0 && src >= p.NI) {
     const int r = src - p.NI;
     bank = 1 + r / p.bankB;
     image = (r - (bank - 1) * p.bankB) * p.bankFl + (bank == 1 ? p.bankFl - 1 : 0);
@@ -76,6 +85,10 @@ struct SrcList {
   int img[kMaxSrc];
   float bias[kMaxSrc];
 };
+// tokens of source i (the second K/V tensor has its own count) and its number of BKV-token tiles
+__device__ __forceinline__ int src_tokens(const AttnParams& p, int image) {
+  return (p.Nkv2 > 0 && image >= p.NIkv) ? p.Nkv2 : p.Nkv;
+}
 __device__ __forceinline__ SrcList load_sources(const AttnParams& p, int img) {
   SrcList L;
   const int* row = p.kv_src + (size_t)img * p.nsrc;
@@ -207,9 +220,10 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int qt0 = blockIdx.x * NQ;     // first 128-row query tile of this CTA
   const int head = blockIdx.y;
   const int img = blockIdx.z;
-  const int tps = (p.Nkv + BKV - 1) / BKV;   // KV tiles per source
   const SrcList SL = load_sources(p, img);
-  const int T = SL.n * tps;                  // KV tiles in total
+  auto tiles_of = [&](int si) { return (src_tokens(p, src_img(SL, si)) + BKV - 1) / BKV; };   // KV tiles of source si
+  int T = 0;                                 // KV tiles in total
+  for (int si = 0; si < SL.n; ++si) T += tiles_of(si);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -272,7 +286,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           resolve_source(p, src_img(SL, sik), bank, image);
           for (int c = 0; c < dch; ++c)
             tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &kvm.k[bank], &k_full[s], c * 64, head, jtk * BKV, image);
-          if (++jtk == tps) {
+          if (++jtk == tiles_of(sik)) {
             jtk = 0;
             ++sik;
           }
@@ -286,7 +300,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           resolve_source(p, src_img(SL, siv), bank, image);
           for (int c = 0; c < dch; ++c)
             tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &kvm.v[bank], &v_full[s], c * 64, head, jtv * BKV, image);
-          if (++jtv == tps) {
+          if (++jtv == tiles_of(siv)) {
             jtv = 0;
             ++siv;
           }
@@ -498,9 +512,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(&s_free[slot]);  // the slot may be overwritten with the next scores from here on
-      const int valid = p.Nkv - jt * BKV;   // >= BKV except on the ragged last tile of a source
+      const int valid = src_tokens(p, src_img(SL, si)) - jt * BKV;   // >= BKV except on the ragged last tile of a source
       const float tbias = bias;
-      if (++jt == tps) {
+      if (++jt == tiles_of(si)) {
         jt = 0;
         bias = src_bias(SL, ++si);
       }
@@ -722,9 +736,10 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const int qt0 = blockIdx.x * NQ;
   const int head = blockIdx.y;
   const int img = blockIdx.z;
-  const int tps = (p.Nkv + BKV - 1) / BKV;
   const SrcList SL = load_sources(p, img);
-  const int T = SL.n * tps;
+  auto tiles_of = [&](int si) { return (src_tokens(p, src_img(SL, si)) + BKV - 1) / BKV; };
+  int T = 0;
+  for (int si = 0; si < SL.n; ++si) T += tiles_of(si);
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -776,7 +791,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           int bank, image;
           resolve_source(p, src_img(SL, sik), bank, image);
           tma_load_4d(sK + s * kTile, &kvm.k[bank], &k_full[s], 0, head, jtk * BKV, image);
-          if (++jtk == tps) {
+          if (++jtk == tiles_of(sik)) {
             jtk = 0;
             ++sik;
           }
@@ -789,7 +804,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           int bank, image;
           resolve_source(p, src_img(SL, siv), bank, image);
           tma_load_4d(sV + s * kTile, &kvm.v[bank], &v_full[s], 0, head, jtv * BKV, image);
-          if (++jtv == tps) {
+          if (++jtv == tiles_of(siv)) {
             jtv = 0;
             ++siv;
           }
@@ -897,9 +912,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       tc_fence_before();
       mbar_arrive(&s_free[g]);
-      const int valid = p.Nkv - jt * BKV - hf * 64;   // valid columns of this half (>= 64 except on a ragged last tile)
+      const int valid = src_tokens(p, src_img(SL, si)) - jt * BKV - hf * 64;   // valid columns of this half
       const float tbias = bias;
-      if (++jt == tps) {
+      if (++jt == tiles_of(si)) {
         jt = 0;
         bias = src_bias(SL, ++si);
       }
@@ -1097,7 +1112,8 @@ extern "C" int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t st
 // banks 1 and 2 may be null (no remote sources).
 static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, const void* const* Vb, int32_t ldkv,
                              int32_t NI, int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const int32_t* kv_src,
-                             int32_t nsrc, void* O, int32_t ldo, int32_t bankB, int32_t bankFl, void* stream) {
+                             int32_t nsrc, void* O, int32_t ldo, int32_t bankB, int32_t bankFl, void* stream,
+                             int32_t ldkv2 = 0, int32_t NIkv2 = 0, int32_t Nkv2 = 0) {
   const void* K = Kb[0];
   const void* V = Vb[0];
   UV_REQUIRE(Q && K && V && O && kv_src, "sc_attention: null pointer");
@@ -1118,6 +1134,8 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
   p.scale_log2 = 1.4426950408889634f / sqrtf((float)d);
   p.bankB = bankB;
   p.bankFl = bankFl;
+  p.NIkv = NIkv;
+  p.Nkv2 = Nkv2;
 
   // tile configuration: d <= 64 -> variant from univst_attention_tune / UNIVST_ATTN_VARIANT (see the switches below).
   // Default 19: d <= 48 -> split rows (two softmax threads per query row, 16 softmax warps) with the row sums on the
@@ -1162,9 +1180,16 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
     uint64_t str[3] = {(uint64_t)d * 2, (uint64_t)ldkv * 2, (uint64_t)Nkv * ldkv * 2};
     uint32_t box[4] = {64, 1, (uint32_t)bkv, 1};
     for (int b = 0; b < 3; ++b) {   // absent banks alias the local buffer (never addressed: bankB = 0 or the table has no such source)
-      int r = make_tmap_f16(&kvm.k[b], Kb[b] ? Kb[b] : K, 4, dims, str, box, true);
+      uint64_t bdims[4] = {dims[0], dims[1], dims[2], dims[3]}, bstr[3] = {str[0], str[1], str[2]};
+      if (b == 1 && Nkv2 > 0) {     // the second K/V tensor of the joint attention has its own geometry
+        bdims[2] = (uint64_t)Nkv2;
+        bdims[3] = (uint64_t)NIkv2;
+        bstr[1] = (uint64_t)ldkv2 * 2;
+        bstr[2] = (uint64_t)Nkv2 * ldkv2 * 2;
+      }
+      int r = make_tmap_f16(&kvm.k[b], Kb[b] ? Kb[b] : K, 4, bdims, bstr, box, true);
       if (r) return r;
-      r = make_tmap_f16(&kvm.v[b], Vb[b] ? Vb[b] : V, 4, dims, str, box, true);
+      r = make_tmap_f16(&kvm.v[b], Vb[b] ? Vb[b] : V, 4, bdims, bstr, box, true);
       if (r) return r;
     }
   }
@@ -1218,4 +1243,15 @@ extern "C" int univst_sc_attention_sharded_f16(const void* Q, int32_t ldq, const
   const void* Kb[3] = {K, K_prev, K_first};
   const void* Vb[3] = {V, V_prev, V_first};
   return sc_attention_impl(Q, ldq, Kb, Vb, ldkv, NI, NI, H, d, N, N, kv_src, nsrc, O, ldo, B, Fl, stream);
+}
+
+extern "C" int univst_joint_attention_f16(const void* Q, int32_t ldq, const void* K, const void* V, int32_t ldkv, int32_t NI,
+                                          int32_t NIkv, int32_t H, int32_t d, int32_t N, int32_t Nkv, const void* K2,
+                                          const void* V2, int32_t ldkv2, int32_t NIkv2, int32_t Nkv2, const int32_t* kv_src,
+                                          int32_t nsrc, void* O, int32_t ldo, void* stream) {
+  UV_REQUIRE(K2 && V2 && NIkv2 > 0 && Nkv2 > 0 && ldkv2 % 8 == 0, "joint_attention: bad second K/V tensor");
+  UV_REQUIRE((((uintptr_t)K2 | (uintptr_t)V2) % 16) == 0, "joint_attention: 16-byte alignment");
+  const void* Kb[3] = {K, K2, nullptr};
+  const void* Vb[3] = {V, V2, nullptr};
+  return sc_attention_impl(Q, ldq, Kb, Vb, ldkv, NI, NIkv, H, d, N, Nkv, kv_src, nsrc, O, ldo, 0, 0, stream, ldkv2, NIkv2, Nkv2);
 }

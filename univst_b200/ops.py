@@ -17,6 +17,10 @@ from ._lib import Epilogue, check
 _vp, _i32, _f32, _i64 = C.c_void_p, C.c_int32, C.c_float, C.c_int64
 _lib.register("univst_sc_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp])
 _lib.register("univst_attention_tune", [_i32, _i32, _i32])
+_lib.register("univst_joint_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp])
+_lib.register("univst_rmsnorm_heads_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _vp])
+_lib.register("univst_sd3_shift_workspace_bytes", [_i32, _i32, _i32], _i64)
+_lib.register("univst_sd3_attn_shift_f16", [_vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _f32, _vp, _vp])
 _lib.register("univst_cross_attention_supported", [_i32, _i32])
 _lib.register("univst_cross_attention_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp])
 _lib.register("univst_sc_attention_sharded_f16", [_vp, _i32, _vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, _vp, _vp, _vp, _vp, _i32, _i32, _vp])
@@ -47,7 +51,7 @@ _lib.register("univst_mask_select_u8", [_vp, _vp, _vp, _i64, _vp, _vp])
 launch_count = 0
 _LAUNCHES = {
     "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 3, "layernorm": 1, "upsample2x": 1,
-    "temporal_attention": 1, "cross_attention": 1, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
+    "temporal_attention": 1, "cross_attention": 1, "joint_attention": 1, "rmsnorm_heads": 1, "sd3_attn_shift": 4, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
 
@@ -202,6 +206,46 @@ def cross_attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, kv_src: t
                                                     _stream()), "univst_cross_attention_f16")
     _count("cross_attention")
     return out
+
+
+def joint_attention(q, k, v, k2, v2, kv_src, *, NI: int, NIkv: int, NIkv2: int, H: int, d: int, N: int, Nkv: int, Nkv2: int,
+                    out: Optional[torch.Tensor] = None):
+    """SD3 joint attention: sources < NIkv are images of (k, v) with Nkv tokens, sources >= NIkv images of (k2, v2) with
+    Nkv2 tokens (the text tokens).  ``kv_src``: int32 CUDA [NI, nsrc]."""
+    _lib.require_device()
+    assert all(t.stride(1) == 1 for t in (q, k, v, k2, v2)) and k.stride(0) == v.stride(0) and k2.stride(0) == v2.stride(0)
+    assert kv_src.dtype == torch.int32 and kv_src.is_cuda and kv_src.is_contiguous() and kv_src.shape[0] == NI
+    if out is None:
+        out = torch.empty((NI * N, H * d), dtype=torch.float16, device=q.device)
+    with _Timed("sc_attention", (NI, H, d, N, Nkv * (kv_src.shape[1] - 1) + Nkv2)):
+        check(_lib.lib().univst_joint_attention_f16(q.data_ptr(), q.stride(0), k.data_ptr(), v.data_ptr(), k.stride(0), NI, NIkv,
+                                                    H, d, N, Nkv, k2.data_ptr(), v2.data_ptr(), k2.stride(0), NIkv2, Nkv2,
+                                                    kv_src.data_ptr(), kv_src.shape[1], out.data_ptr(), out.stride(0),
+                                                    _stream()), "univst_joint_attention_f16")
+    _count("joint_attention")
+    return out
+
+
+def rmsnorm_heads_(qkv: torch.Tensor, H: int, d: int, wq, wk, eps: float = 1e-6):
+    """In-place per-head RMS norm of the Q (weight ``wq``) and K (``wk``) blocks of a fused [rows, 3 H d] buffer."""
+    _lib.require_device()
+    _chk(qkv, "qkv")
+    check(_lib.lib().univst_rmsnorm_heads_f16(qkv.data_ptr(), qkv.stride(0), qkv.shape[0], H, d, _ptr(wq), _ptr(wk), eps,
+                                              _stream()), "univst_rmsnorm_heads_f16")
+    _count("rmsnorm_heads")
+    return qkv
+
+
+def sd3_attn_shift_(qkv: torch.Tensor, F: int, N: int, H: int, d: int, alpha: float, beta: float, gamma: float):
+    """In-place AdaIN-guided shift of the edit branch of the fused [3 F N, 3 H d] buffer, SD3 semantics."""
+    _lib.require_device()
+    _chk(qkv, "qkv")
+    assert qkv.shape[0] == 3 * F * N
+    ws = _workspace(_lib.lib().univst_sd3_shift_workspace_bytes(F, H * d, d), qkv.device)
+    check(_lib.lib().univst_sd3_attn_shift_f16(qkv.data_ptr(), qkv.stride(0), F, N, H, d, alpha, beta, gamma, ws.data_ptr(),
+                                               _stream()), "univst_sd3_attn_shift_f16")
+    _count("sd3_attn_shift")
+    return qkv
 
 
 def sc_attention_sharded(qkv: torch.Tensor, qkv_prev: Optional[torch.Tensor], qkv_first: Optional[torch.Tensor],

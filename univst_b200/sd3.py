@@ -1,0 +1,118 @@
+"""Mirror of the reference's SD3 / SD3.5 joint-attention processors (backbones/video_diffusion_sd3/pnp_utils.py):
+``CrossFrameProcessor`` (:9-132, the inversions) and ``AttentionShiftProcessor`` (:135-271, the three-branch transfer),
+with the diffusers ``AttnProcessor.__call__(attn, hidden_states, encoder_hidden_states, attention_mask, idx=...)``
+protocol -- they are installed with ``transformer.set_attn_processor`` exactly like the reference's
+(run_video_style_transfer_sd3.py:55-63, pnp_utils.py:276-284) and read the projections / RMS-norm weights off the
+``attn`` module they are called with (packed once per module).
+
+The arithmetic runs in the sm_100a kernels: fused QKV / added-QKV GEMMs with bias, in-place per-head RMS norm, the
+AdaIN-guided shift in the (frame, head) layout, and the fused attention kernel with the image K/V gathered from the
+[first, previous, self] frames plus the text tokens as a second K/V tensor (no concatenated K/V is ever built); image and
+text queries are two launches over the same sources.
+
+Scope: the processors only.  The MMDiT around them (``SD3Transformer2DModel``) is third-party
+diffusers code that is not available in this image.  ``thresh2`` (read but never set at pnp_utils.py:185, which makes
+the reference raise inside the shift window) is taken to be ``eta2``.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+CLIP_LENGTH = 16  # hard-coded in the reference processors (pnp_utils.py:25, :153)
+
+
+class _Packed:
+    def __init__(self, attn, device):
+        h = lambda t: t.detach().to(device=device, dtype=torch.float16).contiguous()
+        cat = lambda names, attr: h(torch.cat([getattr(getattr(attn, n), attr) for n in names], 0))
+        self.w_qkv, self.b_qkv = cat(("to_q", "to_k", "to_v"), "weight"), cat(("to_q", "to_k", "to_v"), "bias")
+        self.w_add, self.b_add = cat(("add_q_proj", "add_k_proj", "add_v_proj"), "weight"), cat(("add_q_proj", "add_k_proj", "add_v_proj"), "bias")
+        self.w_out, self.b_out = h(attn.to_out[0].weight), h(attn.to_out[0].bias)
+        self.w_add_out, self.b_add_out = h(attn.to_add_out.weight), h(attn.to_add_out.bias)
+        nw = lambda n: h(getattr(attn, n).weight) if getattr(attn, n, None) is not None else None
+        self.norm_q, self.norm_k, self.norm_added_q, self.norm_added_k = (nw(n) for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
+        self.eps = float(getattr(getattr(attn, "norm_q", None), "eps", 1e-6) or 1e-6)
+        self.heads = attn.heads
+
+
+_tables = {}
+
+
+def _source_table(BF: int, device) -> torch.Tensor:
+    """[first, previous, self] frames of the image K/V (pnp_utils.py:26) + the image's own text tokens (second tensor)."""
+    key = (BF, str(device))
+    if key not in _tables:
+        rows = []
+        for i in range(BF):
+            b, f = divmod(i, CLIP_LENGTH)
+            rows.append([b * CLIP_LENGTH, b * CLIP_LENGTH + max(f - 1, 0), i, BF + i])
+        _tables[key] = torch.tensor(rows, dtype=torch.int32, device=device)
+    return _tables[key]
+
+
+class CrossFrameProcessor:
+    """pnp_utils.py:9-132."""
+
+    def __init__(self):
+        self._packed = {}
+
+    def _shift(self, idx):
+        return None
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, idx=-1, *args, **kwargs):
+        if attention_mask is not None:
+            raise NotImplementedError("attention masks are unused on the UniVST path")
+        if encoder_hidden_states is None:
+            raise NotImplementedError("the SD3 blocks on the UniVST path are joint (text + image) blocks")
+        dev = hidden_states.device
+        pk = self._packed.get(id(attn))
+        if pk is None:
+            pk = self._packed[id(attn)] = _Packed(attn, dev)
+        BF, N, C = hidden_states.shape
+        L = encoder_hidden_states.shape[1]
+        H, d = pk.heads, C // pk.heads
+        if BF % CLIP_LENGTH:
+            raise ValueError(f"the reference processors assume clips of {CLIP_LENGTH} frames (batch {BF})")
+        x = hidden_states.to(torch.float16).reshape(BF * N, C).contiguous()
+        e = encoder_hidden_states.to(torch.float16).reshape(BF * L, C).contiguous()
+        qkv = ops.gemm(x, pk.w_qkv, bias=pk.b_qkv)          # [BF N, 3C]
+        tqkv = ops.gemm(e, pk.w_add, bias=pk.b_add)         # [BF L, 3C]
+        ops.rmsnorm_heads_(qkv, H, d, pk.norm_q, pk.norm_k, pk.eps)
+        ops.rmsnorm_heads_(tqkv, H, d, pk.norm_added_q, pk.norm_added_k, pk.eps)
+        shift = self._shift(idx)
+        if shift is not None:
+            if BF != 3 * CLIP_LENGTH:
+                raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
+            ops.sd3_attn_shift_(qkv, CLIP_LENGTH, N, H, d, *shift)
+        table = _source_table(BF, dev)
+        kw = dict(NI=BF, NIkv=BF, NIkv2=BF, H=H, d=d, Nkv=N, Nkv2=L)
+        o_img = ops.joint_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=N, **kw)
+        o_txt = ops.joint_attention(tqkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=L, **kw)
+        h_out = ops.gemm(o_img, pk.w_out, bias=pk.b_out).view(BF, N, C)
+        if getattr(attn, "context_pre_only", False):
+            return h_out, o_txt.view(BF, L, C)
+        return h_out, ops.gemm(o_txt, pk.w_add_out, bias=pk.b_add_out).view(BF, L, C)
+
+
+class AttentionShiftProcessor(CrossFrameProcessor):
+    """pnp_utils.py:135-271: window ``eta1*50 <= idx <= eta2*50``, alpha 0.8, gamma 2.0, beta 0.9 -> 0.1."""
+
+    def __init__(self, eta1, eta2):
+        super().__init__()
+        self.eta1, self.eta2 = eta1, eta2
+        self.thresh2 = eta2   # read at :185, never set in the reference
+
+    def _shift(self, idx):
+        if idx >= self.eta1 * 50 and idx <= self.eta2 * 50:
+            beta = (0.9 - 0.1) / (self.eta1 * 50 - self.thresh2 * 50) * (idx - self.eta2 * 50) + 0.1
+            return 0.8, beta, 2.0
+        return None
+
+
+def register_spatial_attention_pnp(model, eta1=0.0, eta2=0.6):
+    """pnp_utils.py:276-284: install the shift processor on every attention of ``model.transformer``."""
+    procs = {name: (AttentionShiftProcessor(eta1, eta2) if "attn" in name else proc)
+             for name, proc in model.transformer.attn_processors.items()}
+    model.transformer.set_attn_processor(procs)
