@@ -58,6 +58,36 @@ def main():
     path = os.path.join(ROOT, "tests", "golden", "sd3_processors.pt")
     torch.save(out, path)
     print("wrote sd3_processors.pt", os.path.getsize(path) // 1024, "KiB")
+    gen_rf_loops()
+
+
+def gen_rf_loops():
+    """The reference's own rf_inversion / rf_solver (inversion_tools/flow_inversion.py) on the stand-in pipeline."""
+    import tempfile
+
+    import inversion_tools.flow_inversion as fi
+    from oracle import rf_oracle as ro
+    n = 10
+    g = torch.Generator().manual_seed(21)
+    x0 = torch.randn(4, 16, 8, 8, generator=g)
+    out = {"n": n, "x0_seed": 21, "gamma": 0.5}
+    with tempfile.TemporaryDirectory() as tmp:
+        pipe = ro.FakePipeline()
+        torch.manual_seed(77)                       # rf_inversion draws its target with torch.randn_like (:151)
+        noise = torch.randn_like(x0)
+        torch.manual_seed(77)
+        fi.rf_inversion(pipe, x0.clone(), "", gamma=0.5, num_inference_steps=n, inversion_path=tmp)
+        out["rf_inversion"] = torch.stack([torch.load(os.path.join(tmp, f"ddim_latents_{k}.pt")) for k in range(n + 1)])
+        out["noise"] = noise
+        out["files"] = sorted(os.listdir(tmp))
+    with tempfile.TemporaryDirectory() as tmp:
+        pipe = ro.FakePipeline()
+        fi.rf_solver(pipe, x0.clone(), "", num_inference_steps=n, inversion_path=tmp)
+        out["rf_solver"] = torch.stack([torch.load(os.path.join(tmp, f"ddim_latents_{k}.pt")) for k in range(n + 1)])
+        out["solver_calls"] = len(pipe.calls)
+    path = os.path.join(ROOT, "tests", "golden", "rf_inversion.pt")
+    torch.save(out, path)
+    print("wrote rf_inversion.pt", os.path.getsize(path) // 1024, "KiB")
 
 
 if __name__ == "__main__":

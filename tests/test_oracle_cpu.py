@@ -245,3 +245,16 @@ def test_sd3_processor_oracle_matches_reference():
     # the window is closed interval [0, 30]: idx 30 still shifts, 31 does not; only the edit branch ever changes
     assert so.shift_params(30)[0] and not so.shift_params(31)[0]
     assert torch.equal(outs[0][:32], outs[31][:32]) and not torch.allclose(outs[30][32:], outs[31][32:], atol=1e-3)
+
+
+def test_rf_loop_oracles_match_reference():
+    """oracle/rf_oracle.py vs the trajectories of the reference's own rf_inversion / rf_solver on the stand-in pipeline."""
+    from oracle import rf_oracle as ro
+    g = torch.load(os.path.join(GOLDEN, "rf_inversion.pt"), weights_only=True)
+    x0 = torch.randn(4, 16, 8, 8, generator=torch.Generator().manual_seed(g["x0_seed"]))
+    assert torch.equal(g["rf_inversion"][0], x0) and g["files"] == sorted(f"ddim_latents_{k}.pt" for k in range(g["n"] + 1))
+    inv = torch.stack(ro.rf_inversion(ro.FakePipeline(), x0, g["gamma"], g["n"], g["noise"]))
+    assert torch.allclose(inv, g["rf_inversion"], atol=1e-5)
+    # gamma = 0.5 pulls the latent to the target: the last step (t_prev = 1) lands between model flow and target
+    sol = torch.stack(ro.rf_solver(ro.FakePipeline(), x0, g["n"]))
+    assert torch.allclose(sol, g["rf_solver"], atol=1e-5) and g["solver_calls"] == 2 * g["n"]

@@ -85,3 +85,23 @@ def test_sd3_processors_match_reference(cuda_lib, case):
     print(f"sd3 {case}: hidden rel={_rel(h, rh):.3e} text rel={_rel(e, re):.3e}")
     assert torch.isfinite(h).all() and torch.isfinite(e).all()
     assert _rel(h, rh) < 5e-3 and _rel(e, re) < 5e-3
+
+
+def test_rf_inversion_loops_match_reference(cuda_lib, tmp_path):
+    """univst_b200.flow_inversion (fp16 latents, axpby kernel) vs the trajectories of the reference's own rf_inversion /
+    rf_solver (fp32) on the same stand-in pipeline: rel-L2 <= 5e-3 after 10 steps, same files."""
+    from oracle import rf_oracle as ro
+    from univst_b200 import flow_inversion as fi
+    g = torch.load(os.path.join(GOLDEN, "rf_inversion.pt"), weights_only=True)
+    x0 = torch.randn(4, 16, 8, 8, generator=torch.Generator().manual_seed(g["x0_seed"]))
+    pipe = ro.FakePipeline(device="cuda", dtype=torch.float16)
+    out = fi.rf_inversion(pipe, x0, "", gamma=g["gamma"], num_inference_steps=g["n"], inversion_path=str(tmp_path),
+                          target_noise=g["noise"])
+    assert sorted(os.listdir(tmp_path)) == g["files"]
+    mid = torch.load(tmp_path / "ddim_latents_5.pt", weights_only=True)
+    print(f"rf_inversion: step 5 rel={_rel(mid, g['rf_inversion'][5]):.3e} final rel={_rel(out, g['rf_inversion'][-1]):.3e}")
+    assert _rel(mid, g["rf_inversion"][5]) < 5e-3 and _rel(out, g["rf_inversion"][-1]) < 5e-3
+    pipe = ro.FakePipeline(device="cuda", dtype=torch.float16)
+    out = fi.rf_solver(pipe, x0, "", num_inference_steps=g["n"])
+    print(f"rf_solver: final rel={_rel(out, g['rf_solver'][-1]):.3e}")
+    assert _rel(out, g["rf_solver"][-1]) < 5e-3 and len(pipe.calls) == g["solver_calls"]

@@ -75,6 +75,11 @@ __device__ __forceinline__ void resolve_source(const AttnParams& p, int src, int
   }
 }
 
+// tokens of source i (the second K/V tensor has its own count) and its number of BKV-token tiles
+__device__ __forceinline__ int src_tokens(const AttnParams& p, int image) {
+  return (p.Nkv2 > 0 && image >= p.NIkv) ? p.Nkv2 : p.Nkv;
+}
+
 // Source list of one image with repeated entries collapsed.  softmax over [K_a, K_a, K_b] equals softmax over
 // [K_a, K_b] with the scores of K_a raised by ln 2, so a source that occurs c times is streamed once with log2(c)
 // added to its (log2-domain) scores: frame 0 of a clip ([prev, self, first] = [0, 0, 0]) costs one pass instead of
@@ -83,12 +88,9 @@ static constexpr int kMaxSrc = 4;
 struct SrcList {
   int n;
   int img[kMaxSrc];
+  int ntok[kMaxSrc];   // tokens of the source (the second K/V tensor of the joint attention has its own count)
   float bias[kMaxSrc];
 };
-// tokens of source i (the second K/V tensor has its own count) and its number of BKV-token tiles
-__device__ __forceinline__ int src_tokens(const AttnParams& p, int image) {
-  return (p.Nkv2 > 0 && image >= p.NIkv) ? p.Nkv2 : p.Nkv;
-}
 __device__ __forceinline__ SrcList load_sources(const AttnParams& p, int img) {
   SrcList L;
   const int* row = p.kv_src + (size_t)img * p.nsrc;
@@ -124,11 +126,17 @@ __device__ __forceinline__ SrcList load_sources(const AttnParams& p, int img) {
     }
   }
 #pragma unroll
-  for (int u = 0; u < kMaxSrc; ++u) L.bias[u] = cnt[u] == 2 ? 1.0f : cnt[u] == 3 ? 1.5849625007f : cnt[u] == 4 ? 2.0f : 0.0f;
+  for (int u = 0; u < kMaxSrc; ++u) {
+    L.bias[u] = cnt[u] == 2 ? 1.0f : cnt[u] == 3 ? 1.5849625007f : cnt[u] == 4 ? 2.0f : 0.0f;
+    L.ntok[u] = src_tokens(p, L.img[u]);
+  }
   return L;
 }
 __device__ __forceinline__ int src_img(const SrcList& L, int i) {
   return i == 0 ? L.img[0] : i == 1 ? L.img[1] : i == 2 ? L.img[2] : L.img[3];
+}
+__device__ __forceinline__ int src_ntok(const SrcList& L, int i) {
+  return i == 0 ? L.ntok[0] : i == 1 ? L.ntok[1] : i == 2 ? L.ntok[2] : L.ntok[3];
 }
 __device__ __forceinline__ float src_bias(const SrcList& L, int i) {
   return i == 0 ? L.bias[0] : i == 1 ? L.bias[1] : i == 2 ? L.bias[2] : L.bias[3];
@@ -174,7 +182,8 @@ struct AttnCfg {
 // Work decomposition: query tile q of the CTA streams KV tiles j = 0..T-1.  Tile (q, j) uses S/P slot
 // q * kDepth + j % kDepth for the (j / kDepth)-th time.  Every query tile has its own MMA-issuing thread and its own
 // softmax group, so the tiles only meet at the K/V ring.
-template <int NQ, int BKV, int POLY, int RS>
+// JT = 1: joint attention -- sources may belong to a second K/V tensor with its own token count (ragged tiles per source)
+template <int NQ, int BKV, int POLY, int RS, int JT>
 __global__ void __launch_bounds__(AttnCfg<NQ, BKV>::kThreads, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ KVMaps kvm, const AttnParams p) {
   using L = AttnCfg<NQ, BKV>;
@@ -221,9 +230,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const SrcList SL = load_sources(p, img);
-  auto tiles_of = [&](int si) { return (src_tokens(p, src_img(SL, si)) + BKV - 1) / BKV; };   // KV tiles of source si
-  int T = 0;                                 // KV tiles in total
-  for (int si = 0; si < SL.n; ++si) T += tiles_of(si);
+  const int tps = (p.Nkv + BKV - 1) / BKV;   // KV tiles per source of the first tensor
+  auto tiles_of = [&](int si) { return JT ? (src_ntok(SL, si) + BKV - 1) / BKV : tps; };   // KV tiles of source si
+  int T = SL.n * tps;                        // KV tiles in total
+  if constexpr (JT) {
+    T = 0;
+#pragma unroll
+    for (int si = 0; si < kMaxSrc; ++si)
+      if (si < SL.n) T += (SL.ntok[si] + BKV - 1) / BKV;
+  }
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -277,6 +292,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       // K load back behind the wait for a V slot and leave the score MMA starved by the TMA latency.
       int jk = 0, sik = 0, jtk = 0;   // next K tile, its source index and tile inside the source
       int jv = 0, siv = 0, jtv = 0;
+      int tk = tiles_of(0), tv = tk;  // tiles of the current K / V source
       while (jk < T || jv < T) {
         bool progress = false;
         if (jk < T && (jk < 2 || mbar_test_wait(&k_empty[jk & 1], (uint32_t)(((jk >> 1) & 1) ^ 1)))) {
@@ -286,9 +302,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           resolve_source(p, src_img(SL, sik), bank, image);
           for (int c = 0; c < dch; ++c)
             tma_load_4d(sK + s * kv_bytes + c * L::kKVChunkBytes, &kvm.k[bank], &k_full[s], c * 64, head, jtk * BKV, image);
-          if (++jtk == tiles_of(sik)) {
+          if (++jtk == tk) {
             jtk = 0;
-            ++sik;
+            tk = tiles_of(++sik);
           }
           ++jk;
           progress = true;
@@ -300,9 +316,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
           resolve_source(p, src_img(SL, siv), bank, image);
           for (int c = 0; c < dch; ++c)
             tma_load_4d(sV + s * kv_bytes + c * L::kKVChunkBytes, &kvm.v[bank], &v_full[s], c * 64, head, jtv * BKV, image);
-          if (++jtv == tiles_of(siv)) {
+          if (++jtv == tv) {
             jtv = 0;
-            ++siv;
+            tv = tiles_of(++siv);
           }
           ++jv;
           progress = true;
@@ -491,6 +507,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     int jt = 0;                 // tile index inside the current source image
     int si = 0;                 // current source
     float bias = SL.bias[0];    // log2 multiplicity of the current source
+    int stok = JT ? SL.ntok[0] : p.Nkv, stiles = (stok + BKV - 1) / BKV;   // its tokens / tiles
     for (int j = 0; j < T; ++j) {
       const int slot = g * D + j % D;
       const int pslot = g * 2 + (j & 1);
@@ -512,11 +529,15 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
       }
       tc_fence_before();
       mbar_arrive(&s_free[slot]);  // the slot may be overwritten with the next scores from here on
-      const int valid = src_tokens(p, src_img(SL, si)) - jt * BKV;   // >= BKV except on the ragged last tile of a source
+      const int valid = stok - jt * BKV;   // >= BKV except on the ragged last tile of a source
       const float tbias = bias;
-      if (++jt == tiles_of(si)) {
+      if (++jt == stiles) {
         jt = 0;
         bias = src_bias(SL, ++si);
+        if constexpr (JT) {
+          stok = src_ntok(SL, si);
+          stiles = (stok + BKV - 1) / BKV;
+        }
       }
       if (valid < BKV) {
 #pragma unroll
@@ -737,9 +758,8 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
   const int head = blockIdx.y;
   const int img = blockIdx.z;
   const SrcList SL = load_sources(p, img);
-  auto tiles_of = [&](int si) { return (src_tokens(p, src_img(SL, si)) + BKV - 1) / BKV; };
-  int T = 0;
-  for (int si = 0; si < SL.n; ++si) T += tiles_of(si);
+  const int tps = (p.Nkv + BKV - 1) / BKV;   // every source has Nkv tokens here (no second K/V tensor: see the launcher)
+  const int T = SL.n * tps;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmQ);
@@ -791,7 +811,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           int bank, image;
           resolve_source(p, src_img(SL, sik), bank, image);
           tma_load_4d(sK + s * kTile, &kvm.k[bank], &k_full[s], 0, head, jtk * BKV, image);
-          if (++jtk == tiles_of(sik)) {
+          if (++jtk == tps) {
             jtk = 0;
             ++sik;
           }
@@ -804,7 +824,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
           int bank, image;
           resolve_source(p, src_img(SL, siv), bank, image);
           tma_load_4d(sV + s * kTile, &kvm.v[bank], &v_full[s], 0, head, jtv * BKV, image);
-          if (++jtv == tiles_of(siv)) {
+          if (++jtv == tps) {
             jtv = 0;
             ++siv;
           }
@@ -912,9 +932,9 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
       }
       tc_fence_before();
       mbar_arrive(&s_free[g]);
-      const int valid = src_tokens(p, src_img(SL, si)) - jt * BKV - hf * 64;   // valid columns of this half
+      const int valid = p.Nkv - jt * BKV - hf * 64;   // valid columns of this half (>= 64 except on a ragged last tile)
       const float tbias = bias;
-      if (++jt == tiles_of(si)) {
+      if (++jt == tps) {
         jt = 0;
         bias = src_bias(SL, ++si);
       }
@@ -1069,7 +1089,7 @@ static int launch_attn_split(const CUtensorMap& tq, const KVMaps& kvm, const Att
   return UNIVST_OK;
 }
 
-template <int NQ, int BKV, int POLY, int RS = 0>
+template <int NQ, int BKV, int POLY, int RS = 0, int JT = 0>
 static int launch_attn(const CUtensorMap& tq, const KVMaps& kvm, const AttnParams& p, cudaStream_t stream) {
   using L = AttnCfg<NQ, BKV>;
   const int dch = (p.d + 63) / 64;
@@ -1085,12 +1105,12 @@ static int launch_attn(const CUtensorMap& tq, const KVMaps& kvm, const AttnParam
   static_assert(RS != 2 || (NQ == 2 && BKV == 128), "P in TMEM: 2 query tiles x 128 keys only");
   static bool configured = false;
   if (!configured) {
-    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV, POLY, RS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    UV_CHECK_CUDA(cudaFuncSetAttribute(attention_tc_kernel<NQ, BKV, POLY, RS, JT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        227 * 1024));
     configured = true;
   }
   dim3 grid((p.N + 128 * NQ - 1) / (128 * NQ), p.H, p.NI);
-  attention_tc_kernel<NQ, BKV, POLY, RS><<<grid, L::kThreads, smem, stream>>>(tq, kvm, p);
+  attention_tc_kernel<NQ, BKV, POLY, RS, JT><<<grid, L::kThreads, smem, stream>>>(tq, kvm, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
@@ -1194,6 +1214,11 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
     }
   }
   cudaStream_t st = (cudaStream_t)stream;
+  if (Nkv2 > 0) {   // joint attention (second K/V tensor with its own token count): the ragged-source instantiations
+    if (d <= 64) return launch_attn<2, 128, 6, 1, 1>(tq, kvm, p, st);
+    if (d <= 128) return launch_attn<2, 64, 0, 0, 1>(tq, kvm, p, st);
+    return launch_attn<1, 64, 0, 0, 1>(tq, kvm, p, st);
+  }
   if (d <= 64 && (int64_t)Nkv * nsrc <= 128 && variant == kDefaultVariant)   // one KV tile (cross-attention): the
     return launch_attn<2, 128, 0>(tq, kvm, p, st);                        // row-sum MMA is pure overhead
   if (variant == 18 && d <= 48) return launch_attn<2, 128, 6, 2>(tq, kvm, p, st);   // 16 + P through tensor memory
