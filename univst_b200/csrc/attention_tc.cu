@@ -165,6 +165,24 @@ __device__ __forceinline__ float ex2_poly(float x) {
   return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
 
+// Two of them per call on packed fp32 (FADD2 / FFMA2): 2 FMNMX + 3 FADD2-class + 3 FFMA2 + 2 IMAD for two exponentials, i.e.
+// five issue slots per exponential against eight MUFU-pipe cycles per warp instruction.
+__device__ __forceinline__ void ex2_poly2(float& e0, float& e1) {
+  const float x0 = fmaxf(e0, -126.0f), x1 = fmaxf(e1, -126.0f);
+  const unsigned long long x = pack_f32x2(x0, x1);
+  const unsigned long long t = add2(x, pack_f32x2(12582912.0f, 12582912.0f));
+  const unsigned long long u = add2(t, pack_f32x2(-12582912.0f, -12582912.0f));
+  const unsigned long long f = fma2(u, pack_f32x2(-1.0f, -1.0f), x);
+  unsigned long long q = fma2(pack_f32x2(0.0551716574f, 0.0551716574f), f, pack_f32x2(0.2426111251f, 0.2426111251f));
+  q = fma2(q, f, pack_f32x2(0.6932609677f, 0.6932609677f));
+  q = fma2(q, f, pack_f32x2(0.9999280572f, 0.9999280572f));
+  float p0, p1, t0, t1;
+  unpack_f32x2(q, p0, p1);
+  unpack_f32x2(t, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+
 template <int NQ, int BKV>
 struct AttnCfg {
   static constexpr int kDepth = (NQ == 1) ? 2 : 1;      // S slots per query tile
@@ -991,7 +1009,7 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         // a half with no valid key so far keeps m_used = -inf: its scores are all -inf and must map to P = 0, not NaN
         const float neg_m = (m_used == -INFINITY) ? 0.0f : tbias - m_used;
         float e[32];
-        if constexpr (POLY == 6) {
+        if constexpr (POLY >= 6) {
 #pragma unroll
           for (int x = 0; x < 32; x += 2)
             fma2_bcast(e[x], e[x + 1], __uint_as_float(sraw[c * 32 + x]), __uint_as_float(sraw[c * 32 + x + 1]), p.scale_log2, neg_m);
@@ -999,10 +1017,23 @@ attention_tc_split_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
 #pragma unroll
           for (int x = 0; x < 32; ++x) e[x] = fmaf(__uint_as_float(sraw[c * 32 + x]), p.scale_log2, neg_m);
         }
+        if constexpr (POLY >= 7) {   // packed polynomial exponentials for 1/4 (7), 1/8 (8) or 1/2 (10) of the pairs
 #pragma unroll
-        for (int x = 0; x < 32; ++x) {
-          const bool poly = (POLY == 1 && (x & 3) == 3) || (POLY == 4 && (x & 7) == 7);
-          e[x] = poly ? ex2_poly(e[x]) : ex2_approx(e[x]);
+          for (int x = 0; x < 32; x += 2) {
+            const bool poly = (POLY == 7 && (x & 7) == 6) || (POLY == 8 && (x & 15) == 14) || (POLY == 10 && (x & 3) == 2);
+            if (poly) {
+              ex2_poly2(e[x], e[x + 1]);
+            } else {
+              e[x] = ex2_approx(e[x]);
+              e[x + 1] = ex2_approx(e[x + 1]);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int x = 0; x < 32; ++x) {
+            const bool poly = (POLY == 1 && (x & 3) == 3) || (POLY == 4 && (x & 7) == 7);
+            e[x] = poly ? ex2_poly(e[x]) : ex2_approx(e[x]);
+          }
         }
 #pragma unroll
         for (int q8 = 0; q8 < 4; ++q8) {
@@ -1122,7 +1153,7 @@ using namespace uv;
 static int g_variant = -1, g_dedupe = -1, g_stagger = -2;
 
 extern "C" int univst_attention_tune(int32_t variant, int32_t dedupe, int32_t stagger) {
-  g_variant = (variant < 0 || variant > 19) ? -1 : variant;   // -1: back to the environment / built-in default
+  g_variant = (variant < 0 || variant > 22) ? -1 : variant;   // -1: back to the environment / built-in default
   g_dedupe = dedupe < 0 ? -1 : (dedupe != 0);
   g_stagger = stagger < 0 ? -2 : stagger;
   return UNIVST_OK;
@@ -1170,7 +1201,7 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
   if (variant < 0) {
     const char* e = getenv("UNIVST_ATTN_VARIANT");
     variant = e ? atoi(e) : kDefaultVariant;
-    if (variant < 0 || variant > 19) variant = kDefaultVariant;
+    if (variant < 0 || variant > 22) variant = kDefaultVariant;
   }
   int& dedupe = g_dedupe;
   if (dedupe < 0) {
@@ -1230,6 +1261,9 @@ static int sc_attention_impl(const void* Q, int32_t ldq, const void* const* Kb, 
       case 17: return launch_attn_split<6>(tq, kvm, p, st);   // + packed FFMA2 score scaling
       case 19: return launch_attn_split<6, 1>(tq, kvm, p, st);   // + convergent (whole-warp, elected-lane) MMA issue
       case 14: return launch_attn_split<4>(tq, kvm, p, st);   // + 1/8 of the exp2 as polynomials
+      case 20: return launch_attn_split<7, 1>(tq, kvm, p, st);   // 19 + 1/4 of the exp2 as packed (FFMA2) polynomials
+      case 21: return launch_attn_split<8, 1>(tq, kvm, p, st);   // 19 + 1/8
+      case 22: return launch_attn_split<10, 1>(tq, kvm, p, st);  // 19 + 1/2
       default: return launch_attn_split<1>(tq, kvm, p, st);   // + 1/4
     }
   }

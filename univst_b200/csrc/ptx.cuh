@@ -333,6 +333,24 @@ __device__ __forceinline__ void fma2_bcast(float& d0, float& d1, float a0, float
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(dv) : "l"(av), "l"(bv), "l"(cv));
   asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(dv));
 }
+__device__ __forceinline__ unsigned long long pack_f32x2(float a, float b) {
+  unsigned long long v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(a), "f"(b));
+  return v;
+}
+__device__ __forceinline__ void unpack_f32x2(unsigned long long v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
