@@ -124,6 +124,34 @@ def test_conv3x3_stride2(cuda_lib, NB, H, W, C, Cout):
     _close(out, _conv_ref(x, w, stride=2), 3e-3, 2e-3, f"conv3x3 stride 2 {NB}x{H}x{W}")
 
 
+@pytest.mark.parametrize("NB,H,W,C1,C2,Cout,stride", [
+    (3, 24, 40, 64, 0, 96, 1),      # 128 // 40 = 3 full rows per tile, 8 row blocks per image
+    (5, 3, 5, 64, 0, 64, 1),        # 15-pixel images: 8 whole images per tile, ragged image tail
+    (2, 12, 20, 128, 64, 128, 1),   # two sources, 6 rows per tile
+    (7, 6, 10, 64, 0, 160, 1),      # 60 pixels: 2 images per tile, odd image count
+    (2, 72, 128, 64, 0, 64, 1),     # widest supported row (one row per tile), non-power-of-two height
+    (3, 12, 20, 64, 0, 128, 2),     # stride 2 from 24 x 40
+    (4, 3, 5, 128, 0, 64, 2),       # stride 2 from 6 x 10
+])
+def test_conv3x3_any_size(cuda_lib, NB, H, W, C1, C2, Cout, stride):
+    """Images whose sides are not powers of two (latents of 192 x 320, 576 x 1024 ... frames): row-block tiles."""
+    from univst_b200 import ops
+    Cin = C1 + C2
+    Hi, Wi = H * stride, W * stride
+    x = _rand(NB, Hi, Wi, Cin, seed=1)
+    w = _rand(Cout, 9 * Cin, scale=(9 * Cin) ** -0.5, seed=2)
+    bias, res, rv = _rand(Cout, seed=3), _rand(NB * H * W, Cout, seed=4), _rand(NB, Cout, seed=5)
+    ref = _conv_ref(x, w, stride=stride) + bias.float() + res.float() + rv.float().repeat_interleave(H * W, 0)
+    if stride == 2:
+        out = ops.conv3x3(ops.space_to_depth2(x), w, stride=2, bias=bias, residual=res, rowvec=rv, rows_per_group=H * W)
+    elif C2:
+        out = ops.conv3x3(x[..., :C1].contiguous(), w, x2=x[..., C1:].contiguous(), bias=bias, residual=res, rowvec=rv,
+                          rows_per_group=H * W)
+    else:
+        out = ops.conv3x3(x, w, bias=bias, residual=res, rowvec=rv, rows_per_group=H * W)
+    _close(out, ref, 3e-3, 2e-3, f"conv3x3 {NB}x{H}x{W} stride {stride} {Cin}->{Cout}")
+
+
 def test_upsample2x(cuda_lib):
     from univst_b200 import ops
     x = _rand(3, 8, 16, 64, seed=1)

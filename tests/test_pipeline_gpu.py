@@ -100,3 +100,39 @@ def test_ddim_inversion_matches_reference_golden(pipe, tmp_path):
     rel_p = _rel(torch.stack(lat_p[1:]), g["ddim_loop_plus"])
     print(f"ddim_loop rel={rel:.3e}  feature rel={rel_f:.3e}  ddim_loop_plus rel={rel_p:.3e}")
     assert rel <= 1e-2 and rel_p <= 1e-2 and rel_f <= 1e-2 and tuple(feat.shape) == tuple(g["feature"].shape)
+
+
+def test_video_style_transfer_non_square_clip(pipe):
+    """A 3-frame 192 x 320 clip (latent 24 x 40: no power-of-two side anywhere in the UNet) through the 10-step loop,
+    against the oracle loop + oracle UNet evaluated in fp32 on the same inputs."""
+    from univst_b200 import pnp_utils
+    F_, h, w, n = 3, 24, 40, 10
+    gen = torch.Generator().manual_seed(77)
+    sch = po.DDIMOracle()
+    sch.set_timesteps(n)
+    z0_c = torch.randn(1, 4, F_, h, w, generator=gen)
+    z0_s = torch.randn(1, 4, 1, h, w, generator=gen).repeat(1, 1, F_, 1, 1) + 0.02 * torch.randn(1, 4, F_, h, w, generator=gen)
+    eps = torch.randn(1, 4, F_, h, w, generator=gen)
+    traj_c, traj_s = [z0_c], [z0_s]
+    for t in sch.timesteps[::-1]:
+        a = sch.alpha(t)
+        traj_c.append(a ** 0.5 * z0_c + (1 - a) ** 0.5 * eps)
+        traj_s.append(a ** 0.5 * z0_s + (1 - a) ** 0.5 * eps)
+    yy, xx = np.mgrid[0:8 * h, 0:8 * w]
+    mask_u8 = np.stack([(((xx - (4 * w + 5 * f)) ** 2 + (yy - 4 * h) ** 2) < (2.5 * h) ** 2).astype(np.uint8) * 255
+                        for f in range(F_)])
+    emb = torch.randn(1, 77, uo.TINY_CONFIG["cross_attention_dim"], generator=gen)
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    z_T = pnp_utils.latent_adain(traj_c[n].cuda().half(), traj_s[n].cuda().half())
+    out = pipe.video_style_transfer("", num_inference_steps=n, latents=z_T, content_inv_path=[t.half() for t in traj_c],
+                                    style_inv_path=[t.half() for t in traj_s], mask_path=torch.from_numpy(mask_u8),
+                                    prompt_embeds=emb).latents
+    sd32 = {k: v.cuda() for k, v in uo.seeded_state_dict(uo.TINY_CONFIG, seed=33).items()}
+    with torch.no_grad():
+        unet_fn = lambda x, t, ctx, i: uo.unet_forward(sd32, uo.TINY_CONFIG, x, t, ctx, patched=True, idx=i)
+        truth = po.video_style_transfer(unet_fn, uo.latent_adain(traj_c[n].cuda(), traj_s[n].cuda()),
+                                        [t.cuda() for t in traj_c], [t.cuda() for t in traj_s],
+                                        po.load_mask_values(mask_u8).cuda(), emb.cuda().repeat(3, 1, 1), n)
+    rel, psnr = _rel(out, truth), _psnr(out, truth)
+    print(f"non-square clip, {n} steps: rel={rel:.3e} psnr={psnr:.1f} dB")
+    assert out.shape == truth.shape and torch.isfinite(out).all() and rel <= 3e-2 and psnr >= 30.0

@@ -25,13 +25,16 @@ static constexpr int kThreads = 64 + 32 * kEpiWarps;
 struct GemmParams {
   int M, N, N_out, BN;
   int num_kb;           // k-blocks of 64
-  int mode;             // 0 = linear A[M,K]; 1 = conv taps over NHWC
+  int mode;             // 0 = linear A[M,K]; 1 = conv taps over NHWC; 2 = conv, row-block tiles (any H, W <= 128)
   int kb_split;         // linear: first k-block served by A2; conv: channel blocks per tap served by A (cbs1)
   int K1;               // linear: K columns in A; conv: channels in A (C1)
   int cbs;              // conv: channel blocks per tap (cbs1 + cbs2)
   int Cin;              // conv: total input channels (weight K index = tap * Cin + channel)
   int HW, W;            // conv: output pixels per image, output width (== box width)
   int plane_stride;     // conv: images per parity plane (stride-2 input was rearranged into 4 planes)
+  // mode 2: a tile is `gen_th` full-width rows of one image (`gen_rb` such row blocks per image) or, for images of
+  // <= 128 pixels, `gen_bn` whole images; only its first gen_th * W * gen_bn rows are real (the rest are masked)
+  int gen_th, gen_rb, gen_bn, gen_tiles_m;
   int8_t tap_dy[9], tap_dx[9], tap_plane[9];
   int stages;
   int cluster;          // 2: CTA pairs share every weight tile (each loads half of it and multicasts), 1: independent CTAs
@@ -299,13 +302,26 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t warp = warp_id();
   const uint32_t lane = lane_id();
   const int tiles_n = (p.N + p.BN - 1) / p.BN;
-  const int tiles_m = (p.M + kBM - 1) / kBM;
+  const int tiles_m = (p.mode == 2) ? p.gen_tiles_m : (p.M + kBM - 1) / kBM;
   // work items: CL = 1: tiles (m, n), n fastest, one per CTA; CL = 2: pairs of row blocks (2 mm, 2 mm + 1) x n per cluster
   const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
   const int num_tiles = (CL == 2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
   const int tile_first = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
-  auto tile_m0 = [&](int tile) { return ((tile / tiles_n) * CL + (int)crank) * kBM; };   // may be >= M for the odd tail
+  auto tile_m0 = [&](int tile) {   // first output row of the tile; may be >= M for the odd tail
+    const int mm = (tile / tiles_n) * CL + (int)crank;
+    if (p.mode == 2) return (mm / p.gen_rb) * p.gen_bn * p.HW + (mm % p.gen_rb) * p.gen_th * p.W;
+    return mm * kBM;
+  };
+  auto tile_mlim = [&](int m0) {    // one past the last real output row of the tile
+    if (p.mode != 2) return p.M;
+    const int group_end = (m0 / p.HW + p.gen_bn) * p.HW;   // the row block must not run into the next image (group)
+    int lim = m0 + p.gen_th * p.W * p.gen_bn;
+    lim = lim < group_end ? lim : group_end;
+    return lim < p.M ? lim : p.M;
+  };
+  // bytes one stage receives: in mode 2 the A box holds only the real rows
+  const uint32_t tx_bytes = (p.mode == 2) ? (uint32_t)(p.gen_th * p.W * p.gen_bn) * (kBK * 2) + b_bytes : stage_bytes;
 
   // accumulator stride: BN rounded up to a power of two >= 32 (TMEM allocations are powers of two)
   uint32_t acc_cols = 32;
@@ -345,7 +361,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m0 = tile_m0(tile);
         const int n0 = (tile % tiles_n) * p.BN;
         int cn = 0, cy = 0;
-        if (p.mode == 1) {
+        if (p.mode >= 1) {
           cn = m0 / p.HW;
           cy = (m0 % p.HW) / p.W;
         }
@@ -353,7 +369,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
-          mbar_expect_tx(&full_bar[s], stage_bytes);
+          mbar_expect_tx(&full_bar[s], tx_bytes);
           int kw;  // K coordinate into the weight matrix
           if (p.mode == 0) {
             kw = kb * kBK;
@@ -438,7 +454,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int n0 = tile_n * p.BN;
       const int row = m0 + (int)(q * 32 + lane);
       const uint32_t taddr = tmem_base + a * acc_cols + ((q * 32) << 16);
-      const bool row_ok = row < p.M;
+      const int m_lim = tile_mlim(m0);
+      const bool row_ok = row < m_lim;
       const __half* rv = (p.rowvec && row_ok) ? p.rowvec + (size_t)(row / p.rows_per_group) * p.rowvec_ld : nullptr;
       const __half* res = (p.residual && row_ok) ? p.residual + (size_t)row * p.ldr : nullptr;
       __half* drow = p.D + (size_t)row * p.ldd;
@@ -446,7 +463,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       e.stg = smem_u32(stg) + (warp - 2) * kStageTileBytes;
       e.lane = lane;
       e.row0 = m0 + (int)(q * 32);
-      e.M = p.M;
+      e.M = m_lim;
       epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
@@ -527,7 +544,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
     UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
-  const int tiles_m = (p.M + kBM - 1) / kBM, tiles_n = (p.N + p.BN - 1) / p.BN;
+  const int tiles_m = (p.mode == 2) ? p.gen_tiles_m : (p.M + kBM - 1) / kBM, tiles_n = (p.N + p.BN - 1) / p.BN;
   if (p.cluster == 2) {
     const int pairs = ((tiles_m + 1) / 2) * tiles_n;
     const int max_pairs = num_sms() / 2;
@@ -638,7 +655,9 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
   UV_REQUIRE(stride == 1 || !X2, "conv3x3: stride 2 takes a single (parity-plane) source");
   // output geometry; for stride 2 the caller passes the 4 parity planes [4][NB][H/2][W/2][C] and H, W of the OUTPUT
   const int Ho = H, Wo = W;
-  UV_REQUIRE((Wo & (Wo - 1)) == 0 && Wo <= 128 && (Ho & (Ho - 1)) == 0, "conv3x3: H and W must be powers of two, W <= 128");
+  UV_REQUIRE(Wo <= 128 && Ho > 0 && Wo > 0, "conv3x3: output width must be <= 128 (1024-pixel frames)");
+  // power-of-two images tile exactly into 128-row blocks of consecutive pixels (mode 1); anything else takes row-block tiles
+  const bool pow2 = (Wo & (Wo - 1)) == 0 && (Ho & (Ho - 1)) == 0;
   GemmParams p{};
   fill_epilogue(p, ep);
   UV_REQUIRE(!p.geglu, "conv3x3: no GEGLU epilogue");
@@ -647,7 +666,7 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
   p.N = Cout;
   p.N_out = Cout;
   p.BN = pick_bn(Cout, 0);
-  p.mode = 1;
+  p.mode = pow2 ? 1 : 2;
   p.K1 = C1;
   p.Cin = Cin;
   const int cbs1 = (C1 + kBK - 1) / kBK;
@@ -677,8 +696,22 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
   p.ldd = ldy;
 
   const int bw = Wo;
-  const int bh = (Ho * Wo >= kBM) ? kBM / bw : Ho;
-  const int bn = kBM / (bw * bh);
+  int bh = (Ho * Wo >= kBM) ? kBM / bw : Ho;
+  int bn = kBM / (bw * bh);
+  if (!pow2) {
+    if (Ho * Wo <= kBM) {        // whole images: bn per tile
+      bh = Ho;
+      bn = kBM / (Ho * Wo);
+      p.gen_rb = 1;
+    } else {                     // bh full-width rows of one image
+      bh = kBM / Wo;
+      bn = 1;
+      p.gen_rb = (Ho + bh - 1) / bh;
+    }
+    p.gen_th = bh;
+    p.gen_bn = bn;
+    p.gen_tiles_m = ((NB + bn - 1) / bn) * p.gen_rb;
+  }
   const int planes = (stride == 2) ? 4 : 1;
   CUtensorMap tmA, tmA2, tmB;
   {
@@ -698,7 +731,7 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
     tmA2 = tmA;
   }
   {
-    p.cluster = pick_cluster(p.M, p.BN);
+    p.cluster = pow2 ? pick_cluster(p.M, p.BN) : 1;
     uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
     uint64_t str[1] = {(uint64_t)9 * Cin * 2};
     uint32_t box[2] = {kBK, (uint32_t)(p.BN / p.cluster)};

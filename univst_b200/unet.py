@@ -409,8 +409,10 @@ class UNetPseudo3DConditionModel:
         W, cfg = self.W, self.config
         dev = self.device
         B, Cin, F, H, Wd = sample.shape
-        if H & (H - 1) or Wd & (Wd - 1) or (H >> (self.nlev - 1)) < 1:
-            raise ValueError("latent height / width must be powers of two (64x64 for 512x512 frames)")
+        q = 1 << (self.nlev - 1)
+        if H % q or Wd % q or Wd > 128:
+            raise ValueError(f"latent height / width must be multiples of {q} (the UNet halves them {self.nlev - 1} times) "
+                             "and the width at most 128 (1024-pixel frames)")
         boc = cfg["block_out_channels"]
         sample = sample.to(device=dev, dtype=torch.float16).contiguous()
         F_total = F
