@@ -180,6 +180,11 @@ int univst_mask_resize_u8(const uint8_t* mask, int32_t F, int32_t Hin, int32_t W
 int univst_latent_blend_f16(const void* a, const void* b, const void* mask, int32_t C, int32_t F, int32_t HW, void* out,
                             void* stream);
 int univst_latent_adain_f16(const void* cnt, const void* sty, int32_t C, int32_t F, int32_t HW, void* out, void* stream);
+/* The blend on frame-major (F, C, hw) latents, the layout of the SD3 loop (video_diffusion_sd3/pipelines/
+ * custom_pipeline.py:297-304, :316): out = (1 - m[f, hw]) a + m[f, hw] b.  That loop's latent_adain (sd3 pnp_utils.py:
+ * 304-316, statistics per (frame, channel) plane) is univst_latent_adain_f16 with C = F * C planes and F = 1. */
+int univst_latent_blend_fc_f16(const void* a, const void* b, const void* mask, int32_t F, int32_t C, int32_t HW, void* out,
+                               void* stream);
 /* DDIM step, eta = 0 (diffusers DDIMScheduler.step) and, with the alphas swapped, next_step of
  * inversion_tools/ddim_inversion.py:190-204.  eps is read from the channels-last conv_out buffer of `branch`. */
 int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t ld, int32_t branch, int32_t C, int32_t F,

@@ -8,3 +8,4 @@ be generated from the reference's OWN module code (oracle/gen_golden.py).  It is
 """
 from .modeling_utils import ModelMixin  # noqa: F401
 from .schedulers import DDIMScheduler  # noqa: F401
+from .pipelines.stable_diffusion_3.pipeline_stable_diffusion_3 import StableDiffusion3Pipeline  # noqa: F401,E402

@@ -258,3 +258,32 @@ def test_rf_loop_oracles_match_reference():
     # gamma = 0.5 pulls the latent to the target: the last step (t_prev = 1) lands between model flow and target
     sol = torch.stack(ro.rf_solver(ro.FakePipeline(), x0, g["n"]))
     assert torch.allclose(sol, g["rf_solver"], atol=1e-5) and g["solver_calls"] == 2 * g["n"]
+
+
+def test_sd3_pipeline_oracle_matches_reference_loops():
+    """oracle/sd3_pipeline_oracle.py vs the reference's own CustomStableDiffusion3Pipeline.generate_eta_values /
+    reconstruction / video_style_transfer run on the stand-in members (oracle/gen_golden_sd3_pipeline.py)."""
+    from oracle import pipeline_oracle as po
+    from oracle import sd3_pipeline_oracle as so
+    g = torch.load(os.path.join(GOLDEN, "sd3_pipeline.pt"), weights_only=True)
+    n = g["n"]
+    traj_c, traj_s, mask_u8 = so.synthetic_inputs(g["input_seed"], g["frames"], g["channels"], g["hw"], n)
+    sch, tr = so.FakeFlowMatchScheduler(), so.FakeTransformer(g["channels"], g["transformer_seed"])
+    sch.set_timesteps(n)
+    for trend, ref in g["eta_values"].items():
+        assert so.generate_eta_values(sch.timesteps, 2, 7, 0.85, trend) == pytest.approx(ref, abs=1e-6)
+    z_T = so.latent_adain(traj_c[50], traj_s[50])
+    assert torch.allclose(z_T, g["z_T"], atol=1e-6)
+    for name, mask in (("masked", po.load_mask_values(mask_u8)), ("unmasked", None)):
+        rec = []
+        tr.calls.clear()
+        z = so.video_style_transfer(sch, tr, z_T.clone(), traj_c[0], traj_c, traj_s, mask, n, 0.85, "constant", 5, 8, rec)
+        case = g["cases"][name]
+        assert [c[0] for c in tr.calls] == case["idx_seen"] == list(range(n))
+        for i, ref in case["steps"].items():
+            assert torch.allclose(rec[i], ref, atol=1e-5), (name, i)
+        assert torch.allclose(z, case["final"], atol=1e-5)
+    # the mask keeps the content inside it up to step 0.9 n: the two runs differ
+    assert not torch.allclose(g["cases"]["masked"]["final"], g["cases"]["unmasked"]["final"], atol=1e-3)
+    rc = so.reconstruction(sch, tr, traj_c[0], traj_c[50], 0.9, "linear_decrease", 0, 6, n)
+    assert torch.allclose(rc, g["cases"]["reconstruction"]["final"], atol=1e-5)

@@ -105,3 +105,56 @@ def test_rf_inversion_loops_match_reference(cuda_lib, tmp_path):
     out = fi.rf_solver(pipe, x0, "", num_inference_steps=g["n"])
     print(f"rf_solver: final rel={_rel(out, g['rf_solver'][-1]):.3e}")
     assert _rel(out, g["rf_solver"][-1]) < 5e-3 and len(pipe.calls) == g["solver_calls"]
+
+
+def test_sd3_pipeline_loops_match_reference(cuda_lib, tmp_path):
+    """univst_b200.sd3_pipeline (fp16 latents, blend / AdaIN / axpby kernels) vs the latents of the reference's own
+    CustomStableDiffusion3Pipeline.video_style_transfer / reconstruction (fp32) on the same stand-in members, inputs through
+    the reference's on-disk formats: rel-L2 <= 5e-3 after 10 steps."""
+    from types import SimpleNamespace
+    from PIL import Image
+    from oracle import sd3_pipeline_oracle as so
+    from univst_b200 import ops
+    from univst_b200.sd3_pipeline import CustomStableDiffusion3Pipeline
+    g = torch.load(os.path.join(GOLDEN, "sd3_pipeline.pt"), weights_only=True)
+    n = g["n"]
+    traj_c, traj_s, mask_u8 = so.synthetic_inputs(g["input_seed"], g["frames"], g["channels"], g["hw"], n)
+    cdir, sdir, mdir = (tmp_path / d for d in ("c", "s", "m"))
+    for d in (cdir, sdir, mdir):
+        d.mkdir()
+    for k in traj_c:
+        torch.save(traj_c[k].half(), cdir / f"ddim_latents_{k}.pt")
+        torch.save(traj_s[k].half(), sdir / f"ddim_latents_{k}.pt")
+    for f in range(g["frames"]):
+        Image.fromarray(mask_u8[f], mode="L").save(mdir / ("%05d.png" % f))
+    host = SimpleNamespace(transformer=so.FakeTransformer(g["channels"], g["transformer_seed"], "cuda", torch.float16),
+                           scheduler=so.FakeFlowMatchScheduler(), encode_prompt=so.fake_encode_prompt("cuda", torch.float16),
+                           device="cuda")
+    pipe = CustomStableDiffusion3Pipeline(host)
+    sch = so.FakeFlowMatchScheduler()
+    sch.set_timesteps(n)
+    for trend, ref in g["eta_values"].items():
+        assert pipe.generate_eta_values(sch.timesteps, 2, 7, 0.85, trend) == pytest.approx(ref, abs=1e-6)
+    z_T = ops.plane_adain(traj_c[50].cuda().half(), traj_s[50].cuda().half())
+    assert _rel(z_T, g["z_T"]) < 2e-3
+    for name, mpath in (("masked", str(mdir)), ("unmasked", None)):
+        rec = {}
+        host.transformer.calls.clear()
+        out = pipe.video_style_transfer("", latents=z_T, img_latents=traj_c[0], num_inference_steps=n,
+                                        content_inv_path=str(cdir), style_inv_path=str(sdir), mask_path=mpath, eta_base=0.85,
+                                        eta_trend="constant", start_step=5, end_step=8, output_type="latent",
+                                        callback_on_step_end=lambda p, i, t, kw: rec.__setitem__(i, kw["latents"].clone())).images
+        case = g["cases"][name]
+        assert [c[0] for c in host.transformer.calls] == case["idx_seen"]
+        errs = {i: _rel(rec[i], ref) for i, ref in case["steps"].items()}
+        print(f"sd3 video_style_transfer ({name}): steps {errs} final rel={_rel(out, case['final']):.3e}")
+        assert max(errs.values()) < 5e-3 and _rel(out, case["final"]) < 5e-3
+    # in-memory trajectories / mask tensor give the same latents as the on-disk formats
+    mem = pipe.video_style_transfer("", latents=z_T, img_latents=traj_c[0], num_inference_steps=n,
+                                    content_inv_path={k: v.half() for k, v in traj_c.items()},
+                                    style_inv_path={k: v.half() for k, v in traj_s.items()}, mask_path=None, eta_base=0.85,
+                                    eta_trend="constant", start_step=5, end_step=8, output_type="latent").images
+    assert torch.equal(mem, out)
+    rc = pipe.reconstruction(traj_c[0], traj_c[50], 0.9, "linear_decrease", 0, 6, num_inference_steps=n, output_type="latent")
+    print(f"sd3 reconstruction: final rel={_rel(rc, g['cases']['reconstruction']['final']):.3e}")
+    assert _rel(rc, g["cases"]["reconstruction"]["final"]) < 5e-3

@@ -116,6 +116,15 @@ __global__ void latent_blend_kernel(const __half* __restrict__ a, const __half* 
   }
 }
 
+// the same blend on frame-major (F, C, HW) latents -- the SD3 layout (custom_pipeline.py:300-303): m[f, hw] over channels
+__global__ void latent_blend_fc_kernel(const __half* __restrict__ a, const __half* __restrict__ b,
+                                       const __half* __restrict__ m, int C, int HW, int total, __half* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const float w = __half2float(m[(i / (C * HW)) * HW + i % HW]);
+    out[i] = __float2half_rn((1.0f - w) * __half2float(a[i]) + w * __half2float(b[i]));
+  }
+}
+
 __device__ __forceinline__ float block_sum(float v, float* sh) {
   v = warp_sum(v);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
@@ -265,6 +274,15 @@ extern "C" int univst_latent_blend_f16(const void* a, const void* b, const void*
   UV_REQUIRE(a && b && mask && out && C > 0 && F > 0 && HW > 0, "latent_blend: bad arguments");
   latent_blend_kernel<<<grid_for((size_t)C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(
       (const __half*)a, (const __half*)b, (const __half*)mask, C, F * HW, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_latent_blend_fc_f16(const void* a, const void* b, const void* mask, int32_t F, int32_t C, int32_t HW,
+                                          void* out, void* stream) {
+  UV_REQUIRE(a && b && mask && out && C > 0 && F > 0 && HW > 0 && (int64_t)F * C * HW < (1ll << 31), "latent_blend_fc: bad arguments");
+  latent_blend_fc_kernel<<<grid_for((size_t)C * F * HW, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)a, (const __half*)b, (const __half*)mask, C, HW, F * C * HW, (__half*)out);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

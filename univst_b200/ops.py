@@ -39,6 +39,7 @@ _lib.register("univst_unpack_latents_f16", [_vp, _i32, _i32, _i32, _i32, _i32, _
 _lib.register("univst_timestep_embedding_f16", [_vp, _i32, _i32, _vp, _vp])
 _lib.register("univst_mask_resize_u8", [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_latent_blend_f16", [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp])
+_lib.register("univst_latent_blend_fc_f16", [_vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_latent_adain_f16", [_vp, _vp, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp])
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
@@ -453,6 +454,36 @@ def latent_adain(cnt, sty, out=None):
     if out is None:
         out = torch.empty_like(cnt)
     check(_lib.lib().univst_latent_adain_f16(cnt.data_ptr(), sty.data_ptr(), C_, F, h * w, out.data_ptr(), _stream()),
+          "univst_latent_adain_f16")
+    _count("latent_adain")
+    return out
+
+
+def latent_blend_fc(a, b, mask, out=None):
+    """(1 - m) * a + m * b on frame-major (F, C, h, w) latents (the SD3 loop), m: [F, h, w]."""
+    _lib.require_device()
+    _chk(a, "a"), _chk(b, "b"), _chk(mask, "mask")
+    F, C_, h, w = a.shape
+    assert b.shape == a.shape and tuple(mask.shape) == (F, h, w)
+    if out is None:
+        out = torch.empty_like(a)
+    check(_lib.lib().univst_latent_blend_fc_f16(a.data_ptr(), b.data_ptr(), mask.data_ptr(), F, C_, h * w, out.data_ptr(),
+                                                _stream()), "univst_latent_blend_fc_f16")
+    _count("latent_blend")
+    return out
+
+
+def plane_adain(cnt, sty, out=None):
+    """SD3 ``latent_adain`` (video_diffusion_sd3/pnp_utils.py:304-316) on (F, C, h, w): instance norm of every content
+    plane re-scaled by the unbiased std / mean of the same style plane -- the latent-AdaIN kernel with F * C one-frame
+    channels."""
+    _lib.require_device()
+    _chk(cnt, "cnt"), _chk(sty, "sty")
+    F, C_, h, w = cnt.shape
+    assert sty.shape == cnt.shape
+    if out is None:
+        out = torch.empty_like(cnt)
+    check(_lib.lib().univst_latent_adain_f16(cnt.data_ptr(), sty.data_ptr(), F * C_, 1, h * w, out.data_ptr(), _stream()),
           "univst_latent_adain_f16")
     _count("latent_adain")
     return out
