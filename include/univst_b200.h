@@ -189,6 +189,13 @@ int univst_latent_blend_fc_f16(const void* a, const void* b, const void* mask, i
  * inversion_tools/ddim_inversion.py:190-204.  eps is read from the channels-last conv_out buffer of `branch`. */
 int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t ld, int32_t branch, int32_t C, int32_t F,
                          int32_t HW, float alpha_t, float alpha_prev, void* z_out, void* x0_out, void* stream);
+/* Frames <-> pixels exchange of the frame-sharded AnimateDiff motion modules (the temporal attention of
+ * backbones/animatediff/models/motion_module.py:279 runs over ALL frames of a pixel): the local [rows, C] activations
+ * are stored straight into the ranks' symmetric-memory buffers (dst: HOST array of P device pointers, peers mapped over
+ * NVLink) at their place in the owner's layout.  dir 0: rows (b, local frame, pixel) -> rank pixel / (N / P), row
+ * (b, global frame, local pixel); dir 1: the inverse.  The caller places a cross-rank barrier after it. */
+int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P, int32_t B,
+                             int32_t Fl, int32_t N, int32_t C, void* stream);
 int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -34,10 +34,11 @@ def test_animatediff_frame_sharded_forward_matches_single_gpu():
         pytest.skip("needs 2 GPUs")
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
                           "--master-addr", "127.0.0.1", "--master-port", "29633",
-                          os.path.join(ROOT, "tools", "check_frame_sharding.py"), "4", "32", "--animatediff"],
+                          os.path.join(ROOT, "tools", "check_frame_sharding.py"), "4", "32", "--animatediff", "--push"],
                          capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
     # every kernel sees the same operands in the same order as on one GPU (GroupNorm is per frame here): bit-identical
+    # ... with the NCCL all-to-all and with the rows pushed into the peers' symmetric memory (univst_exchange_push_f16)
     for key in ("idx5", "idx30"):
-        assert res[key]["max_abs"] == 0.0, res
+        assert res[key]["max_abs"] == 0.0 and res[key]["push_vs_single_max_abs"] == 0.0, res

@@ -307,6 +307,69 @@ extern "C" int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t
   return UNIVST_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Frames <-> pixels exchange of the frame-sharded AnimateDiff motion modules, written straight into the
+// peers' symmetric-memory buffers over NVLink: every 16-byte piece of a local row is stored at its place in the owner's
+// final layout, so the permute-copy, the NCCL all-to-all and the permute-copy back of the library path are ONE pass
+// (one read of the local rows, one write -- remote for (P - 1) / P of them).  The caller orders it with a cross-rank
+// barrier on the stream (torch symmetric memory) before anybody reads.
+//   dir 0: local rows (b, fl, pix)         -> rank pix / n, row (b, rank * Fl + fl, pix % n)      "all frames, my pixels"
+//   dir 1: local rows (b, f_global, pix_l) -> rank f_global / Fl, row (b, f_global % Fl, rank * n + pix_l)
+struct PeerPtrs {
+  __half* p[16];
+};
+
+template <int DIR>
+__global__ void exchange_push_kernel(const __half* __restrict__ src, int ld, PeerPtrs dst, int rank, int P, int B, int Fl,
+                                     int N, int C) {
+  const int vpr = C >> 3;                       // 16-byte vectors per row
+  const int n = N / P;
+  const long long rows = (long long)B * Fl * N;   // = B * (P Fl) * n
+  const long long total = rows * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vpr;
+    const int v = (int)(i - row * vpr);
+    int owner;
+    long long drow;
+    if (DIR == 0) {
+      const int pix = (int)(row % N);
+      const long long bf = row / N;                // b * Fl + fl
+      const int fl = (int)(bf % Fl), b = (int)(bf / Fl);
+      owner = pix / n;
+      drow = ((long long)b * (P * Fl) + rank * Fl + fl) * n + (pix - owner * n);
+    } else {
+      const int pl = (int)(row % n);
+      const long long bf = row / n;                // b * (P Fl) + f_global
+      const int fg = (int)(bf % (P * Fl)), b = (int)(bf / (P * Fl));
+      owner = fg / Fl;
+      drow = ((long long)b * Fl + (fg - owner * Fl)) * N + rank * n + pl;
+    }
+    const uint4 val = *reinterpret_cast<const uint4*>(src + row * ld + v * 8);
+    *reinterpret_cast<uint4*>(dst.p[owner] + drow * C + v * 8) = val;
+  }
+}
+
+extern "C" int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P,
+                                        int32_t B, int32_t Fl, int32_t N, int32_t C, void* stream) {
+  UV_REQUIRE(src && dst && (dir == 0 || dir == 1), "exchange_push: null pointer or bad direction");
+  UV_REQUIRE(P >= 1 && P <= 16 && rank >= 0 && rank < P && B > 0 && Fl > 0 && N > 0 && N % P == 0,
+             "exchange_push: up to 16 ranks, pixels divisible by the rank count");
+  UV_REQUIRE(C > 0 && C % 8 == 0 && ld % 8 == 0 && ld >= C, "exchange_push: channels and row stride must be multiples of 8");
+  PeerPtrs pp{};
+  for (int r = 0; r < P; ++r) {
+    UV_REQUIRE(dst[r], "exchange_push: null peer buffer");
+    pp.p[r] = (__half*)dst[r];
+  }
+  const size_t total = (size_t)B * Fl * N * (C / 8);
+  const int grid = grid_for(total, 256);
+  if (dir == 0)
+    exchange_push_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld, pp, rank, P, B, Fl, N, C);
+  else
+    exchange_push_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld, pp, rank, P, B, Fl, N, C);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
 extern "C" int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n, void* out, void* stream) {
   UV_REQUIRE(a && b && out && n > 0 && n < (1ll << 31), "axpby: bad arguments");
   axpby_kernel<<<grid_for((size_t)n, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)a, (const __half*)b, wa, wb,

@@ -43,6 +43,7 @@ _lib.register("univst_latent_blend_fc_f16", [_vp, _vp, _vp, _i32, _i32, _i32, _v
 _lib.register("univst_latent_adain_f16", [_vp, _vp, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp])
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
+_lib.register("univst_exchange_push_f16", [_i32, _vp, _i32, C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _vp])
 _lib.register("univst_maskprop_workspace_bytes", [_i32, _i32, _i32], _i64)
 _lib.register("univst_maskprop_f32", [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp])
 _lib.register("univst_flow_warp_key_u8", [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp), _f32, _vp])
@@ -53,7 +54,7 @@ launch_count = 0
 _LAUNCHES = {
     "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 3, "layernorm": 1, "upsample2x": 1,
     "temporal_attention": 1, "cross_attention": 1, "joint_attention": 1, "rmsnorm_heads": 1, "sd3_attn_shift": 4, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
-    "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
+    "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "exchange_push": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
 
 
@@ -512,6 +513,18 @@ def axpby(a, b, wa: float, wb: float, out=None):
           "univst_axpby_f16")
     _count("axpby")
     return out
+
+
+def exchange_push(direction: int, src: torch.Tensor, dst_ptrs, rank: int, P: int, B: int, Fl: int, N: int):
+    """Frames <-> pixels exchange of the frame-sharded motion modules: store the local rows [B * Fl * N, C] at their place
+    in every owner's buffer (``dst_ptrs``: device pointers of the P ranks' symmetric-memory buffers, each [rows, C]).
+    direction 0: frames -> pixels, 1: pixels -> frames.  The caller issues the cross-rank barrier."""
+    _lib.require_device()
+    assert src.dtype == torch.float16 and src.is_cuda and src.stride(1) == 1 and src.shape[0] == B * Fl * N and len(dst_ptrs) == P
+    arr = (_vp * P)(*dst_ptrs)
+    check(_lib.lib().univst_exchange_push_f16(direction, src.data_ptr(), src.stride(0), arr, rank, P, B, Fl, N, src.shape[1],
+                                              _stream()), "univst_exchange_push_f16")
+    _count("exchange_push")
 
 
 def maskprop(feat_tar, feat_src, segs, temperature: float = 0.2, topk: int = 15, return_kept: int = 0):
