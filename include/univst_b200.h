@@ -196,6 +196,12 @@ int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t ld, int32_
  * (b, global frame, local pixel); dir 1: the inverse.  The caller places a cross-rank barrier after it. */
 int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P, int32_t B,
                              int32_t Fl, int32_t N, int32_t C, void* stream);
+/* K/V halo of the frame-sharded sparse-causal attention (attention.py:395-410 needs frame f-1 and frame 0 of every
+ * branch): nblk blocks of [rows, cols] halves (block b at src + b * src_blk_rows * ld_src) are stored into every non-null
+ * dst[r] (HOST array of P device pointers into the ranks' symmetric-memory projection buffers; block b at
+ * dst[r] + b * dst_blk_rows * ld_dst).  One read, up to P peer writes over NVLink; the caller places the barrier. */
+int univst_halo_push_f16(const void* src, int32_t ld_src, int64_t src_blk_rows, void* const* dst, int32_t P, int32_t ld_dst,
+                         int64_t dst_blk_rows, int32_t nblk, int32_t rows, int32_t cols, void* stream);
 int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

@@ -75,7 +75,7 @@ def main():
         pnp_utils.register_time(pipe, idx)
         unet.set_frame_sharding_off()
         ref, t_single = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
-        unet.set_frame_sharding(**({"push_exchange": False} if AD else {}))
+        unet.set_frame_sharding(**({"push_exchange": False} if AD else {"push_halo": False}))   # the NCCL exchanges
         out, t_shard = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
         diff = (out.float() - ref.float())
         res[f"idx{idx}"] = {"max_abs": float(diff.abs().max()), "rel_l2": float(diff.norm() / ref.float().norm()),
@@ -85,6 +85,11 @@ def main():
             out_p, t_push = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
             res[f"idx{idx}"].update({"ms_sharded_push_exchange": t_push,
                                      "push_vs_single_max_abs": float((out_p.float() - ref.float()).abs().max())})
+        if "--push" in sys.argv and not AD:   # K/V halo stored straight into the peers' symmetric-memory banks
+            unet.set_frame_sharding(push_halo=True)
+            out_p, t_push = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
+            res[f"idx{idx}"].update({"ms_sharded_push_halo": t_push,
+                                     "push_vs_nccl_max_abs": float((out_p.float() - out.float()).abs().max())})
         if "--fused" in sys.argv and not AD:   # K/V halo read from peer memory by the attention kernel itself
             unet.set_frame_sharding(fused_halo=True)
             out_f, t_fused = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)

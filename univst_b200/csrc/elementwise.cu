@@ -349,6 +349,45 @@ __global__ void exchange_push_kernel(const __half* __restrict__ src, int ld, Pee
   }
 }
 
+// K/V halo of the frame-sharded sparse-causal attention: `nblk` blocks of [rows, cols] (one per branch: a
+// boundary frame's K|V columns of the fused projection) are read once and stored into every non-null destination -- the
+// next rank's "previous frame" bank, or, from rank 0, every rank's "first frame" bank -- over NVLink peer mappings.
+__global__ void halo_push_kernel(const __half* __restrict__ src, int ld_src, long long src_blk, PeerPtrs dst, int P,
+                                 int ld_dst, long long dst_blk, int nblk, int rows, int cols) {
+  const int vpr = cols >> 3;
+  const long long total = (long long)nblk * rows * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int v = (int)(i % vpr);
+    const long long rr = i / vpr;
+    const int row = (int)(rr % rows), blk = (int)(rr / rows);
+    const uint4 val = *reinterpret_cast<const uint4*>(src + (blk * src_blk + row) * ld_src + v * 8);
+    const long long off = (blk * dst_blk + row) * ld_dst + v * 8;
+    for (int r = 0; r < P; ++r)
+      if (dst.p[r]) *reinterpret_cast<uint4*>(dst.p[r] + off) = val;
+  }
+}
+
+extern "C" int univst_halo_push_f16(const void* src, int32_t ld_src, int64_t src_blk_rows, void* const* dst, int32_t P,
+                                    int32_t ld_dst, int64_t dst_blk_rows, int32_t nblk, int32_t rows, int32_t cols,
+                                    void* stream) {
+  UV_REQUIRE(src && dst && P >= 1 && P <= 16 && nblk > 0 && rows > 0 && cols > 0, "halo_push: bad arguments (up to 16 ranks)");
+  UV_REQUIRE(cols % 8 == 0 && ld_src % 8 == 0 && ld_dst % 8 == 0, "halo_push: columns and row strides must be multiples of 8");
+  UV_REQUIRE(((uintptr_t)src & 15) == 0, "halo_push: source must be 16-byte aligned");
+  PeerPtrs pp{};
+  int any = 0;
+  for (int r = 0; r < P; ++r) {
+    pp.p[r] = (__half*)dst[r];
+    UV_REQUIRE(((uintptr_t)dst[r] & 15) == 0, "halo_push: destinations must be 16-byte aligned");
+    any |= dst[r] != nullptr;
+  }
+  if (!any) return UNIVST_OK;
+  const size_t total = (size_t)nblk * rows * (cols / 8);
+  halo_push_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld_src, src_blk_rows, pp, P,
+                                                                         ld_dst, dst_blk_rows, nblk, rows, cols);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
 extern "C" int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P,
                                         int32_t B, int32_t Fl, int32_t N, int32_t C, void* stream) {
   UV_REQUIRE(src && dst && (dir == 0 || dir == 1), "exchange_push: null pointer or bad direction");

@@ -43,6 +43,7 @@ _lib.register("univst_latent_blend_fc_f16", [_vp, _vp, _vp, _i32, _i32, _i32, _v
 _lib.register("univst_latent_adain_f16", [_vp, _vp, _i32, _i32, _i32, _vp, _vp])
 _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _f32, _f32, _vp, _vp, _vp])
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
+_lib.register("univst_halo_push_f16", [_vp, _i32, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _vp])
 _lib.register("univst_exchange_push_f16", [_i32, _vp, _i32, C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _vp])
 _lib.register("univst_maskprop_workspace_bytes", [_i32, _i32, _i32], _i64)
 _lib.register("univst_maskprop_f32", [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp])
@@ -54,7 +55,7 @@ launch_count = 0
 _LAUNCHES = {
     "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 3, "layernorm": 1, "upsample2x": 1,
     "temporal_attention": 1, "cross_attention": 1, "joint_attention": 1, "rmsnorm_heads": 1, "sd3_attn_shift": 4, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
-    "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "exchange_push": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
+    "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "exchange_push": 1, "halo_push": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
 }
 
 
@@ -513,6 +514,18 @@ def axpby(a, b, wa: float, wb: float, out=None):
           "univst_axpby_f16")
     _count("axpby")
     return out
+
+
+def halo_push(src: torch.Tensor, src_blk_rows: int, dst_ptrs, ld_dst: int, dst_blk_rows: int, nblk: int, rows: int):
+    """Store ``nblk`` blocks [rows, src.shape[1]] of the strided view ``src`` (block b starts ``b * src_blk_rows`` rows in)
+    into every non-zero destination pointer (block b at ``b * dst_blk_rows`` rows of stride ``ld_dst``)."""
+    _lib.require_device()
+    assert src.dtype == torch.float16 and src.is_cuda and src.stride(1) == 1
+    P = len(dst_ptrs)
+    arr = (_vp * P)(*[p or None for p in dst_ptrs])
+    check(_lib.lib().univst_halo_push_f16(src.data_ptr(), src.stride(0), src_blk_rows, arr, P, ld_dst, dst_blk_rows, nblk, rows,
+                                          src.shape[1], _stream()), "univst_halo_push_f16")
+    _count("halo_push")
 
 
 def exchange_push(direction: int, src: torch.Tensor, dst_ptrs, rank: int, P: int, B: int, Fl: int, N: int):

@@ -127,6 +127,7 @@ class UNetPseudo3DConditionModel:
         self._ctx_cache = None
         self._shard = None  # (process group, rank, world) when frames are sharded over GPUs
         self._fused_halo = False
+        self._push_halo = False
         self._build_tree()
         self._pack(state_dict)
 
@@ -138,12 +139,16 @@ class UNetPseudo3DConditionModel:
         cfg = {k: c[k] for k in SD15_CONFIG if k in c}
         return cls(module.state_dict(), cfg, device=device)
 
-    def set_frame_sharding(self, group=None, fused_halo: bool = False):
+    def set_frame_sharding(self, group=None, fused_halo: bool = False, push_halo=None):
         """Shard the frames of every clip over the ranks of ``group`` (default: the world group): rank r evaluates
         frames [r F/P, (r+1) F/P) of all branches.  Every cross-frame GroupNorm all-reduces B x 32 x 2 floats; the
         predicted noise is all-gathered at the end.  The K/V of the neighbouring frames that attn1 needs from other
         ranks (last frame of the previous rank, frame 0 of the clip) arrive in one of two ways:
-        * ``fused_halo=False``: NCCL send/recv + broadcast into two halo banks behind the local images;
+        * ``push_halo=True`` (the default on NCCL groups): the fused projection lives in torch symmetric memory with two
+          halo banks behind the local images; one kernel stores the K|V columns of the boundary frame into the next
+          rank's bank, and rank 0's first frame into every rank's bank, over NVLink (``univst_halo_push_f16``), followed
+          by one cross-rank barrier (double buffering makes a second one unnecessary);
+        * ``push_halo=False``: the same banks filled by NCCL send/recv + broadcast;
         * ``fused_halo=True``: no exchange step at all -- the fused projection is written into torch symmetric memory
           and the attention kernel's TMA producer reads the peers' K/V tiles straight over NVLink while the tensor pipe
           works on the previous tile (``univst_sc_attention_sharded_f16``); one cross-rank barrier per layer orders
@@ -156,6 +161,9 @@ class UNetPseudo3DConditionModel:
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
         self._tables = {}
         self._fused_halo = bool(fused_halo) and self._shard is not None
+        if push_halo is None:
+            push_halo = self._shard is not None and dist.get_backend(group) == "nccl"
+        self._push_halo = bool(push_halo) and self._shard is not None and not self._fused_halo
         if not hasattr(self, "_symm"):
             self._symm = {}
 
@@ -179,9 +187,42 @@ class UNetPseudo3DConditionModel:
         first = peers[0][par] if rank > 0 else None
         return t[par], prev, first, hdl
 
+    def _symm_halo(self, rows, cols):
+        """Double-buffered symmetric-memory projection buffer WITH halo banks: (local [rows, cols] tensor to fill, device
+        pointers of every rank's copy of the same buffer, handle)."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group, rank, world = self._shard
+        key = ("halo", rows, cols)
+        if key not in self._symm:
+            t = symm_mem.empty(2, rows, cols, dtype=torch.float16, device=self.device)
+            hdl = symm_mem.rendezvous(t, group if group is not None else dist.group.WORLD)
+            ptrs = [hdl.get_buffer(r, (2, rows, cols), torch.float16).data_ptr() for r in range(world)]
+            self._symm[key] = [t, hdl, ptrs, 0]
+        ent = self._symm[key]
+        t, hdl, ptrs, par = ent
+        ent[3] = par ^ 1
+        return t[par], [p + par * rows * cols * 2 for p in ptrs], hdl
+
+    def _push_kv_halo(self, qkv, ptrs, hdl, B, F, N, C):
+        """Frame-sharded attn1, push flavour of :meth:`_exchange_kv_halo`: K|V columns (C .. 3C) of my last frame -> bank 1
+        of rank + 1, of the clip's first frame (rank 0) -> bank 2 of every rank; then the barrier."""
+        group, rank, world = self._shard
+        NI, ld = B * F, qkv.stride(0)
+        kv = qkv[:, C:]                                   # [rows, 2C] strided view of the K|V columns
+        if rank + 1 < world:
+            dst = [0] * world
+            dst[rank + 1] = ptrs[rank + 1] + (NI * N * ld + C) * 2
+            ops.halo_push(kv[(F - 1) * N:], F * N, dst, ld, N, B, N)
+        if rank == 0:
+            dst = [p + ((NI + B) * N * ld + C) * 2 for p in ptrs]
+            ops.halo_push(kv, F * N, dst, ld, N, B, N)
+        hdl.barrier(channel=0)
+
     def set_frame_sharding_off(self):
         self._shard = None
         self._fused_halo = False
+        self._push_halo = False
         self._tables = {}
 
     def _heads(self, level):
@@ -369,7 +410,10 @@ class UNetPseudo3DConditionModel:
             qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"], out=qkv_buf)
         else:  # two halo banks of B images each behind the local images
             NIkv = NI + 2 * B
-            qkv_all = torch.empty((NIkv * N, 3 * C), dtype=torch.float16, device=x.device)
+            if self._push_halo:
+                qkv_all, halo_ptrs, symm_hdl = self._symm_halo(NIkv * N, 3 * C)
+            else:
+                qkv_all = torch.empty((NIkv * N, 3 * C), dtype=torch.float16, device=x.device)
             qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"], out=qkv_all[: NI * N])
         if shift is not None:
             if B != 3:
@@ -380,7 +424,10 @@ class UNetPseudo3DConditionModel:
             o = ops.sc_attention_sharded(qkv, qkv_prev, qkv_first, self._table(B, F, mode), B=B, Fl=F, H=heads, d=d, N=N)
         else:
             if halo:
-                self._exchange_kv_halo(qkv_all, B, F, N)
+                if self._push_halo:
+                    self._push_kv_halo(qkv_all, halo_ptrs, symm_hdl, B, F, N, C)
+                else:
+                    self._exchange_kv_halo(qkv_all, B, F, N)
                 kv = qkv_all
             else:
                 kv = qkv
