@@ -250,7 +250,18 @@ def run_ours(args):
             for t in (v if isinstance(v, list) else [v]):
                 dist.broadcast(t, src=0)
         ref0 = stylize(shared)           # rank-local evaluation of rank 0's clip
-        unet.set_frame_sharding()
+        # K/V halo pushed into the peers' symmetric memory when that works on every rank of this box, else through NCCL
+        ok = torch.ones(1, device=dev)
+        try:
+            import torch.distributed._symmetric_memory as symm_mem
+            probe = symm_mem.empty(64, dtype=torch.float16, device=dev)
+            symm_mem.rendezvous(probe, dist.group.WORLD).barrier(channel=0)
+            torch.cuda.synchronize()
+        except Exception:
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        push_halo = bool(ok.item() > 0)
+        unet.set_frame_sharding(push_halo=push_halo)
         stylize(shared)                  # warm-up (NCCL channels, halo buffers)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -359,7 +370,9 @@ def run_ours(args):
     if ms_fs > 0:
         line["config"]["one_clip_frame_sharded"] = {"frames_per_s": F_FRAMES / (ms_fs / 1e3), "scaling": "strong",
                                                     "ms_per_clip": ms_fs, "rel_l2_vs_single_gpu": fs_rel,
-                                                    "collectives": "K/V halo send/recv + frame-0 broadcast per attn1, GroupNorm stat all-reduce, eps all-gather (NCCL)"}
+                                                    "collectives": ("K/V halo pushed into the peers' symmetric-memory banks over NVLink + one barrier per attn1"
+                                                                    if push_halo else "K/V halo send/recv + frame-0 broadcast per attn1 (NCCL)")
+                                                    + "; GroupNorm stat all-reduce, eps all-gather (NCCL)"}
     if ms_inv != 0.0:
         line["config"]["ddim_inversion_50_steps"] = {"frames_per_s": F_FRAMES / (ms_inv / 1e3) if ms_inv > 0 else None,
                                                      "ms_per_clip": ms_inv, "note": "content inversion of the same clip, "
