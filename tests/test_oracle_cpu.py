@@ -287,3 +287,50 @@ def test_sd3_pipeline_oracle_matches_reference_loops():
     assert not torch.allclose(g["cases"]["masked"]["final"], g["cases"]["unmasked"]["final"], atol=1e-3)
     rc = so.reconstruction(sch, tr, traj_c[0], traj_c[50], 0.9, "linear_decrease", 0, 6, n)
     assert torch.allclose(rc, g["cases"]["reconstruction"]["final"], atol=1e-5)
+
+
+def test_sd3_pipeline_host_logic_on_cpu(monkeypatch):
+    """Host side of univst_b200.sd3_pipeline (schedule, eta window, trajectory index, mask / AdaIN windows, folded velocity
+    interpolation + Euler step, input formats) with the five kernels it calls replaced by their torch definitions: must
+    land on the reference's latents up to the fp16 storage of the latents (the kernels themselves are checked on the GPU)."""
+    import torch.nn.functional as F
+    from types import SimpleNamespace
+    from oracle import sd3_pipeline_oracle as so
+    from univst_b200 import ops
+    from univst_b200.sd3_pipeline import CustomStableDiffusion3Pipeline, calculate_shift
+    monkeypatch.setattr(ops, "axpby", lambda a, b, wa, wb, out=None: (wa * a.float() + wb * b.float()).half())
+    monkeypatch.setattr(ops, "latent_blend_fc", lambda a, b, m, out=None:
+                        ((1 - m[:, None].float()) * a.float() + m[:, None].float() * b.float()).half())
+    monkeypatch.setattr(ops, "plane_adain", lambda c, s, out=None: so.latent_adain(c.float(), s.float()).half())
+    monkeypatch.setattr(ops, "mask_resize", lambda m, h, w:
+                        F.interpolate(m[None].float(), size=(h, w), mode="bilinear", align_corners=False)[0].half())
+    g = torch.load(os.path.join(GOLDEN, "sd3_pipeline.pt"), weights_only=True)
+    n = g["n"]
+    traj_c, traj_s, mask_u8 = so.synthetic_inputs(g["input_seed"], g["frames"], g["channels"], g["hw"], n)
+    tr = so.FakeTransformer(g["channels"], g["transformer_seed"])
+
+    class Fp32Transformer:   # CPU has no fp16 einsum speed to speak of: evaluate the stand-in field in fp32
+        config, calls = tr.config, tr.calls
+
+        def __call__(self, hidden_states, **kw):
+            return (tr(hidden_states.float(), **kw)[0],)
+
+    host = SimpleNamespace(transformer=Fp32Transformer(), scheduler=so.FakeFlowMatchScheduler(),
+                           encode_prompt=so.fake_encode_prompt(), device="cpu")
+    pipe = CustomStableDiffusion3Pipeline(host)
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    z_T = so.latent_adain(traj_c[50], traj_s[50])
+    for name, m in (("masked", torch.from_numpy(mask_u8)), ("unmasked", None)):
+        tr.calls.clear()
+        out = pipe.video_style_transfer("", latents=z_T, img_latents=traj_c[0], num_inference_steps=n, content_inv_path=traj_c,
+                                        style_inv_path=traj_s, mask_path=m, eta_base=0.85, eta_trend="constant", start_step=5,
+                                        end_step=8, output_type="latent").images
+        assert [c[0] for c in tr.calls] == list(range(n))
+        assert rel(out, g["cases"][name]["final"]) < 3e-3
+    rc = pipe.reconstruction(traj_c[0], traj_c[50], 0.9, "linear_decrease", 0, 6, num_inference_steps=n, output_type="latent")
+    assert rel(rc, g["cases"]["reconstruction"]["final"]) < 3e-3
+    with pytest.raises(ValueError):   # a 3-frame mask for a 16-frame clip
+        pipe.video_style_transfer("", latents=z_T, img_latents=traj_c[0], num_inference_steps=n, content_inv_path=traj_c,
+                                  style_inv_path=traj_s, mask_path=torch.from_numpy(mask_u8[:3]), start_step=5, end_step=8,
+                                  output_type="latent")
+    assert calculate_shift(4096) == pytest.approx(1.15) and calculate_shift(256) == pytest.approx(0.5)
