@@ -63,7 +63,7 @@ typedef struct univst_epilogue {
 int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32_t lda2, int32_t K1, const void* W, int32_t M,
                     int32_t N, int32_t K, void* D, int32_t ldd, const univst_epilogue_t* ep, void* stream);
 
-/* Y[NB*H*W, Cout] = epilogue( conv3x3(X, Wt[Cout, 3, 3, C1 + C2], padding 1) ), H x W = OUTPUT size, W <= 128 (power-of-two sizes tile exactly; any other size takes row-block tiles).
+/* Y[NB*H*W, Cout] = epilogue( conv3x3(X, Wt[Cout, 3, 3, C1 + C2], padding 1) ), H x W = OUTPUT size (power-of-two sizes up to W = 128 tile exactly; any other size takes row-block / row-segment tiles).
  * Implicit GEMM: the 9 taps are 4-D TMA boxes over the NHWC activation with out-of-bounds zero fill (no im2col).
  *   stride 1: X is [NB, H, W, C1]; X2 (optional) is [NB, H, W, C2] -- the skip-connection concat of the up blocks
  *             (unet_3d_blocks.py:523,618) is folded into the K loop, the concatenated tensor never exists.

@@ -130,6 +130,9 @@ def test_conv3x3_stride2(cuda_lib, NB, H, W, C, Cout):
     (2, 12, 20, 128, 64, 128, 1),   # two sources, 6 rows per tile
     (7, 6, 10, 64, 0, 160, 1),      # 60 pixels: 2 images per tile, odd image count
     (2, 72, 128, 64, 0, 64, 1),     # widest supported row (one row per tile), non-power-of-two height
+    (1, 6, 160, 64, 0, 64, 1),      # rows wider than a tile (1280-pixel frames): one 128-pixel segment of a row per tile
+    (2, 3, 256, 64, 64, 96, 1),     # power-of-two width above 128, two sources
+    (2, 4, 144, 64, 0, 64, 2),      # stride 2 from 8 x 288
     (3, 12, 20, 64, 0, 128, 2),     # stride 2 from 24 x 40
     (4, 3, 5, 128, 0, 64, 2),       # stride 2 from 6 x 10
 ])

@@ -115,6 +115,7 @@ def test_feature_dump_matches_oracle(setup, tmp_path):
     (3, 1, 16, 16, True),     # three branches of a single frame through the shift
     (3, 3, 24, 40, True),     # non-square latent: 960 / 240 / 60 / 15 tokens -- ragged tiles at every level
     (3, 5, 40, 8, True),      # odd frame count, tall latent
+    (3, 2, 8, 136, True),     # rows wider than one 128-pixel tile (1088-pixel frames)
 ])
 def test_unet_forward_edge_shapes(setup, B, F, h, w, patched):
     """Shapes the goldens do not hold, against the (golden-pinned) oracle in fp32 on the same seeded inputs."""

@@ -25,7 +25,7 @@ static constexpr int kThreads = 64 + 32 * kEpiWarps;
 struct GemmParams {
   int M, N, N_out, BN;
   int num_kb;           // k-blocks of 64
-  int mode;             // 0 = linear A[M,K]; 1 = conv taps over NHWC; 2 = conv, row-block tiles (any H, W <= 128)
+  int mode;             // 0 = linear A[M,K]; 1 = conv taps over NHWC; 2 = conv, row-block tiles (any H, W)
   int kb_split;         // linear: first k-block served by A2; conv: channel blocks per tap served by A (cbs1)
   int K1;               // linear: K columns in A; conv: channels in A (C1)
   int cbs;              // conv: channel blocks per tap (cbs1 + cbs2)
@@ -33,8 +33,9 @@ struct GemmParams {
   int HW, W;            // conv: output pixels per image, output width (== box width)
   int plane_stride;     // conv: images per parity plane (stride-2 input was rearranged into 4 planes)
   // mode 2: a tile is `gen_th` full-width rows of one image (`gen_rb` such row blocks per image) or, for images of
-  // <= 128 pixels, `gen_bn` whole images; only its first gen_th * W * gen_bn rows are real (the rest are masked)
-  int gen_th, gen_rb, gen_bn, gen_tiles_m;
+  // <= 128 pixels, `gen_bn` whole images; only its first gen_th * W * gen_bn rows are real (the rest are masked).
+  // Rows wider than 128 pixels (gen_seg > 1) are cut into gen_seg segments of 128: a tile is one segment of one row.
+  int gen_th, gen_rb, gen_bn, gen_tiles_m, gen_seg;
   int8_t tap_dy[9], tap_dx[9], tap_plane[9];
   int stages;
   int cluster;          // 2: CTA pairs share every weight tile (each loads half of it and multicasts), 1: independent CTAs
@@ -310,18 +311,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tile_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   auto tile_m0 = [&](int tile) {   // first output row of the tile; may be >= M for the odd tail
     const int mm = (tile / tiles_n) * CL + (int)crank;
-    if (p.mode == 2) return (mm / p.gen_rb) * p.gen_bn * p.HW + (mm % p.gen_rb) * p.gen_th * p.W;
+    if (p.mode == 2) {
+      if (p.gen_seg > 1) return (mm / p.gen_seg) * p.W + (mm % p.gen_seg) * kBM;   // (image, row) = mm / gen_seg: rows are consecutive
+      return (mm / p.gen_rb) * p.gen_bn * p.HW + (mm % p.gen_rb) * p.gen_th * p.W;
+    }
     return mm * kBM;
   };
   auto tile_mlim = [&](int m0) {    // one past the last real output row of the tile
     if (p.mode != 2) return p.M;
+    if (p.gen_seg > 1) {                                    // a segment ends with its image row
+      const int row_end = (m0 / p.W + 1) * p.W;
+      return m0 + kBM < row_end ? m0 + kBM : row_end;
+    }
     const int group_end = (m0 / p.HW + p.gen_bn) * p.HW;   // the row block must not run into the next image (group)
     int lim = m0 + p.gen_th * p.W * p.gen_bn;
     lim = lim < group_end ? lim : group_end;
     return lim < p.M ? lim : p.M;
   };
   // bytes one stage receives: in mode 2 the A box holds only the real rows
-  const uint32_t tx_bytes = (p.mode == 2) ? (uint32_t)(p.gen_th * p.W * p.gen_bn) * (kBK * 2) + b_bytes : stage_bytes;
+  const uint32_t tx_bytes = (p.mode == 2 && p.gen_seg == 1) ? (uint32_t)(p.gen_th * p.W * p.gen_bn) * (kBK * 2) + b_bytes : stage_bytes;
 
   // accumulator stride: BN rounded up to a power of two >= 32 (TMEM allocations are powers of two)
   uint32_t acc_cols = 32;
@@ -360,10 +368,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
         const int m0 = tile_m0(tile);
         const int n0 = (tile % tiles_n) * p.BN;
-        int cn = 0, cy = 0;
+        int cn = 0, cy = 0, cx = 0;
         if (p.mode >= 1) {
           cn = m0 / p.HW;
           cy = (m0 % p.HW) / p.W;
+          if (p.mode == 2) cx = m0 % p.W;   // non-zero only for the segments of rows wider than 128 pixels
         }
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
@@ -380,7 +389,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           } else {
             const int tap = kb / p.cbs;
             const int cb = kb - tap * p.cbs;
-            const int x = p.tap_dx[tap], y = cy + p.tap_dy[tap], n = cn + p.tap_plane[tap] * p.plane_stride;
+            const int x = cx + p.tap_dx[tap], y = cy + p.tap_dy[tap], n = cn + p.tap_plane[tap] * p.plane_stride;
             if (cb < p.kb_split) {
               kw = tap * p.Cin + cb * kBK;
               tma_load_4d(sa, &tmA, &full_bar[s], cb * kBK, x, y, n);
@@ -655,9 +664,10 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
   UV_REQUIRE(stride == 1 || !X2, "conv3x3: stride 2 takes a single (parity-plane) source");
   // output geometry; for stride 2 the caller passes the 4 parity planes [4][NB][H/2][W/2][C] and H, W of the OUTPUT
   const int Ho = H, Wo = W;
-  UV_REQUIRE(Wo <= 128 && Ho > 0 && Wo > 0, "conv3x3: output width must be <= 128 (1024-pixel frames)");
-  // power-of-two images tile exactly into 128-row blocks of consecutive pixels (mode 1); anything else takes row-block tiles
-  const bool pow2 = (Wo & (Wo - 1)) == 0 && (Ho & (Ho - 1)) == 0;
+  UV_REQUIRE(Ho > 0 && Wo > 0, "conv3x3: empty image");
+  // power-of-two images (width <= 128) tile exactly into 128-row blocks of consecutive pixels (mode 1); anything else takes
+  // row-block tiles
+  const bool pow2 = (Wo & (Wo - 1)) == 0 && (Ho & (Ho - 1)) == 0 && Wo <= 128;
   GemmParams p{};
   fill_epilogue(p, ep);
   UV_REQUIRE(!p.geglu, "conv3x3: no GEGLU epilogue");
@@ -695,10 +705,20 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
   p.D = (__half*)Y;
   p.ldd = ldy;
 
-  const int bw = Wo;
+  int bw = Wo;
   int bh = (Ho * Wo >= kBM) ? kBM / bw : Ho;
   int bn = kBM / (bw * bh);
-  if (!pow2) {
+  p.gen_seg = 1;
+  if (!pow2 && Wo > kBM) {       // one 128-pixel segment of one row per tile
+    bw = kBM;
+    bh = 1;
+    bn = 1;
+    p.gen_seg = (Wo + kBM - 1) / kBM;
+    p.gen_th = 1;
+    p.gen_bn = 1;
+    p.gen_rb = Ho * p.gen_seg;
+    p.gen_tiles_m = NB * Ho * p.gen_seg;
+  } else if (!pow2) {
     if (Ho * Wo <= kBM) {        // whole images: bn per tile
       bh = Ho;
       bn = kBM / (Ho * Wo);

@@ -457,9 +457,8 @@ class UNetPseudo3DConditionModel:
         dev = self.device
         B, Cin, F, H, Wd = sample.shape
         q = 1 << (self.nlev - 1)
-        if H % q or Wd % q or Wd > 128:
-            raise ValueError(f"latent height / width must be multiples of {q} (the UNet halves them {self.nlev - 1} times) "
-                             "and the width at most 128 (1024-pixel frames)")
+        if H % q or Wd % q:
+            raise ValueError(f"latent height / width must be multiples of {q} (the UNet halves them {self.nlev - 1} times)")
         boc = cfg["block_out_channels"]
         sample = sample.to(device=dev, dtype=torch.float16).contiguous()
         F_total = F
