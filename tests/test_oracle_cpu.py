@@ -334,3 +334,40 @@ def test_sd3_pipeline_host_logic_on_cpu(monkeypatch):
                                   style_inv_path=traj_s, mask_path=torch.from_numpy(mask_u8[:3]), start_step=5, end_step=8,
                                   output_type="latent")
     assert calculate_shift(4096) == pytest.approx(1.15) and calculate_shift(256) == pytest.approx(0.5)
+
+
+def test_sd3_feature_dump_wrapper(tmp_path):
+    """FeatureDumpTransformer == the reference's CustomSD3Transformer2DModel side effect (transformer_3D_model.py:77-84):
+    after block i in ft_indices, at step idx in ft_timesteps, the image stream as (B, h/2, w/2, C) in
+    inversion_feature_map_{i}_block_{idx}_step.pt -- and nothing otherwise."""
+    from univst_b200.sd3 import FeatureDumpTransformer
+
+    class Block(torch.nn.Module):
+        def forward(self, hidden_states, encoder_hidden_states):
+            return encoder_hidden_states, hidden_states + 1
+
+    class Stock(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.transformer_blocks = torch.nn.ModuleList([Block() for _ in range(3)])
+            self.config = {}
+
+        def forward(self, hidden_states, encoder_hidden_states=None, **kw):
+            B, C, h, w = hidden_states.shape
+            x = hidden_states.reshape(B, C, h // 2, 2, w // 2, 2).permute(0, 2, 4, 1, 3, 5).reshape(B, (h // 2) * (w // 2), C * 4)
+            e = encoder_hidden_states
+            for blk in self.transformer_blocks:
+                e, x = blk(x, e)
+            return (x,)
+
+    m = FeatureDumpTransformer(Stock())
+    x, e = torch.zeros(2, 4, 8, 6), torch.zeros(2, 3, 5)
+    out = m(x, encoder_hidden_states=e, idx=4, ft_indices=[0, 2], ft_timesteps=[4, 7], ft_path=str(tmp_path))[0]
+    m(x, encoder_hidden_states=e, idx=5, ft_indices=[0, 2], ft_timesteps=[4, 7], ft_path=str(tmp_path))   # not a dump step
+    m(x, encoder_hidden_states=e)                                                                         # plain call
+    assert sorted(os.listdir(tmp_path)) == ["inversion_feature_map_0_block_4_step.pt", "inversion_feature_map_2_block_4_step.pt"]
+    f0 = torch.load(tmp_path / "inversion_feature_map_0_block_4_step.pt", weights_only=True)
+    f2 = torch.load(tmp_path / "inversion_feature_map_2_block_4_step.pt", weights_only=True)
+    assert tuple(f0.shape) == (2, 4, 3, 16) and float(f0.mean()) == 1.0 and float(f2.mean()) == 3.0
+    assert torch.equal(out, f2.view(2, 12, 16)) and not Stock().transformer_blocks[0]._forward_hooks
+    assert not m.transformer.transformer_blocks[0]._forward_hooks   # hooks are removed after the call

@@ -116,3 +116,40 @@ def register_spatial_attention_pnp(model, eta1=0.0, eta2=0.6):
     procs = {name: (AttentionShiftProcessor(eta1, eta2) if "attn" in name else proc)
              for name, proc in model.transformer.attn_processors.items()}
     model.transformer.set_attn_processor(procs)
+
+
+class FeatureDumpTransformer:
+    """``CustomSD3Transformer2DModel`` (backbones/video_diffusion_sd3/models/transformer_3D_model.py:12-113) without
+    re-stating the third-party forward: the reference subclasses diffusers' ``SD3Transformer2DModel`` only to accept
+    ``idx`` / ``ft_indices`` / ``ft_timesteps`` / ``ft_path`` and to save, after block ``i`` in ``ft_indices`` when ``idx`` in
+    ``ft_timesteps``, the image stream as ``inversion_feature_map_{i}_block_{idx}_step.pt`` with shape
+    (B, h / 2, w / 2, C) (:77-84 -- the features mask propagation reads).  This wrapper adds the same keywords and the same
+    files to a stock transformer through forward hooks on ``transformer_blocks[i]`` (a joint block returns
+    ``(encoder_hidden_states, hidden_states)``; the last block's first element may be None)."""
+
+    def __init__(self, transformer):
+        self.transformer = transformer
+        self.config = transformer.config
+
+    def __getattr__(self, name):   # attn_processors, set_attn_processor, dtype, device, ...
+        return getattr(self.transformer, name)
+
+    def __call__(self, hidden_states, *args, idx=0, ft_indices=None, ft_timesteps=None, ft_path=None, **kwargs):
+        import os
+        hooks = []
+        if ft_indices is not None and ft_timesteps and ft_path is not None and idx in ft_timesteps:
+            h2, w2 = hidden_states.shape[-2] // 2, hidden_states.shape[-1] // 2
+
+            def saver(i):
+                def hook(_module, _inputs, output):
+                    hs = output[1] if isinstance(output, (tuple, list)) else output
+                    path = os.path.join(ft_path, f"inversion_feature_map_{i}_block_{idx}_step.pt")
+                    torch.save(hs.view(hs.shape[0], h2, w2, -1).detach(), path)
+                return hook
+            for i in ft_indices:
+                hooks.append(self.transformer.transformer_blocks[i].register_forward_hook(saver(i)))
+        try:
+            return self.transformer(hidden_states, *args, **kwargs)
+        finally:
+            for h in hooks:
+                h.remove()
