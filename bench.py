@@ -159,7 +159,7 @@ def run_reference(args):
             "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
                              "sample": f"{k} three-branch DDIM step(s), 3 x {sample_frames} frames at 64x64 latents, full SD-1.5 width, fp32"},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -387,9 +387,12 @@ def run_ours(args):
         dt = step()
         line["cpu_baseline"] = {"value": 2 / (STEPS_DDIM * dt), "unit": "frames/s", "cores": threads, "kind": "port",
                                 "sample": "1 three-branch DDIM step, 3 x 2 frames at 64x64 latents, full SD-1.5 width, fp32 oracle port"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+_OUT = sys.stdout   # where the JSON line goes (main() re-points it at a private duplicate of fd 1)
 
 
 def main():
@@ -402,6 +405,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-animatediff", action="store_true")
     args = ap.parse_args()
+    # stdout carries exactly ONE line, the JSON: libraries that write banners to fd 1 from C (NCCL prints its version there
+    # under torchrun) are sent to stderr, and the line itself goes to a duplicate of the original descriptor
+    global _OUT
+    sys.stdout.flush()
+    _OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:
