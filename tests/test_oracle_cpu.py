@@ -371,3 +371,33 @@ def test_sd3_feature_dump_wrapper(tmp_path):
     assert tuple(f0.shape) == (2, 4, 3, 16) and float(f0.mean()) == 1.0 and float(f2.mean()) == 3.0
     assert torch.equal(out, f2.view(2, 12, 16)) and not Stock().transformer_blocks[0]._forward_hooks
     assert not m.transformer.transformer_blocks[0]._forward_hooks   # hooks are removed after the call
+
+
+def test_accelerate_swaps_the_unet_of_a_reference_pipeline():
+    """univst_b200.accelerate(pipe): the reference pipeline keeps its identity, its .unet becomes the B200 UNet built from
+    the reference module's state_dict / config, with the handles the reference's patch protocol walks and a config that
+    answers both config["x"] and config.x (construction needs no GPU; the forward does)."""
+    from types import SimpleNamespace
+    import univst_b200
+    from univst_b200 import pnp_utils
+    from univst_b200.unet import UNetPseudo3DConditionModel
+
+    class RefUNet(torch.nn.Module):   # what accelerate() reads off the reference module
+        def __init__(self):
+            super().__init__()
+            self._sd = uo.seeded_state_dict(uo.TINY_CONFIG, seed=1)
+            self.config = dict(uo.TINY_CONFIG, sample_size=64)
+
+        def state_dict(self):
+            return self._sd
+
+    pipe = SimpleNamespace(unet=RefUNet(), scheduler="kept")
+    assert univst_b200.accelerate(pipe, device="cpu") is pipe and pipe.scheduler == "kept"
+    assert isinstance(pipe.unet, UNetPseudo3DConditionModel)
+    assert pipe.unet.config.in_channels == 4 and pipe.unet.config["sample_size"] == 64
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    pnp_utils.register_time(pipe, 7)
+    a1 = pipe.unet.up_blocks[3].attentions[2].transformer_blocks[0].attn1
+    assert a1.idx == 7 and a1.eta1 == 0.0 and a1.eta2 == 0.5
+    with pytest.raises(AttributeError):
+        pipe.unet.config.no_such_key

@@ -38,6 +38,16 @@ SD21_CONFIG = dict(SD15_CONFIG, attention_head_dim=(5, 10, 20, 20), cross_attent
 CIN_PAD = 64  # conv_in reads a latent zero-padded to one 128-byte swizzle row of channels
 
 
+class _Config(dict):
+    """The UNet configuration with diffusers' FrozenDict-style access: ``config["x"]`` and ``config.x``."""
+
+    def __getattr__(self, name):
+        try:
+            return self[name]
+        except KeyError:
+            raise AttributeError(name) from None
+
+
 def kv_source_table(B: int, F: int, mode: str) -> torch.Tensor:
     """int32 [B*F, nsrc]: K/V source images of image (b, f) for the sparse-causal modes of the reference:
     ``prev_first`` = SparseCausalAttention_index [-1, 'first'] (patched attn1, pnp_utils.py:25),
@@ -118,7 +128,7 @@ class UNetPseudo3DConditionModel:
     def __init__(self, state_dict: Dict[str, torch.Tensor], config: Optional[dict] = None, device="cuda"):
         cfg = dict(SD15_CONFIG)
         cfg.update(config or {})
-        self.config = cfg
+        self.config = _Config(cfg)   # item and attribute access (stable_diffusion.py:572 reads unet.config.in_channels)
         self.device = torch.device(device)
         self.dtype = torch.float16
         boc = cfg["block_out_channels"]
@@ -137,6 +147,8 @@ class UNetPseudo3DConditionModel:
         """Build from a reference ``UNetPseudo3DConditionModel`` nn.Module (weights are copied and packed once)."""
         c = module.config
         cfg = {k: c[k] for k in SD15_CONFIG if k in c}
+        if "sample_size" in c:
+            cfg["sample_size"] = c["sample_size"]
         return cls(module.state_dict(), cfg, device=device)
 
     def set_frame_sharding(self, group=None, fused_halo: bool = False, push_halo=None):
