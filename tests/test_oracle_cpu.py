@@ -401,3 +401,35 @@ def test_accelerate_swaps_the_unet_of_a_reference_pipeline():
     assert a1.idx == 7 and a1.eta1 == 0.0 and a1.eta2 == 0.5
     with pytest.raises(AttributeError):
         pipe.unet.config.no_such_key
+
+
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Error behaviour of the boundary: every entry point validates its arguments first and returns a negative code with a
+    message in univst_last_error() -- null pointers, unsupported strides / shapes / rank counts -- instead of launching."""
+    import ctypes as C
+    from univst_b200 import _lib, build, ops  # noqa: F401
+    build.build()
+    lib = _lib.lib()
+    ep = _lib.Epilogue()
+    P16 = 16   # any non-null, 16-byte aligned "pointer": validation must fail before it would be dereferenced
+    two = (C.c_void_p * 2)(P16, P16)
+    cases = {
+        "univst_axpby_f16": (None, None, 1.0, 1.0, 0, None, None),
+        "univst_gemm_f16": (None, 0, None, 0, 0, None, 128, 64, 64, None, 64, C.byref(ep), None),
+        "univst_conv3x3_f16": (P16, None, 1, 8, 8, 16, 0, P16, 8, 3, P16, 8, C.byref(ep), None),            # stride 3
+        "univst_sc_attention_f16": (None, 0, None, None, 0, 1, 1, 8, 40, 64, 64, None, 2, None, 0, None),
+        "univst_temporal_attention_f16": (P16, 960, 1, 33, 64, 8, 40, P16, 320, None),                      # F > 32
+        "univst_groupnorm_f16": (P16, None, 30, 0, 1, 64, 32, P16, P16, 1e-5, 0, P16, P16, None),           # 30 channels
+        "univst_layernorm_f16": (None, 4, 320, None, None, 1e-5, None, None),
+        "univst_latent_adain_f16": (P16, P16, 4, 65, 4096, P16, None),                                      # F > 64
+        "univst_latent_blend_fc_f16": (P16, P16, None, 16, 16, 64, P16, None),
+        "univst_exchange_push_f16": (0, P16, 320, two, 0, 2, 3, 8, 4095, 320, None),                        # pixels % ranks
+        "univst_halo_push_f16": (P16, 960, 0, two, 2, 960, 0, 3, 64, 636, None),                            # cols % 8
+        "univst_maskprop_f32": (None, None, None, 0, 0, 0, 0, 0.2, 15, None, None, None, 0, None, None),
+    }
+    for name, args in cases.items():
+        rc = getattr(lib, name)(*args)
+        msg = lib.univst_last_error()
+        assert rc < 0 and msg, (name, rc, msg)
+        with pytest.raises(_lib.UnivstError):
+            _lib.check(rc, name)
