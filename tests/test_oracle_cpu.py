@@ -433,3 +433,37 @@ def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
         assert rc < 0 and msg, (name, rc, msg)
         with pytest.raises(_lib.UnivstError):
             _lib.check(rc, name)
+
+
+def test_header_is_valid_c_and_links_against_the_library(tmp_path):
+    """include/univst_b200.h compiles as plain C99 (no C++ / torch types in the signatures) and a C program that takes the
+    address of every declared entry point links against the shared library and runs: the boundary is usable without Python."""
+    import re
+    import shutil
+    import subprocess
+    from univst_b200 import build
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    so = build.build()
+    root = os.path.abspath(os.path.join(os.path.dirname(GOLDEN), ".."))
+    header = open(os.path.join(root, "include", "univst_b200.h")).read()
+    names = sorted(set(re.findall(r"^(?:int|int64_t|const char\*)\s+(univst_[a-z0-9_]+)\s*\(", header, re.M)))
+    src = tmp_path / "abi.c"
+    src.write_text(
+        '#include <stdio.h>\n#include <string.h>\n#include "univst_b200.h"\n'
+        "typedef void (*fn_t)(void);\n"
+        "int main(void) {\n"
+        "  fn_t fns[] = {" + ", ".join(f"(fn_t)&{n}" for n in names) + "};\n"
+        "  size_t i, n = sizeof(fns) / sizeof(fns[0]);\n"
+        "  for (i = 0; i < n; ++i) if (!fns[i]) return 2;\n"
+        "  if (univst_abi_version() != 1) return 3;\n"
+        "  if (univst_axpby_f16(NULL, NULL, 1.0f, 1.0f, 0, NULL, NULL) >= 0) return 4;\n"
+        "  if (!strstr(univst_last_error(), \"axpby\")) return 5;\n"
+        '  printf("%u entry points\\n", (unsigned)n);\n  return 0;\n}\n')
+    exe = tmp_path / "abi"
+    cc = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-Wno-cast-function-type",
+                         "-I", os.path.join(root, "include"), str(src), "-o", str(exe), so,
+                         "-Wl,-rpath," + os.path.dirname(so)], capture_output=True, text=True)
+    assert cc.returncode == 0, cc.stderr[-3000:]
+    run = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert run.returncode == 0 and f"{len(names)} entry points" in run.stdout, (run.returncode, run.stdout, run.stderr[-2000:])
