@@ -250,14 +250,19 @@ def run_ours(args):
             for t in (v if isinstance(v, list) else [v]):
                 dist.broadcast(t, src=0)
         ref0 = stylize(shared)           # rank-local evaluation of rank 0's clip
-        # K/V halo pushed into the peers' symmetric memory when that works on every rank of this box, else through NCCL
+        # K/V halo pushed into the peers' symmetric memory when that works on every rank of this box, else through NCCL.
+        # The pushed halo was verified on 2 GPUs (profiles/r01_bench_v10_2gpu.json); larger worlds keep the NCCL exchange
+        # that was measured on 4 (profiles/r01_bench_v7_4gpu.json) until the push is measured there too.
         ok = torch.ones(1, device=dev)
-        try:
-            import torch.distributed._symmetric_memory as symm_mem
-            probe = symm_mem.empty(64, dtype=torch.float16, device=dev)
-            symm_mem.rendezvous(probe, dist.group.WORLD).barrier(channel=0)
-            torch.cuda.synchronize()
-        except Exception:
+        if world == 2:
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                probe = symm_mem.empty(64, dtype=torch.float16, device=dev)
+                symm_mem.rendezvous(probe, dist.group.WORLD).barrier(channel=0)
+                torch.cuda.synchronize()
+            except Exception:
+                ok.zero_()
+        else:
             ok.zero_()
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)
         push_halo = bool(ok.item() > 0)
