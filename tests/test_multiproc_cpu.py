@@ -146,3 +146,52 @@ def test_two_rank_gloo_frames_pixels_all_to_all(tmp_path):
     import json
     res = json.loads([l for l in out.stdout.splitlines() if l.startswith("[")][-1])
     assert res == [[True, True], [True, True]]
+
+
+def test_pushed_kv_halo_offsets_for_2_to_4_ranks(monkeypatch):
+    """Host side of the pushed K/V halo (unet._push_kv_halo): with ``ops.halo_push`` replaced by a byte-exact emulation
+    that treats the destination pointers as addresses inside the ranks' (CPU) buffers, every rank's two halo banks must end
+    up holding the K|V columns of the previous rank's last frame and of the clip's first frame -- for 2, 3 and 4 ranks."""
+    import torch
+    from types import SimpleNamespace
+    from univst_b200 import ops
+    from univst_b200.unet import UNetPseudo3DConditionModel
+
+    B, Fl, N, C = 3, 2, 5, 8
+    ld = 3 * C
+    for P in (2, 3, 4):
+        NI = B * Fl
+        g = torch.Generator().manual_seed(P)
+        clip = torch.randn(B, P * Fl, N, ld, generator=g).half()           # the projection of the whole clip
+        bufs = [torch.zeros((NI + 2 * B) * N, ld, dtype=torch.float16) for _ in range(P)]
+        for r in range(P):
+            bufs[r][: NI * N] = clip[:, r * Fl:(r + 1) * Fl].reshape(NI * N, ld)
+        bases = [b.data_ptr() for b in bufs]
+
+        def fake_halo_push(src, src_blk_rows, dst_ptrs, ld_dst, dst_blk_rows, nblk, rows):
+            cols = src.shape[1]
+            for r, p in enumerate(dst_ptrs):
+                if not p:
+                    continue
+                owner = next(i for i in range(P) if bases[i] <= p < bases[i] + bufs[i].numel() * 2)   # whose buffer
+                off = (p - bases[owner]) // 2
+                flat = bufs[owner].view(-1)
+                for blk in range(nblk):
+                    for row in range(rows):
+                        d0 = off + (blk * dst_blk_rows + row) * ld_dst
+                        flat[d0:d0 + cols] = src[blk * src_blk_rows + row]
+
+        monkeypatch.setattr(ops, "halo_push", fake_halo_push)
+        hdl = SimpleNamespace(barrier=lambda channel=0: None)
+        for r in range(P):
+            fake_self = SimpleNamespace(_shard=(None, r, P))
+            UNetPseudo3DConditionModel._push_kv_halo(fake_self, bufs[r], bases, hdl, B, Fl, N, C)
+        for r in range(P):
+            prev = bufs[r][NI * N:(NI + B) * N].view(B, N, ld)
+            first = bufs[r][(NI + B) * N:].view(B, N, ld)
+            assert torch.equal(first[:, :, C:], clip[:, 0, :, C:]), (P, r)
+            assert torch.all(first[:, :, :C] == 0)                        # the Q columns are not sent
+            if r > 0:
+                assert torch.equal(prev[:, :, C:], clip[:, r * Fl - 1, :, C:]), (P, r)
+            else:
+                assert torch.all(prev == 0)
