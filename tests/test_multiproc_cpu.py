@@ -195,3 +195,73 @@ def test_pushed_kv_halo_offsets_for_2_to_4_ranks(monkeypatch):
                 assert torch.equal(prev[:, :, C:], clip[:, r * Fl - 1, :, C:]), (P, r)
             else:
                 assert torch.all(prev == 0)
+
+
+def test_pushed_frames_pixels_exchange_for_2_to_4_ranks(monkeypatch):
+    """Host side of the AnimateDiff push exchange (animatediff._exchange: arena allocation, per-direction buffer offsets,
+    peer pointer list) with ``ops.exchange_push`` replaced by a Python restatement of the kernel's index maps and torch
+    symmetric memory by per-rank CPU tensors: after every rank has pushed, each rank must hold "all frames, my pixels" in
+    (b, frame, pixel) order, and the inverse exchange must give back "my frames, all pixels" -- for 2, 3 and 4 ranks."""
+    import torch
+    import torch.distributed._symmetric_memory as symm_mem
+    from types import SimpleNamespace
+    from univst_b200 import ops
+    from univst_b200.animatediff import UNet3DConditionModel
+
+    B, Fl, n, C = 3, 2, 4, 8
+    for P in (2, 3, 4):
+        N = n * P
+        g = torch.Generator().manual_seed(10 + P)
+        clip = torch.randn(B, P * Fl, N, C, generator=g).half()
+        arenas, cur = {}, {"rank": 0}
+
+        def fake_empty(*shape, dtype=None, device=None):
+            if cur["rank"] not in arenas:   # a peer that pushed earlier in this sequential emulation has already mapped it
+                arenas[cur["rank"]] = torch.zeros(*shape, dtype=dtype)
+            return arenas[cur["rank"]]
+
+        def fake_rendezvous(t, group):
+            def get_buffer(r, shape, dtype):
+                if r not in arenas:
+                    arenas[r] = torch.zeros(*shape, dtype=dtype)
+                return arenas[r]
+            return SimpleNamespace(get_buffer=get_buffer, barrier=lambda channel=0: None)
+
+        def fake_exchange_push(direction, src, dst_ptrs, rank, P_, B_, Fl_, N_):
+            n_ = N_ // P_
+            flats = {r: arenas[r].view(-1) for r in range(P_)}
+            base = {r: arenas[r].data_ptr() for r in range(P_)}
+            for row in range(src.shape[0]):
+                if direction == 0:      # rows (b, fl, pix) -> rank pix / n, row (b, rank Fl + fl, pix % n)
+                    pix, bf = row % N_, row // N_
+                    fl, b = bf % Fl_, bf // Fl_
+                    owner = pix // n_
+                    drow = (b * (P_ * Fl_) + rank * Fl_ + fl) * n_ + pix % n_
+                else:                   # rows (b, f_global, pix_local) -> rank f_global / Fl, row (b, f % Fl, rank n + pix_local)
+                    pl, bf = row % n_, row // n_
+                    fg, b = bf % (P_ * Fl_), bf // (P_ * Fl_)
+                    owner = fg // Fl_
+                    drow = (b * Fl_ + fg % Fl_) * N_ + rank * n_ + pl
+                off = (dst_ptrs[owner] - base[owner]) // 2 + drow * src.shape[1]
+                flats[owner][off:off + src.shape[1]] = src[row]
+
+        monkeypatch.setattr(symm_mem, "empty", fake_empty)
+        monkeypatch.setattr(symm_mem, "rendezvous", fake_rendezvous)
+        monkeypatch.setattr(ops, "exchange_push", fake_exchange_push)
+        ranks = [SimpleNamespace(_shard=(object(), r, P), _push=True, _arena=None, device="cpu") for r in range(P)]
+
+        def exchange(direction, ys):
+            outs = []
+            for r in range(P):
+                cur["rank"] = r
+                outs.append(UNet3DConditionModel._exchange(ranks[r], direction, ys[r], B, Fl, N))
+            return outs
+
+        local = [clip[:, r * Fl:(r + 1) * Fl].reshape(B * Fl * N, C).contiguous() for r in range(P)]
+        pix = exchange(0, local)                      # views of the arenas: complete once every rank has pushed
+        for r in range(P):
+            assert torch.equal(pix[r], clip[:, :, r * n:(r + 1) * n].reshape(-1, C)), (P, r)
+        back = exchange(1, [p.clone() for p in pix])
+        for r in range(P):
+            assert torch.equal(back[r], local[r]), (P, r)
+            assert back[r].data_ptr() != pix[r].data_ptr()   # one buffer per direction
