@@ -467,3 +467,67 @@ def test_header_is_valid_c_and_links_against_the_library(tmp_path):
     assert cc.returncode == 0, cc.stderr[-3000:]
     run = subprocess.run([str(exe)], capture_output=True, text=True)
     assert run.returncode == 0 and f"{len(names)} entry points" in run.stdout, (run.returncode, run.stdout, run.stderr[-2000:])
+
+
+def test_sd_pipeline_host_logic_on_cpu(monkeypatch, tiny_sd, tmp_path):
+    """Host side of univst_b200.pipeline.video_style_transfer -- trajectory indices, mask / late-AdaIN windows, register_time,
+    the dead-branch decision, on-disk loaders, DDIM alphas -- on the CPU: the four elementwise kernels are replaced by their
+    torch definitions and the UNet call by the oracle forward (driven by the idx the pipeline registered on the product
+    UNet's own handles).  Must reproduce the latents of the REFERENCE's own pipeline up to the fp16 storage of the latents."""
+    import torch.nn.functional as F
+    from PIL import Image
+    from oracle import pipeline_oracle as po
+    from univst_b200 import ops, pnp_utils
+    from univst_b200.pipeline import SpatioTemporalStableDiffusionPipeline
+    from univst_b200.unet import UNetPseudo3DConditionModel
+    g = torch.load(os.path.join(GOLDEN, "style_transfer_tiny.pt"), weights_only=True)
+    n, Fr, hw = g["n"], g["F"], g["hw"]
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], Fr, hw, n)
+
+    monkeypatch.setattr(ops, "mask_resize", lambda m, h, w: F.interpolate(m[None].float(), size=(h, w), mode="bilinear",
+                                                                          align_corners=False)[0].half())
+    monkeypatch.setattr(ops, "latent_blend", lambda a, b, m, out=None: ((1 - m.float()) * a.float() + m.float() * b.float()).half())
+    monkeypatch.setattr(ops, "latent_adain", lambda c, s, out=None: uo.latent_adain(c.float(), s.float()).half())
+
+    def ddim_step(z, eps_rows, branch, a_t, a_prev, out=None, x0_out=None):
+        C_, Fz, h, w = z.shape[-4:]
+        e = eps_rows[branch * Fz * h * w:(branch + 1) * Fz * h * w, :C_].float().view(Fz, h, w, C_).permute(3, 0, 1, 2)
+        x0 = (z.float() - (1 - a_t) ** 0.5 * e) / a_t ** 0.5
+        return (a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * e).half()
+    monkeypatch.setattr(ops, "ddim_step", ddim_step)
+
+    unet = UNetPseudo3DConditionModel(tiny_sd, uo.TINY_CONFIG, device="cpu")   # packing needs no GPU, only the forward does
+    batches = []
+
+    def oracle_forward(x, t, encoder_hidden_states=None, **kw):
+        a1 = unet.up_blocks[1].attentions[1].transformer_blocks[0].attn1
+        B = x.shape[0]
+        batches.append(B)
+        with torch.no_grad():
+            eps = uo.unet_forward(tiny_sd, uo.TINY_CONFIG, x.float(), int(t), encoder_hidden_states.float(),
+                                  patched=True, idx=a1.idx)   # closed window: still the patched [prev, first] K/V
+        unet.last_eps_rows = eps.permute(0, 2, 3, 4, 1).reshape(-1, eps.shape[1]).half().contiguous()   # [(b f) h w, C]
+        return None
+    unet.forward = oracle_forward
+    pipe = SpatioTemporalStableDiffusionPipeline(unet)
+    pipe.device = torch.device("cpu")
+    pnp_utils.register_spatial_attention_pnp(pipe)
+
+    cdir, sdir, mdir = (tmp_path / d for d in ("c", "s", "m"))
+    for d in (cdir, sdir, mdir):
+        d.mkdir()
+    for k in range(1, n + 1):
+        torch.save(traj_c[k].half(), cdir / f"ddim_latents_{k}.pt")
+        torch.save(traj_s[k].half(), sdir / f"ddim_latents_{k}.pt")
+    for f in range(Fr):
+        Image.fromarray(mask_u8[f], mode="L").save(mdir / ("%05d.png" % f))
+    z_T = uo.latent_adain(traj_c[n], traj_s[n]).half()
+    rec = {}
+    out = pipe.video_style_transfer("", num_inference_steps=n, latents=z_T, content_inv_path=str(cdir), style_inv_path=str(sdir),
+                                    mask_path=str(mdir), prompt_embeds=g["emb"], skip_dead_branches=True,
+                                    callback=lambda i, t, z: rec.__setitem__(i, z.clone())).latents
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    for i, ref in g["steps"].items():
+        assert rel(rec[i], ref) < 3e-3, (i, rel(rec[i], ref))
+    assert rel(out, g["final"]) < 3e-3
+    assert batches == [3] * 26 + [1] * 24      # shift window idx 0..25 (pnp_utils.py:47): edit branch only afterwards
