@@ -531,3 +531,43 @@ def test_sd_pipeline_host_logic_on_cpu(monkeypatch, tiny_sd, tmp_path):
         assert rel(rec[i], ref) < 3e-3, (i, rel(rec[i], ref))
     assert rel(out, g["final"]) < 3e-3
     assert batches == [3] * 26 + [1] * 24      # shift window idx 0..25 (pnp_utils.py:47): edit branch only afterwards
+
+
+def test_ddim_inversion_host_logic_on_cpu(monkeypatch, tiny_sd, tmp_path):
+    """Host side of univst_b200.ddim_inversion (ascending timesteps, inversion alphas, Easy-Inv window, file side effects)
+    on the CPU, with the DDIM-step / blend kernels replaced by their torch definitions and the UNet call by the oracle's
+    stock forward: must reproduce the trajectories of the REFERENCE's own ddim_loop / ddim_loop_plus."""
+    from oracle import pipeline_oracle as po
+    from types import SimpleNamespace
+    from univst_b200 import ddim_inversion as di
+    from univst_b200 import ops
+    from univst_b200.scheduler import DDIMScheduler
+    g = torch.load(os.path.join(GOLDEN, "ddim_inversion_tiny.pt"), weights_only=True)
+    traj_c, _, _ = po.synthetic_inputs(g["seed"], g["F"], g["hw"], 50)
+
+    def ddim_step(z, eps_rows, branch, a_t, a_prev, out=None, x0_out=None):
+        C_, Fz, h, w = z.shape[-4:]
+        e = eps_rows[branch * Fz * h * w:(branch + 1) * Fz * h * w, :C_].float().view(Fz, h, w, C_).permute(3, 0, 1, 2)
+        x0 = (z.float() - (1 - a_t) ** 0.5 * e) / a_t ** 0.5
+        return (a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * e).half()
+    monkeypatch.setattr(ops, "ddim_step", ddim_step)
+    monkeypatch.setattr(ops, "axpby", lambda a, b, wa, wb, out=None: (wa * a.float() + wb * b.float()).half())
+
+    unet = SimpleNamespace(last_eps_rows=None)
+
+    def forward(x, t, encoder_hidden_states=None, **kw):
+        with torch.no_grad():
+            eps = uo.unet_forward(tiny_sd, uo.TINY_CONFIG, x.float(), int(t), encoder_hidden_states.float(), patched=False)
+        unet.last_eps_rows = eps.permute(0, 2, 3, 4, 1).reshape(-1, eps.shape[1]).half().contiguous()
+    pipe = SimpleNamespace(device=torch.device("cpu"),
+                           unet=type("U", (), {"__call__": staticmethod(forward),
+                                               "last_eps_rows": property(lambda s: unet.last_eps_rows)})())
+    sch = DDIMScheduler()
+    sch.set_timesteps(g["n"])
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    lat = di.ddim_inversion(pipe, sch, traj_c[0], g["n"], "", inversion_path=str(tmp_path), prompt_embeds=g["emb"])
+    assert sorted(f for f in os.listdir(tmp_path) if f.startswith("ddim_latents")) == [f for f in g["files"] if f.startswith("ddim_latents")]
+    assert rel(torch.stack(lat[1:]), g["ddim_loop"]) < 3e-3
+    lat_p = di.ddim_inversion(pipe, sch, traj_c[0], g["n"], "", is_opt=True, prompt_embeds=g["emb"])
+    assert rel(torch.stack(lat_p[1:]), g["ddim_loop_plus"]) < 3e-3
+    assert rel(torch.stack(lat_p[1:]), g["ddim_loop"]) > 1e-3      # the Easy-Inv blend is live in this golden
