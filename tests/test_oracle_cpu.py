@@ -571,3 +571,23 @@ def test_ddim_inversion_host_logic_on_cpu(monkeypatch, tiny_sd, tmp_path):
     lat_p = di.ddim_inversion(pipe, sch, traj_c[0], g["n"], "", is_opt=True, prompt_embeds=g["emb"])
     assert rel(torch.stack(lat_p[1:]), g["ddim_loop_plus"]) < 3e-3
     assert rel(torch.stack(lat_p[1:]), g["ddim_loop"]) > 1e-3      # the Easy-Inv blend is live in this golden
+
+
+@pytest.mark.parametrize("name", ["smooth", "separated"])
+def test_mask_propogation_host_logic_on_cpu(monkeypatch, name):
+    """Host side of univst_b200.mask_propagation.mask_propogation (return contract, fore / back split, the reference's RNG call
+    sequence for the anchor subsample) with the kernel replaced by the oracle core: the sampled feature / label columns must be
+    the ones the REFERENCE drew under the same seed (golden from its own mask_propogation)."""
+    from types import SimpleNamespace
+    from oracle import maskprop_oracle as mo
+    from univst_b200 import mask_propagation as mp
+    from univst_b200 import ops
+    g = torch.load(os.path.join(GOLDEN, "maskprop.pt"), weights_only=True)[name]
+    feat_src, feat_tar, segs = _maskprop_inputs(g)
+    monkeypatch.setattr(ops, "maskprop", lambda ft, fs, sg, temperature=0.2, topk=15, return_kept=0:
+                        mo.mask_propogation_core(fs, ft, sg, temperature, topk)[0])
+    torch.manual_seed(0)
+    segs_tar, feat_s, segs_s = mp.mask_propogation(feat_src, feat_tar, segs, SimpleNamespace(temperature=0.2, topk=15, sample_ratio=0.3))
+    assert torch.allclose(segs_tar, g["segs_tar"], atol=1e-6)
+    assert feat_s.shape[1] == segs_s.shape[1] == g["n_sample"]
+    assert torch.equal(feat_s, g["feat_sample"]) and torch.allclose(segs_s, g["segs_sample"], atol=1e-6)
