@@ -591,3 +591,30 @@ def test_mask_propogation_host_logic_on_cpu(monkeypatch, name):
     assert torch.allclose(segs_tar, g["segs_tar"], atol=1e-6)
     assert feat_s.shape[1] == segs_s.shape[1] == g["n_sample"]
     assert torch.equal(feat_s, g["feat_sample"]) and torch.allclose(segs_s, g["segs_sample"], atol=1e-6)
+
+
+def test_rf_inversion_host_logic_on_cpu(monkeypatch, tmp_path):
+    """Host side of univst_b200.flow_inversion (sigma schedule flipped to ascending time, step coefficients folded into two
+    axpby calls, second-order RF-Solver midpoint, file side effects) with the axpby kernel replaced by its torch definition:
+    must reproduce the trajectories of the REFERENCE's own rf_inversion / rf_solver on the stand-in pipeline."""
+    from oracle import rf_oracle as ro
+    from univst_b200 import flow_inversion as fi
+    from univst_b200 import ops
+    monkeypatch.setattr(ops, "axpby", lambda a, b, wa, wb, out=None: (wa * a.float() + wb * b.float()).half())
+    g = torch.load(os.path.join(GOLDEN, "rf_inversion.pt"), weights_only=True)
+    x0 = torch.randn(4, 16, 8, 8, generator=torch.Generator().manual_seed(g["x0_seed"]))
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+
+    class Fp32Pipe(ro.FakePipeline):   # the stand-in field evaluated in fp32 on the fp16 latents the loops keep
+        def transformer(self, hidden_states, timestep, *a, **kw):
+            return (super().transformer(hidden_states.float(), timestep.float(), *a, **kw)[0],)
+
+    pipe = Fp32Pipe()
+    out = fi.rf_inversion(pipe, x0, "", gamma=g["gamma"], num_inference_steps=g["n"], inversion_path=str(tmp_path),
+                          target_noise=g["noise"])
+    assert sorted(os.listdir(tmp_path)) == g["files"]
+    mid = torch.load(tmp_path / "ddim_latents_5.pt", weights_only=True)
+    assert rel(mid, g["rf_inversion"][5]) < 3e-3 and rel(out, g["rf_inversion"][-1]) < 3e-3
+    pipe = Fp32Pipe()
+    out = fi.rf_solver(pipe, x0, "", num_inference_steps=g["n"])
+    assert rel(out, g["rf_solver"][-1]) < 3e-3 and len(pipe.calls) == g["solver_calls"]
