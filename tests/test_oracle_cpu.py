@@ -618,3 +618,80 @@ def test_rf_inversion_host_logic_on_cpu(monkeypatch, tmp_path):
     pipe = Fp32Pipe()
     out = fi.rf_solver(pipe, x0, "", num_inference_steps=g["n"])
     assert rel(out, g["rf_solver"][-1]) < 3e-3 and len(pipe.calls) == g["solver_calls"]
+
+
+@pytest.mark.parametrize("case", ["cross_frame", "shift_idx0", "shift_idx30", "shift_idx31"])
+def test_sd3_processors_host_logic_on_cpu(monkeypatch, case):
+    """Host side of univst_b200.sd3 (weight packing, fused-buffer column layout, [first, prev, self] + text source table, shift
+    window and beta schedule with thresh2 := eta2, context_pre_only / output projections) with the four kernels replaced by
+    torch definitions of what each computes: must reproduce the outputs of the REFERENCE's own processor classes."""
+    import torch.nn.functional as F
+    from oracle import sd3_oracle as so
+    from univst_b200 import ops, sd3
+    g = torch.load(os.path.join(GOLDEN, "sd3_processors.pt"), weights_only=True)
+    heads = g["heads"]
+    C = heads * 64
+
+    def gemm(a, w, bias=None, **kw):
+        return (a.float() @ w.float().T + (bias.float() if bias is not None else 0.0)).half()
+
+    def rmsnorm_heads_(qkv, H, d, wq, wk, eps=1e-6):
+        rows, Cc = qkv.shape[0], H * d
+        for blk, wgt in ((0, wq), (1, wk)):
+            if wgt is not None:
+                x = qkv[:, blk * Cc:(blk + 1) * Cc].float().view(rows, H, d)
+                qkv[:, blk * Cc:(blk + 1) * Cc] = so.rms_norm(x, wgt.float(), eps).view(rows, Cc).half()
+        return qkv
+
+    def sd3_attn_shift_(qkv, Fr, N, H, d, alpha, beta, gamma):
+        Cc = H * d
+        blocks = [qkv[:, i * Cc:(i + 1) * Cc].float().view(3 * Fr, N, H, d).transpose(1, 2) for i in range(3)]   # (3F, H, N, d)
+        q, k, v = (b.clone() for b in blocks)
+        q[2 * Fr:] = gamma * (alpha * q[:Fr] + (1 - alpha) * q[2 * Fr:])
+        k[2 * Fr:] = beta * so.attention_adain(k[2 * Fr:], k[Fr:2 * Fr]) + (1 - beta) * k[Fr:2 * Fr]
+        v[2 * Fr:] = beta * so.attention_adain(v[2 * Fr:], v[Fr:2 * Fr]) + (1 - beta) * v[Fr:2 * Fr]
+        for i, t in enumerate((q, k, v)):
+            qkv[:, i * Cc:(i + 1) * Cc] = t.transpose(1, 2).reshape(3 * Fr * N, Cc).half()
+        return qkv
+
+    def joint_attention(q, k, v, k2, v2, kv_src, *, NI, NIkv, NIkv2, H, d, N, Nkv, Nkv2, out=None):
+        res = torch.empty(NI * N, H * d, dtype=torch.float16)
+        heads_of = lambda t, img, n: t[img * n:(img + 1) * n].float().view(n, H, d).transpose(0, 1)   # (H, n, d)
+        for i in range(NI):
+            ks, vs = [], []
+            for s in kv_src[i].tolist():
+                if s < NIkv:
+                    ks.append(heads_of(k, s, Nkv)), vs.append(heads_of(v, s, Nkv))
+                else:
+                    ks.append(heads_of(k2, s - NIkv, Nkv2)), vs.append(heads_of(v2, s - NIkv, Nkv2))
+            o = F.scaled_dot_product_attention(heads_of(q, i, N), torch.cat(ks, 1), torch.cat(vs, 1))
+            res[i * N:(i + 1) * N] = o.transpose(0, 1).reshape(N, H * d).half()
+        return res
+
+    for name, fn in (("gemm", gemm), ("rmsnorm_heads_", rmsnorm_heads_), ("sd3_attn_shift_", sd3_attn_shift_),
+                     ("joint_attention", joint_attention)):
+        monkeypatch.setattr(ops, name, fn)
+
+    w = so.seeded_attn_weights(C, heads, g["seed"])
+    attn = torch.nn.Module()
+    for n in ("to_q", "to_k", "to_v", "add_q_proj", "add_k_proj", "add_v_proj", "to_add_out"):
+        setattr(attn, n, torch.nn.Linear(C, C))
+    attn.to_out = torch.nn.ModuleList([torch.nn.Linear(C, C), torch.nn.Dropout(0.0)])
+
+    class Norm(torch.nn.Module):
+        def __init__(self, dim):
+            super().__init__()
+            self.weight, self.eps = torch.nn.Parameter(torch.ones(dim)), 1e-6
+    for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"):
+        setattr(attn, n, Norm(C // heads))
+    attn.heads, attn.context_pre_only = heads, False
+    attn.load_state_dict(w)
+    hidden, enc = so.synthetic_inputs(g["input_seed"], g["N"], g["L"], C)
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    if case == "cross_frame":
+        h, e = sd3.CrossFrameProcessor()(attn, hidden[:16].half(), enc[:16].half())
+    else:
+        h, e = sd3.AttentionShiftProcessor(0.0, 0.6)(attn, hidden.half(), enc.half(), idx=int(case.split("idx")[1]))
+        h, e = h[g["keep"]], e[g["keep"]]
+    rh, re = g["cases"][case]
+    assert rel(h, rh) < 5e-3 and rel(e, re) < 5e-3, (rel(h, rh), rel(e, re))
