@@ -93,3 +93,26 @@ def test_animation_pipeline_oracle_matches_reference_pipeline():
     for i, ref in g["steps"].items():
         assert (rec[i] - ref).abs().max().item() < 2e-4, i
     assert (z - g["final"]).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("case", ["stock_t981", "patched_idx13_t721", "patched_idx24_t501", "patched_idx25_t481"])
+def test_animatediff_unet_host_logic_on_cpu(monkeypatch, golden, case):
+    """Host side of the AnimateDiff UNet mirror -- per-frame GroupNorm spans, per-frame attn1 tables, the half-open shift window,
+    motion-module packing (fused QKV, the positional encoding folded through the projection as an epilogue row vector,
+    tile-interleaved GEGLU) -- on the CPU, with every kernel replaced by a plain-torch definition (tests/_torch_ops.py):
+    must give the output of the REFERENCE's own UNet3DConditionModel (golden) up to the fp16 storage between layers."""
+    import _torch_ops
+    from types import SimpleNamespace
+    from univst_b200 import pnp_utils
+    from univst_b200.animatediff import UNet3DConditionModel
+    _torch_ops.install(monkeypatch)
+    sd = ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=golden["seed"])
+    unet = UNet3DConditionModel(sd, ao.AD_TINY_CONFIG, device="cpu")
+    if case.startswith("patched"):
+        pipe = SimpleNamespace(unet=unet)
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        pnp_utils.register_time(pipe, int(case.split("idx")[1].split("_")[0]))
+    y = unet(golden["x"].half(), torch.tensor(int(case.split("_t")[-1])), encoder_hidden_states=golden["ctx"].half()).sample
+    ref = golden["cases"][case]
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    assert y.shape == ref.shape and rel < 5e-3, rel

@@ -695,3 +695,48 @@ def test_sd3_processors_host_logic_on_cpu(monkeypatch, case):
         h, e = h[g["keep"]], e[g["keep"]]
     rh, re = g["cases"][case]
     assert rel(h, rh) < 5e-3 and rel(e, re) < 5e-3, (rel(h, rh), rel(e, re))
+
+
+@pytest.mark.parametrize("case", ["stock_t981", "patched_idx0_t981", "patched_idx13_t721", "patched_idx26_t461"])
+def test_unet_host_logic_on_cpu(monkeypatch, unet_golden, tiny_sd, case):
+    """Host side of the whole product UNet -- weight packing (tap-major convs, fused QKV / KV, tile-interleaved GEGLU, the
+    concatenated time-embedding projection), channels-last buffers, K/V source tables, epilogue arguments, skip concats, the
+    patch protocol -- on the CPU: every kernel is replaced by a plain-torch definition of what it computes
+    (tests/_torch_ops.py) and the result must be the output of the REFERENCE's own module (golden), up to the fp16 storage
+    between layers."""
+    import _torch_ops
+    from types import SimpleNamespace
+    from univst_b200 import pnp_utils
+    from univst_b200.unet import UNetPseudo3DConditionModel
+    _torch_ops.install(monkeypatch)
+    g = unet_golden
+    unet = UNetPseudo3DConditionModel(tiny_sd, uo.TINY_CONFIG, device="cpu")
+    t = int(case.split("_t")[-1])
+    if case.startswith("patched"):
+        pipe = SimpleNamespace(unet=unet)
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        pnp_utils.register_time(pipe, int(case.split("idx")[1].split("_")[0]))
+    y = unet(g["x"].half(), torch.tensor(t), encoder_hidden_states=g["ctx"].half()).sample
+    ref = g["cases"][case]
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    assert y.shape == ref.shape and rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("case", ["stock_t501", "patched_idx10_t781"])
+def test_unet_host_logic_on_cpu_sd21_layout(monkeypatch, case):
+    """The same for the SD-2.1 layout (Linear proj_in / proj_out, per-level head counts, 1024-wide context)."""
+    import _torch_ops
+    from types import SimpleNamespace
+    from univst_b200 import pnp_utils
+    from univst_b200.unet import UNetPseudo3DConditionModel
+    _torch_ops.install(monkeypatch)
+    g = torch.load(os.path.join(GOLDEN, "unet_tiny_sd21.pt"), weights_only=True)
+    unet = UNetPseudo3DConditionModel(uo.seeded_state_dict(uo.TINY_SD21_CONFIG, seed=g["seed"]), uo.TINY_SD21_CONFIG, device="cpu")
+    if case.startswith("patched"):
+        pipe = SimpleNamespace(unet=unet)
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        pnp_utils.register_time(pipe, 10)
+    y = unet(g["x"].half(), torch.tensor(int(case.split("_t")[-1])), encoder_hidden_states=g["ctx"].half()).sample
+    ref = g["cases"][case]
+    rel = ((y.float() - ref).norm() / ref.norm()).item()
+    assert y.shape == ref.shape and rel < 5e-3, rel
