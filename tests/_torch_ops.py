@@ -91,6 +91,22 @@ def groupnorm(x1, gamma, beta, *, NB, rows, groups=32, eps=1e-5, silu=False, x2=
     return (F.silu(y) if silu else y).half()
 
 
+def groupnorm_sharded(x1, gamma, beta, *, NB, rows, group, world, groups=32, eps=1e-5, silu=False, x2=None, reduce_fn=None):
+    """GroupNorm over the rows of ALL ranks: local sums -> all-reduce -> apply with the global count (frame-sharded UNet)."""
+    import torch.distributed as dist
+    x = _f(x1) if x2 is None else torch.cat([_f(x1), _f(x2)], dim=-1)
+    C = x.shape[-1]
+    xg = x.reshape(NB, rows, groups, C // groups)
+    sums = torch.stack([xg.sum(dim=(1, 3)), (xg * xg).sum(dim=(1, 3))], dim=-1)      # [NB, groups, 2]
+    dist.all_reduce(sums, group=group)
+    cnt = rows * world * (C // groups)
+    mean = sums[..., 0] / cnt
+    var = sums[..., 1] / cnt - mean * mean
+    y = (xg - mean[:, None, :, None]) * torch.rsqrt(var + eps)[:, None, :, None]
+    y = y.reshape(NB * rows, C) * _f(gamma) + _f(beta)
+    return (F.silu(y) if silu else y).half()
+
+
 def layernorm(x, gamma, beta, eps=1e-5, out=None):
     return F.layer_norm(_f(x), (x.shape[-1],), _f(gamma), _f(beta), eps).half()
 
@@ -143,8 +159,13 @@ def space_to_depth2(x):
     return torch.stack([x[:, hp::2, wp::2] for hp in range(2) for wp in range(2)]).contiguous()
 
 
-def install(monkeypatch):
+def install(monkeypatch=None):
+    """Swap the definitions into ``univst_b200.ops`` (through ``monkeypatch`` in a test, directly in a worker script)."""
     from univst_b200 import ops
-    for name in ("pack_latents", "unpack_latents", "timestep_embedding", "gemm", "conv3x3", "groupnorm", "layernorm",
-                 "sc_attention", "cross_attention", "temporal_attention", "attn_shift_", "upsample2x", "space_to_depth2"):
-        monkeypatch.setattr(ops, name, globals()[name])
+    for name in ("pack_latents", "unpack_latents", "timestep_embedding", "gemm", "conv3x3", "groupnorm", "groupnorm_sharded",
+                 "layernorm", "sc_attention", "cross_attention", "temporal_attention", "attn_shift_", "upsample2x",
+                 "space_to_depth2"):
+        if monkeypatch is not None:
+            monkeypatch.setattr(ops, name, globals()[name])
+        else:
+            setattr(ops, name, globals()[name])

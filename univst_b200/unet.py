@@ -553,7 +553,8 @@ class UNetPseudo3DConditionModel:
             import torch.distributed as dist
             group, rank, world = self._shard
             gathered = torch.empty((world, B, F, h * w, 8), dtype=torch.float16, device=dev)
-            dist.all_gather_into_tensor(gathered, eps_rows.view(B, F, h * w, 8), group=group)
+            # output given in the concatenated form (rank-major dim 0), which every backend accepts
+            dist.all_gather_into_tensor(gathered.view(world * B, F, h * w, 8), eps_rows.view(B, F, h * w, 8), group=group)
             eps_rows = gathered.permute(1, 0, 2, 3, 4).reshape(B * F_total * h * w, 8).contiguous()
             F = F_total
         self.last_eps_rows = eps_rows
