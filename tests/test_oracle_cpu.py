@@ -740,3 +740,28 @@ def test_unet_host_logic_on_cpu_sd21_layout(monkeypatch, case):
     ref = g["cases"][case]
     rel = ((y.float() - ref).norm() / ref.norm()).item()
     assert y.shape == ref.shape and rel < 5e-3, rel
+
+
+@pytest.mark.parametrize("B,Fr,h,w,patched", [(1, 1, 16, 16, False), (1, 3, 8, 8, False), (3, 3, 24, 40, True), (3, 5, 40, 8, True)])
+def test_unet_host_logic_edge_shapes_on_cpu(monkeypatch, tiny_sd, B, Fr, h, w, patched):
+    """Host logic on shapes the goldens do not hold (one frame, batch 1, odd frame counts, non-square latents without a
+    power-of-two side), kernels replaced by torch definitions, against the golden-pinned oracle on the same inputs."""
+    import _torch_ops
+    from types import SimpleNamespace
+    from univst_b200 import pnp_utils
+    from univst_b200.unet import UNetPseudo3DConditionModel
+    _torch_ops.install(monkeypatch)
+    unet = UNetPseudo3DConditionModel(tiny_sd, uo.TINY_CONFIG, device="cpu")
+    idx = 7 if patched else None
+    if patched:
+        pipe = SimpleNamespace(unet=unet)
+        pnp_utils.register_spatial_attention_pnp(pipe)
+        pnp_utils.register_time(pipe, idx)
+    gen = torch.Generator().manual_seed(1000 * B + 100 * Fr + h + w)
+    x = torch.randn(B, 4, Fr, h, w, generator=gen)
+    ctx = torch.randn(B, 77, uo.TINY_CONFIG["cross_attention_dim"], generator=gen)
+    y = unet(x.half(), torch.tensor(621), encoder_hidden_states=ctx.half()).sample
+    with torch.no_grad():
+        truth = uo.unet_forward(tiny_sd, uo.TINY_CONFIG, x, 621, ctx, patched=patched, idx=idx)
+    rel = ((y.float() - truth).norm() / truth.norm()).item()
+    assert y.shape == truth.shape and rel < 5e-3, rel
