@@ -159,12 +159,38 @@ def space_to_depth2(x):
     return torch.stack([x[:, hp::2, wp::2] for hp in range(2) for wp in range(2)]).contiguous()
 
 
+def mask_resize(mask_u8, h, w):
+    return F.interpolate((mask_u8 != 0)[None].float(), size=(h, w), mode="bilinear", align_corners=False)[0].half()
+
+
+def latent_blend(a, b, mask, out=None):
+    return ((1 - _f(mask)) * _f(a) + _f(mask) * _f(b)).half()
+
+
+def latent_adain(cnt, sty, out=None):
+    """pnp_utils.py:128-139 on (.., C, F, h, w): instance norm over (F, h, w) per channel, style statistics per (channel, frame)."""
+    c, s = _f(cnt).reshape(1, *cnt.shape[-4:]), _f(sty).reshape(1, *sty.shape[-4:])
+    sm, ss = s.mean(dim=[0, 3, 4], keepdim=True), s.std(dim=[0, 3, 4], keepdim=True)
+    return (F.instance_norm(c) * ss + sm).reshape(cnt.shape).half()
+
+
+def ddim_step(z, eps_rows, branch, alpha_t, alpha_prev, out=None, x0_out=None):
+    C_, Fz, h, w = z.shape[-4:]
+    e = _f(eps_rows[branch * Fz * h * w:(branch + 1) * Fz * h * w, :C_]).view(Fz, h, w, C_).permute(3, 0, 1, 2)
+    x0 = (_f(z) - (1 - alpha_t) ** 0.5 * e) / alpha_t ** 0.5
+    return (alpha_prev ** 0.5 * x0 + (1 - alpha_prev) ** 0.5 * e).half()
+
+
+def axpby(a, b, wa, wb, out=None):
+    return (wa * _f(a) + wb * _f(b)).half()
+
+
 def install(monkeypatch=None):
     """Swap the definitions into ``univst_b200.ops`` (through ``monkeypatch`` in a test, directly in a worker script)."""
     from univst_b200 import ops
     for name in ("pack_latents", "unpack_latents", "timestep_embedding", "gemm", "conv3x3", "groupnorm", "groupnorm_sharded",
                  "layernorm", "sc_attention", "cross_attention", "temporal_attention", "attn_shift_", "upsample2x",
-                 "space_to_depth2"):
+                 "space_to_depth2", "mask_resize", "latent_blend", "latent_adain", "ddim_step", "axpby"):
         if monkeypatch is not None:
             monkeypatch.setattr(ops, name, globals()[name])
         else:

@@ -116,3 +116,36 @@ def test_animatediff_unet_host_logic_on_cpu(monkeypatch, golden, case):
     ref = golden["cases"][case]
     rel = ((y.float() - ref).norm() / ref.norm()).item()
     assert y.shape == ref.shape and rel < 5e-3, rel
+
+
+def test_full_animatediff_stack_on_cpu_matches_reference_pipeline(monkeypatch):
+    """The whole AnimateDiff product stack -- AnimationPipeline.video_style_transfer (trajectory index 50 - i, late AdaIN from
+    0.8 n, linear betas) driving the UNet3DConditionModel mirror with its 21 motion modules, dead-branch skipping on -- on the
+    CPU with every kernel replaced by a torch definition (tests/_torch_ops.py), against the latents of the REFERENCE's own
+    AnimationPipeline (golden)."""
+    import _torch_ops
+    from oracle import pipeline_oracle as po
+    from univst_b200 import pnp_utils
+    from univst_b200.animatediff import AnimationPipeline, UNet3DConditionModel
+    from univst_b200.scheduler import DDIMScheduler
+    _torch_ops.install(monkeypatch)
+    g = torch.load(os.path.join(GOLDEN, "style_transfer_animatediff_tiny.pt"), weights_only=True)
+    n = g["n"]
+    unet = UNet3DConditionModel(ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=44), ao.AD_TINY_CONFIG, device="cpu")
+    pipe = AnimationPipeline(unet, DDIMScheduler(beta_schedule="linear"))   # animatediff-v2.yaml:16-21
+    pipe.device = torch.device("cpu")
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], n)
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    z_T = pnp_utils.latent_adain(traj_c[n].half(), traj_s[n].half())
+    rec, batches = {}, []
+    fwd = unet.forward
+    unet.forward = lambda x, *a, **k: (batches.append(x.shape[0]), fwd(x, *a, **k))[1]
+    out = pipe.video_style_transfer("", num_inference_steps=n, latents=z_T, content_inv_path=[t.half() for t in traj_c],
+                                    style_inv_path=[t.half() for t in traj_s], mask_path=torch.from_numpy(mask_u8),
+                                    prompt_embeds=g["emb"], skip_dead_branches=True,
+                                    callback=lambda i, t, z: rec.__setitem__(i, z.clone())).latents
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    for i, ref in g["steps"].items():
+        assert rel(rec[i], ref) < 1e-2, (i, rel(rec[i], ref))
+    assert rel(out, g["final"]) < 1e-2
+    assert batches == [3] * 25 + [1] * 25      # shift window idx < 25 (backbones/animatediff/pnp_utils.py:45)

@@ -765,3 +765,46 @@ def test_unet_host_logic_edge_shapes_on_cpu(monkeypatch, tiny_sd, B, Fr, h, w, p
         truth = uo.unet_forward(tiny_sd, uo.TINY_CONFIG, x, 621, ctx, patched=patched, idx=idx)
     rel = ((y.float() - truth).norm() / truth.norm()).item()
     assert y.shape == truth.shape and rel < 5e-3, rel
+
+
+def test_full_product_stack_on_cpu_matches_reference_pipeline(monkeypatch, tiny_sd):
+    """The whole product -- SpatioTemporalStableDiffusionPipeline.video_style_transfer driving the product UNet mirror, 50
+    steps, 16 frames, mask, late AdaIN, shift window, dead-branch skipping -- on the CPU with every kernel replaced by a
+    torch definition (tests/_torch_ops.py), against the latents of the REFERENCE's own pipeline (golden): rel-L2 <= 1e-2
+    (the GPU bar is 3e-2), and the skipped run must equal the full one bit for bit."""
+    import _torch_ops
+    from oracle import pipeline_oracle as po
+    from univst_b200 import pnp_utils
+    from univst_b200.pipeline import SpatioTemporalStableDiffusionPipeline
+    from univst_b200.unet import UNetPseudo3DConditionModel
+    _torch_ops.install(monkeypatch)
+    g = torch.load(os.path.join(GOLDEN, "style_transfer_tiny.pt"), weights_only=True)
+    n = g["n"]
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], n)
+    pipe = SpatioTemporalStableDiffusionPipeline(UNetPseudo3DConditionModel(tiny_sd, uo.TINY_CONFIG, device="cpu"))
+    pipe.device = torch.device("cpu")
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    z_T = pnp_utils.latent_adain(traj_c[n].half(), traj_s[n].half())
+    kw = dict(num_inference_steps=n, latents=z_T, content_inv_path=[t.half() for t in traj_c],
+              style_inv_path=[t.half() for t in traj_s], mask_path=torch.from_numpy(mask_u8), prompt_embeds=g["emb"])
+    rec = {}
+    skip = pipe.video_style_transfer("", skip_dead_branches=True, callback=lambda i, t, z: rec.__setitem__(i, z.clone()), **kw).latents
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    for i, ref in g["steps"].items():
+        assert rel(rec[i], ref) < 1e-2, (i, rel(rec[i], ref))
+    assert rel(skip, g["final"]) < 1e-2
+    # Up to step 25 both runs evaluate three branches: identical.  Step 26 is the first edit-branch-only call: with the real
+    # kernels it is bit-identical as well (tests/test_pipeline_gpu.py); the CPU matmuls behind the torch definitions block
+    # differently for a batch of 1, so here it only has to agree to fp16 noise.
+    full_rec = {}
+
+    class Stop(Exception):
+        pass
+
+    def until_27(i, t, z):
+        full_rec[i] = z.clone()
+        if i == 26:
+            raise Stop
+    with pytest.raises(Stop):
+        pipe.video_style_transfer("", callback=until_27, **kw)
+    assert torch.equal(full_rec[25], rec[25]) and rel(full_rec[26], rec[26]) < 2e-3
