@@ -87,7 +87,7 @@ def synthetic_clip(seed_offset: int = 0, device="cpu"):
     """content / style inversion trajectories x_k = sqrt(a_k) x_0 + sqrt(1 - a_k) eps held in
     memory, a moving-disc mask, a fixed (77, 768) context.  Returned on the host (pinned when CUDA is present)."""
     from univst_b200.scheduler import DDIMScheduler
-    sch = DDIMScheduler()
+    sch = DDIMScheduler.sd15()
     sch.set_timesteps(STEPS_DDIM)
     g = lambda s: torch.Generator().manual_seed(s + seed_offset)
     z0_c = torch.randn(1, 4, F_FRAMES, LAT, LAT, generator=g(1234))
@@ -307,7 +307,7 @@ def run_ours(args):
         del unet, pipe
         torch.cuda.empty_cache()
         unet_ad = UNet3DConditionModel(random_state_dict(AD_SD15_CONFIG, seed=34, device=dev, animatediff=True), AD_SD15_CONFIG, device=dev)
-        pipe_ad = AnimationPipeline(unet_ad, DDIMScheduler(beta_schedule="linear"))
+        pipe_ad = AnimationPipeline(unet_ad, DDIMScheduler.animatediff_v2())
         pnp_utils.register_spatial_attention_pnp(pipe_ad)
 
         def stylize_ad(c):

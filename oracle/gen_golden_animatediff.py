@@ -91,8 +91,10 @@ def gen_style_transfer():
         pipe = P.__new__(P)
         pipe.unet = m
         # animatediff-v2.yaml:16-21 (run_video_style_transfer_animatediff.py builds DDIMScheduler(**noise_scheduler_kwargs))
+        # nothing else is named there, so set_alpha_to_one keeps the library default True: the last step returns x0
         pipe.scheduler = DDIMScheduler(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", steps_offset=1,
                                        clip_sample=False)
+        assert float(pipe.scheduler.final_alpha_cumprod) == 1.0
         pipe._encode_prompt = lambda *a, **k: emb
         final = []
         pipe.decode_latents = lambda lat: (final.append(lat.clone()), np.zeros((1, 3, 1, 1, 1), np.float32))[1]

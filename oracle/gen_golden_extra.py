@@ -24,6 +24,7 @@ def gen_style_transfer(save):
     from backbones.video_diffusion_sd import pnp_utils
     from backbones.video_diffusion_sd.pipelines.stable_diffusion import SpatioTemporalStableDiffusionPipeline as P
     from diffusers import DDIMScheduler
+    from diffusers.schedulers import SD15_SCHEDULER_CONFIG
     from oracle import pipeline_oracle as po
 
     m, cfg = _tiny_reference_unet()
@@ -41,7 +42,7 @@ def gen_style_transfer(save):
         for f in range(F_):
             Image.fromarray(mask_u8[f], mode="L").save(os.path.join(mdir, "%05d.png" % f))
         pipe = P.__new__(P)
-        pipe.unet, pipe.scheduler = m, DDIMScheduler()
+        pipe.unet, pipe.scheduler = m, DDIMScheduler(**SD15_SCHEDULER_CONFIG)   # from_pretrained(.., subfolder='scheduler')
         pipe._encode_prompt = lambda *a, **k: emb
         final = []
         pipe.decode_latents = lambda lat: (final.append(lat.clone()), np.zeros((1, 1, 1, 1, 3), np.float32))[1]
@@ -59,6 +60,7 @@ def gen_style_transfer(save):
 def gen_inversion(save):
     import inversion_tools.ddim_inversion as di
     from diffusers import DDIMScheduler
+    from diffusers.schedulers import SD15_SCHEDULER_CONFIG
     from oracle import pipeline_oracle as po
 
     m, cfg = _tiny_reference_unet()
@@ -67,7 +69,7 @@ def gen_inversion(save):
     g = torch.Generator().manual_seed(seed + 1)
     emb = torch.randn(1, 77, cfg["cross_attention_dim"], generator=g)
     di.init_prompt = lambda pipeline, prompt: torch.cat([emb, emb])  # CLIP is a third-party network: fixed embeddings
-    sch = DDIMScheduler()
+    sch = DDIMScheduler(**SD15_SCHEDULER_CONFIG)
     sch.set_timesteps(n)
     pipe = types.SimpleNamespace(unet=m)
     out = {"seed": seed, "F": F_, "hw": hw, "n": n, "emb": emb}

@@ -17,15 +17,17 @@ from . import unet_oracle as uo
 
 
 class DDIMOracle:
-    """beta_schedule scaled_linear [0.00085, 0.012], T = 1000, set_alpha_to_one False, steps_offset 1, leading spacing."""
+    """SD-1.5's scheduler_config.json: beta_schedule scaled_linear [0.00085, 0.012], T = 1000, set_alpha_to_one False,
+    steps_offset 1, leading spacing.  AnimateDiff (animatediff-v2.yaml:16-21 -> DDIMScheduler(**kwargs)): "linear" betas and
+    the library default set_alpha_to_one True, i.e. the last DDIM step lands on x0 exactly."""
 
-    def __init__(self, T=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear"):
+    def __init__(self, T=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", set_alpha_to_one=False):
         if beta_schedule == "scaled_linear":
             betas = torch.linspace(beta_start ** 0.5, beta_end ** 0.5, T, dtype=torch.float32) ** 2
         else:  # "linear": backbones/animatediff/animatediff-v2.yaml:16-21
             betas = torch.linspace(beta_start, beta_end, T, dtype=torch.float32)
         self.alphas_cumprod = torch.cumprod(1.0 - betas, dim=0)
-        self.final_alpha_cumprod = self.alphas_cumprod[0]
+        self.final_alpha_cumprod = torch.tensor(1.0) if set_alpha_to_one else self.alphas_cumprod[0]
         self.T = T
 
     def set_timesteps(self, n):
@@ -67,7 +69,7 @@ def video_style_transfer(unet_fn, latents, traj_c, traj_s, mask_1fhw, ctx3, n=50
     ``traj_*[k]`` = inversion latent k (k = 1..n); ``mask_1fhw`` (1, F, H, W) in {0, 1} or None.
     ``animatediff``: the AnimationPipeline flavour (backbones/animatediff/pipelines/pipeline_animation.py:501-584):
     trajectory index hard-coded ``50 - i`` (:505-506), late AdaIN from ``i >= 0.8 n`` (:515), linear betas."""
-    sch = DDIMOracle(beta_schedule="linear" if animatediff else "scaled_linear")
+    sch = DDIMOracle(beta_schedule="linear" if animatediff else "scaled_linear", set_alpha_to_one=bool(animatediff))
     sch.set_timesteps(n)
     z = latents.clone()
     for i, t in enumerate(sch.timesteps):

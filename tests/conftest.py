@@ -12,6 +12,19 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a B200 (sm_100) GPU; run with -m gpu on the GPU box")
 
 
+def pytest_collection_modifyitems(config, items):
+    """A plain ``pytest tests`` on a host without a GPU skips the gpu-marked tests instead of erroring in them.  When they
+    were asked for explicitly (``-m gpu``) they still fail loudly: a GPU box without a visible device is an error."""
+    import torch
+
+    if torch.cuda.is_available() or "gpu" in (config.getoption("-m") or ""):
+        return
+    skip = pytest.mark.skip(reason="no CUDA device visible (gpu-marked tests run with -m gpu on the B200 box)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
 @pytest.fixture(scope="session")
 def cuda_lib():
     """Build (if needed) and load the kernel library; GPU tests fail loudly when it is missing."""
@@ -20,7 +33,6 @@ def cuda_lib():
     assert torch.cuda.is_available(), "GPU test selected but no CUDA device is visible"
     from univst_b200 import _lib, build
 
-    if not os.path.exists(_lib.LIB_PATH):
-        build.build()
+    build.build()   # content-hash stamped: a no-op unless a .cu / header changed since the library was linked
     _lib.require_device()
     return _lib.lib()

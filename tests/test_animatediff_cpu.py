@@ -132,7 +132,7 @@ def test_full_animatediff_stack_on_cpu_matches_reference_pipeline(monkeypatch):
     g = torch.load(os.path.join(GOLDEN, "style_transfer_animatediff_tiny.pt"), weights_only=True)
     n = g["n"]
     unet = UNet3DConditionModel(ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=44), ao.AD_TINY_CONFIG, device="cpu")
-    pipe = AnimationPipeline(unet, DDIMScheduler(beta_schedule="linear"))   # animatediff-v2.yaml:16-21
+    pipe = AnimationPipeline(unet, DDIMScheduler.animatediff_v2())   # animatediff-v2.yaml:16-21
     pipe.device = torch.device("cpu")
     traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], n)
     pnp_utils.register_spatial_attention_pnp(pipe)

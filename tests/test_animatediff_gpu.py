@@ -107,7 +107,7 @@ def test_animation_pipeline_matches_reference_golden(cuda_lib, tmp_path):
     g = torch.load(os.path.join(GOLDEN, "style_transfer_animatediff_tiny.pt"), weights_only=True)
     n = g["n"]
     unet = UNet3DConditionModel(ao.seeded_state_dict(ao.AD_TINY_CONFIG, seed=44), ao.AD_TINY_CONFIG)
-    pipe = AnimationPipeline(unet, DDIMScheduler(beta_schedule="linear"))   # animatediff-v2.yaml:16-21
+    pipe = AnimationPipeline(unet, DDIMScheduler.animatediff_v2())   # animatediff-v2.yaml:16-21
     traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], n)
     cdir, sdir, mdir = (tmp_path / d for d in ("c", "s", "m"))
     for d in (cdir, sdir, mdir):
@@ -122,7 +122,7 @@ def test_animation_pipeline_matches_reference_golden(cuda_lib, tmp_path):
     rec = {}
     out = pipe.video_style_transfer("", num_inference_steps=n, latents=z_T, content_inv_path=str(cdir),
                                     style_inv_path=str(sdir), mask_path=str(mdir), prompt_embeds=g["emb"],
-                                    callback=lambda i, t, z: rec.__setitem__(i, z.clone()))
+                                    skip_dead_branches=False, callback=lambda i, t, z: rec.__setitem__(i, z.clone()))
     for i, ref in g["steps"].items():
         print(f"animatediff step {i}: rel={_errs(rec[i], ref)[0]:.3e}")
     a, b = out.latents.float().cpu(), g["final"].float()

@@ -143,7 +143,7 @@ def test_load_mask_wraparound_semantics():
 def test_scheduler_mirror_matches_oracle():
     from oracle import pipeline_oracle as po
     from univst_b200.scheduler import DDIMScheduler
-    a, b = DDIMScheduler(), po.DDIMOracle()
+    a, b = DDIMScheduler.sd15(), po.DDIMOracle()
     for n in (50, 10):
         a.set_timesteps(n), b.set_timesteps(n)
         assert [int(t) for t in a.timesteps] == b.timesteps
@@ -507,6 +507,7 @@ def test_sd_pipeline_host_logic_on_cpu(monkeypatch, tiny_sd, tmp_path):
             eps = uo.unet_forward(tiny_sd, uo.TINY_CONFIG, x.float(), int(t), encoder_hidden_states.float(),
                                   patched=True, idx=a1.idx)   # closed window: still the patched [prev, first] K/V
         unet.last_eps_rows = eps.permute(0, 2, 3, 4, 1).reshape(-1, eps.shape[1]).half().contiguous()   # [(b f) h w, C]
+        unet.last_edit_branch = B - 1
         return None
     unet.forward = oracle_forward
     pipe = SpatioTemporalStableDiffusionPipeline(unet)
@@ -562,7 +563,7 @@ def test_ddim_inversion_host_logic_on_cpu(monkeypatch, tiny_sd, tmp_path):
     pipe = SimpleNamespace(device=torch.device("cpu"),
                            unet=type("U", (), {"__call__": staticmethod(forward),
                                                "last_eps_rows": property(lambda s: unet.last_eps_rows)})())
-    sch = DDIMScheduler()
+    sch = DDIMScheduler.sd15()
     sch.set_timesteps(g["n"])
     rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
     lat = di.ddim_inversion(pipe, sch, traj_c[0], g["n"], "", inversion_path=str(tmp_path), prompt_embeds=g["emb"])
@@ -793,9 +794,10 @@ def test_full_product_stack_on_cpu_matches_reference_pipeline(monkeypatch, tiny_
     for i, ref in g["steps"].items():
         assert rel(rec[i], ref) < 1e-2, (i, rel(rec[i], ref))
     assert rel(skip, g["final"]) < 1e-2
-    # Up to step 25 both runs evaluate three branches: identical.  Step 26 is the first edit-branch-only call: with the real
-    # kernels it is bit-identical as well (tests/test_pipeline_gpu.py); the CPU matmuls behind the torch definitions block
-    # differently for a batch of 1, so here it only has to agree to fp16 noise.
+    # The skipped run evaluates the content / style branches only where they matter (up to the last patched projection while
+    # the shift window is open, not at all afterwards).  With the real kernels it is bit-identical to the full evaluation
+    # (tests/test_pipeline_gpu.py); the CPU matmuls behind the torch definitions block differently for a batch of 1, so
+    # here it only has to agree to fp16 noise.
     full_rec = {}
 
     class Stop(Exception):
@@ -806,5 +808,5 @@ def test_full_product_stack_on_cpu_matches_reference_pipeline(monkeypatch, tiny_
         if i == 26:
             raise Stop
     with pytest.raises(Stop):
-        pipe.video_style_transfer("", callback=until_27, **kw)
-    assert torch.equal(full_rec[25], rec[25]) and rel(full_rec[26], rec[26]) < 2e-3
+        pipe.video_style_transfer("", callback=until_27, skip_dead_branches=False, **kw)
+    assert rel(full_rec[25], rec[25]) < 2e-3 and rel(full_rec[26], rec[26]) < 2e-3

@@ -90,8 +90,8 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
         super().set_frame_sharding(group)
         self._pe_rows = {}
         if push_exchange is None:
-            push_exchange = dist.get_backend(group) == "nccl"
-        self._push = bool(push_exchange)
+            push_exchange = self._shard is not None and dist.get_backend(group) == "nccl"
+        self._push = bool(push_exchange) and self._shard is not None
         self._arena = None
 
     def _exchange(self, direction, y, B, F, N):
@@ -213,6 +213,20 @@ class AnimationPipeline(SpatioTemporalStableDiffusionPipeline):
     @staticmethod
     def _traj_index(i, n):
         return 50 - i
+
+    def _trajectory(self, path_or_list, n):
+        # the reference reads ddim_latents_{50 - i}.pt whatever num_inference_steps is: load exactly the files the loop
+        # will touch (indices 50 - n + 1 .. 50), leaving the others None
+        if isinstance(path_or_list, (list, tuple)):
+            return super()._trajectory(path_or_list, n)
+        from .util import load_ddim_latents_at_t
+        lat = [None] * 51
+        for i in range(n):
+            k = 50 - i
+            if k < 1:
+                raise ValueError(f"{n} steps: the reference's hard-coded index 50 - i (pipeline_animation.py:505) leaves the trajectory")
+            lat[k] = load_ddim_latents_at_t(k, path_or_list).to(self.device, torch.float16).contiguous()
+        return lat
 
     @staticmethod
     def _late_adain(i, n):

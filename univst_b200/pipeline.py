@@ -27,7 +27,7 @@ from .util import load_ddim_latents_at_t, load_mask
 class SpatioTemporalStableDiffusionPipeline:
     def __init__(self, unet, scheduler: Optional[DDIMScheduler] = None, vae=None, text_encoder=None, tokenizer=None):
         self.unet = unet
-        self.scheduler = scheduler or DDIMScheduler()
+        self.scheduler = (scheduler or DDIMScheduler.sd15()).patch_for_pipeline()   # stable_diffusion.py:68-93
         self.vae, self.text_encoder, self.tokenizer = vae, text_encoder, tokenizer
         self.device = unet.device
 
@@ -70,13 +70,24 @@ class SpatioTemporalStableDiffusionPipeline:
     @torch.no_grad()
     def video_style_transfer(self, prompt: Union[str, List[str]], num_inference_steps: int = 50, latents=None,
                              content_inv_path=None, style_inv_path=None, mask_path=None, prompt_embeds=None,
-                             output_type="tensor", skip_dead_branches: bool = False, callback=None, **kwargs):
+                             output_type="tensor", skip_dead_branches: bool = True, callback=None,
+                             inv_prompt_embeds=None, **kwargs):
         """stable_diffusion.py:631-780.  ``content_inv_path`` / ``style_inv_path``: directory with the inversion's
         ``ddim_latents_{k}.pt`` files (reference format) or an in-memory list [x_0 .. x_n]; ``mask_path``: directory
-        of ``%05d.png`` masks or a (F, H, W) tensor (non-zero = keep content)."""
+        of ``%05d.png`` masks or a (F, H, W) tensor (non-zero = keep content).  ``prompt_embeds`` /
+        ``inv_prompt_embeds``: embeddings of ``prompt`` (edit branch) and of the empty prompt the inversion branches are
+        conditioned on (:659-668); the latter defaults to ``prompt_embeds`` only when ``prompt`` itself is empty.
+        ``skip_dead_branches`` (default on; exact): the content / style branches are evaluated only
+        where they can still influence the edit branch -- not at all once the shift window is closed, and up to the
+        last patched attn1 projection while it is open.  The edit latents are bit-identical to the full evaluation."""
         n = num_inference_steps
         emb = self._encode_prompt(prompt, prompt_embeds)
-        emb_inv = self._encode_prompt("", prompt_embeds)
+        if inv_prompt_embeds is None and prompt_embeds is not None and prompt not in ("", [""]) \
+                and (self.text_encoder is None or self.tokenizer is None):
+            raise ValueError("a non-empty prompt needs inv_prompt_embeds (the empty-prompt embedding of the content / "
+                             "style branches, stable_diffusion.py:659-668) or a text encoder")
+        emb_inv = self._encode_prompt("", inv_prompt_embeds if inv_prompt_embeds is not None
+                                      else (prompt_embeds if prompt in ("", [""]) else None))
         ctx = torch.cat([emb_inv, emb_inv, emb])  # :668
         self.scheduler.set_timesteps(n)
         timesteps = [int(t) for t in self.scheduler.timesteps]
@@ -95,12 +106,14 @@ class SpatioTemporalStableDiffusionPipeline:
             a1 = self.unet.up_blocks[1].attentions[1].transformer_blocks[0].attn1
             if skip_dead_branches and not self.unet.shift_live(a1):
                 self.unet(z, t, encoder_hidden_states=ctx[2:3])
-                branch = 0
             else:
-                self.unet(torch.cat([zc, zs, z]), t, encoder_hidden_states=ctx)
-                branch = 2
+                self.unet.truncate_dead_branches = bool(skip_dead_branches)
+                try:
+                    self.unet(torch.cat([zc, zs, z]), t, encoder_hidden_states=ctx)
+                finally:
+                    self.unet.truncate_dead_branches = False
             a_t, a_prev = self.scheduler.step_alphas(t)
-            z = ops.ddim_step(z, self.unet.last_eps_rows, branch, a_t, a_prev)  # :761, eta = 0
+            z = ops.ddim_step(z, self.unet.last_eps_rows, self.unet.last_edit_branch, a_t, a_prev)  # :761, eta = 0
             if callback is not None:
                 callback(i, t, z)
         images = self.decode_latents(z) if self.vae is not None else None

@@ -1,5 +1,8 @@
-"""Host-side DDIM scheduler scalars, mirroring diffusers' ``DDIMScheduler`` as SD-1.5's scheduler_config.json sets it
-up (third-party to the reference: called at stable_diffusion.py:670,761; semantics in SURVEY.md Appendix B).
+"""Host-side DDIM scheduler scalars, mirroring diffusers' ``DDIMScheduler`` (third-party to the reference: called at
+stable_diffusion.py:670,761; semantics in SURVEY.md Appendix B).  The constructor has the library's own defaults;
+``DDIMScheduler.sd15()`` is SD-1.5's scheduler_config.json (what ``from_pretrained(.., subfolder="scheduler")`` gives the
+SD scripts, run_video_style_transfer_sd.py:45) and ``DDIMScheduler.animatediff_v2()`` the ``noise_scheduler_kwargs`` of
+animatediff-v2.yaml:16-21 (which leave ``set_alpha_to_one`` at the library default True: the last DDIM step returns x0).
 All per-step coefficients are Python floats, so stepping never synchronises with the device; the arithmetic on the
 latents is the ``univst_ddim_step_f16`` kernel."""
 from __future__ import annotations
@@ -14,11 +17,11 @@ class DDIMScheduler:
     order = 1
     init_noise_sigma = 1.0
 
-    def __init__(self, num_train_timesteps=1000, beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear",
-                 set_alpha_to_one=False, steps_offset=1, clip_sample=False, prediction_type="epsilon",
+    def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
+                 clip_sample=True, set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon",
                  timestep_spacing="leading"):
-        if prediction_type != "epsilon" or clip_sample or timestep_spacing != "leading":
-            raise NotImplementedError("only the epsilon / no-clip / leading configuration of the reference is mirrored")
+        if prediction_type != "epsilon" or timestep_spacing != "leading":
+            raise NotImplementedError("only the epsilon / leading configuration of the reference is mirrored")
         self.config = SimpleNamespace(num_train_timesteps=num_train_timesteps, steps_offset=steps_offset,
                                       clip_sample=clip_sample, prediction_type=prediction_type,
                                       timestep_spacing=timestep_spacing, beta_schedule=beta_schedule,
@@ -35,6 +38,25 @@ class DDIMScheduler:
         self.num_inference_steps = None
         self.timesteps = torch.from_numpy(np.arange(0, num_train_timesteps)[::-1].copy().astype(np.int64))
 
+    @classmethod
+    def sd15(cls, **overrides):
+        """scheduler/scheduler_config.json of SD-1.5 (and SD-2.1-base: same values)."""
+        return cls(**dict(dict(beta_start=0.00085, beta_end=0.012, beta_schedule="scaled_linear", clip_sample=False,
+                               set_alpha_to_one=False, steps_offset=1), **overrides))
+
+    @classmethod
+    def animatediff_v2(cls, **overrides):
+        """DDIMScheduler(**noise_scheduler_kwargs) of backbones/animatediff/animatediff-v2.yaml:16-21."""
+        return cls(**dict(dict(beta_start=0.00085, beta_end=0.012, beta_schedule="linear", steps_offset=1,
+                               clip_sample=False), **overrides))
+
+    def patch_for_pipeline(self):
+        """What the reference pipelines' constructors do to an outdated config (stable_diffusion.py:68-93,
+        pipeline_animation.py:71-95): steps_offset := 1, clip_sample := False."""
+        self.config.steps_offset = 1
+        self.config.clip_sample = False
+        return self
+
     def set_timesteps(self, num_inference_steps: int, device=None):
         self.num_inference_steps = num_inference_steps
         ratio = self.config.num_train_timesteps // num_inference_steps
@@ -48,7 +70,10 @@ class DDIMScheduler:
         return self._alphas[t] if t >= 0 else float(self.final_alpha_cumprod)
 
     def step_alphas(self, t: int):
-        """(alpha_t, alpha_prev) of DDIMScheduler.step."""
+        """(alpha_t, alpha_prev) of DDIMScheduler.step (eta = 0; x0 is not clipped: the pipelines force clip_sample off)."""
+        if self.config.clip_sample:
+            raise NotImplementedError("clip_sample=True: build the scheduler through a pipeline (which patches it to False "
+                                      "like the reference's constructors) or pass clip_sample=False")
         return self.alpha(int(t)), self.alpha(int(t) - self.config.num_train_timesteps // self.num_inference_steps)
 
     def inversion_alphas(self, t: int):

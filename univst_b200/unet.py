@@ -138,6 +138,12 @@ class UNetPseudo3DConditionModel:
         self._shard = None  # (process group, rank, world) when frames are sharded over GPUs
         self._fused_halo = False
         self._push_halo = False
+        # SURVEY 2.3 D3, second half: while the shift is live the content / style branches only feed Q_content and
+        # K/V_style to the patched attn1 layers, so after the LAST live patched layer's projection (+ shift) they are dead.
+        # When set (the pipeline sets it together with skip_dead_branches) a three-branch call evaluates the rest of the
+        # network on the edit branch alone and ``.sample`` holds that branch only: (1, C, F, h, w).
+        self.truncate_dead_branches = False
+        self.last_edit_branch = None   # index of the edit branch inside ``last_eps_rows`` after a call
         self._build_tree()
         self._pack(state_dict)
 
@@ -270,7 +276,20 @@ class UNetPseudo3DConditionModel:
         temb_w, temb_b, self._temb_slices, off = [], [], {}, 0
         for key, t in sd.items():
             if "conv_temporal" in key:
-                continue  # Dirac / zero-bias identity (resnet.py:54-55); never loaded (unet_3d_condition.py:503)
+                # Dirac / zero-bias identity (resnet.py:54-55); never loaded (unet_3d_condition.py:503) -- verified, since a
+                # checkpoint with trained temporal convolutions would silently give wrong results otherwise
+                if key.endswith("weight"):
+                    ident = torch.zeros_like(t)
+                    k = t.shape[-1]
+                    idx = torch.arange(min(t.shape[0], t.shape[1]))
+                    ident.reshape(t.shape[0], t.shape[1], k)[idx, idx, k // 2] = 1
+                    ok = t.shape[0] == t.shape[1] and bool(torch.equal(t, ident))
+                else:
+                    ok = not bool((t != 0).any())
+                if not ok:
+                    raise NotImplementedError(f"{key} is not the Dirac / zero-bias identity of the pseudo-3D inflation: "
+                                              "trained temporal convolutions are not on the UniVST path")
+                continue
             if "attn_temporal" in key or "norm_temporal" in key:
                 if key.endswith("attn_temporal.to_out.0.weight") and bool((t != 0).any()):
                     raise NotImplementedError(
@@ -399,8 +418,10 @@ class UNetPseudo3DConditionModel:
             sc = x
         return ops.conv3x3(h.view(NI, H, Wd, -1), W[pre + "conv2.weight"], bias=W[pre + "conv2.bias"], residual=sc)
 
-    def _transformer(self, tr: _Transformer, x, ctx_kv_of, B, F, H, Wd):
-        """SpatioTemporalTransformerModel.forward (attention.py:104-153) + its block (:280-334).  x: [M, C]."""
+    def _transformer(self, tr: _Transformer, x, ctx_kv_of, B, F, H, Wd, cut: bool = False):
+        """SpatioTemporalTransformerModel.forward (attention.py:104-153) + its block (:280-334).  x: [M, C].
+        ``cut``: this is the last layer in which the content / style branches matter -- after the fused projection and
+        the shift only the edit branch (the last F images) goes on: returns [F * N, C]."""
         W, cfg = self.W, self.config
         pre, heads = tr.prefix, tr.heads
         NI, N, C = B * F, H * Wd, x.shape[1]
@@ -443,14 +464,21 @@ class UNetPseudo3DConditionModel:
                 kv = qkv_all
             else:
                 kv = qkv
-            o = ops.sc_attention(qkv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], self._table(B, F, mode), NI=NI, NIkv=NIkv,
+            table, qrows = self._table(B, F, mode), qkv
+            if cut:  # queries of the edit branch only; its K/V sources keep their image numbers in the full buffer
+                e0 = (B - 1) * F
+                table, qrows, x, y, NI = table[e0:], qkv[e0 * N:], x[e0 * N:], y[e0 * N:], F
+            o = ops.sc_attention(qrows[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], table, NI=NI, NIkv=NIkv,
                                  H=heads, d=d, N=N, Nkv=N)
         y = ops.gemm(o, W[b + "attn1.to_out.0.weight"], bias=W[b + "attn1.to_out.0.bias"], residual=y)
         # 2. cross-attention over the (per-branch) context
         n2 = ops.layernorm(y, W[b + "norm2.weight"], W[b + "norm2.bias"])
         q2 = ops.gemm(n2, W[b + "attn2.to_q.weight"])
         kv2, L = ctx_kv_of(b)
-        o2 = ops.cross_attention(q2, kv2[:, :C], kv2[:, C:], self._table(B, F, "branch"), NI=NI, NIkv=B, H=heads, d=d, N=N,
+        Bx = B
+        if cut:
+            kv2, Bx = kv2[(B - 1) * L:], 1
+        o2 = ops.cross_attention(q2, kv2[:, :C], kv2[:, C:], self._table(Bx, F, "branch"), NI=NI, NIkv=Bx, H=heads, d=d, N=N,
                                  Nkv=L)
         y = ops.gemm(o2, W[b + "attn2.to_out.0.weight"], bias=W[b + "attn2.to_out.0.bias"], residual=y)
         # 3. GEGLU feed-forward; the dead temporal attention (attention.py:331-346) is its bias, added in the epilogue
@@ -503,8 +531,30 @@ class UNetPseudo3DConditionModel:
         L = ctx.shape[1]
         ctx2d = ctx.reshape(B * L, -1).contiguous()
 
-        def ctx_kv_of(bprefix):
-            return ops.gemm(ctx2d, W[bprefix + "attn2.to_kv.weight"]), L
+        # SURVEY 2.3 D3 (second half): the transformer after whose projection the content / style branches are dead
+        cut_tr = None
+        if self.truncate_dead_branches and B == 3 and not self._fused_halo:
+            for tr in self._all_transformers():
+                a1 = tr.transformer_blocks[0].attn1
+                if a1.patched and self._attn1_plan(a1)[1] is not None:
+                    cut_tr = tr   # the last one in execution order
+        live = {"B": B, "off": 0}   # branches still evaluated / index of the first of them in the call's batch
+
+        def ctx_kv_of(bprefix):   # context rows of the branches still evaluated
+            return ops.gemm(ctx2d[live["off"] * L:], W[bprefix + "attn2.to_kv.weight"]), L
+
+        def transformer(tr, x, h, w):
+            if tr is not cut_tr:
+                return self._transformer(tr, x, ctx_kv_of, live["B"], F, h, w)
+            x = self._transformer(tr, x, ctx_kv_of, B, F, h, w, cut=True)
+            live["B"], live["off"] = 1, B - 1
+            return x
+
+        def cur(t, rows_per_branch):
+            """Rows of the branches that are still evaluated of a tensor produced before the cut."""
+            if live["off"] and t.shape[0] == B * rows_per_branch:
+                return t[live["off"] * rows_per_branch:]
+            return t
 
         x = ops.conv3x3(x, W["conv_in.weight"], bias=W["conv_in.bias"])
         h, w = H, Wd
@@ -512,53 +562,57 @@ class UNetPseudo3DConditionModel:
         n, lpb = self.nlev, cfg["layers_per_block"]
         for i, blk in enumerate(self.down_blocks):
             for j in range(lpb):
-                x = self._resnet(blk.resnets[j], x, None, temb_all, B, F, h, w)
+                x = self._resnet(blk.resnets[j], x, None, temb_all[live["off"]:], live["B"], F, h, w)
                 if blk.attentions:
-                    x = self._transformer(blk.attentions[j], x, ctx_kv_of, B, F, h, w)
-                x = self._motion(f"down_blocks.{i}.motion_modules.{j}.", x, B, F, h, w)
+                    x = transformer(blk.attentions[j], x, h, w)
+                x = self._motion(f"down_blocks.{i}.motion_modules.{j}.", x, live["B"], F, h, w)
                 skips.append(x)
             if i < n - 1:
-                planes = ops.space_to_depth2(x.view(B * F, h, w, -1))
+                planes = ops.space_to_depth2(x.view(live["B"] * F, h, w, -1))
                 h, w = h // 2, w // 2
                 pre = f"down_blocks.{i}.downsamplers.0.conv."
                 x = ops.conv3x3(planes, W[pre + "weight"], stride=2, bias=W[pre + "bias"])
                 skips.append(x)
-        x = self._resnet("mid_block.resnets.0.", x, None, temb_all, B, F, h, w)
-        x = self._transformer(self.mid_block.attentions[0], x, ctx_kv_of, B, F, h, w)
-        x = self._motion("mid_block.motion_modules.0.", x, B, F, h, w)
-        x = self._resnet("mid_block.resnets.1.", x, None, temb_all, B, F, h, w)
+        x = self._resnet("mid_block.resnets.0.", x, None, temb_all[live["off"]:], live["B"], F, h, w)
+        x = transformer(self.mid_block.attentions[0], x, h, w)
+        x = self._motion("mid_block.motion_modules.0.", x, live["B"], F, h, w)
+        x = self._resnet("mid_block.resnets.1.", x, None, temb_all[live["off"]:], live["B"], F, h, w)
         for i, blk in enumerate(self.up_blocks):
             for j in range(lpb + 1):
-                x = self._resnet(blk.resnets[j], x, skips.pop(), temb_all, B, F, h, w)
+                x = self._resnet(blk.resnets[j], x, cur(skips.pop(), F * h * w), temb_all[live["off"]:], live["B"], F, h, w)
                 if blk.attentions:
-                    x = self._transformer(blk.attentions[j], x, ctx_kv_of, B, F, h, w)
-                x = self._motion(f"up_blocks.{i}.motion_modules.{j}.", x, B, F, h, w)
+                    x = transformer(blk.attentions[j], x, h, w)
+                x = self._motion(f"up_blocks.{i}.motion_modules.{j}.", x, live["B"], F, h, w)
             if i < n - 1:
-                up = ops.upsample2x(x.view(B * F, h, w, -1))
+                up = ops.upsample2x(x.view(live["B"] * F, h, w, -1))
                 h, w = h * 2, w * 2
                 pre = f"up_blocks.{i}.upsamplers.0.conv."
                 x = ops.conv3x3(up, W[pre + "weight"], bias=W[pre + "bias"])
             if ft_indices is not None and ft_timesteps is not None and ft_path is not None:
                 # unet_3d_condition.py:430-436: sample[0].permute(1, 2, 3, 0) == our channels-last rows of branch 0
                 if i in ft_indices and timestep in ft_timesteps:
+                    if live["off"]:
+                        raise NotImplementedError("feature dumps need branch 0: do not combine with truncate_dead_branches")
                     path = os.path.join(ft_path, f"inversion_feature_map_{i}_block_{timestep}_step.pt")
                     torch.save(x[: F * h * w].view(F, h, w, -1).clone(), path)
                     print(f"save feature map at: {path}")
-        NBg, rows = self._gn_span(B, F, h * w)
+        Bo = live["B"]   # branches in the output (1 after a cut: the edit branch)
+        NBg, rows = self._gn_span(Bo, F, h * w)
         y = self._gn(x, W["conv_norm_out.weight"], W["conv_norm_out.bias"], NB=NBg, rows=rows, eps=cfg["norm_eps"],
                      silu=True)
-        eps_rows = ops.conv3x3(y.view(B * F, h, w, -1), W["conv_out.weight"], bias=W["conv_out.bias"],
-                               out=torch.empty((B * F * h * w, 8), dtype=torch.float16, device=dev))
+        eps_rows = ops.conv3x3(y.view(Bo * F, h, w, -1), W["conv_out.weight"], bias=W["conv_out.bias"],
+                               out=torch.empty((Bo * F * h * w, 8), dtype=torch.float16, device=dev))
         if self._shard is not None:  # all-gather the (tiny) noise prediction: [P][B][Fl] -> [B][P Fl]
             import torch.distributed as dist
             group, rank, world = self._shard
-            gathered = torch.empty((world, B, F, h * w, 8), dtype=torch.float16, device=dev)
+            gathered = torch.empty((world, Bo, F, h * w, 8), dtype=torch.float16, device=dev)
             # output given in the concatenated form (rank-major dim 0), which every backend accepts
-            dist.all_gather_into_tensor(gathered.view(world * B, F, h * w, 8), eps_rows.view(B, F, h * w, 8), group=group)
-            eps_rows = gathered.permute(1, 0, 2, 3, 4).reshape(B * F_total * h * w, 8).contiguous()
+            dist.all_gather_into_tensor(gathered.view(world * Bo, F, h * w, 8), eps_rows.view(Bo, F, h * w, 8), group=group)
+            eps_rows = gathered.permute(1, 0, 2, 3, 4).reshape(Bo * F_total * h * w, 8).contiguous()
             F = F_total
         self.last_eps_rows = eps_rows
-        out = ops.unpack_latents(self.last_eps_rows, B, cfg["out_channels"], F, h, w)
+        self.last_edit_branch = Bo - 1
+        out = ops.unpack_latents(self.last_eps_rows, Bo, cfg["out_channels"], F, h, w)
         return UNetPseudo3DConditionOutput(sample=out)
 
     def __call__(self, *args, **kwargs):
