@@ -7,18 +7,27 @@ One "step" = one complete pass of the hot path over one synthetic clip: 50 DDIM 
 [content, style, edit] SD-1.5 UNet on 16 frames of 512x512 (latents 64x64), mask blending and late latent AdaIN
 included (configs[1] of BASELINE.json).  ``value`` = frames / second with all inputs resident in HBM; ``e2e`` = the
 same through the public pipeline call with pinned HOST buffers (trajectories, mask, prompt embeddings copied in and the
-stylized latents read back inside the timed region).  N > 1: one process per GPU, each rank stylizes its own clip
-(independent clips shard with no data-path collective -> weak scaling); timing is CUDA events, max over ranks.
+stylized latents read back inside the timed region).
+
+N = 1: one clip on one GPU.  N > 1 (one process per GPU under torchrun): ONE clip whose 16 frames are sharded over the N
+ranks -- strong scaling, the split BASELINE.json's north_star names: per attn1 layer the boundary frame's K/V and the
+clip's first frame's K/V are stored into the peers' banks over NVLink, every cross-frame GroupNorm exchanges 3 x 32 x 2
+partial sums, the noise prediction is stored into every rank's buffer (csrc/xrank.cu: no collective-library call), and the
+forward is a replayed CUDA graph.  The result is asserted against the single-GPU evaluation of the same clip.  The
+clip-parallel replica rate (each rank its own clip, no communication) is reported as a side number.
 
 The ``roofline`` object describes the dominant kernel (fused sparse-causal attention at the 64x64 level, patched
 KV = 2N): algorithmic FLOPs per launch / mean launch duration measured with CUDA events inside the timed region.
 ``cpu_baseline`` / ``--impl reference``: the reference's algorithm has no CPU entry point of its own and needs
 diffusers + model weights that do not exist offline, so the CPU arm is the oracle port (oracle/unet_oracle.py, pinned
 to golden vectors of the reference's module code) timed on the host cores on a bounded sample of the same workload.
+``config.torch_eager_fp16``: the same oracle code in torch fp16 eager on the GPU (cuDNN / cuBLAS / flash SDPA -- the
+library kernels the reference's modules would run), a second reported baseline.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -33,7 +42,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 F_FRAMES, LAT, STEPS_DDIM = 16, 64, 50
-FLOP_PER_CLIP = 2.340e15  # 50 steps x 48 images x 975.1 GF (reference-equivalent live work)
+# live work of one image (one frame of one branch) in one UNet call, and of a clip
+GF_IMAGE = 975.1e9
+FLOP_PER_CLIP_REFERENCE = 50 * 48 * GF_IMAGE                       # 2.340 PF: all three branches at every step
+# what dead-branch skipping leaves (exact): 26 live steps of 48 images minus the part of the last patched
+# transformer + conv_out that runs on the edit branch only (56.87 GF x 32 images), 24 steps of the edit branch alone
+FLOP_PER_CLIP_EXECUTED = 26 * (48 * GF_IMAGE - 32 * 56.87e9) + 24 * 16 * GF_IMAGE
 
 
 def peaks():
@@ -83,7 +97,7 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def synthetic_clip(seed_offset: int = 0, device="cpu"):
+def synthetic_clip(seed_offset: int = 0):
     """content / style inversion trajectories x_k = sqrt(a_k) x_0 + sqrt(1 - a_k) eps held in
     memory, a moving-disc mask, a fixed (77, 768) context.  Returned on the host (pinned when CUDA is present)."""
     from univst_b200.scheduler import DDIMScheduler
@@ -114,6 +128,9 @@ def h2d_bytes(clip):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle port)
+CPU_SAMPLE_FRAMES = 4   # >= 3 so that [previous, first] name two frames other than the query's own for most of the sample
+
+
 def cpu_reference_step(sample_frames: int, threads: int):
     """One three-branch DDIM step (mask blend -> UNet -> DDIM update) of the oracle port on the host cores, fp32,
     at full SD-1.5 width and 64x64 latents but only ``sample_frames`` frames (cost is linear in frames)."""
@@ -144,22 +161,101 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample_frames = 2
-    step = cpu_reference_step(sample_frames, threads)
+    step = cpu_reference_step(CPU_SAMPLE_FRAMES, threads)
     for _ in range(min(args.warmup, 1)):
         step()
     k = max(1, min(args.steps, 2))  # each CPU step is tens of seconds: bound the run
     dt = sum(step() for _ in range(k)) / k
-    fps = sample_frames / (STEPS_DDIM * dt)
+    fps = CPU_SAMPLE_FRAMES / (STEPS_DDIM * dt)
+    sample = (f"{k} three-branch DDIM step(s), 3 x {CPU_SAMPLE_FRAMES} frames at 64x64 latents, full SD-1.5 width, fp32; all "
+              "three branches at every step (the reference's own work, no dead-branch skipping)")
     line = {"impl": "reference", "metric": "stylized frames/sec (16x512x512, 50 DDIM steps)", "value": fps,
             "unit": "frames/s", "n_gpus": args.gpus, "steps": k, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "SD-v1.5 three-branch localized transfer, 16x512x512, 50 steps",
                        "note": "CPU oracle port; value extrapolated: frames_sample / (50 x seconds per DDIM step)"},
-            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
-                             "sample": f"{k} three-branch DDIM step(s), 3 x {sample_frames} frames at 64x64 latents, full SD-1.5 width, fp32"},
+            "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), file=_OUT, flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU library baseline
+def torch_eager_forward_baseline(unet, pipe, dev):
+    """SURVEY.md 8(d) "library kernel to beat": one three-branch UNet call (3 x 16 x 64 x 64, shift window open) of the
+    oracle's restatement of the reference forward in torch fp16 eager on this GPU (cuDNN convolutions, cuBLAS linears,
+    flash SDPA) next to this library's forward on the same inputs.  A baseline leg: not on the product path."""
+    from oracle import unet_oracle as uo
+    from univst_b200 import pnp_utils
+    cfg = uo.SD15_CONFIG
+    sd16 = {k: v.to(dev).half() for k, v in uo.seeded_state_dict(cfg, seed=33).items()}
+    g = torch.Generator(device=dev).manual_seed(7)
+    x = torch.randn(3, 4, F_FRAMES, LAT, LAT, device=dev, generator=g).half()
+    ctx = torch.randn(3, 77, cfg["cross_attention_dim"], device=dev, generator=g).half()
+    pnp_utils.register_time(pipe, 5)
+    torch.backends.cudnn.benchmark = True
+
+    def med(fn, iters=5):
+        for _ in range(2):
+            out = fn()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(iters):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        return out, statistics.median(ts)
+
+    with torch.no_grad():
+        ours, ms_ours = med(lambda: unet(x, 881, encoder_hidden_states=ctx).sample)
+        eager, ms_eager = med(lambda: uo.unet_forward(sd16, cfg, x, 881, ctx, patched=True, idx=5))
+    rel = float((ours.float() - eager.float()).norm() / eager.float().norm())
+    return {"ms_per_forward": ms_eager, "ms_per_forward_univst_b200": ms_ours, "speedup": ms_eager / ms_ours,
+            "rel_l2_between": rel, "note": "three-branch call, 3 x 16 frames at 64x64 latents, shift window open; the same "
+            "seeded weights; oracle code in torch " + torch.__version__ + " fp16 eager (cuDNN / cuBLAS / flash SDPA)"}
+
+
+def attention_traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture -- only while the kernel source is the
+    one that capture was taken from (profiles/attention_traffic.json records its hash)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "attention_traffic.json")) as f:
+            t = json.load(f)
+        h = hashlib.sha256()
+        for name in ("attention_tc.cu", "ptx.cuh"):
+            with open(os.path.join(ROOT, "univst_b200", "csrc", name), "rb") as f:
+                h.update(f.read())
+        if t.get("kernel_source_sha256_16") == h.hexdigest()[:16]:
+            return t["dram_bytes_per_launch"], t.get("source")
+    except Exception:
+        pass
+    return None, None
+
+
+def dominant_attention(prof, pk, clocks_mhz):
+    """roofline object of the fused SC-attention launches at the 64x64 level with the patched KV = [prev, first]."""
+    cand = [(m_, meta) for m_, meta in prof.get("sc_attention", []) if meta[3] == LAT * LAT and meta[4] == 2 * LAT * LAT]
+    if not cand:
+        return None
+    ni = max(meta[0] for _, meta in cand)
+    dom = [(m_, meta) for m_, meta in cand if meta[0] == ni]
+    NI, H, d, N, Nkv = dom[0][1]
+    flops = 4.0 * N * Nkv * H * d * NI
+    avg_ms = sum(m_ for m_, _ in dom) / len(dom)
+    ach = flops / (avg_ms * 1e-3) / 1e12
+    traffic, tsrc = attention_traffic() if NI == 3 * F_FRAMES else (None, None)
+    clk = clocks_mhz or 1900.0
+    # secondary limit of this kernel: one exponential per (query, key, head) on the MUFU pipe, 16 / clock / SM,
+    # 4 d = 160 useful FLOP per exponential at head dim 40
+    mufu_bound = 16 * 148 * clk * 1e6 * 4 * d / 1e12
+    return {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
+            "traffic": traffic, "traffic_source": tsrc, "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": ach / mufu_bound,
+            "kernel": f"attention_tc_split_kernel<6,1> (2 query tiles x 128 keys, two softmax threads per row; N={N}, "
+                      f"Nkv={Nkv}, H={H}, d={d}, {NI} images)",
+            "flop_per_launch": flops, "launches_timed": len(dom), "avg_ms": avg_ms,
+            "peak_source": pk["src"] + " (sustained bf16 dense)"}
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -177,156 +273,173 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = torch.device("cuda", local)
+    if world > 1 and F_FRAMES % world:
+        raise SystemExit(f"{F_FRAMES} frames do not shard over {world} GPUs")
 
     unet = UNetPseudo3DConditionModel(random_state_dict(SD15_CONFIG, seed=33, device=dev), SD15_CONFIG, device=dev)
     pipe = SpatioTemporalStableDiffusionPipeline(unet)
     pnp_utils.register_spatial_attention_pnp(pipe)
-    clip = synthetic_clip(seed_offset=1000 * rank)
+    # N > 1: every rank works on rank 0's clip (frames sharded); the replica side number uses a clip per rank
+    clip = synthetic_clip(seed_offset=0)
 
-    def to_dev():
-        return {"traj_c": [t.to(dev, non_blocking=True) for t in clip["traj_c"]],
-                "traj_s": [t.to(dev, non_blocking=True) for t in clip["traj_s"]],
-                "mask": clip["mask"].to(dev, non_blocking=True), "ctx": clip["ctx"].to(dev, non_blocking=True)}
+    def to_dev(c=None):
+        c = c or clip
+        return {"traj_c": [t.to(dev, non_blocking=True) for t in c["traj_c"]],
+                "traj_s": [t.to(dev, non_blocking=True) for t in c["traj_s"]],
+                "mask": c["mask"].to(dev, non_blocking=True), "ctx": c["ctx"].to(dev, non_blocking=True)}
 
-    def stylize(c, skip=None):
+    def stylize(c, skip=True, p=None):
+        p = p or pipe
         z_T = ops.latent_adain(c["traj_c"][STEPS_DDIM], c["traj_s"][STEPS_DDIM])  # run_video_style_transfer_sd.py:57
-        return pipe.video_style_transfer("", num_inference_steps=STEPS_DDIM, latents=z_T, content_inv_path=c["traj_c"],
-                                         style_inv_path=c["traj_s"], mask_path=c["mask"], prompt_embeds=c["ctx"],
-                                         skip_dead_branches=args.skip_dead_branches if skip is None else skip).latents
+        return p.video_style_transfer("", num_inference_steps=STEPS_DDIM, latents=z_T, content_inv_path=c["traj_c"],
+                                      style_inv_path=c["traj_s"], mask_path=c["mask"], prompt_embeds=c["ctx"],
+                                      skip_dead_branches=skip).latents
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def timed(fn, k=1):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(k):
+            out = fn()
+        b.record()
+        barrier()
+        return out, a.elapsed_time(b)
+
+    rel = lambda a, b: float((a.float() - b.float()).norm() / b.float().norm())
     resident = to_dev()
+    extra, fs = {}, None
+
+    if world > 1:
+        # ---- single-GPU evaluation of the same clip on every rank: the parity reference and the same-box 1-GPU time
+        stylize(resident)
+        ref0, ms_single = timed(lambda: stylize(resident))
+        # ---- frames sharded over the ranks: peer-memory transport + CUDA graphs when symmetric memory works on every rank
+        ok = torch.ones(1, device=dev)
+        try:
+            unet.set_frame_sharding(transport="xrank")
+        except Exception as e:  # noqa: BLE001
+            print(f"[rank {rank}] xrank transport unavailable: {e!r}", file=sys.stderr)
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        xrank = bool(ok.item() > 0)
+        if not xrank:
+            unet.set_frame_sharding(transport="nccl", push_halo=False)
+        unet.use_cuda_graphs = xrank and not args.no_cuda_graphs
+        fs = {"transport": "peer-memory stores + device-side flags (csrc/xrank.cu), no collective-library call" if xrank
+              else "NCCL send/recv + broadcast + all-reduce + all-gather (symmetric memory unavailable on this box)",
+              "cuda_graphs": bool(unet.use_cuda_graphs), "ms_per_clip_1gpu_same_box": ms_single}
+
     for _ in range(args.warmup):
         out = stylize(resident)
     barrier()
     assert torch.isfinite(out).all(), "non-finite latents"
 
     # ---- timed region 1: inputs resident in HBM
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     n0 = ops.launch_count
-    ops.profile_start({"sc_attention"})
+    profiling = not unet.use_cuda_graphs     # per-kernel CUDA events cannot be recorded inside a replayed graph
+    if profiling:
+        ops.profile_start({"sc_attention"})
     with ClockSampler(local) as clocks:
-        barrier()
-        ev[0].record()
-        for _ in range(args.steps):
-            out = stylize(resident)
-        ev[1].record()
-        barrier()
-    prof = ops.profile_stop()
+        out, ms = timed(lambda: stylize(resident), args.steps)
+    prof = ops.profile_stop() if profiling else {}
     launches = ops.launch_count - n0
-    ms = ev[0].elapsed_time(ev[1])
 
     # ---- timed region 2: end to end through the public call with host buffers
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        host_out = stylize(to_dev()).cpu()
-    e1.record()
-    barrier()
-    ms_e2e = e0.elapsed_time(e1)
+    host_out, ms_e2e = timed(lambda: stylize(to_dev()).cpu(), args.steps)
 
-    # ---- extra (not the headline): exact dead-branch skipping (content / style branches only while the shift is live)
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    out_skip = stylize(resident, skip=True)
-    s1.record()
-    barrier()
-    ms_skip = s0.elapsed_time(s1)
-    skip_identical = bool(torch.equal(out_skip, out)) if not args.skip_dead_branches else True
-
-    # ---- extra (N > 1, not the headline): ONE clip with its frames sharded over the ranks (strong scaling): per attn1
-    # layer the boundary frame's K/V goes to the next rank and frame 0's K/V is broadcast (NCCL over NVLink), every
-    # cross-frame GroupNorm all-reduces 3 x 32 x 2 floats, the predicted noise is all-gathered
-    ms_fs, fs_rel = 0.0, None
-    if world > 1 and F_FRAMES % world == 0:
-        shared = {k: ([t.clone() for t in v] if isinstance(v, list) else v.clone()) for k, v in resident.items()}
-        for v in shared.values():
-            for t in (v if isinstance(v, list) else [v]):
-                dist.broadcast(t, src=0)
-        ref0 = stylize(shared)           # rank-local evaluation of rank 0's clip
-        # K/V halo pushed into the peers' symmetric memory when that works on every rank of this box, else through NCCL.
-        # The pushed halo was verified on 2 GPUs (profiles/r01_bench_v10_2gpu.json); larger worlds keep the NCCL exchange
-        # that was measured on 4 (profiles/r01_bench_v7_4gpu.json) until the push is measured there too.
-        ok = torch.ones(1, device=dev)
-        if world == 2:
-            try:
-                import torch.distributed._symmetric_memory as symm_mem
-                probe = symm_mem.empty(64, dtype=torch.float16, device=dev)
-                symm_mem.rendezvous(probe, dist.group.WORLD).barrier(channel=0)
-                torch.cuda.synchronize()
-            except Exception:
-                ok.zero_()
-        else:
-            ok.zero_()
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        push_halo = bool(ok.item() > 0)
-        unet.set_frame_sharding(push_halo=push_halo)
-        stylize(shared)                  # warm-up (NCCL channels, halo buffers)
-        barrier()
-        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        f0.record()
-        out_fs = stylize(shared)
-        f1.record()
-        barrier()
-        ms_fs = f0.elapsed_time(f1)
+    if world > 1:
+        if unet._xr is not None:
+            unet._xr.check()
+        fs["rel_l2_vs_single_gpu"] = rel(out, ref0)
+        assert fs["rel_l2_vs_single_gpu"] < 5e-3, f"frame-sharded result differs from the single-GPU one: {fs}"
+        # one eager pass with per-kernel events for the roofline object (not part of the timed region)
+        if unet.use_cuda_graphs:
+            unet.use_cuda_graphs = False
+            ops.profile_start({"sc_attention"})
+            _, fs["ms_per_clip_without_cuda_graphs"] = timed(lambda: stylize(resident))
+            prof = ops.profile_stop()
         unet.set_frame_sharding_off()
-        fs_rel = float((out_fs.float() - ref0.float()).norm() / ref0.float().norm())
+        unet.use_cuda_graphs = False
+        # ---- side number: clip-parallel replicas (each rank its own clip, no communication; weak scaling)
+        own = to_dev(synthetic_clip(seed_offset=1000 * rank))
+        stylize(own)
+        _, ms_rep = timed(lambda: stylize(own), 2)
+        fs["clip_parallel_replicas"] = {"ms_per_clip_per_gpu": ms_rep / 2}
+    else:
+        # ---- extra: the reference's own amount of work (all three branches at every step); must give the same latents
+        out_full, ms_full = timed(lambda: stylize(resident, skip=False))
+        extra["all_branches_every_step"] = {"frames_per_s": F_FRAMES / (ms_full / 1e3), "ms_per_clip": ms_full,
+                                            "edit_latents_bit_identical": bool(torch.equal(out_full, out)),
+                                            "flop_per_clip": FLOP_PER_CLIP_REFERENCE}
+        # ---- extra: the forward as a replayed CUDA graph (one cudaGraphLaunch per UNet call)
+        if not args.no_cuda_graphs:
+            unet.use_cuda_graphs = True
+            out_g = stylize(resident)
+            _, ms_graph = timed(lambda: stylize(resident), 2)
+            unet.use_cuda_graphs = False
+            unet._graphs.clear()
+            extra["cuda_graphs"] = {"frames_per_s": F_FRAMES / (ms_graph / 2e3), "ms_per_clip": ms_graph / 2,
+                                    "edit_latents_bit_identical": bool(torch.equal(out_g, out))}
+        if not args.no_extras:
+            extra["torch_eager_fp16"] = torch_eager_forward_baseline(unet, pipe, dev)
 
-    # ---- extra (N = 1, not the headline): 50-step DDIM content inversion of the clip (the stage that produces the
-    # trajectories the loop consumes: stock sparse-causal attention in all 16 layers, one branch; inversion_tools/
-    # ddim_inversion.py:88-113) through the mirror of the reference API, latents kept in memory
-    ms_inv = 0.0
-    if world == 1 and not args.no_animatediff:
+    # ---- extra (N = 1): 50-step DDIM content inversion of the clip (the stage that produces the trajectories the loop
+    # consumes: stock sparse-causal attention in all 16 layers, one branch; inversion_tools/ddim_inversion.py:88-113)
+    if world == 1 and not args.no_extras:
         from univst_b200 import ddim_inversion as di
         for tr in unet._all_transformers():   # inversion runs the UNPATCHED model (run_content_inversion_sd.py)
             tr.transformer_blocks[0].attn1.__dict__.pop("_patched", None)
         pipe.scheduler.set_timesteps(STEPS_DDIM)
         z0 = resident["traj_c"][0]
         di.ddim_inversion(pipe, pipe.scheduler, z0, 2, "", None, prompt_embeds=resident["ctx"])   # warm-up
-        barrier()
-        i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        i0.record()
-        inv = di.ddim_inversion(pipe, pipe.scheduler, z0, STEPS_DDIM, "", None, prompt_embeds=resident["ctx"])
-        i1.record()
-        barrier()
-        ms_inv = i0.elapsed_time(i1) if bool(torch.isfinite(inv[-1]).all()) else -1.0
+        inv, ms_inv = timed(lambda: di.ddim_inversion(pipe, pipe.scheduler, z0, STEPS_DDIM, "", None, prompt_embeds=resident["ctx"]))
+        if bool(torch.isfinite(inv[-1]).all()):
+            extra["ddim_inversion_50_steps"] = {"frames_per_s": F_FRAMES / (ms_inv / 1e3), "ms_per_clip": ms_inv,
+                                                "note": "content inversion of the same clip, stock [prev, self, first] "
+                                                        "attention in all layers, supplementary"}
         pnp_utils.register_spatial_attention_pnp(pipe)
 
-    # ---- extra (N = 1, not the headline): the same clip through the AnimateDiff-v2 backbone (BASELINE.json configs[3]
-    # architecture: per-frame self-attention + 21 motion modules), AnimationPipeline loop, one timed pass
-    ms_ad = 0.0
-    if world == 1 and not args.no_animatediff:
+    # ---- extra: the same clip through the AnimateDiff-v2 backbone (BASELINE.json configs[3] architecture: per-frame
+    # self-attention + 21 motion modules), AnimationPipeline loop; N > 1: its frames sharded over the ranks (the motion
+    # modules exchange frames <-> pixels through peer memory), checked bit-identical against one GPU
+    if not args.no_extras:
         from univst_b200.animatediff import AD_SD15_CONFIG, AnimationPipeline, UNet3DConditionModel
         from univst_b200.scheduler import DDIMScheduler
+        xr_ok = fs is not None and fs["transport"].startswith("peer")
         del unet, pipe
         torch.cuda.empty_cache()
         unet_ad = UNet3DConditionModel(random_state_dict(AD_SD15_CONFIG, seed=34, device=dev, animatediff=True), AD_SD15_CONFIG, device=dev)
         pipe_ad = AnimationPipeline(unet_ad, DDIMScheduler.animatediff_v2())
         pnp_utils.register_spatial_attention_pnp(pipe_ad)
+        stylize(resident, p=pipe_ad)   # warm-up
+        out_ad, ms_ad = timed(lambda: stylize(resident, p=pipe_ad))
+        ad = {"frames_per_s": F_FRAMES / (ms_ad / 1e3), "ms_per_clip": ms_ad, "finite": bool(torch.isfinite(out_ad).all()),
+              "note": "same clip and loop, AnimateDiff-v2 UNet (21 motion modules, per-frame attention), one GPU, supplementary"}
+        if world > 1:
+            unet_ad.set_frame_sharding(transport="xrank" if xr_ok else "nccl")
+            unet_ad.use_cuda_graphs = xr_ok and not args.no_cuda_graphs
+            stylize(resident, p=pipe_ad)
+            out_ads, ms_ads = timed(lambda: stylize(resident, p=pipe_ad), 2)
+            if unet_ad._xr is not None:
+                unet_ad._xr.check()
+            ad["frame_sharded"] = {"frames_per_s": F_FRAMES / (ms_ads / 2e3), "ms_per_clip": ms_ads / 2, "n_gpus": world,
+                                   "speedup_vs_1gpu_same_box": ms_ad / (ms_ads / 2),
+                                   "bit_identical_to_1gpu": bool(torch.equal(out_ads, out_ad)),
+                                   "cuda_graphs": bool(unet_ad.use_cuda_graphs)}
+            assert ad["frame_sharded"]["bit_identical_to_1gpu"], "AnimateDiff frame-sharded result differs from one GPU"
+        extra["animatediff_v2_backbone"] = ad
 
-        def stylize_ad(c):
-            z_T = ops.latent_adain(c["traj_c"][STEPS_DDIM], c["traj_s"][STEPS_DDIM])
-            return pipe_ad.video_style_transfer("", num_inference_steps=STEPS_DDIM, latents=z_T, content_inv_path=c["traj_c"],
-                                                style_inv_path=c["traj_s"], mask_path=c["mask"], prompt_embeds=c["ctx"]).latents
-        out_ad = stylize_ad(resident)   # warm-up
-        barrier()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        out_ad = stylize_ad(resident)
-        a1.record()
-        barrier()
-        ms_ad = a0.elapsed_time(a1) if bool(torch.isfinite(out_ad).all()) else -1.0
-
-    t = torch.tensor([ms, ms_e2e, ms_skip, ms_fs], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms, ms_e2e] + ([fs["clip_parallel_replicas"]["ms_per_clip_per_gpu"]] if fs else []), device=dev,
+                     dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e, ms_skip, ms_fs = t.tolist()
+    tl = t.tolist()
+    ms, ms_e2e = tl[0], tl[1]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -334,64 +447,41 @@ def run_ours(args):
 
     pk = peaks()
     ms_per_step = ms / args.steps
-    fps = world * F_FRAMES / (ms_per_step / 1e3)
-    fps_e2e = world * F_FRAMES / (ms_e2e / args.steps / 1e3)
-    # dominant kernel: fused SC-attention at the 64x64 level with the patched KV = [prev, first] (3 layers / forward)
-    dom = [(m_, meta) for m_, meta in prof["sc_attention"] if meta[3] == LAT * LAT and meta[4] == 2 * LAT * LAT and meta[0] == 3 * F_FRAMES]
-    roof = None
-    if dom:
-        NI, H, d, N, Nkv = dom[0][1]
-        flops = 4.0 * N * Nkv * H * d * NI
-        avg_ms = sum(m_ for m_, _ in dom) / len(dom)
-        ach = flops / (avg_ms * 1e-3) / 1e12
-        traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "attention_traffic.json")) as f:
-                traffic = json.load(f)["dram_bytes_per_launch"]
-        except Exception:
-            pass
-        clk = clocks.summary()["sm_mhz"] or 1900.0
-        # secondary limit of this kernel: one exponential per (query, key, head) on the MUFU pipe, 16 / clock / SM,
-        # 4 d = 160 useful FLOP per exponential at head dim 40
-        mufu_bound = 16 * 148 * clk * 1e6 * 4 * d / 1e12
-        roof = {"bound": "tensor", "achieved": ach, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": ach / pk["tflops"],
-                "traffic": traffic, "mufu_bound_tflops": mufu_bound, "frac_of_mufu_bound": ach / mufu_bound, "kernel": "attention_tc_split_kernel<6,1> (2 query tiles x 128 keys, two softmax threads per row; N=4096, Nkv=8192, H=8, d=40, 48 images)",
-                "launches_timed": len(dom), "avg_ms": avg_ms, "peak_source": pk["src"] + " (sustained bf16 dense)"}
-    attn_ms = sum(m_ for m_, _ in prof["sc_attention"]) / args.steps
+    fps = F_FRAMES / (ms_per_step / 1e3)                 # one clip per step at every N (N > 1: its frames are sharded)
+    fps_e2e = F_FRAMES / (ms_e2e / args.steps / 1e3)
+    clk = clocks.summary()
+    roof = dominant_attention(prof, pk, clk["sm_mhz"])
+    attn_ms = sum(m_ for m_, _ in prof.get("sc_attention", [])) / (args.steps if profiling else 1)
+    config = {"workload": "SD-v1.5 three-branch localized transfer, 16x512x512, 50 steps, one clip"
+                          + (f", frames sharded over {world} GPUs" if world > 1 else ""),
+              "weights": "random init (seed 33), SD-1.5 UNet shapes", "l2": "working set per UNet call ~5 GiB >> 126 MB L2",
+              "skip_dead_branches": True,
+              "parallelism": f"frame-sharded x{world} (one clip, {F_FRAMES // world} frames per GPU)" if world > 1 else "1 GPU",
+              "flop_per_clip_executed": FLOP_PER_CLIP_EXECUTED, "flop_per_clip_reference_equivalent": FLOP_PER_CLIP_REFERENCE,
+              "whole_loop_tensor_frac": FLOP_PER_CLIP_EXECUTED / (ms_per_step / 1e3) / 1e12 / (pk["tflops"] * world),
+              "sc_attention_ms_per_clip" + ("" if world == 1 else "_per_gpu"): attn_ms}
+    config.update(extra)
+    if fs is not None:
+        fs.pop("clip_parallel_replicas")
+        fs["speedup_vs_1gpu_same_box"] = fs["ms_per_clip_1gpu_same_box"] / ms_per_step
+        fs["clip_parallel_replicas"] = {"frames_per_s": world * F_FRAMES / (tl[2] / 1e3), "scaling": "weak",
+                                        "note": "side number: each rank stylizes its own clip, no communication"}
+        config["frame_sharding"] = fs
     line = {
         "metric": "stylized frames/sec (16x512x512, 50 DDIM steps)", "value": fps, "unit": "frames/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-        "config": {"workload": "SD-v1.5 three-branch localized transfer, 16x512x512, 50 steps, 1 clip per GPU",
-                   "weights": "random init (seed 33), SD-1.5 UNet shapes", "l2": "working set per UNet call ~5 GiB >> 126 MB L2",
-                   "skip_dead_branches": bool(args.skip_dead_branches), "parallelism": f"clip-parallel x{world}",
-                   "whole_loop_tensor_frac": (fps / world / F_FRAMES) * FLOP_PER_CLIP / 1e12 / pk["tflops"],
-                   "sc_attention_ms_per_clip": attn_ms,
-                   "with_exact_dead_branch_skipping": {"frames_per_s": world * F_FRAMES / (ms_skip / 1e3),
-                                                       "edit_latents_bit_identical": skip_identical}},
+        "scaling": "strong" if world > 1 else "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": config,
         "e2e": {"value": fps_e2e, "unit": "frames/s", "h2d_bytes_per_step": h2d_bytes(clip), "d2h_bytes_per_step": host_out.numel() * 2},
-        "gpu_launches": launches, "clocks": clocks.summary(), "roofline": roof,
+        "gpu_launches": launches, "clocks": clk, "roofline": roof,
     }
-    if ms_fs > 0:
-        line["config"]["one_clip_frame_sharded"] = {"frames_per_s": F_FRAMES / (ms_fs / 1e3), "scaling": "strong",
-                                                    "ms_per_clip": ms_fs, "rel_l2_vs_single_gpu": fs_rel,
-                                                    "collectives": ("K/V halo pushed into the peers' symmetric-memory banks over NVLink + one barrier per attn1"
-                                                                    if push_halo else "K/V halo send/recv + frame-0 broadcast per attn1 (NCCL)")
-                                                    + "; GroupNorm stat all-reduce, eps all-gather (NCCL)"}
-    if ms_inv != 0.0:
-        line["config"]["ddim_inversion_50_steps"] = {"frames_per_s": F_FRAMES / (ms_inv / 1e3) if ms_inv > 0 else None,
-                                                     "ms_per_clip": ms_inv, "note": "content inversion of the same clip, "
-                                                     "stock [prev, self, first] attention in all layers, supplementary"}
-    if ms_ad != 0.0:
-        line["config"]["animatediff_v2_backbone"] = {"frames_per_s": F_FRAMES / (ms_ad / 1e3) if ms_ad > 0 else None,
-                                                     "ms_per_clip": ms_ad, "note": "same clip and loop, AnimateDiff-v2 UNet "
-                                                     "(21 motion modules, per-frame attention), one timed pass, supplementary"}
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        step = cpu_reference_step(2, threads)
+        step = cpu_reference_step(CPU_SAMPLE_FRAMES, threads)
         dt = step()
-        line["cpu_baseline"] = {"value": 2 / (STEPS_DDIM * dt), "unit": "frames/s", "cores": threads, "kind": "port",
-                                "sample": "1 three-branch DDIM step, 3 x 2 frames at 64x64 latents, full SD-1.5 width, fp32 oracle port"}
+        line["cpu_baseline"] = {"value": CPU_SAMPLE_FRAMES / (STEPS_DDIM * dt), "unit": "frames/s", "cores": threads, "kind": "port",
+                                "sample": f"1 three-branch DDIM step, 3 x {CPU_SAMPLE_FRAMES} frames at 64x64 latents, full SD-1.5 "
+                                          "width, fp32 oracle port, all three branches (the reference's own work)"}
     print(json.dumps(line), file=_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -406,9 +496,10 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--skip-dead-branches", dest="skip_dead_branches", action="store_true", default=False)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-animatediff", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the supplementary passes (inversion, AnimateDiff, torch eager)")
+    ap.add_argument("--no-animatediff", dest="no_extras", action="store_true")
+    ap.add_argument("--no-cuda-graphs", action="store_true")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: libraries that write banners to fd 1 from C (NCCL prints its version there
     # under torchrun) are sent to stderr, and the line itself goes to a duplicate of the original descriptor

@@ -142,6 +142,12 @@ int univst_temporal_attention_f16(const void* QKV, int32_t ld, int32_t B, int32_
 int64_t univst_attn_shift_workspace_bytes(int32_t F, int32_t C);
 int univst_attn_shift_f16(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t C, float alpha, float beta, float gamma,
                           void* workspace, void* stream);
+/* The same with (alpha, beta, gamma) read from three floats in DEVICE memory: the launch no longer depends on the DDIM
+ * step, so a captured UNet forward can be replayed for every step of the shift window (beta changes per step,
+ * pnp_utils.py:50).  univst_set_floats writes up to 64 host floats (passed by value at launch) to device memory. */
+int univst_attn_shift_dev_f16(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t C, const float* abg, void* workspace,
+                              void* stream);
+int univst_set_floats(float* dst, const float* vals, int32_t n, void* stream);
 
 /* GroupNorm(+SiLU) over [NB, rows, C1 + C2] channels-last (second source optional = skip-connection concat):
  * statistics per (batch, group) over rows x channels-per-group.  resnet.py:338,369 / unet_3d_condition.py:439
@@ -196,12 +202,50 @@ int univst_ddim_step_f16(const void* z, const void* eps_nhwc, int32_t ld, int32_
  * (b, global frame, local pixel); dir 1: the inverse.  The caller places a cross-rank barrier after it. */
 int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P, int32_t B,
                              int32_t Fl, int32_t N, int32_t C, void* stream);
+/* The same with the cross-rank synchronisation (univst_xrank_*, below) as the tail of the kernel: no barrier launch. */
+int univst_exchange_push_xrank_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, void* const* ctl,
+                                   int32_t rank, int32_t P, int32_t B, int32_t Fl, int32_t N, int32_t C, void* stream);
 /* K/V halo of the frame-sharded sparse-causal attention (attention.py:395-410 needs frame f-1 and frame 0 of every
  * branch): nblk blocks of [rows, cols] halves (block b at src + b * src_blk_rows * ld_src) are stored into every non-null
  * dst[r] (HOST array of P device pointers into the ranks' symmetric-memory projection buffers; block b at
  * dst[r] + b * dst_blk_rows * ld_dst).  One read, up to P peer writes over NVLink; the caller places the barrier. */
 int univst_halo_push_f16(const void* src, int32_t ld_src, int64_t src_blk_rows, void* const* dst, int32_t P, int32_t ld_dst,
                          int64_t dst_blk_rows, int32_t nblk, int32_t rows, int32_t cols, void* stream);
+
+/* ------------------------------------------------------------------------------------------------------------
+ * Cross-rank synchronisation of the frame-sharded UNet over peer-mapped memory (no reference counterpart: the
+ * reference is single-GPU; SURVEY.md 8e lists the exchanges frame sharding needs).  Every rank owns one control block
+ * of univst_xrank_ctl_bytes() bytes, zero-initialised, in memory that ALL ranks have mapped (e.g. torch symmetric
+ * memory); `ctl` is a HOST array of `world` device pointers, ctl[r] = rank r's block as mapped into this process.
+ * A synchronisation stores this rank's next epoch into every peer's block and spins until every peer's epoch has
+ * arrived in the local block; the epoch counter lives in the block and is advanced on the device, so launches take no
+ * per-call host state and can be captured in a CUDA graph.  All ranks must issue the same sequence of synchronising
+ * calls.  A wait that exceeds 4 s sets the sticky error word (uint32 at byte 72 of the local block) instead of hanging.
+ * ---------------------------------------------------------------------------------------------------------- */
+int64_t univst_xrank_ctl_bytes(void);
+int32_t univst_xrank_slot_floats(void);
+int univst_xrank_barrier(void* const* ctl, int32_t rank, int32_t world, void* stream);
+/* Up to two block copies into peer memory (same block layout as univst_halo_push_f16; dst[r] = NULL skips rank r)
+ * followed by the synchronisation as the tail of the same kernel: when it retires, the peers' copies of this step have
+ * landed locally.  K/V halo of attn1 (attention.py:395-410): copy 0 = my last frame -> rank + 1's "previous frame" bank,
+ * copy 1 (rank 0) = the clip's first frame -> every rank's "first frame" bank.  Also the gather of the noise prediction. */
+typedef struct univst_push {
+  const void* src;
+  int32_t ld_src;
+  int64_t src_blk_rows;
+  void* dst[16];
+  int32_t ld_dst;
+  int64_t dst_blk_rows;
+  int32_t nblk, rows, cols;
+} univst_push_t;
+int univst_xrank_push_f16(const univst_push_t* pushes, int32_t npush, void* const* ctl, int32_t rank, int32_t world,
+                          void* stream);
+/* univst_groupnorm_f16 whose statistics span the rows of ALL ranks (resnet.py:338,369; unet_3d_condition.py:439 with the
+ * frames sharded): chunk partials -> fold + store into every rank's slot + synchronise + add the slots in rank order
+ * (bit-identical statistics on every rank) -> apply with rows * world rows.  Three launches, no collective call. */
+int univst_groupnorm_xrank_f16(const void* X1, const void* X2, int32_t C1, int32_t C2, int32_t NB, int32_t rows,
+                               int32_t groups, const void* gamma, const void* beta, float eps, int32_t silu, void* Y,
+                               void* workspace, void* const* ctl, int32_t rank, int32_t world, void* stream);
 int univst_axpby_f16(const void* a, const void* b, float wa, float wb, int64_t n, void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------

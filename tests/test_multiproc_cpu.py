@@ -209,7 +209,7 @@ def test_pushed_frames_pixels_exchange_for_2_to_4_ranks(monkeypatch):
     from univst_b200.animatediff import UNet3DConditionModel
 
     B, Fl, n, C = 3, 2, 4, 8
-    for P in (2, 3, 4):
+    for P, xrank in ((2, False), (3, False), (4, False), (2, True), (4, True)):
         N = n * P
         g = torch.Generator().manual_seed(10 + P)
         clip = torch.randn(B, P * Fl, N, C, generator=g).half()
@@ -227,7 +227,7 @@ def test_pushed_frames_pixels_exchange_for_2_to_4_ranks(monkeypatch):
                 return arenas[r]
             return SimpleNamespace(get_buffer=get_buffer, barrier=lambda channel=0: None)
 
-        def fake_exchange_push(direction, src, dst_ptrs, rank, P_, B_, Fl_, N_):
+        def fake_exchange_push(direction, src, dst_ptrs, rank, P_, B_, Fl_, N_, xr=None):
             n_ = N_ // P_
             flats = {r: arenas[r].view(-1) for r in range(P_)}
             base = {r: arenas[r].data_ptr() for r in range(P_)}
@@ -248,7 +248,15 @@ def test_pushed_frames_pixels_exchange_for_2_to_4_ranks(monkeypatch):
         monkeypatch.setattr(symm_mem, "empty", fake_empty)
         monkeypatch.setattr(symm_mem, "rendezvous", fake_rendezvous)
         monkeypatch.setattr(ops, "exchange_push", fake_exchange_push)
-        ranks = [SimpleNamespace(_shard=(object(), r, P), _push=True, _arena=None, device="cpu") for r in range(P)]
+        ranks = [SimpleNamespace(_shard=(object(), r, P), _push=True, _arena=None, _xr=None, device="cpu") for r in range(P)]
+        if xrank:   # the xrank transport: buffers come from XRank.buffer (same arenas), the kernel's tail synchronises
+            def fake_buffer(key, shape, dtype=torch.float16):
+                for r in range(P):
+                    if r not in arenas:
+                        arenas[r] = torch.zeros(*shape, dtype=dtype)
+                return arenas[cur["rank"]], [arenas[r].data_ptr() for r in range(P)]
+            for ns in ranks:
+                ns._xr, ns._push = SimpleNamespace(buffer=fake_buffer), False
 
         def exchange(direction, ys):
             outs = []

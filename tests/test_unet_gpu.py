@@ -144,3 +144,37 @@ def test_unet_forward_edge_shapes(setup, B, F, h, w, patched):
     print(f"B{B} F{F} {h}x{w} patched={patched}: ours rel={rel:.3e} max={mx:.3e} | torch-fp16 rel={rel16:.3e} max={mx16:.3e}")
     assert y.shape == truth.shape and torch.isfinite(y).all()
     assert rel <= 1e-2 and rel <= 2.0 * rel16 + 1e-3
+
+
+def test_cuda_graph_forward_and_truncation_are_bit_identical(setup):
+    """The forward replayed as a CUDA graph (step scalars -- timestep, shift parameters -- read from device memory) equals
+    the eager launch sequence bit for bit, across DDIM steps that share one captured graph (idx 3 and 17: different beta)
+    and across a plan change (idx 30: shift window closed -> another graph); and the edit branch of a call that drops the
+    dead content / style branches after the last patched projection equals the edit branch of the full call."""
+    from univst_b200 import pnp_utils
+    from types import SimpleNamespace
+    g, sd, sd16, unet = setup
+    pipe = SimpleNamespace(unet=unet)
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    x, ctx = g["x"].cuda().half(), g["ctx"].cuda().half()
+    try:
+        for idx, t in ((3, 921), (17, 641), (30, 381), (3, 921)):
+            pnp_utils.register_time(pipe, idx)
+            unet.use_cuda_graphs = False
+            eager = unet(x, t, encoder_hidden_states=ctx).sample.clone()
+            unet.truncate_dead_branches = True
+            cut = unet(x, t, encoder_hidden_states=ctx).sample.clone()
+            live = unet.shift_live(unet.up_blocks[1].attentions[1].transformer_blocks[0].attn1)
+            assert cut.shape[0] == (1 if live else 3) and unet.last_edit_branch == cut.shape[0] - 1
+            assert torch.equal(cut[-1], eager[2]), f"idx {idx}: truncated edit branch differs"
+            unet.use_cuda_graphs = True
+            cut_g = unet(x, t, encoder_hidden_states=ctx).sample.clone()
+            unet.truncate_dead_branches = False
+            graphed = unet(x, t, encoder_hidden_states=ctx).sample.clone()
+            assert torch.equal(graphed, eager), f"idx {idx}: graphed forward differs"
+            assert torch.equal(cut_g, cut), f"idx {idx}: graphed truncated forward differs"
+        assert len(unet._graphs) == 4   # (open, closed) x (full, truncated): idx 3 and 17 share their graphs
+    finally:
+        unet.use_cuda_graphs = False
+        unet.truncate_dead_branches = False
+        unet._graphs.clear()

@@ -90,6 +90,22 @@ def main():
             out_p, t_push = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)
             res[f"idx{idx}"].update({"ms_sharded_push_halo": t_push,
                                      "push_vs_nccl_max_abs": float((out_p.float() - out.float()).abs().max())})
+        if "--xrank" in sys.argv:   # everything through peer memory + device-side flags (csrc/xrank.cu), eager and as a CUDA graph
+            unet.set_frame_sharding(transport="xrank")
+            out_x, t_x = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 3)
+            unet.use_cuda_graphs = True
+            out_g, t_g = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 5)
+            unet.use_cuda_graphs = False
+            unet._xr.check()
+            dx = out_x.float() - ref.float()
+            res[f"idx{idx}"].update({"ms_sharded_xrank": t_x, "ms_sharded_xrank_graph": t_g,
+                                     "xrank_vs_single_max_abs": float(dx.abs().max()),
+                                     "xrank_vs_single_rel_l2": float(dx.norm() / ref.float().norm()),
+                                     "xrank_graph_vs_eager_max_abs": float((out_g.float() - out_x.float()).abs().max())})
+            # all ranks must hold the same result (the statistics are added in the same order everywhere)
+            gathered = [torch.empty_like(out_x) for _ in range(world)]
+            dist.all_gather(gathered, out_x.contiguous())
+            res[f"idx{idx}"]["xrank_ranks_agree"] = all(bool(torch.equal(gathered[0], g_)) for g_ in gathered)
         if "--fused" in sys.argv and not AD:   # K/V halo read from peer memory by the attention kernel itself
             unet.set_frame_sharding(fused_halo=True)
             out_f, t_fused = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 2)

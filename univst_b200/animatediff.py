@@ -77,7 +77,7 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
         self._push, self._arena = False, None
         super().__init__(state_dict, cfg, device=device)
 
-    def set_frame_sharding(self, group=None, push_exchange=None):
+    def set_frame_sharding(self, group=None, push_exchange=None, transport=None):
         """Shard the frames of every clip over the ranks of ``group``.  Everything spatial is frame-local in this backbone
         (per-frame GroupNorm, per-frame attn1); the only exchange is inside the motion modules, whose attention runs over
         the frames of one pixel: an all-to-all turns "my frames, all pixels" into "all frames, my pixels" before the
@@ -87,7 +87,11 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
         the default on NCCL process groups (2 GPUs, 16 frames at 64 x 64: 78.0 ms on one GPU, 47.4 ms with the all-to-all,
         43.5 ms pushed; all three bit-identical, profiles/r01_animatediff_sharding_exchange_2gpu.json)."""
         import torch.distributed as dist
-        super().set_frame_sharding(group)
+        # default on NCCL groups: the xrank transport (unet.py) -- the exchange kernel's tail is the cross-rank
+        # synchronisation and the noise prediction is stored into every rank's buffer: no collective-library call at all
+        if transport is None and push_exchange is not None:
+            transport = "nccl"
+        super().set_frame_sharding(group, transport=transport)
         self._pe_rows = {}
         if push_exchange is None:
             push_exchange = self._shard is not None and dist.get_backend(group) == "nccl"
@@ -97,6 +101,14 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
     def _exchange(self, direction, y, B, F, N):
         """frames -> pixels (0) / pixels -> frames (1) of the [rows, C] activations ``y``."""
         group, rank, P = self._shard
+        if self._xr is not None:
+            rows, C = y.shape
+            need = rows * C
+            # two buffers (one per direction): a buffer is rewritten only after the synchronisation that follows the OTHER
+            # direction's push, which every rank passes after its last read of this one
+            t, ptrs = self._xr.buffer(("arena", need), (2, need))
+            ops.exchange_push(direction, y, [p + direction * need * 2 for p in ptrs], rank, P, B, F, N, xr=self._xr)
+            return t[direction].view(rows, C)
         if not self._push:
             return (frames_to_pixels if direction == 0 else pixels_to_frames)(y, B, F, N, P, group)
         import torch.distributed as dist

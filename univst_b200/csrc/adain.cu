@@ -151,9 +151,14 @@ __device__ __forceinline__ void shift_kv_row(const __half* __restrict__ sty, __h
 // one warp per (frame, token) of the edit branch
 template <int MAXV>
 __global__ void attn_shift_kernel(__half* __restrict__ qkv, int ld, int F, int N, int C, const float* __restrict__ stats,
-                                  float alpha, float beta, float gamma) {
+                                  float alpha, float beta, float gamma, const float* __restrict__ abg) {
   const int tok = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= F * N) return;
+  if (abg) {   // step parameters in device memory: the launch is the same for every DDIM step (CUDA-graph replay)
+    alpha = __ldg(abg);
+    beta = __ldg(abg + 1);
+    gamma = __ldg(abg + 2);
+  }
   const int lane = threadIdx.x & 31;
   const int f = tok / N;
   const size_t branch = (size_t)F * N * ld;
@@ -190,8 +195,8 @@ extern "C" int64_t univst_attn_shift_workspace_bytes(int32_t F, int32_t C) {
   return ((int64_t)F * kStatChunks * (2 * C / 8) * 16 + (int64_t)F * 2 * C * 2) * sizeof(float);
 }
 
-extern "C" int univst_attn_shift_f16(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t C, float alpha, float beta,
-                                     float gamma, void* workspace, void* stream) {
+static int attn_shift(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t C, float alpha, float beta, float gamma,
+                      const float* abg, void* workspace, void* stream) {
   UV_REQUIRE(QKV && workspace, "attn_shift: null pointer");
   UV_REQUIRE(F > 0 && N > 1 && C % 8 == 0 && C <= 2048 && ld % 8 == 0 && ld >= 3 * C, "attn_shift: bad shape");
   cudaStream_t st = (cudaStream_t)stream;
@@ -221,9 +226,20 @@ extern "C" int univst_attn_shift_f16(void* QKV, int32_t ld, int32_t F, int32_t N
   const int warps = 8;
   const int blocks = (F * N + warps - 1) / warps;
   if (C <= 1024)
-    attn_shift_kernel<4><<<blocks, warps * 32, 0, st>>>(base, ld, F, N, C, stats, alpha, beta, gamma);
+    attn_shift_kernel<4><<<blocks, warps * 32, 0, st>>>(base, ld, F, N, C, stats, alpha, beta, gamma, abg);
   else
-    attn_shift_kernel<8><<<blocks, warps * 32, 0, st>>>(base, ld, F, N, C, stats, alpha, beta, gamma);
+    attn_shift_kernel<8><<<blocks, warps * 32, 0, st>>>(base, ld, F, N, C, stats, alpha, beta, gamma, abg);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
+}
+
+extern "C" int univst_attn_shift_f16(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t C, float alpha, float beta,
+                                     float gamma, void* workspace, void* stream) {
+  return attn_shift(QKV, ld, F, N, C, alpha, beta, gamma, nullptr, workspace, stream);
+}
+
+extern "C" int univst_attn_shift_dev_f16(void* QKV, int32_t ld, int32_t F, int32_t N, int32_t C, const float* abg,
+                                         void* workspace, void* stream) {
+  UV_REQUIRE(abg, "attn_shift_dev: null parameter pointer");
+  return attn_shift(QKV, ld, F, N, C, 0.0f, 0.0f, 0.0f, abg, workspace, stream);
 }

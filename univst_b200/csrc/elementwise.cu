@@ -1,7 +1,7 @@
 // Small HBM-bound kernels around the UNet: resampling of channels-last activations, latent pack / unpack
 // between the reference's (B, 4, F, h, w) layout and the kernels' [(b f), h, w, C], the sinusoidal timestep
 // embedding, and the per-step latent arithmetic of the denoising loop (mask blend, late latent AdaIN, DDIM step).
-#include "host_util.h"
+#include "xrank.cuh"
 #include "ptx.cuh"
 
 namespace uv {
@@ -319,9 +319,9 @@ struct PeerPtrs {
   __half* p[16];
 };
 
-template <int DIR>
+template <int DIR, bool SYNC>
 __global__ void exchange_push_kernel(const __half* __restrict__ src, int ld, PeerPtrs dst, int rank, int P, int B, int Fl,
-                                     int N, int C) {
+                                     int N, int C, XrankPeers xp) {
   const int vpr = C >> 3;                       // 16-byte vectors per row
   const int n = N / P;
   const long long rows = (long long)B * Fl * N;   // = B * (P Fl) * n
@@ -347,6 +347,7 @@ __global__ void exchange_push_kernel(const __half* __restrict__ src, int ld, Pee
     const uint4 val = *reinterpret_cast<const uint4*>(src + row * ld + v * 8);
     *reinterpret_cast<uint4*>(dst.p[owner] + drow * C + v * 8) = val;
   }
+  if (SYNC) xrank_kernel_tail(xp, rank, P);   // every rank's rows have landed when the kernel retires
 }
 
 // K/V halo of the frame-sharded sparse-causal attention: `nblk` blocks of [rows, cols] (one per branch: a
@@ -388,8 +389,8 @@ extern "C" int univst_halo_push_f16(const void* src, int32_t ld_src, int64_t src
   return UNIVST_OK;
 }
 
-extern "C" int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P,
-                                        int32_t B, int32_t Fl, int32_t N, int32_t C, void* stream) {
+static int exchange_push(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P, int32_t B,
+                         int32_t Fl, int32_t N, int32_t C, void* const* ctl, void* stream) {
   UV_REQUIRE(src && dst && (dir == 0 || dir == 1), "exchange_push: null pointer or bad direction");
   UV_REQUIRE(P >= 1 && P <= 16 && rank >= 0 && rank < P && B > 0 && Fl > 0 && N > 0 && N % P == 0,
              "exchange_push: up to 16 ranks, pixels divisible by the rank count");
@@ -401,10 +402,47 @@ extern "C" int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld
   }
   const size_t total = (size_t)B * Fl * N * (C / 8);
   const int grid = grid_for(total, 256);
-  if (dir == 0)
-    exchange_push_kernel<0><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld, pp, rank, P, B, Fl, N, C);
-  else
-    exchange_push_kernel<1><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)src, ld, pp, rank, P, B, Fl, N, C);
+  XrankPeers xp{};
+  if (ctl) {
+    int r = fill_peers(xp, ctl, rank, P, "exchange_push");
+    if (r) return r;
+  }
+  const __half* s = (const __half*)src;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (dir == 0 && !ctl) exchange_push_kernel<0, false><<<grid, 256, 0, st>>>(s, ld, pp, rank, P, B, Fl, N, C, xp);
+  if (dir == 1 && !ctl) exchange_push_kernel<1, false><<<grid, 256, 0, st>>>(s, ld, pp, rank, P, B, Fl, N, C, xp);
+  if (dir == 0 && ctl) exchange_push_kernel<0, true><<<grid, 256, 0, st>>>(s, ld, pp, rank, P, B, Fl, N, C, xp);
+  if (dir == 1 && ctl) exchange_push_kernel<1, true><<<grid, 256, 0, st>>>(s, ld, pp, rank, P, B, Fl, N, C, xp);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
+
+extern "C" int univst_exchange_push_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, int32_t rank, int32_t P,
+                                        int32_t B, int32_t Fl, int32_t N, int32_t C, void* stream) {
+  return exchange_push(dir, src, ld, dst, rank, P, B, Fl, N, C, nullptr, stream);
+}
+
+extern "C" int univst_exchange_push_xrank_f16(int32_t dir, const void* src, int32_t ld, void* const* dst, void* const* ctl,
+                                              int32_t rank, int32_t P, int32_t B, int32_t Fl, int32_t N, int32_t C,
+                                              void* stream) {
+  UV_REQUIRE(ctl, "exchange_push_xrank: null control blocks");
+  return exchange_push(dir, src, ld, dst, rank, P, B, Fl, N, C, ctl, stream);
+}
+
+namespace uv {
+struct FloatVals {
+  float v[64];
+};
+__global__ void set_floats_kernel(float* __restrict__ dst, FloatVals vals, int n) {
+  if ((int)threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
+}
+}  // namespace uv
+
+extern "C" int univst_set_floats(float* dst, const float* vals, int32_t n, void* stream) {
+  UV_REQUIRE(dst && vals && n > 0 && n <= 64, "set_floats: 1..64 values");
+  FloatVals fv{};
+  for (int i = 0; i < n; ++i) fv.v[i] = vals[i];
+  set_floats_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(dst, fv, n);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

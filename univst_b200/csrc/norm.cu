@@ -267,6 +267,23 @@ static int gn_launch_apply(const void* X1, const void* X2, int C1, int C2, int N
   return UNIVST_OK;
 }
 
+// entry points for the cross-rank form (xrank.cu): chunk partials only / apply only / shape check / folded-sum location
+int gn_stats_partials(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, void* workspace,
+                      int* nchunks, int* nchunks_stride, cudaStream_t st) {
+  const GnPlan g = gn_plan(C1 + C2, rows);
+  gn_stats_kernel<<<dim3(g.nchunks, NB), g.threads, g.threads * 8 * sizeof(float), st>>>(
+      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace);
+  UV_CHECK_CUDA(cudaGetLastError());
+  *nchunks = g.nchunks;
+  *nchunks_stride = g.nchunks;
+  return UNIVST_OK;
+}
+int gn_apply_launch(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, const float* sums,
+                    int64_t stat_rows, const void* gamma, const void* beta, float eps, int silu, void* Y, cudaStream_t st) {
+  return gn_launch_apply(X1, X2, C1, C2, NB, rows, groups, sums, stat_rows, gamma, beta, eps, silu, Y, st);
+}
+float* gn_sums_of(void* workspace, int NB, int groups) { return (float*)workspace + (size_t)NB * kGnMaxChunks * groups * 2; }
+
 }  // namespace uv
 
 using namespace uv;
@@ -276,7 +293,13 @@ extern "C" int64_t univst_groupnorm_workspace_bytes(int32_t NB, int32_t groups) 
   return (int64_t)NB * (kGnMaxChunks + 1) * groups * 2 * sizeof(float);
 }
 
+namespace uv {
+int gn_check_shape(const void* X1, const void* X2, int32_t& C1, int32_t& C2, int32_t NB, int32_t rows, int32_t groups);
+}
 static int gn_check(const void* X1, const void* X2, int32_t& C1, int32_t& C2, int32_t NB, int32_t rows, int32_t groups) {
+  return uv::gn_check_shape(X1, X2, C1, C2, NB, rows, groups);
+}
+int uv::gn_check_shape(const void* X1, const void* X2, int32_t& C1, int32_t& C2, int32_t NB, int32_t rows, int32_t groups) {
   if (!X2) C2 = 0;
   const int C = C1 + C2;
   UV_REQUIRE(NB > 0 && rows > 0 && groups > 0 && groups <= 64 && C % groups == 0, "groupnorm: bad shape");

@@ -45,6 +45,22 @@ _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
 _lib.register("univst_halo_push_f16", [_vp, _i32, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _vp])
 _lib.register("univst_exchange_push_f16", [_i32, _vp, _i32, C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _vp])
+_lib.register("univst_xrank_ctl_bytes", [], _i64)
+_lib.register("univst_xrank_slot_floats", [], _i32)
+_lib.register("univst_xrank_barrier", [_vp, _i32, _i32, _vp])
+
+
+class Push(C.Structure):
+    """Mirror of ``univst_push_t``."""
+    _fields_ = [("src", _vp), ("ld_src", _i32), ("src_blk_rows", _i64), ("dst", _vp * 16), ("ld_dst", _i32),
+                ("dst_blk_rows", _i64), ("nblk", _i32), ("rows", _i32), ("cols", _i32)]
+
+
+_lib.register("univst_xrank_push_f16", [C.POINTER(Push), _i32, _vp, _i32, _i32, _vp])
+_lib.register("univst_groupnorm_xrank_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _f32, _i32, _vp, _vp, _vp, _i32, _i32, _vp])
+_lib.register("univst_exchange_push_xrank_f16", [_i32, _vp, _i32, C.POINTER(_vp), _vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp])
+_lib.register("univst_attn_shift_dev_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp])
+_lib.register("univst_set_floats", [_vp, C.POINTER(_f32), _i32, _vp])
 _lib.register("univst_maskprop_workspace_bytes", [_i32, _i32, _i32], _i64)
 _lib.register("univst_maskprop_f32", [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _f32, _i32, _vp, _vp, _vp, _i32, _vp, _vp])
 _lib.register("univst_flow_warp_key_u8", [_vp, _i32, _i32, _i32, _i32, _i32, C.POINTER(_i32), C.POINTER(_vp), C.POINTER(_vp), _f32, _vp])
@@ -56,6 +72,7 @@ _LAUNCHES = {
     "groupnorm_stats": 2, "groupnorm_apply": 1, "gemm": 1, "conv3x3": 1, "sc_attention": 1, "attn_shift": 3, "groupnorm": 3, "layernorm": 1, "upsample2x": 1,
     "temporal_attention": 1, "cross_attention": 1, "joint_attention": 1, "rmsnorm_heads": 1, "sd3_attn_shift": 4, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "exchange_push": 1, "halo_push": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
+    "xrank_barrier": 1, "xrank_push": 1, "groupnorm_xrank": 3, "set_floats": 1,
 }
 
 
@@ -318,6 +335,72 @@ def attn_shift_(qkv: torch.Tensor, F: int, N: int, C_: int, alpha: float, beta: 
     return qkv
 
 
+def attn_shift_dev_(qkv: torch.Tensor, F: int, N: int, C_: int, abg: torch.Tensor):
+    """:func:`attn_shift_` with (alpha, beta, gamma) read from a float32 CUDA tensor (>= 3 elements) at run time."""
+    _lib.require_device()
+    _chk(qkv, "qkv")
+    assert qkv.shape[0] == 3 * F * N and abg.dtype == torch.float32 and abg.is_cuda and abg.numel() >= 3
+    ws = _workspace(_lib.lib().univst_attn_shift_workspace_bytes(F, C_), qkv.device)
+    check(_lib.lib().univst_attn_shift_dev_f16(qkv.data_ptr(), qkv.stride(0), F, N, C_, abg.data_ptr(), ws.data_ptr(),
+                                               _stream()), "univst_attn_shift_dev_f16")
+    _count("attn_shift")
+    return qkv
+
+
+def set_floats(dst: torch.Tensor, values):
+    """Write up to 64 Python floats into the float32 CUDA tensor ``dst`` (values travel as launch arguments: no host
+    buffer has to stay alive, nothing synchronises)."""
+    _lib.require_device()
+    n = len(values)
+    assert dst.dtype == torch.float32 and dst.is_cuda and dst.is_contiguous() and dst.numel() >= n
+    arr = (_f32 * n)(*[float(v) for v in values])
+    check(_lib.lib().univst_set_floats(dst.data_ptr(), arr, n, _stream()), "univst_set_floats")
+    _count("set_floats")
+    return dst
+
+
+def xrank_barrier(xr):
+    """Cross-rank synchronisation on the current stream (``xr``: :class:`univst_b200.xrank.XRank`)."""
+    _lib.require_device()
+    check(_lib.lib().univst_xrank_barrier(xr.ctl, xr.rank, xr.world, _stream()), "univst_xrank_barrier")
+    _count("xrank_barrier")
+
+
+def xrank_push(xr, pushes):
+    """Up to two block copies into peer memory + the cross-rank synchronisation as the tail of the same kernel.
+    ``pushes``: list of dicts(src=strided 2-D fp16 view, src_blk_rows, dst=[device pointer or 0 per rank], ld_dst,
+    dst_blk_rows, nblk, rows); an empty list is a plain synchronisation."""
+    _lib.require_device()
+    n = len(pushes)
+    arr = (Push * max(n, 1))()
+    for k, p in enumerate(pushes):
+        src = p["src"]
+        assert src.dtype == torch.float16 and src.is_cuda and src.stride(1) == 1
+        arr[k].src, arr[k].ld_src, arr[k].src_blk_rows = src.data_ptr(), src.stride(0), p["src_blk_rows"]
+        for r in range(16):
+            arr[k].dst[r] = (p["dst"][r] or None) if r < len(p["dst"]) else None
+        arr[k].ld_dst, arr[k].dst_blk_rows = p["ld_dst"], p["dst_blk_rows"]
+        arr[k].nblk, arr[k].rows, arr[k].cols = p["nblk"], p["rows"], src.shape[1]
+    check(_lib.lib().univst_xrank_push_f16(arr, n, xr.ctl, xr.rank, xr.world, _stream()), "univst_xrank_push_f16")
+    _count("xrank_push")
+
+
+def groupnorm_xrank(x1, gamma, beta, *, NB, rows, xr, groups=32, eps=1e-5, silu=False, x2=None):
+    """GroupNorm whose statistics span the rows of all ranks of ``xr``: partial sums exchanged through the ranks' control
+    blocks inside the fold kernel (no collective call); every rank normalises with bit-identical statistics."""
+    _lib.require_device()
+    _chk(x1, "x1")
+    C1 = x1.shape[-1]
+    C2 = x2.shape[-1] if x2 is not None else 0
+    out = torch.empty((NB * rows, C1 + C2), dtype=torch.float16, device=x1.device)
+    ws = _workspace(_lib.lib().univst_groupnorm_workspace_bytes(NB, groups), x1.device)
+    check(_lib.lib().univst_groupnorm_xrank_f16(x1.data_ptr(), _ptr(x2), C1, C2, NB, rows, groups, gamma.data_ptr(),
+                                                beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
+                                                xr.ctl, xr.rank, xr.world, _stream()), "univst_groupnorm_xrank_f16")
+    _count("groupnorm_xrank")
+    return out
+
+
 def groupnorm(x1: torch.Tensor, gamma, beta, *, NB: int, rows: int, groups: int = 32, eps: float = 1e-5,
               silu: bool = False, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None):
     _lib.require_device()
@@ -528,15 +611,20 @@ def halo_push(src: torch.Tensor, src_blk_rows: int, dst_ptrs, ld_dst: int, dst_b
     _count("halo_push")
 
 
-def exchange_push(direction: int, src: torch.Tensor, dst_ptrs, rank: int, P: int, B: int, Fl: int, N: int):
+def exchange_push(direction: int, src: torch.Tensor, dst_ptrs, rank: int, P: int, B: int, Fl: int, N: int, xr=None):
     """Frames <-> pixels exchange of the frame-sharded motion modules: store the local rows [B * Fl * N, C] at their place
     in every owner's buffer (``dst_ptrs``: device pointers of the P ranks' symmetric-memory buffers, each [rows, C]).
-    direction 0: frames -> pixels, 1: pixels -> frames.  The caller issues the cross-rank barrier."""
+    direction 0: frames -> pixels, 1: pixels -> frames.  With ``xr`` the cross-rank synchronisation is the tail of the
+    kernel; without it the caller issues a barrier."""
     _lib.require_device()
     assert src.dtype == torch.float16 and src.is_cuda and src.stride(1) == 1 and src.shape[0] == B * Fl * N and len(dst_ptrs) == P
     arr = (_vp * P)(*dst_ptrs)
-    check(_lib.lib().univst_exchange_push_f16(direction, src.data_ptr(), src.stride(0), arr, rank, P, B, Fl, N, src.shape[1],
-                                              _stream()), "univst_exchange_push_f16")
+    if xr is None:
+        check(_lib.lib().univst_exchange_push_f16(direction, src.data_ptr(), src.stride(0), arr, rank, P, B, Fl, N,
+                                                  src.shape[1], _stream()), "univst_exchange_push_f16")
+    else:
+        check(_lib.lib().univst_exchange_push_xrank_f16(direction, src.data_ptr(), src.stride(0), arr, xr.ctl, rank, P, B, Fl,
+                                                        N, src.shape[1], _stream()), "univst_exchange_push_xrank_f16")
     _count("exchange_push")
 
 

@@ -144,7 +144,15 @@ class UNetPseudo3DConditionModel:
         # network on the edit branch alone and ``.sample`` holds that branch only: (1, C, F, h, w).
         self.truncate_dead_branches = False
         self.last_edit_branch = None   # index of the edit branch inside ``last_eps_rows`` after a call
+        self._xr = None                # cross-rank control block + symmetric buffers (xrank.XRank) of the sharded forward
+        # CUDA graphs: one captured forward per (shapes, attention plan, sharding) key, replayed with the step's inputs
+        # copied into static buffers and its scalars (timestep, shift parameters) written to device memory
+        self.use_cuda_graphs = False
+        self._graphs, self._graph_pool, self._graph_stream = {}, None, None
+        self._step_params = None       # device float32 [64] while a graph-safe forward is being issued
         self._build_tree()
+        for i, tr in enumerate(self._all_transformers()):
+            tr.index = i
         self._pack(state_dict)
 
     # ------------------------------------------------------------------------------------------ construction
@@ -157,11 +165,20 @@ class UNetPseudo3DConditionModel:
             cfg["sample_size"] = c["sample_size"]
         return cls(module.state_dict(), cfg, device=device)
 
-    def set_frame_sharding(self, group=None, fused_halo: bool = False, push_halo=None):
+    def set_frame_sharding(self, group=None, fused_halo: bool = False, push_halo=None, transport=None):
         """Shard the frames of every clip over the ranks of ``group`` (default: the world group): rank r evaluates
-        frames [r F/P, (r+1) F/P) of all branches.  Every cross-frame GroupNorm all-reduces B x 32 x 2 floats; the
-        predicted noise is all-gathered at the end.  The K/V of the neighbouring frames that attn1 needs from other
-        ranks (last frame of the previous rank, frame 0 of the clip) arrive in one of two ways:
+        frames [r F/P, (r+1) F/P) of all branches.  What crosses ranks: B x 32 x 2 partial sums per cross-frame
+        GroupNorm, the K/V of the neighbouring frames that attn1 needs (last frame of the previous rank, frame 0 of the
+        clip), the predicted noise at the end.
+
+        ``transport="xrank"`` (the default on NCCL groups when neither ``push_halo`` nor ``fused_halo`` is given): all of
+        it goes through peer-mapped memory with the library's own kernels (csrc/xrank.cu) -- the halo is stored into
+        the peers' banks and the GroupNorm sums into the peers' control blocks by the kernel that produced them, whose
+        tail is the cross-rank synchronisation; the noise prediction is stored into every rank's full-clip buffer.  No
+        collective-library call is left in the forward (any world size up to 16), so it can be captured in a CUDA graph.
+
+        ``transport="nccl"`` keeps the collectives of the first implementation (GroupNorm all-reduce, noise all-gather;
+        works on any backend, e.g. gloo), with the halo exchanged in one of these ways:
         * ``push_halo=True`` (the default on NCCL groups): the fused projection lives in torch symmetric memory with two
           halo banks behind the local images; one kernel stores the K|V columns of the boundary frame into the next
           rank's bank, and rank 0's first frame into every rank's bank, over NVLink (``univst_halo_push_f16``), followed
@@ -178,9 +195,25 @@ class UNetPseudo3DConditionModel:
         world = dist.get_world_size(group)
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
         self._tables = {}
+        self._graphs = {}
+        nccl = self._shard is not None and dist.get_backend(group) == "nccl"
+        if transport is None:
+            transport = "xrank" if (nccl and push_halo is None and not fused_halo) else "nccl"
+        if transport not in ("xrank", "nccl"):
+            raise ValueError(transport)
+        self._xr = None
+        if transport == "xrank" and self._shard is not None:
+            from .xrank import XRank
+            key = id(group) if group is not None else 0
+            if not hasattr(self, "_xr_cache"):
+                self._xr_cache = {}
+            if key not in self._xr_cache:
+                self._xr_cache[key] = XRank(group, self.device)
+            self._xr = self._xr_cache[key]
+            fused_halo, push_halo = False, False
         self._fused_halo = bool(fused_halo) and self._shard is not None
         if push_halo is None:
-            push_halo = self._shard is not None and dist.get_backend(group) == "nccl"
+            push_halo = nccl
         self._push_halo = bool(push_halo) and self._shard is not None and not self._fused_halo
         if not hasattr(self, "_symm"):
             self._symm = {}
@@ -237,11 +270,40 @@ class UNetPseudo3DConditionModel:
             ops.halo_push(kv, F * N, dst, ld, N, B, N)
         hdl.barrier(channel=0)
 
+    def _xr_halo(self, rows, cols):
+        """Double-buffered symmetric projection buffer with halo banks (xrank transport): (local [rows, cols] tensor,
+        device pointers of every rank's copy of the same half)."""
+        key = ("qkv", rows, cols)
+        if not hasattr(self, "_xr_par"):
+            self._xr_par = {}
+        par = self._xr_par.get(key, 0)
+        self._xr_par[key] = par ^ 1
+        t, ptrs = self._xr.buffer(key, (2, rows, cols))
+        return t[par], [p + par * rows * cols * 2 for p in ptrs]
+
+    def _xr_push_kv_halo(self, qkv, ptrs, B, F, N, C):
+        """xrank transport of the K/V halo: K|V columns (C .. 3C) of my last frame -> bank 1 of rank + 1, of the clip's
+        first frame (rank 0) -> bank 2 of every other rank; the synchronisation is the tail of the same kernel."""
+        _, rank, world = self._shard
+        NI, ld = B * F, qkv.stride(0)
+        kv = qkv[:, C:]
+        pushes = []
+        if rank + 1 < world:
+            dst = [0] * world
+            dst[rank + 1] = ptrs[rank + 1] + (NI * N * ld + C) * 2
+            pushes.append(dict(src=kv[(F - 1) * N:], src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N))
+        if rank == 0:
+            dst = [0] + [p + ((NI + B) * N * ld + C) * 2 for p in ptrs[1:]]
+            pushes.append(dict(src=kv, src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N))
+        ops.xrank_push(self._xr, pushes)
+
     def set_frame_sharding_off(self):
         self._shard = None
+        self._xr = None
         self._fused_halo = False
         self._push_halo = False
         self._tables = {}
+        self._graphs = {}
 
     def _heads(self, level):
         h = self.config["attention_head_dim"]
@@ -376,6 +438,8 @@ class UNetPseudo3DConditionModel:
         g = self.config["norm_num_groups"]
         if self._shard is None:
             return ops.groupnorm(x, gamma, beta, NB=NB, rows=rows, groups=g, eps=eps, silu=silu, x2=x2)
+        if self._xr is not None:
+            return ops.groupnorm_xrank(x, gamma, beta, NB=NB, rows=rows, xr=self._xr, groups=g, eps=eps, silu=silu, x2=x2)
         return ops.groupnorm_sharded(x, gamma, beta, NB=NB, rows=rows, group=self._shard[0], world=self._shard[2],
                                      groups=g, eps=eps, silu=silu, x2=x2)
 
@@ -443,7 +507,9 @@ class UNetPseudo3DConditionModel:
             qkv = ops.gemm(n1, W[b + "attn1.to_qkv.weight"], out=qkv_buf)
         else:  # two halo banks of B images each behind the local images
             NIkv = NI + 2 * B
-            if self._push_halo:
+            if self._xr is not None:
+                qkv_all, halo_ptrs = self._xr_halo(NIkv * N, 3 * C)
+            elif self._push_halo:
                 qkv_all, halo_ptrs, symm_hdl = self._symm_halo(NIkv * N, 3 * C)
             else:
                 qkv_all = torch.empty((NIkv * N, 3 * C), dtype=torch.float16, device=x.device)
@@ -451,13 +517,18 @@ class UNetPseudo3DConditionModel:
         if shift is not None:
             if B != 3:
                 raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
-            ops.attn_shift_(qkv, F, N, C, *shift)
+            if self._step_params is not None:   # graph-safe: (alpha, beta, gamma) of this layer in device memory
+                ops.attn_shift_dev_(qkv, F, N, C, self._step_params[8 + 4 * tr.index: 12 + 4 * tr.index])
+            else:
+                ops.attn_shift_(qkv, F, N, C, *shift)
         if halo and self._fused_halo:
             symm_hdl.barrier(channel=0)   # every rank's projection (and shift) of this layer is complete and visible
             o = ops.sc_attention_sharded(qkv, qkv_prev, qkv_first, self._table(B, F, mode), B=B, Fl=F, H=heads, d=d, N=N)
         else:
             if halo:
-                if self._push_halo:
+                if self._xr is not None:
+                    self._xr_push_kv_halo(qkv_all, halo_ptrs, B, F, N, C)
+                elif self._push_halo:
                     self._push_kv_halo(qkv_all, halo_ptrs, symm_hdl, B, F, N, C)
                 else:
                     self._exchange_kv_halo(qkv_all, B, F, N)
@@ -493,6 +564,94 @@ class UNetPseudo3DConditionModel:
                 ft_indices=None, ft_timesteps=None, ft_path=None, **kwargs):
         if class_labels is not None or attention_mask is not None:
             raise NotImplementedError("class_labels / attention_mask are unused on the UniVST path")
+        if self.use_cuda_graphs and ft_path is None:
+            return self._forward_graphed(sample, timestep, encoder_hidden_states)
+        return self._forward_impl(sample, timestep, encoder_hidden_states, ft_indices, ft_timesteps, ft_path)
+
+    # ------------------------------------------------------------------------------------------ CUDA graphs
+    def _plan_signature(self):
+        sig = []
+        for tr in self._all_transformers():
+            mode, shift = self._attn1_plan(tr.transformer_blocks[0].attn1)
+            sig.append((mode, shift is not None))
+        return tuple(sig)
+
+    def _step_values(self, timestep, B):
+        """The 64 floats a captured forward reads from device memory: [0, B) the timestep of every sample, then from 8 on
+        (alpha, beta, gamma, 0) of the AdaIN-guided shift of every transformer (zeros where it is not active)."""
+        if B > 8:
+            raise ValueError("a graphed forward takes at most 8 samples (branches)")
+        if torch.is_tensor(timestep):
+            tl = [float(v) for v in timestep.reshape(-1).tolist()]   # (synchronises: pass Python numbers on the hot path)
+            tl = tl * B if len(tl) == 1 else tl
+        else:
+            tl = [float(timestep)] * B
+        vals = tl + [0.0] * (8 - B)
+        for tr in self._all_transformers():
+            shift = self._attn1_plan(tr.transformer_blocks[0].attn1)[1]
+            vals += list(shift) + [0.0] if shift is not None else [0.0] * 4
+        if len(vals) > 64:
+            raise ValueError("too many transformer blocks for the step-parameter block")
+        return vals
+
+    def _forward_graphed(self, sample, timestep, encoder_hidden_states):
+        """The forward as a replayed CUDA graph.  One graph per (input shapes, attention plan, truncation, sharding) key is
+        captured on first use -- after an eager warm-up call that sizes workspaces, source tables and symmetric buffers
+        -- and replayed afterwards: the step's latents / context are copied into the graph's static inputs, its scalars
+        (timestep; alpha, beta, gamma of the shift) go to device memory through one tiny launch, and the ~500 kernel
+        launches of the forward cost one ``cudaGraphLaunch``.  Under frame sharding the cross-rank synchronisations are
+        kernels of the graph (device-side epochs), so every rank replays independently."""
+        dev = self.device
+        sample = sample.to(device=dev, dtype=torch.float16)
+        ctx = encoder_hidden_states.to(device=dev, dtype=torch.float16)
+        B = sample.shape[0]
+        key = (tuple(sample.shape), tuple(ctx.shape), self._plan_signature(), bool(self.truncate_dead_branches),
+               None if self._shard is None else (self._shard[1], self._shard[2], self._xr is not None))
+        if self._shard is not None and self._xr is None:
+            raise NotImplementedError("CUDA graphs under frame sharding need the xrank transport (no collective-library calls)")
+        vals = self._step_values(timestep, B)
+        ent = self._graphs.get(key)
+        if ent is None:
+            st = {"sample": torch.empty_like(sample, memory_format=torch.contiguous_format),
+                  "ctx": torch.empty_like(ctx, memory_format=torch.contiguous_format),
+                  "params": torch.zeros(64, dtype=torch.float32, device=dev)}
+            st["sample"].copy_(sample)
+            st["ctx"].copy_(ctx)
+            ops.set_floats(st["params"], vals)
+            if self._graph_stream is None:
+                self._graph_stream = torch.cuda.Stream(device=dev)
+                self._graph_pool = torch.cuda.graph_pool_handle()
+            side, cur = self._graph_stream, torch.cuda.current_stream(dev)
+
+            def run():
+                self._step_params = st["params"]
+                try:
+                    out = self._forward_impl(st["sample"], st["params"][:B], st["ctx"], None, None, None)
+                finally:
+                    self._step_params = None
+                return out, self.last_eps_rows, self.last_edit_branch
+
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                run()                      # eager warm-up on the capture stream (allocations, tables, symmetric buffers)
+            cur.wait_stream(side)
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count
+            with torch.cuda.graph(graph, pool=self._graph_pool, stream=side):
+                res = run()
+            ent = self._graphs[key] = (graph, st, res, ops.launch_count - n0)
+            ops.launch_count = n0          # capturing launches nothing
+        graph, st, (out, eps_rows, edit_branch), nkernels = ent
+        st["sample"].copy_(sample)
+        st["ctx"].copy_(ctx)
+        ops.set_floats(st["params"], vals)
+        graph.replay()
+        ops.launch_count += nkernels       # the kernels of this library inside the replayed graph
+        self.last_eps_rows, self.last_edit_branch = eps_rows, edit_branch
+        return out
+
+    def _forward_impl(self, sample, timestep, encoder_hidden_states, ft_indices=None, ft_timesteps=None, ft_path=None):
         W, cfg = self.W, self.config
         dev = self.device
         B, Cin, F, H, Wd = sample.shape
@@ -602,7 +761,13 @@ class UNetPseudo3DConditionModel:
                      silu=True)
         eps_rows = ops.conv3x3(y.view(Bo * F, h, w, -1), W["conv_out.weight"], bias=W["conv_out.bias"],
                                out=torch.empty((Bo * F * h * w, 8), dtype=torch.float16, device=dev))
-        if self._shard is not None:  # all-gather the (tiny) noise prediction: [P][B][Fl] -> [B][P Fl]
+        if self._xr is not None:   # store my frames of the (tiny) noise prediction into every rank's full-clip buffer
+            _, rank, world = self._shard
+            full, ptrs = self._xr.buffer(("eps", Bo, F_total, h * w), (Bo * F_total * h * w, 8))
+            ops.xrank_push(self._xr, [dict(src=eps_rows, src_blk_rows=F * h * w, dst=[p + rank * F * h * w * 16 for p in ptrs],
+                                           ld_dst=8, dst_blk_rows=F_total * h * w, nblk=Bo, rows=F * h * w)])
+            eps_rows, F = full, F_total
+        elif self._shard is not None:  # all-gather the (tiny) noise prediction: [P][B][Fl] -> [B][P Fl]
             import torch.distributed as dist
             group, rank, world = self._shard
             gathered = torch.empty((world, Bo, F, h * w, 8), dtype=torch.float16, device=dev)

@@ -1,0 +1,61 @@
+"""Cross-rank plumbing of the frame-sharded UNet: one peer-mapped control block per rank plus symmetric data buffers.
+
+PyTorch supplies the memory (``torch.distributed._symmetric_memory``: allocation + rendezvous = every rank's buffer
+mapped into every process over NVLink) and nothing else: signalling, waiting and the exchanges themselves are the
+library's own kernels (``csrc/xrank.cu``), so a frame-sharded forward contains no collective-library call and can be
+captured in a CUDA graph.  The reference is single-GPU (SURVEY.md 8e lists what frame sharding has to exchange).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+class XRank:
+    """Control block + symmetric buffers of one process group (ranks of one NVLink domain)."""
+
+    def __init__(self, group=None, device=None):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.rank, self.world = dist.get_rank(self.group), dist.get_world_size(self.group)
+        if self.world > 16:
+            raise ValueError("at most 16 ranks (one NVLink domain)")
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._symm_mem = symm_mem
+        nbytes = int(_lib.lib().univst_xrank_ctl_bytes())
+        self._ctl = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        self._ctl.zero_()
+        self._ctl_hdl = symm_mem.rendezvous(self._ctl, self.group)
+        ptrs = [self._ctl_hdl.get_buffer(r, (nbytes,), torch.uint8).data_ptr() for r in range(self.world)]
+        self.ctl = (C.c_void_p * self.world)(*ptrs)
+        self._buffers = {}
+        # nobody may signal into a block that its owner has not zeroed yet
+        torch.cuda.synchronize(self.device)
+        dist.barrier(self.group)
+        torch.cuda.synchronize(self.device)
+
+    def buffer(self, key, shape, dtype=torch.float16):
+        """Symmetric buffer ``key`` of ``shape`` (same call sequence on every rank): (local tensor, [device pointer of every
+        rank's copy])."""
+        ent = self._buffers.get(key)
+        if ent is None:
+            t = self._symm_mem.empty(*shape, dtype=dtype, device=self.device)
+            hdl = self._symm_mem.rendezvous(t, self.group)
+            ptrs = [hdl.get_buffer(r, tuple(shape), dtype).data_ptr() for r in range(self.world)]
+            ent = self._buffers[key] = (t, ptrs, hdl)
+        return ent[0], ent[1]
+
+    def error(self) -> int:
+        """0, or 1 + the rank a wait timed out on (sticky).  Synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        return int(self._ctl[72:76].view(torch.int32).item())
+
+    def check(self):
+        e = self.error()
+        if e:
+            raise RuntimeError(f"cross-rank wait timed out on rank {self.rank} waiting for rank {e - 1}: the results of "
+                               "this process group are invalid")
