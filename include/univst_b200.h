@@ -220,7 +220,7 @@ int univst_halo_push_f16(const void* src, int32_t ld_src, int64_t src_blk_rows, 
  * A synchronisation stores this rank's next epoch into every peer's block and spins until every peer's epoch has
  * arrived in the local block; the epoch counter lives in the block and is advanced on the device, so launches take no
  * per-call host state and can be captured in a CUDA graph.  All ranks must issue the same sequence of synchronising
- * calls.  A wait that exceeds 4 s sets the sticky error word (uint32 at byte 72 of the local block) instead of hanging.
+ * calls.  A wait that exceeds 10 s sets the sticky error word (uint32 at byte 72 of the local block) instead of hanging.
  * ---------------------------------------------------------------------------------------------------------- */
 int64_t univst_xrank_ctl_bytes(void);
 int32_t univst_xrank_slot_floats(void);

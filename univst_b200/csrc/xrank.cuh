@@ -7,7 +7,7 @@ namespace uv {
 
 static constexpr int kXrankMaxRanks = 16;
 static constexpr int kXrankSlotFloats = 1024;          // payload of the small exchange: NB * groups * 2 floats
-static constexpr unsigned long long kXrankTimeoutNs = 4000000000ull;
+static constexpr unsigned long long kXrankTimeoutNs = 10000000000ull;
 
 // word offsets inside the control block
 static constexpr int kXrFlags = 0;                       // [16] flags[src] = last epoch signalled by rank src (peers write)
