@@ -24,8 +24,12 @@ def build_unet(cfg):
     else:
         shapes, cls = uo.unet_param_shapes(cfg), UNetPseudo3DConditionModel
     for k, s in shapes.items():
-        if "attn_temporal.to_out.0.weight" in k:
+        if "attn_temporal.to_out.0.weight" in k or "conv_temporal.bias" in k:
             sd[k] = torch.zeros(s, device="cuda", dtype=torch.float16)
+        elif "conv_temporal.weight" in k:   # the Dirac identity of the pseudo-3D inflation (resnet.py:54)
+            sd[k] = torch.zeros(s, device="cuda", dtype=torch.float16)
+            i = torch.arange(min(s[0], s[1]))
+            sd[k][i, i, s[2] // 2] = 1
         elif k.endswith("weight") and len(s) == 1:
             sd[k] = torch.ones(s, device="cuda", dtype=torch.float16)
         elif k.endswith("bias"):

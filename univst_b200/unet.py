@@ -518,7 +518,7 @@ class UNetPseudo3DConditionModel:
             if B != 3:
                 raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
             if self._step_params is not None:   # graph-safe: (alpha, beta, gamma) of this layer in device memory
-                ops.attn_shift_dev_(qkv, F, N, C, self._step_params[8 + 4 * tr.index: 12 + 4 * tr.index])
+                ops.attn_shift_dev_(qkv, F, N, C, self._step_params[8 + 3 * tr.index: 11 + 3 * tr.index])
             else:
                 ops.attn_shift_(qkv, F, N, C, *shift)
         if halo and self._fused_halo:
@@ -578,7 +578,7 @@ class UNetPseudo3DConditionModel:
 
     def _step_values(self, timestep, B):
         """The 64 floats a captured forward reads from device memory: [0, B) the timestep of every sample, then from 8 on
-        (alpha, beta, gamma, 0) of the AdaIN-guided shift of every transformer (zeros where it is not active)."""
+        (alpha, beta, gamma) of the AdaIN-guided shift of every transformer (zeros where it is not active)."""
         if B > 8:
             raise ValueError("a graphed forward takes at most 8 samples (branches)")
         if torch.is_tensor(timestep):
@@ -589,7 +589,7 @@ class UNetPseudo3DConditionModel:
         vals = tl + [0.0] * (8 - B)
         for tr in self._all_transformers():
             shift = self._attn1_plan(tr.transformer_blocks[0].attn1)[1]
-            vals += list(shift) + [0.0] if shift is not None else [0.0] * 4
+            vals += list(shift) if shift is not None else [0.0] * 3
         if len(vals) > 64:
             raise ValueError("too many transformer blocks for the step-parameter block")
         return vals
