@@ -382,7 +382,7 @@ def run_ours(args):
             out_g = stylize(resident)
             _, ms_graph = timed(lambda: stylize(resident), 2)
             unet.use_cuda_graphs = False
-            unet._graphs.clear()
+            unet.drop_cuda_graphs()
             extra["cuda_graphs"] = {"frames_per_s": F_FRAMES / (ms_graph / 2e3), "ms_per_clip": ms_graph / 2,
                                     "edit_latents_bit_identical": bool(torch.equal(out_g, out))}
         if not args.no_extras:

@@ -177,4 +177,4 @@ def test_cuda_graph_forward_and_truncation_are_bit_identical(setup):
     finally:
         unet.use_cuda_graphs = False
         unet.truncate_dead_branches = False
-        unet._graphs.clear()
+        unet.drop_cuda_graphs()

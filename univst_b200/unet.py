@@ -195,7 +195,7 @@ class UNetPseudo3DConditionModel:
         world = dist.get_world_size(group)
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
         self._tables = {}
-        self._graphs = {}
+        self.drop_cuda_graphs()
         nccl = self._shard is not None and dist.get_backend(group) == "nccl"
         if transport is None:
             transport = "xrank" if (nccl and push_halo is None and not fused_halo) else "nccl"
@@ -303,7 +303,7 @@ class UNetPseudo3DConditionModel:
         self._fused_halo = False
         self._push_halo = False
         self._tables = {}
-        self._graphs = {}
+        self.drop_cuda_graphs()
 
     def _heads(self, level):
         h = self.config["attention_head_dim"]
@@ -569,6 +569,12 @@ class UNetPseudo3DConditionModel:
         return self._forward_impl(sample, timestep, encoder_hidden_states, ft_indices, ft_timesteps, ft_path)
 
     # ------------------------------------------------------------------------------------------ CUDA graphs
+    def drop_cuda_graphs(self):
+        """Forget the captured forwards (their memory pool goes with them: a pool whose graphs are gone cannot be captured
+        into again, so the next capture starts a new one)."""
+        self._graphs = {}
+        self._graph_pool = None
+
     def _plan_signature(self):
         sig = []
         for tr in self._all_transformers():
@@ -620,6 +626,7 @@ class UNetPseudo3DConditionModel:
             ops.set_floats(st["params"], vals)
             if self._graph_stream is None:
                 self._graph_stream = torch.cuda.Stream(device=dev)
+            if self._graph_pool is None:
                 self._graph_pool = torch.cuda.graph_pool_handle()
             side, cur = self._graph_stream, torch.cuda.current_stream(dev)
 
