@@ -11,6 +11,6 @@ for spec in "2 20 --branches 3 --idx 5 --truncate" "2 20 --branches 1 --idx 30" 
   timeout 300 python tools/time_unet.py $spec --graph 2>&1 | grep UNet >> gpurun_out/${tag}_small.log
 done
 KR="regex:gemm_tc|attention_tc|cross_attention|temporal_attention|gn_|layernorm|colstats|attn_shift|upsample2x|space_to_depth|pack_latents|unpack_latents|timestep_emb|ddim_step|latent_|mask_resize|axpby|set_floats"
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -s 1600 -c 520 --csv --log-file gpurun_out/${tag}_launches_3x2.csv python tools/time_unet.py 2 1 --branches 3 --idx 5 --truncate > /dev/null 2>&1
-timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -s 1500 -c 500 --csv --log-file gpurun_out/${tag}_launches_1x2.csv python tools/time_unet.py 2 1 --branches 1 --idx 30 > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 2400 --csv --log-file gpurun_out/${tag}_launches_3x2.csv python tools/time_unet.py 2 1 --branches 3 --idx 5 --truncate > /dev/null 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -k "$KR" -c 2400 --csv --log-file gpurun_out/${tag}_launches_1x2.csv python tools/time_unet.py 2 1 --branches 1 --idx 30 > /dev/null 2>&1
 tail -8 gpurun_out/${tag}_tests.log; cat gpurun_out/${tag}_bench.json; tail -5 gpurun_out/${tag}_bench.err; cat gpurun_out/${tag}_small.log
