@@ -186,8 +186,9 @@ def torch_eager_forward_baseline(unet, pipe, dev):
     flash SDPA) next to this library's forward on the same inputs.  A baseline leg: not on the product path."""
     from oracle import unet_oracle as uo
     from univst_b200 import pnp_utils
+    from univst_b200.weights import random_state_dict
     cfg = uo.SD15_CONFIG
-    sd16 = {k: v.to(dev).half() for k, v in uo.seeded_state_dict(cfg, seed=33).items()}
+    sd16 = random_state_dict(cfg, seed=33, device=dev)   # the same seeded fp16 weights the library's UNet was packed from
     g = torch.Generator(device=dev).manual_seed(7)
     x = torch.randn(3, 4, F_FRAMES, LAT, LAT, device=dev, generator=g).half()
     ctx = torch.randn(3, 77, cfg["cross_attention_dim"], device=dev, generator=g).half()
@@ -332,7 +333,8 @@ def run_ours(args):
         unet.use_cuda_graphs = xrank and not args.no_cuda_graphs
         fs = {"transport": "peer-memory stores + device-side flags (csrc/xrank.cu), no collective-library call" if xrank
               else "NCCL send/recv + broadcast + all-reduce + all-gather (symmetric memory unavailable on this box)",
-              "cuda_graphs": bool(unet.use_cuda_graphs), "ms_per_clip_1gpu_same_box": ms_single}
+              "cuda_graphs": bool(unet.use_cuda_graphs), "split_k_of_few_tile_gemms": bool(getattr(unet, "_split_k", False)),
+              "ms_per_clip_1gpu_same_box": ms_single}
 
     for _ in range(args.warmup):
         out = stylize(resident)
@@ -427,11 +429,16 @@ def run_ours(args):
             out_ads, ms_ads = timed(lambda: stylize(resident, p=pipe_ad), 2)
             if unet_ad._xr is not None:
                 unet_ad._xr.check()
+            # everything is frame-local or exchanged verbatim in this backbone: bit-identical to one GPU -- unless the K
+            # loops of the few-tile GEMMs are split over the idle SMs (from 4 ranks up), which changes fp32 summation order
+            split_k = bool(getattr(unet_ad, "_split_k", False))
             ad["frame_sharded"] = {"frames_per_s": F_FRAMES / (ms_ads / 2e3), "ms_per_clip": ms_ads / 2, "n_gpus": world,
                                    "speedup_vs_1gpu_same_box": ms_ad / (ms_ads / 2),
                                    "bit_identical_to_1gpu": bool(torch.equal(out_ads, out_ad)),
+                                   "rel_l2_vs_1gpu": rel(out_ads, out_ad), "split_k": split_k,
                                    "cuda_graphs": bool(unet_ad.use_cuda_graphs)}
-            assert ad["frame_sharded"]["bit_identical_to_1gpu"], "AnimateDiff frame-sharded result differs from one GPU"
+            assert ad["frame_sharded"]["rel_l2_vs_1gpu"] < 5e-3 and (split_k or ad["frame_sharded"]["bit_identical_to_1gpu"]), \
+                f"AnimateDiff frame-sharded result differs from one GPU: {ad['frame_sharded']}"
         extra["animatediff_v2_backbone"] = ad
 
     t = torch.tensor([ms, ms_e2e] + ([fs["clip_parallel_replicas"]["ms_per_clip_per_gpu"]] if fs else []), device=dev,

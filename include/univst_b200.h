@@ -62,6 +62,14 @@ typedef struct univst_epilogue {
  * resnet.py:390 (conv_shortcut). */
 int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32_t lda2, int32_t K1, const void* W, int32_t M,
                     int32_t N, int32_t K, void* D, int32_t ldd, const univst_epilogue_t* ep, void* stream);
+/* Split-K for launches with few output tiles and a long reduction (the deep UNet levels when a frame shard holds only a
+ * few images: 5 tiles x 180 k-blocks would keep 5 of 148 SMs busy).  Opt-in: univst_gemm_tune(max_tiles) splits the
+ * K loop of GEMM / conv launches with at most max_tiles tiles (0 = never, the default) over the idle SMs; the slices park
+ * their fp32 accumulators in a caller-owned workspace registered for the launching stream (first 256 KiB = arrival
+ * counters, zeroed by the caller once) and the last slice to arrive adds them in slice order -- deterministic, but the
+ * fp32 summation order differs from the unsplit kernel's.  No workspace registered for a stream: no split on it. */
+int univst_gemm_set_workspace(void* ws, int64_t bytes, void* stream);
+int univst_gemm_tune(int32_t splitk_max_tiles);
 
 /* Y[NB*H*W, Cout] = epilogue( conv3x3(X, Wt[Cout, 3, 3, C1 + C2], padding 1) ), H x W = OUTPUT size (power-of-two sizes up to W = 128 tile exactly; any other size takes row-block / row-segment tiles).
  * Implicit GEMM: the 9 taps are 4-D TMA boxes over the NHWC activation with out-of-bounds zero fill (no im2col).

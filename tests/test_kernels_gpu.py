@@ -124,6 +124,45 @@ def test_conv3x3_stride2(cuda_lib, NB, H, W, C, Cout):
     _close(out, _conv_ref(x, w, stride=2), 3e-3, 2e-3, f"conv3x3 stride 2 {NB}x{H}x{W}")
 
 
+@pytest.mark.parametrize("kind,shape", [
+    ("conv", (2, 8, 8, 1280, 0, 1280)),      # the 8 x 8 level of a 2-frame shard: 5 tiles x 180 k-blocks -> 29 slices
+    ("conv", (2, 16, 16, 640, 640, 1280)),   # two sources (skip concat), 20 tiles x 180 k-blocks -> 7 slices
+    ("conv", (6, 8, 8, 1280, 1280, 1280)),   # 15 tiles x 360 k-blocks, residual + per-branch row vector
+    ("gemm", (384, 1280, 5120)),             # GEGLU output projection at the deepest level: 15 tiles x 80 k-blocks
+    ("gemm", (130, 320, 2560)),              # ragged M (two row tiles, the second almost empty), 2 column tiles
+])
+def test_split_k_matches_reference_and_unsplit(cuda_lib, kind, shape):
+    """Split-K (univst_gemm_tune): the K loop of launches with few output tiles is spread over the idle SMs, the slices'
+    fp32 accumulators are added in slice order by the last epilogue warp to arrive.  Against the fp32 reference within the
+    usual bound, against the unsplit kernel within fp32 summation-order noise (a few fp16 ulps), and repeatable bit for bit."""
+    from univst_b200 import ops
+    if kind == "conv":
+        NB, H, W, C1, C2, Cout = shape
+        x1 = _rand(NB, H, W, C1, seed=1)
+        x2 = _rand(NB, H, W, C2, seed=2) if C2 else None
+        w = _rand(Cout, 9 * (C1 + C2), scale=(9 * (C1 + C2)) ** -0.5, seed=3)
+        bias, res, rv = _rand(Cout, seed=4), _rand(NB * H * W, Cout, seed=5), _rand(NB, Cout, seed=6)
+        run = lambda: ops.conv3x3(x1, w, x2=x2, bias=bias, residual=res, rowvec=rv, rows_per_group=H * W)
+        xin = x1 if x2 is None else torch.cat([x1, x2], -1)
+        ref = _conv_ref(xin, w) + bias.float() + res.float() + rv.float().repeat_interleave(H * W, 0)
+    else:
+        M, N, K = shape
+        a, w = _rand(M, K, seed=1), _rand(N, K, scale=K ** -0.5, seed=2)
+        bias, res = _rand(N, seed=3), _rand(M, N, seed=4)
+        run = lambda: ops.gemm(a, w, bias=bias, residual=res)
+        ref = a.float() @ w.float().t() + bias.float() + res.float()
+    unsplit = run()
+    try:
+        ops.gemm_splitk(74)
+        split = run()
+        again = run()
+    finally:
+        ops.gemm_splitk(0)
+    _close(split, ref, 3e-3, 2e-3, f"split-K {kind} {shape}")
+    _close(split, unsplit, 2e-3, 2e-3, f"split-K vs unsplit {kind} {shape}")
+    assert torch.equal(split, again), "split-K must be deterministic (slices are added in slice order)"
+
+
 @pytest.mark.parametrize("NB,H,W,C1,C2,Cout,stride", [
     (3, 24, 40, 64, 0, 96, 1),      # 128 // 40 = 3 full rows per tile, 8 row blocks per image
     (5, 3, 5, 64, 0, 64, 1),        # 15-pixel images: 8 whole images per tile, ragged image tail

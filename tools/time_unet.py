@@ -1,6 +1,6 @@
 """Device timing of one UNet forward (SD-1.5 shapes, seeded random weights) on one GPU.
 
-    python tools/time_unet.py [F] [iters] [--branches B] [--idx I] [--truncate] [--graph] [--shapes] [--kernels]
+    python tools/time_unet.py [F] [iters] [--branches B] [--idx I] [--truncate] [--graph] [--splitk] [--shapes] [--kernels]
                               [--animatediff] [--sd21]
 
 F frames per branch (16 = the whole clip; 2 = what one rank of an 8-GPU frame-sharded run evaluates, without its
@@ -39,6 +39,8 @@ print("built in", round(time.time() - t0, 2), "s")
 pipe = SimpleNamespace(unet=unet)
 pnp_utils.register_spatial_attention_pnp(pipe)
 pnp_utils.register_time(pipe, idx)
+if "--splitk" in sys.argv:
+    ops.gemm_splitk(74)
 unet.truncate_dead_branches = "--truncate" in sys.argv
 unet.use_cuda_graphs = "--graph" in sys.argv
 x = torch.randn(B, 4, F, hw, hw, device="cuda").half()

@@ -77,7 +77,7 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
         self._push, self._arena = False, None
         super().__init__(state_dict, cfg, device=device)
 
-    def set_frame_sharding(self, group=None, push_exchange=None, transport=None):
+    def set_frame_sharding(self, group=None, push_exchange=None, transport=None, split_k=None):
         """Shard the frames of every clip over the ranks of ``group``.  Everything spatial is frame-local in this backbone
         (per-frame GroupNorm, per-frame attn1); the only exchange is inside the motion modules, whose attention runs over
         the frames of one pixel: an all-to-all turns "my frames, all pixels" into "all frames, my pixels" before the
@@ -91,7 +91,7 @@ class UNet3DConditionModel(UNetPseudo3DConditionModel):
         # synchronisation and the noise prediction is stored into every rank's buffer: no collective-library call at all
         if transport is None and push_exchange is not None:
             transport = "nccl"
-        super().set_frame_sharding(group, transport=transport)
+        super().set_frame_sharding(group, transport=transport, split_k=split_k)
         self._pe_rows = {}
         if push_exchange is None:
             push_exchange = self._shard is not None and dist.get_backend(group) == "nccl"

@@ -12,6 +12,9 @@
 // Reference call sites replaced: see include/univst_b200.h (univst_gemm_f16 / univst_conv3x3_f16).
 #include <stdlib.h>
 
+#include <mutex>
+#include <vector>
+
 #include "host_util.h"
 #include "ptx.cuh"
 
@@ -39,6 +42,12 @@ struct GemmParams {
   int8_t tap_dy[9], tap_dx[9], tap_plane[9];
   int stages;
   int cluster;          // 2: CTA pairs share every weight tile (each loads half of it and multicasts), 1: independent CTAs
+  // split-K (few output tiles, long reductions: the deep UNet levels of a frame shard): a work item is (tile, K slice);
+  // every slice parks its fp32 accumulator in `part`, the last epilogue warp to arrive at a sub-block adds the slices in
+  // slice order (deterministic) and runs the epilogue
+  int splits, kb_per_split;
+  float* part;          // [tile][slice][128][BN]
+  unsigned* cnt;        // [tile][kEpiWarps] arrival counters, zero between launches
   // epilogue
   const __half* bias;
   const __half* rowvec;
@@ -116,9 +125,12 @@ __device__ __forceinline__ void staged_store(const GemmParams& p, const EpiCtx& 
   __syncwarp();   // the tile is rewritten by the next chunk
 }
 
+// sum_part != nullptr (split-K): the accumulator of this sub-block is the sum of the `p.splits` parked slices, row
+// `sum_part + slice * 128 * BN` each, added in slice order
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, bool row_ok, const __half* rv,
                                               const __half* res, __half* drow, int n0, int tile_n, int chunk0,
-                                              const EpiCtx& e, uint64_t* acc_full, uint32_t acc_parity) {
+                                              const EpiCtx& e, uint64_t* acc_full, uint32_t acc_parity,
+                                              const float* sum_part = nullptr) {
   const bool staged = (p.N_out & 7) == 0;   // whole 8-column groups only: every 16-byte piece is all in or all out
   uint4 rnext[4];
   // the first residual chunk is requested before the accumulator is even complete
@@ -159,6 +171,24 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
         }
       }
       tc_wait_ld();
+      if (sum_part) {
+        float sacc[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) sacc[j] = 0.0f;
+        for (int sl = 0; sl < p.splits; ++sl) {
+          const float4* src = reinterpret_cast<const float4*>(sum_part + (size_t)sl * kBM * p.BN + c0);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 v = __ldcg(src + j);
+            sacc[4 * j] += v.x;
+            sacc[4 * j + 1] += v.y;
+            sacc[4 * j + 2] += v.z;
+            sacc[4 * j + 3] += v.w;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sacc[j]);
+      }
       if (staged) {
         uint32_t o[16];
 #pragma unroll
@@ -306,9 +336,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int tiles_m = (p.mode == 2) ? p.gen_tiles_m : (p.M + kBM - 1) / kBM;
   // work items: CL = 1: tiles (m, n), n fastest, one per CTA; CL = 2: pairs of row blocks (2 mm, 2 mm + 1) x n per cluster
   const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
-  const int num_tiles = (CL == 2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n;
+  // (split-K: work item = tile * splits + slice, slice fastest -- the slices of a tile run side by side)
+  const int S = (CL == 2) ? 1 : p.splits;
+  const int num_tiles = (CL == 2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n * S;
   const int tile_first = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  auto kb_begin = [&](int work) { return S == 1 ? 0 : (work % S) * p.kb_per_split; };
+  auto kb_end = [&](int work) {
+    if (S == 1) return p.num_kb;
+    const int e = (work % S + 1) * p.kb_per_split;
+    return e < p.num_kb ? e : p.num_kb;
+  };
   auto tile_m0 = [&](int tile) {   // first output row of the tile; may be >= M for the odd tail
     const int mm = (tile / tiles_n) * CL + (int)crank;
     if (p.mode == 2) {
@@ -365,7 +403,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // ------------------------------------------------ TMA producer
       uint32_t phase = 0;
       int s = 0;
-      for (int tile = tile_first; tile < num_tiles; tile += tile_step) {
+      for (int work = tile_first; work < num_tiles; work += tile_step) {
+        const int tile = work / S;
         const int m0 = tile_m0(tile);
         const int n0 = (tile % tiles_n) * p.BN;
         int cn = 0, cy = 0, cx = 0;
@@ -374,7 +413,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           cy = (m0 % p.HW) / p.W;
           if (p.mode == 2) cx = m0 % p.W;   // non-zero only for the segments of rows wider than 128 pixels
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb = kb_begin(work), kbe = kb_end(work); kb < kbe; ++kb) {
           mbar_wait(&empty_bar[s], phase ^ 1);
           uint8_t* sa = smem + (size_t)s * stage_bytes;
           uint8_t* sb = sa + a_bytes;
@@ -422,13 +461,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t phase = 0;
     int s = 0;
     int it = 0;
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+    for (int work = tile_first; work < num_tiles; work += tile_step, ++it) {
       const int a = it & 1;
       // wait until the epilogue has drained this accumulator (its (it / 2)-th use)
       mbar_wait_warp(&tmem_empty_bar[a], (uint32_t)(((it >> 1) & 1) ^ 1));
       tc_fence_after();
       const uint32_t acc = tmem_base + a * acc_cols;
-      for (int kb = 0; kb < p.num_kb; ++kb) {
+      const int kb0 = kb_begin(work);
+      for (int kb = kb0, kbe = kb_end(work); kb < kbe; ++kb) {
         mbar_wait_warp(&full_bar[s], phase);
         tc_fence_after();
         const uint32_t sa = smem0 + (uint32_t)s * stage_bytes;
@@ -437,7 +477,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < kBK / 16; ++k) {
           // advance 16 halves = 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-          umma_f16_ss_elect(acc, desc_advance(da, k * 2), desc_advance(db, k * 2), idesc, (kb | k) ? 1u : 0u);
+          umma_f16_ss_elect(acc, desc_advance(da, k * 2), desc_advance(db, k * 2), idesc, ((kb - kb0) | k) ? 1u : 0u);
         }
         if constexpr (CL == 2) {
           if (elect_one()) tc_commit_mcast(&empty_bar[s], 0x3);   // the stage is free when BOTH CTAs' MMAs have retired
@@ -456,7 +496,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t q = warp & 3;
     const int chunk0 = (int)((warp - 2) >> 2);  // which half of the 32-column chunks this warp drains
     int it = 0;
-    for (int tile = tile_first; tile < num_tiles; tile += tile_step, ++it) {
+    for (int work = tile_first; work < num_tiles; work += tile_step, ++it) {
+      const int tile = work / S;
       const int a = it & 1;
       const int tile_n = tile % tiles_n;
       const int m0 = tile_m0(tile);
@@ -473,7 +514,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       e.lane = lane;
       e.row0 = m0 + (int)(q * 32);
       e.M = m_lim;
-      epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
+      if (S == 1) {
+        epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
+      } else {
+        // park this slice's rows of the warp's column chunks, then count the arrival; the last slice to arrive adds them up
+        mbar_wait(&tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
+        tc_fence_after();
+        float* tile_part = p.part + (size_t)tile * S * kBM * p.BN + (size_t)(q * 32 + lane) * p.BN;
+        float* mine = tile_part + (size_t)(work % S) * kBM * p.BN;
+        for (int c0 = chunk0 * 32; c0 < p.BN; c0 += 64) {
+          uint32_t acc[32];
+          tmem_ld32(taddr + c0, acc);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            __stcg(reinterpret_cast<float4*>(mine + c0) + j,
+                   make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
+                               __uint_as_float(acc[4 * j + 3])));
+        }
+        __threadfence();
+        __syncwarp();
+        unsigned arrived = 0;
+        unsigned* ctr = p.cnt + (size_t)tile * kEpiWarps + (warp - 2);
+        if (lane == 0) arrived = atomicAdd(ctr, 1u);
+        arrived = __shfl_sync(0xffffffffu, arrived, 0);
+        if (arrived == (unsigned)S - 1) {
+          if (lane == 0) *ctr = 0;   // ready for the next launch
+          __threadfence();
+          epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1),
+                        tile_part);
+        }
+      }
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
       mbar_arrive(&tmem_empty_bar[a]);
@@ -536,6 +607,45 @@ static int pick_cluster(int M, int BN) {
   return (enabled && M > kBM && BN % 16 == 0) ? 2 : 1;
 }
 
+// split-K workspace: caller-owned device memory registered per stream (univst_gemm_set_workspace); no workspace, no split
+static constexpr size_t kSplitCounterBytes = 256 * 1024;
+struct SplitWs {
+  cudaStream_t stream;
+  void* ptr;
+  size_t bytes;
+};
+static std::mutex g_ws_mutex;
+static std::vector<SplitWs> g_ws;
+static int g_splitk_max_tiles = 0;   // univst_gemm_tune: split the reduction when a launch has at most this many tiles
+
+static void pick_splits(GemmParams& p, int num_tiles, cudaStream_t stream) {
+  p.splits = 1;
+  p.kb_per_split = p.num_kb;
+  p.part = nullptr;
+  p.cnt = nullptr;
+  if (g_splitk_max_tiles <= 0 || p.cluster != 1 || p.geglu || num_tiles > g_splitk_max_tiles || p.num_kb < 16) return;
+  int S = num_sms() / num_tiles;
+  if (S > p.num_kb / 4) S = p.num_kb / 4;
+  if (S > 32) S = 32;
+  if (S < 2) return;
+  SplitWs ws{};
+  {
+    std::lock_guard<std::mutex> lock(g_ws_mutex);
+    for (const SplitWs& w : g_ws)
+      if (w.stream == stream) ws = w;
+  }
+  if (!ws.ptr || (size_t)num_tiles * kEpiWarps * sizeof(unsigned) > kSplitCounterBytes) return;
+  const size_t per_slice = (size_t)num_tiles * kBM * p.BN * sizeof(float);
+  const size_t room = ws.bytes - kSplitCounterBytes;
+  if ((size_t)S * per_slice > room) S = (int)(room / per_slice);
+  if (S < 2) return;
+  const int kbs = (p.num_kb + S - 1) / S;
+  p.kb_per_split = kbs;
+  p.splits = (p.num_kb + kbs - 1) / kbs;   // no empty slice
+  p.cnt = (unsigned*)ws.ptr;
+  p.part = (float*)((uint8_t*)ws.ptr + kSplitCounterBytes);
+}
+
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtensorMap& tmB, GemmParams& p,
                   cudaStream_t stream) {
   const uint32_t stage_bytes = kBM * kBK * 2 + (uint32_t)p.BN * kBK * 2;
@@ -555,6 +665,8 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   }
   const int tiles_m = (p.mode == 2) ? p.gen_tiles_m : (p.M + kBM - 1) / kBM, tiles_n = (p.N + p.BN - 1) / p.BN;
   if (p.cluster == 2) {
+    p.splits = 1;
+    p.kb_per_split = p.num_kb;
     const int pairs = ((tiles_m + 1) / 2) * tiles_n;
     const int max_pairs = num_sms() / 2;
     cudaLaunchConfig_t cfg = {};
@@ -573,7 +685,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
     return UNIVST_OK;
   }
   const int num_tiles = tiles_m * tiles_n;
-  const int grid = num_tiles < num_sms() ? num_tiles : num_sms();
+  pick_splits(p, num_tiles, stream);
+  const int num_work = num_tiles * p.splits;
+  const int grid = num_work < num_sms() ? num_work : num_sms();
   gemm_tc_kernel<1><<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
@@ -604,6 +718,24 @@ static void fill_epilogue(GemmParams& p, const univst_epilogue_t* ep) {
 }  // namespace uv
 
 using namespace uv;
+
+extern "C" int univst_gemm_set_workspace(void* ws, int64_t bytes, void* stream) {
+  UV_REQUIRE(!ws || (bytes >= (int64_t)(kSplitCounterBytes + (1 << 20)) && ((uintptr_t)ws & 255) == 0),
+             "gemm_set_workspace: at least 1.25 MiB, 256-byte aligned (or NULL to unregister)");
+  std::lock_guard<std::mutex> lock(g_ws_mutex);
+  for (size_t i = 0; i < g_ws.size(); ++i)
+    if (g_ws[i].stream == (cudaStream_t)stream) {
+      g_ws.erase(g_ws.begin() + i);
+      break;
+    }
+  if (ws) g_ws.push_back(SplitWs{(cudaStream_t)stream, ws, (size_t)bytes});
+  return UNIVST_OK;
+}
+
+extern "C" int univst_gemm_tune(int32_t splitk_max_tiles) {
+  g_splitk_max_tiles = splitk_max_tiles;
+  return UNIVST_OK;
+}
 
 extern "C" int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32_t lda2, int32_t K1, const void* W,
                                int32_t M, int32_t N, int32_t K, void* D, int32_t ldd, const univst_epilogue_t* ep,

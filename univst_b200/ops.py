@@ -45,6 +45,8 @@ _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
 _lib.register("univst_halo_push_f16", [_vp, _i32, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _vp])
 _lib.register("univst_exchange_push_f16", [_i32, _vp, _i32, C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _vp])
+_lib.register("univst_gemm_set_workspace", [_vp, _i64, _vp])
+_lib.register("univst_gemm_tune", [_i32])
 _lib.register("univst_xrank_ctl_bytes", [], _i64)
 _lib.register("univst_xrank_slot_floats", [], _i32)
 _lib.register("univst_xrank_barrier", [_vp, _i32, _i32, _vp])
@@ -148,6 +150,33 @@ def make_epilogue(bias=None, rowvec=None, rows_per_group=1, residual=None, bias2
     return ep
 
 
+# split-K of the tensor-core GEMM / conv (univst_gemm_tune): off unless a caller turns it on -- the frame-sharded UNet does
+# for shards of a few images, whose deep levels would otherwise occupy a handful of SMs
+_splitk_max_tiles = 0
+_splitk_ws = {}
+SPLITK_WORKSPACE_BYTES = 64 << 20
+
+
+def gemm_splitk(max_tiles: int):
+    """Split the K loop of GEMM / conv launches with at most ``max_tiles`` output tiles over the idle SMs (0 = never).
+    Deterministic; the fp32 summation order differs from the unsplit kernel's (last-bit differences in fp16 outputs)."""
+    global _splitk_max_tiles
+    _splitk_max_tiles = int(max_tiles)
+    check(_lib.lib().univst_gemm_tune(_splitk_max_tiles), "univst_gemm_tune")
+
+
+def _splitk_ready(device):
+    """Register the split-K workspace of the current stream (once per device and stream)."""
+    if not _splitk_max_tiles:
+        return
+    st = _stream()
+    key = (device, st)
+    if key not in _splitk_ws:
+        ws = torch.zeros(SPLITK_WORKSPACE_BYTES, dtype=torch.uint8, device=device)
+        check(_lib.lib().univst_gemm_set_workspace(ws.data_ptr(), ws.numel(), st), "univst_gemm_set_workspace")
+        _splitk_ws[key] = ws
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
          bias=None, rowvec=None, rows_per_group=1, residual=None, bias2=None, geglu=False, out_scale=1.0, act=False):
     """``out[M, N_out] = epilogue([a | a2] @ w.T)``; ``a``/``a2``/``residual``/``out`` may be row-strided 2-D views."""
@@ -161,6 +190,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None,
         out = torch.empty((M, n_out), dtype=torch.float16, device=a.device)
     assert out.shape == (M, n_out) and out.stride(1) == 1
     ep = make_epilogue(bias, rowvec, rows_per_group, residual, bias2, geglu, out_scale, act)
+    _splitk_ready(a.device)
     with _Timed("gemm", (M, N, K)):
         check(_lib.lib().univst_gemm_f16(a.data_ptr(), a.stride(0), _ptr(a2), a2.stride(0) if a2 is not None else 0, K1,
                                          w.data_ptr(), M, N, K, out.data_ptr(), out.stride(0), C.byref(ep), _stream()),
@@ -186,6 +216,7 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, x2: Optional[torch.Tensor] = No
     if out is None:
         out = torch.empty((NB * H * W, Cout), dtype=torch.float16, device=x.device)
     ep = make_epilogue(bias, rowvec, rows_per_group, residual, None, False, out_scale)
+    _splitk_ready(x.device)
     with _Timed("conv3x3", (NB * H * W, Cout, 9 * (C1 + C2))):
         check(_lib.lib().univst_conv3x3_f16(x.data_ptr(), _ptr(x2), NB, H, W, C1, C2, w.data_ptr(), Cout, stride,
                                             out.data_ptr(), out.stride(0), C.byref(ep), _stream()), "univst_conv3x3_f16")

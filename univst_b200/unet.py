@@ -165,7 +165,7 @@ class UNetPseudo3DConditionModel:
             cfg["sample_size"] = c["sample_size"]
         return cls(module.state_dict(), cfg, device=device)
 
-    def set_frame_sharding(self, group=None, fused_halo: bool = False, push_halo=None, transport=None):
+    def set_frame_sharding(self, group=None, fused_halo: bool = False, push_halo=None, transport=None, split_k=None):
         """Shard the frames of every clip over the ranks of ``group`` (default: the world group): rank r evaluates
         frames [r F/P, (r+1) F/P) of all branches.  What crosses ranks: B x 32 x 2 partial sums per cross-frame
         GroupNorm, the K/V of the neighbouring frames that attn1 needs (last frame of the previous rank, frame 0 of the
@@ -176,6 +176,11 @@ class UNetPseudo3DConditionModel:
         the peers' banks and the GroupNorm sums into the peers' control blocks by the kernel that produced them, whose
         tail is the cross-rank synchronisation; the noise prediction is stored into every rank's full-clip buffer.  No
         collective-library call is left in the forward (any world size up to 16), so it can be captured in a CUDA graph.
+
+        ``split_k`` (default: on from 4 ranks up): shards of a few images leave the deep UNet levels with a handful of
+        output tiles per GEMM / conv; their K loops are then split over the idle SMs (``ops.gemm_splitk``) --
+        deterministic, but the fp32 summation order, hence the last bits of some fp16 outputs, differ from the unsplit
+        kernel's.
 
         ``transport="nccl"`` keeps the collectives of the first implementation (GroupNorm all-reduce, noise all-gather;
         works on any backend, e.g. gloo), with the halo exchanged in one of these ways:
@@ -196,6 +201,12 @@ class UNetPseudo3DConditionModel:
         self._shard = (group, dist.get_rank(group), world) if world > 1 else None
         self._tables = {}
         self.drop_cuda_graphs()
+        if split_k is None:
+            split_k = world >= 4
+        self._split_k = bool(split_k) and self._shard is not None
+        if self._split_k or getattr(self, "_split_k_was_on", False):
+            ops.gemm_splitk(74 if self._split_k else 0)   # at most half of the SMs' worth of tiles
+        self._split_k_was_on = self._split_k
         nccl = self._shard is not None and dist.get_backend(group) == "nccl"
         if transport is None:
             transport = "xrank" if (nccl and push_halo is None and not fused_halo) else "nccl"
@@ -304,6 +315,9 @@ class UNetPseudo3DConditionModel:
         self._push_halo = False
         self._tables = {}
         self.drop_cuda_graphs()
+        if getattr(self, "_split_k_was_on", False):
+            ops.gemm_splitk(0)
+            self._split_k_was_on = self._split_k = False
 
     def _heads(self, level):
         h = self.config["attention_head_dim"]
