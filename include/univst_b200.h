@@ -66,8 +66,9 @@ int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32_t lda2, in
  * few images: 5 tiles x 180 k-blocks would keep 5 of 148 SMs busy).  Opt-in: univst_gemm_tune(max_tiles) splits the
  * K loop of GEMM / conv launches with at most max_tiles tiles (0 = never, the default) over the idle SMs; the slices park
  * their fp32 accumulators in a caller-owned workspace registered for the launching stream (first 256 KiB = arrival
- * counters, zeroed by the caller once) and the last slice to arrive adds them in slice order -- deterministic, but the
- * fp32 summation order differs from the unsplit kernel's.  No workspace registered for a stream: no split on it. */
+ * counters, zeroed by the caller once); then every slice adds up ITS share of the tile over all slices in slice order and
+ * runs the epilogue on it (a reduce-scatter through L2) -- deterministic, but the fp32 summation order differs from the
+ * unsplit kernel's.  No workspace registered for a stream: no split on it. */
 int univst_gemm_set_workspace(void* ws, int64_t bytes, void* stream);
 int univst_gemm_tune(int32_t splitk_max_tiles);
 

@@ -43,11 +43,11 @@ struct GemmParams {
   int stages;
   int cluster;          // 2: CTA pairs share every weight tile (each loads half of it and multicasts), 1: independent CTAs
   // split-K (few output tiles, long reductions: the deep UNet levels of a frame shard): a work item is (tile, K slice);
-  // every slice parks its fp32 accumulator in `part`, the last epilogue warp to arrive at a sub-block adds the slices in
-  // slice order (deterministic) and runs the epilogue
+  // every slice parks its fp32 accumulator in `part`, then each slice adds up its share of the tile in slice order
+  // (deterministic) and runs the epilogue on it
   int splits, kb_per_split;
-  float* part;          // [tile][slice][128][BN]
-  unsigned* cnt;        // [tile][kEpiWarps] arrival counters, zero between launches
+  float* part;          // [tile][slice][epilogue warp][chunk][8][32] float4 (split_epilogue)
+  unsigned* cnt;        // [tile][kEpiWarps][2] parked / done counters, zero between launches
   // epilogue
   const __half* bias;
   const __half* rowvec;
@@ -125,12 +125,9 @@ __device__ __forceinline__ void staged_store(const GemmParams& p, const EpiCtx& 
   __syncwarp();   // the tile is rewritten by the next chunk
 }
 
-// sum_part != nullptr (split-K): the accumulator of this sub-block is the sum of the `p.splits` parked slices, row
-// `sum_part + slice * 128 * BN` each, added in slice order
 __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t taddr, bool row_ok, const __half* rv,
                                               const __half* res, __half* drow, int n0, int tile_n, int chunk0,
-                                              const EpiCtx& e, uint64_t* acc_full, uint32_t acc_parity,
-                                              const float* sum_part = nullptr) {
+                                              const EpiCtx& e, uint64_t* acc_full, uint32_t acc_parity) {
   const bool staged = (p.N_out & 7) == 0;   // whole 8-column groups only: every 16-byte piece is all in or all out
   uint4 rnext[4];
   // the first residual chunk is requested before the accumulator is even complete
@@ -171,24 +168,6 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
         }
       }
       tc_wait_ld();
-      if (sum_part) {
-        float sacc[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) sacc[j] = 0.0f;
-        for (int sl = 0; sl < p.splits; ++sl) {
-          const float4* src = reinterpret_cast<const float4*>(sum_part + (size_t)sl * kBM * p.BN + c0);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 v = __ldcg(src + j);
-            sacc[4 * j] += v.x;
-            sacc[4 * j + 1] += v.y;
-            sacc[4 * j + 2] += v.z;
-            sacc[4 * j + 3] += v.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) acc[j] = __float_as_uint(sacc[j]);
-      }
       if (staged) {
         uint32_t o[16];
 #pragma unroll
@@ -301,6 +280,112 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
         }
       }
       staged_store(p, e, no0 + c0, o);   // GEGLU outputs are whole 8-column groups (N % 128 == 0)
+    }
+  }
+}
+
+// Split-K epilogue of one epilogue warp (sub-block j = its 32 accumulator rows x every other 32-column chunk).
+//  1. park: the slice's fp32 accumulator chunks go to the workspace in a warp-coalesced layout -- chunk ci, 4-column group
+//     jj, row lane -> float4 at ((ci * 8 + jj) * 32 + lane): every store / load instruction moves 512 contiguous bytes;
+//  2. arrive on the sub-block's counter and wait until all S slices have parked it (all work items of a split launch are
+//     co-resident: the host never creates more of them than there are SMs);
+//  3. reduce-scatter: the (chunks x 8) float4 rows of the sub-block are dealt round-robin to the S slices; each slice adds
+//     ITS rows over all slices in slice order (deterministic), applies the epilogue to the 4 columns x 32 rows it now
+//     holds and stores them -- the reduction traffic is spread over all the CTAs of the launch instead of funnelling
+//     S x 128 x BN floats through the one SM that happened to finish last;
+//  4. a second counter tells when every slice is done reading; the last one re-arms both counters for the next launch.
+__device__ __forceinline__ void split_epilogue(const GemmParams& p, uint32_t taddr, int tile, int slice, int S, int j,
+                                               int chunk0, int q, int lane, int m0, int m_lim, int n0, uint64_t* acc_full,
+                                               uint32_t acc_parity) {
+  const int maxch = (p.BN + 63) >> 6;
+  const int nch = (p.BN - chunk0 * 32 + 63) >> 6;                    // chunks this warp owns
+  const size_t sub_floats = (size_t)maxch * 1024;                     // one sub-block of one slice
+  float* tile_part = p.part + ((size_t)tile * S * kEpiWarps + j) * sub_floats;   // slice s at + s * kEpiWarps * sub_floats
+  const size_t slice_stride = (size_t)kEpiWarps * sub_floats;
+  mbar_wait(acc_full, acc_parity);
+  tc_fence_after();
+  {
+    float4* mine = reinterpret_cast<float4*>(tile_part + (size_t)slice * slice_stride) + lane;
+    for (int ci = 0; ci < nch; ++ci) {
+      uint32_t acc[32];
+      tmem_ld32(taddr + chunk0 * 32 + ci * 64, acc);
+      tc_wait_ld();
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj)
+        __stcg(mine + (ci * 8 + jj) * 32,
+               make_float4(__uint_as_float(acc[4 * jj]), __uint_as_float(acc[4 * jj + 1]), __uint_as_float(acc[4 * jj + 2]),
+                           __uint_as_float(acc[4 * jj + 3])));
+    }
+  }
+  __threadfence();
+  __syncwarp();
+  unsigned* parked = p.cnt + ((size_t)tile * kEpiWarps + j) * 2;
+  unsigned* done = parked + 1;
+  if (lane == 0) {
+    atomicAdd(parked, 1u);
+    // (bounded: a launch whose slices are not all resident -- which the host never creates -- gives up after seconds
+    // instead of hanging the GPU)
+    for (unsigned spins = 0; *reinterpret_cast<volatile unsigned*>(parked) < (unsigned)S && spins < (1u << 23); ++spins) {
+    }
+    __threadfence();
+  }
+  __syncwarp();
+  const int row = m0 + q * 32 + lane;
+  const bool row_ok = row < m_lim;
+  const __half* rv = (p.rowvec && row_ok) ? p.rowvec + (size_t)(row / p.rows_per_group) * p.rowvec_ld : nullptr;
+  for (int vr = slice; vr < nch * 8; vr += S) {
+    const float4* src = reinterpret_cast<const float4*>(tile_part) + (size_t)vr * 32 + lane;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    int sl = 0;
+    for (; sl + 4 <= S; sl += 4) {   // four loads in flight, added in slice order
+      const float4 v0 = __ldcg(src + (size_t)sl * (slice_stride / 4));
+      const float4 v1 = __ldcg(src + (size_t)(sl + 1) * (slice_stride / 4));
+      const float4 v2 = __ldcg(src + (size_t)(sl + 2) * (slice_stride / 4));
+      const float4 v3 = __ldcg(src + (size_t)(sl + 3) * (slice_stride / 4));
+      acc.x = ((acc.x + v0.x) + v1.x) + v2.x + v3.x;
+      acc.y = ((acc.y + v0.y) + v1.y) + v2.y + v3.y;
+      acc.z = ((acc.z + v0.z) + v1.z) + v2.z + v3.z;
+      acc.w = ((acc.w + v0.w) + v1.w) + v2.w + v3.w;
+    }
+    for (; sl < S; ++sl) {
+      const float4 v = __ldcg(src + (size_t)sl * (slice_stride / 4));
+      acc.x += v.x;
+      acc.y += v.y;
+      acc.z += v.z;
+      acc.w += v.w;
+    }
+    const int col = n0 + chunk0 * 32 + (vr >> 3) * 64 + (vr & 7) * 4;
+    if (!row_ok || col >= p.N_out) continue;
+    float v[4] = {acc.x, acc.y, acc.z, acc.w};
+    __half out[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      if (col + c >= p.N_out) break;
+      float x = v[c];
+      if (p.bias) x += __half2float(__ldg(p.bias + col + c));
+      if (rv) x += __half2float(__ldg(rv + col + c));
+      if (p.residual) x += __half2float(__ldg(p.residual + (size_t)row * p.ldr + col + c));
+      __half y = __float2half_rn(x * p.out_scale);
+      if (p.act) {
+        const float yf = __half2float(y);
+        y = __float2half_rn(yf / (1.0f + __expf(-yf)));
+      }
+      if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(__ldg(p.bias2 + col + c)));
+      out[c] = y;
+    }
+    __half* d = p.D + (size_t)row * p.ldd + col;
+    if (col + 4 <= p.N_out && (p.ldd & 3) == 0) {
+      *reinterpret_cast<uint2*>(d) = *reinterpret_cast<const uint2*>(out);
+    } else {
+      for (int c = 0; c < 4 && col + c < p.N_out; ++c) d[c] = out[c];
+    }
+  }
+  __syncwarp();
+  if (lane == 0) {
+    __threadfence();
+    if (atomicAdd(done, 1u) == (unsigned)S - 1) {   // every slice has finished reading: re-arm for the next launch
+      *reinterpret_cast<volatile unsigned*>(parked) = 0;
+      *reinterpret_cast<volatile unsigned*>(done) = 0;
     }
   }
 }
@@ -517,33 +602,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (S == 1) {
         epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
       } else {
-        // park this slice's rows of the warp's column chunks, then count the arrival; the last slice to arrive adds them up
-        mbar_wait(&tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
-        tc_fence_after();
-        float* tile_part = p.part + (size_t)tile * S * kBM * p.BN + (size_t)(q * 32 + lane) * p.BN;
-        float* mine = tile_part + (size_t)(work % S) * kBM * p.BN;
-        for (int c0 = chunk0 * 32; c0 < p.BN; c0 += 64) {
-          uint32_t acc[32];
-          tmem_ld32(taddr + c0, acc);
-          tc_wait_ld();
-#pragma unroll
-          for (int j = 0; j < 8; ++j)
-            __stcg(reinterpret_cast<float4*>(mine + c0) + j,
-                   make_float4(__uint_as_float(acc[4 * j]), __uint_as_float(acc[4 * j + 1]), __uint_as_float(acc[4 * j + 2]),
-                               __uint_as_float(acc[4 * j + 3])));
-        }
-        __threadfence();
-        __syncwarp();
-        unsigned arrived = 0;
-        unsigned* ctr = p.cnt + (size_t)tile * kEpiWarps + (warp - 2);
-        if (lane == 0) arrived = atomicAdd(ctr, 1u);
-        arrived = __shfl_sync(0xffffffffu, arrived, 0);
-        if (arrived == (unsigned)S - 1) {
-          if (lane == 0) *ctr = 0;   // ready for the next launch
-          __threadfence();
-          epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1),
-                        tile_part);
-        }
+        split_epilogue(p, taddr, tile, work % S, S, (int)(warp - 2), chunk0, (int)q, (int)lane, m0, m_lim, n0,
+                       &tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
       }
       // accumulator drained: hand it back to the MMA warp
       tc_fence_before();
@@ -634,8 +694,8 @@ static void pick_splits(GemmParams& p, int num_tiles, cudaStream_t stream) {
     for (const SplitWs& w : g_ws)
       if (w.stream == stream) ws = w;
   }
-  if (!ws.ptr || (size_t)num_tiles * kEpiWarps * sizeof(unsigned) > kSplitCounterBytes) return;
-  const size_t per_slice = (size_t)num_tiles * kBM * p.BN * sizeof(float);
+  if (!ws.ptr || (size_t)num_tiles * kEpiWarps * 2 * sizeof(unsigned) > kSplitCounterBytes) return;
+  const size_t per_slice = (size_t)num_tiles * kEpiWarps * ((p.BN + 63) / 64) * 1024 * sizeof(float);
   const size_t room = ws.bytes - kSplitCounterBytes;
   if ((size_t)S * per_slice > room) S = (int)(room / per_slice);
   if (S < 2) return;
