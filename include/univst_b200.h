@@ -246,6 +246,9 @@ typedef struct univst_push {
   int32_t ld_dst;
   int64_t dst_blk_rows;
   int32_t nblk, rows, cols;
+  void* mc_dst; /* optional: MULTICAST address of the destination (same offset in every rank's buffer, e.g. torch symmetric
+                   memory's multicast_ptr): one multimem.st per 16 bytes, replicated by the NVSwitch, instead of one
+                   store per peer -- the frame-0 K/V "broadcast" then costs rank 0 one copy of egress, not world - 1 */
 } univst_push_t;
 int univst_xrank_push_f16(const univst_push_t* pushes, int32_t npush, void* const* ctl, int32_t rank, int32_t world,
                           void* stream);

@@ -79,6 +79,37 @@ def test_maskprop_many_classes_and_mirror(cuda_lib):
         assert torch.equal(feat_s.cpu(), feat_tar.T[:, idx]) and feat_s.shape[1] == segs_s.shape[1] == len(idx)
 
 
+@pytest.mark.parametrize("name", ["shipped_antialiased", "clean_two_class"])
+def test_video_mask_propogation_driver_matches_reference(cuda_lib, name, tmp_path):
+    """The whole driver through the CUDA kernel against the PNGs of the REFERENCE's own video_mask_propogation (golden): both
+    call forms (the reference's ``args`` object with paths, and in-memory arrays).  The kernel's fp32 similarity sums are
+    ordered differently from torch's GEMM, so a label near a tie may flip: at most 0.5 % of the pixels may differ (measured
+    0); the two call forms must agree exactly."""
+    from PIL import Image
+    from types import SimpleNamespace
+    from univst_b200 import mask_propagation as mp
+    g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "maskprop_video.pt"), weights_only=True)[name]
+    mpath, fpath = str(tmp_path / "mask.png"), str(tmp_path / "feat.pt")
+    Image.fromarray(g["first_mask"].numpy(), mode="L").save(mpath)
+    torch.save(g["features"], fpath)
+    args = SimpleNamespace(temperature=0.2, n_last_frames=g["n_last_frames"], topk=15, sample_ratio=0.3,
+                           num_frames=g["features"].shape[0], mask_path=mpath, backbone="sd", feature_path=fpath,
+                           output_path=str(tmp_path / "out"))
+    torch.manual_seed(g["seed"])
+    masks = np.stack(mp.video_mask_propogation(args))
+    odir = os.path.join(args.output_path, "sd", "mask")
+    assert sorted(os.listdir(odir)) == g["names"]
+    on_disk = np.stack([np.asarray(Image.open(os.path.join(odir, n))) for n in g["names"]])
+    assert np.array_equal(on_disk, masks) and list(masks.shape) == g["shape"]
+    ref = np.unpackbits(g["masks_bits"].numpy())[: masks[1:].size].reshape(masks[1:].shape).astype(bool)
+    mismatch = float(((masks[1:] != 0) != ref).mean())
+    print(f"{name}: {mismatch * 100:.4f} % of the pixels differ from the reference's masks")
+    assert mismatch <= 5e-3
+    torch.manual_seed(g["seed"])
+    mem = np.stack(mp.video_mask_propogation(g["first_mask"].numpy(), g["features"], args))
+    assert np.array_equal(mem, masks)
+
+
 def test_flow_warp_bit_exact(cuda_lib):
     from univst_b200 import flow_warp, ops
     g = torch.load(os.path.join(os.path.dirname(__file__), "golden", "flow_warp.pt"), weights_only=True)

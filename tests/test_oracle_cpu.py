@@ -594,6 +594,41 @@ def test_mask_propogation_host_logic_on_cpu(monkeypatch, name):
     assert torch.equal(feat_s, g["feat_sample"]) and torch.allclose(segs_s, g["segs_sample"], atol=1e-6)
 
 
+@pytest.mark.parametrize("name", ["shipped_antialiased", "clean_two_class"])
+def test_video_mask_propogation_driver_on_cpu(monkeypatch, name, tmp_path):
+    """The mask-propagation DRIVER (univst_b200.mask_propagation.video_mask_propogation: first-mask resize + one-hot -- 256
+    classes for the shipped anti-aliased mask --, anchor queue with eviction, per-frame propagation + RNG subsample, bilinear
+    upsampling, per-class min-max normalisation, argmax, != 0 -> 255, PNG files) with the kernel replaced by the oracle core,
+    called the REFERENCE's way (an ``args`` object with paths): the PNGs must equal the ones the reference's own
+    ``video_mask_propogation`` wrote under the same seed (golden, oracle/gen_golden_maskprop_video.py) pixel for pixel."""
+    import numpy as np
+    from PIL import Image
+    from types import SimpleNamespace
+    from oracle import maskprop_oracle as mo
+    from univst_b200 import mask_propagation as mp
+    from univst_b200 import ops
+    g = torch.load(os.path.join(GOLDEN, "maskprop_video.pt"), weights_only=True)[name]
+    monkeypatch.setattr(ops, "maskprop", lambda ft, fs, sg, temperature=0.2, topk=15, return_kept=0:
+                        mo.mask_propogation_core(fs, ft, sg, temperature, topk)[0])
+    monkeypatch.setattr(mp, "_DEVICE", "cpu")
+    mpath, fpath = str(tmp_path / "mask.png"), str(tmp_path / "feat.pt")
+    Image.fromarray(g["first_mask"].numpy(), mode="L").save(mpath)
+    torch.save(g["features"], fpath)
+    args = SimpleNamespace(temperature=0.2, n_last_frames=g["n_last_frames"], topk=15, sample_ratio=0.3,
+                           num_frames=g["features"].shape[0], mask_path=mpath, backbone="sd", feature_path=fpath,
+                           output_path=str(tmp_path / "out"))
+    torch.manual_seed(g["seed"])
+    masks = mp.video_mask_propogation(args)
+    odir = os.path.join(args.output_path, "sd", "mask")
+    assert sorted(os.listdir(odir)) == g["names"]
+    on_disk = np.stack([np.asarray(Image.open(os.path.join(odir, n))) for n in g["names"]])
+    assert list(on_disk.shape) == g["shape"] and np.array_equal(on_disk, np.stack(masks))
+    assert np.array_equal(on_disk[0], g["first_mask"].numpy())
+    ref_bits = np.unpackbits(g["masks_bits"].numpy())[: on_disk[1:].size].reshape(on_disk[1:].shape)
+    assert np.array_equal(on_disk[1:] != 0, ref_bits.astype(bool))
+    assert set(np.unique(on_disk[1:])) <= {0, 255}
+
+
 def test_rf_inversion_host_logic_on_cpu(monkeypatch, tmp_path):
     """Host side of univst_b200.flow_inversion (sigma schedule flipped to ascending time, step coefficients folded into two
     axpby calls, second-order RF-Solver midpoint, file side effects) with the axpby kernel replaced by its torch definition:

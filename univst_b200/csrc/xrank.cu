@@ -24,6 +24,7 @@ __global__ void xrank_barrier_kernel(XrankPeers P, int rank, int world) { xrank_
 // noise prediction (my frames -> their place in every rank's full-clip buffer).
 struct PushDesc {
   const __half* src;
+  __half* mc;                   // multicast address of the destination (NVSwitch replicates one store to every rank) or null
   __half* dst[kXrankMaxRanks];
   long long src_blk, dst_blk;   // rows between consecutive blocks
   int ld_src, ld_dst, nblk, rows, cols;
@@ -44,6 +45,10 @@ __global__ void xrank_push_kernel(PushArgs a, XrankPeers P, int rank, int world)
       const int row = (int)(rr % d.rows), blk = (int)(rr / d.rows);
       const uint4 val = *reinterpret_cast<const uint4*>(d.src + (blk * d.src_blk + row) * d.ld_src + v * 8);
       const long long off = (blk * d.dst_blk + row) * d.ld_dst + v * 8;
+      if (d.mc) {
+        multimem_st_v4(d.mc + off, val);
+        continue;
+      }
 #pragma unroll 4
       for (int r = 0; r < world; ++r)
         if (d.dst[r]) *reinterpret_cast<uint4*>(d.dst[r] + off) = val;
@@ -139,8 +144,10 @@ extern "C" int univst_xrank_push_f16(const univst_push_t* pushes, int32_t npush,
       UV_REQUIRE(((uintptr_t)d.dst[q] & 15) == 0, "xrank_push: destinations must be 16-byte aligned");
       any |= d.dst[q] != nullptr;
     }
-    if (!any) continue;
+    if (!any && !p.mc_dst) continue;
     d.src = (const __half*)p.src;
+    d.mc = (__half*)p.mc_dst;
+    UV_REQUIRE(((uintptr_t)d.mc & 15) == 0, "xrank_push: the multicast destination must be 16-byte aligned");
     d.src_blk = p.src_blk_rows;
     d.dst_blk = p.dst_blk_rows;
     d.ld_src = p.ld_src;

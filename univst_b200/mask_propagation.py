@@ -15,6 +15,7 @@ import torch.nn.functional as F
 
 from . import ops
 
+_DEVICE = "cuda"   # where the features live (the kernel is CUDA-only; CPU host-logic tests re-point this)
 DEFAULT_ARGS = SimpleNamespace(temperature=0.2, n_last_frames=9, topk=15, sample_ratio=0.3, num_frames=16)
 
 
@@ -53,18 +54,44 @@ def norm_mask(mask):
     return mask
 
 
+def read_feature(path_or_tensor, frame_index=None, return_h_w=False):
+    """mask_propagation.py:102-111 (one frame of the dumped feature map as [h w, C] fp32) -- or, without a frame index, the
+    whole (F, h, w, C) map on the device, which is what the driver below reads ONCE instead of once per frame (:104)."""
+    data = path_or_tensor if torch.is_tensor(path_or_tensor) else torch.load(path_or_tensor, weights_only=True)
+    data = data.to(_DEVICE).float()
+    if frame_index is None:
+        return data
+    data = data[frame_index]
+    _h, _w, _ = data.shape
+    data = data.reshape(_h * _w, -1).contiguous()
+    return (data, _h, _w) if return_h_w else data
+
+
 @torch.no_grad()
-def video_mask_propogation(first_mask: np.ndarray, features: torch.Tensor, args=DEFAULT_ARGS, output_path=None):
-    """mask_propagation.py:15-69.  ``first_mask``: (H, W) uint8 label image of frame 0; ``features``: (F, h, w, C)
-    tensor as dumped by the inversion stage (``inversion_feature_map_2_block_301_step.pt``) -- read ONCE, not once per
-    frame as the reference does (:104).  Returns the list of (H, W) uint8 masks (frame 0 = the input), written as
-    ``%05d.png`` when ``output_path`` is given."""
+def video_mask_propogation(args_or_mask, features=None, args=None, output_path=None):
+    """mask_propagation.py:15-69.  Two call forms:
+
+    * the reference's: ``video_mask_propogation(args)`` with ``args.mask_path`` (first-frame label PNG),
+      ``args.feature_path`` (``inversion_feature_map_2_block_301_step.pt``), ``args.output_path``, ``args.backbone`` and
+      the hyper-parameters -- writes ``<output_path>/<backbone>/<mask name>/%05d.png`` like the reference (:18-20, :30, :69);
+    * in memory: ``video_mask_propogation(first_mask (H, W) uint8, features (F, h, w, C), args, output_path)``.
+
+    Returns the list of (H, W) uint8 masks (frame 0 = the input)."""
     from PIL import Image
-    feats = features.to("cuda").float()
+    if not isinstance(args_or_mask, np.ndarray) and hasattr(args_or_mask, "mask_path"):
+        args = args_or_mask
+        name = args.mask_path.split("/")[-1].split(".")[0]
+        output_path = os.path.join(args.output_path, args.backbone, name)
+        first_mask = np.asarray(Image.open(args.mask_path))
+        features = args.feature_path
+    else:
+        first_mask = np.asarray(args_or_mask)
+        args = args if args is not None else DEFAULT_ARGS
+    feats = read_feature(features)
     nF, h, w, C = feats.shape
     ori_h, ori_w = first_mask.shape
     seg0 = np.array(Image.fromarray(first_mask).resize((w, h), 0))
-    first_seg = to_one_hot(torch.from_numpy(seg0).float().unsqueeze(0).cuda())
+    first_seg = to_one_hot(torch.from_numpy(seg0).float().unsqueeze(0).to(feats.device))
     Ccls = first_seg.shape[1]
     que = queue.Queue(args.n_last_frames)
     feat_first = feats[0].reshape(h * w, C).T.contiguous()
@@ -79,7 +106,7 @@ def video_mask_propogation(first_mask: np.ndarray, features: torch.Tensor, args=
         que.put([feat_s, segs_s])
         up = F.interpolate(final_mask.reshape(1, Ccls, h, w), size=(ori_h, ori_w), mode="bilinear", align_corners=False)[0]
         lab = torch.max(norm_mask(up), dim=0)[1]
-        m = np.array(lab.cpu(), dtype=np.uint8)
+        m = lab.cpu().numpy().astype(np.uint8)
         m[m != 0] = 255
         masks.append(m)
     if output_path is not None:

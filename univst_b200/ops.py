@@ -55,7 +55,7 @@ _lib.register("univst_xrank_barrier", [_vp, _i32, _i32, _vp])
 class Push(C.Structure):
     """Mirror of ``univst_push_t``."""
     _fields_ = [("src", _vp), ("ld_src", _i32), ("src_blk_rows", _i64), ("dst", _vp * 16), ("ld_dst", _i32),
-                ("dst_blk_rows", _i64), ("nblk", _i32), ("rows", _i32), ("cols", _i32)]
+                ("dst_blk_rows", _i64), ("nblk", _i32), ("rows", _i32), ("cols", _i32), ("mc_dst", _vp)]
 
 
 _lib.register("univst_xrank_push_f16", [C.POINTER(Push), _i32, _vp, _i32, _i32, _vp])
@@ -400,7 +400,8 @@ def xrank_barrier(xr):
 def xrank_push(xr, pushes):
     """Up to two block copies into peer memory + the cross-rank synchronisation as the tail of the same kernel.
     ``pushes``: list of dicts(src=strided 2-D fp16 view, src_blk_rows, dst=[device pointer or 0 per rank], ld_dst,
-    dst_blk_rows, nblk, rows); an empty list is a plain synchronisation."""
+    dst_blk_rows, nblk, rows[, mc=multicast address: one switch-replicated store instead of one per peer]); an empty
+    list is a plain synchronisation."""
     _lib.require_device()
     n = len(pushes)
     arr = (Push * max(n, 1))()
@@ -412,6 +413,7 @@ def xrank_push(xr, pushes):
             arr[k].dst[r] = (p["dst"][r] or None) if r < len(p["dst"]) else None
         arr[k].ld_dst, arr[k].dst_blk_rows = p["ld_dst"], p["dst_blk_rows"]
         arr[k].nblk, arr[k].rows, arr[k].cols = p["nblk"], p["rows"], src.shape[1]
+        arr[k].mc_dst = p.get("mc") or None
     check(_lib.lib().univst_xrank_push_f16(arr, n, xr.ctl, xr.rank, xr.world, _stream()), "univst_xrank_push_f16")
     _count("xrank_push")
 

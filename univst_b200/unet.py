@@ -290,9 +290,10 @@ class UNetPseudo3DConditionModel:
         par = self._xr_par.get(key, 0)
         self._xr_par[key] = par ^ 1
         t, ptrs = self._xr.buffer(key, (2, rows, cols))
-        return t[par], [p + par * rows * cols * 2 for p in ptrs]
+        mc = self._xr.multicast(key)
+        return t[par], [p + par * rows * cols * 2 for p in ptrs], (mc + par * rows * cols * 2 if mc else 0)
 
-    def _xr_push_kv_halo(self, qkv, ptrs, B, F, N, C):
+    def _xr_push_kv_halo(self, qkv, ptrs, mc, B, F, N, C):
         """xrank transport of the K/V halo: K|V columns (C .. 3C) of my last frame -> bank 1 of rank + 1, of the clip's
         first frame (rank 0) -> bank 2 of every other rank; the synchronisation is the tail of the same kernel."""
         _, rank, world = self._shard
@@ -303,9 +304,11 @@ class UNetPseudo3DConditionModel:
             dst = [0] * world
             dst[rank + 1] = ptrs[rank + 1] + (NI * N * ld + C) * 2
             pushes.append(dict(src=kv[(F - 1) * N:], src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N))
-        if rank == 0:
-            dst = [0] + [p + ((NI + B) * N * ld + C) * 2 for p in ptrs[1:]]
-            pushes.append(dict(src=kv, src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N))
+        if rank == 0:   # one switch-replicated store per 16 bytes where the fabric multicasts, else one store per peer
+            off = ((NI + B) * N * ld + C) * 2
+            dst = [0] + [p + off for p in ptrs[1:]]
+            pushes.append(dict(src=kv, src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N,
+                               mc=mc + off if mc else 0))
         ops.xrank_push(self._xr, pushes)
 
     def set_frame_sharding_off(self):
@@ -522,7 +525,7 @@ class UNetPseudo3DConditionModel:
         else:  # two halo banks of B images each behind the local images
             NIkv = NI + 2 * B
             if self._xr is not None:
-                qkv_all, halo_ptrs = self._xr_halo(NIkv * N, 3 * C)
+                qkv_all, halo_ptrs, halo_mc = self._xr_halo(NIkv * N, 3 * C)
             elif self._push_halo:
                 qkv_all, halo_ptrs, symm_hdl = self._symm_halo(NIkv * N, 3 * C)
             else:
@@ -541,7 +544,7 @@ class UNetPseudo3DConditionModel:
         else:
             if halo:
                 if self._xr is not None:
-                    self._xr_push_kv_halo(qkv_all, halo_ptrs, B, F, N, C)
+                    self._xr_push_kv_halo(qkv_all, halo_ptrs, halo_mc, B, F, N, C)
                 elif self._push_halo:
                     self._push_kv_halo(qkv_all, halo_ptrs, symm_hdl, B, F, N, C)
                 else:
@@ -784,9 +787,12 @@ class UNetPseudo3DConditionModel:
                                out=torch.empty((Bo * F * h * w, 8), dtype=torch.float16, device=dev))
         if self._xr is not None:   # store my frames of the (tiny) noise prediction into every rank's full-clip buffer
             _, rank, world = self._shard
-            full, ptrs = self._xr.buffer(("eps", Bo, F_total, h * w), (Bo * F_total * h * w, 8))
+            key = ("eps", Bo, F_total, h * w)
+            full, ptrs = self._xr.buffer(key, (Bo * F_total * h * w, 8))
+            mc = self._xr.multicast(key)
             ops.xrank_push(self._xr, [dict(src=eps_rows, src_blk_rows=F * h * w, dst=[p + rank * F * h * w * 16 for p in ptrs],
-                                           ld_dst=8, dst_blk_rows=F_total * h * w, nblk=Bo, rows=F * h * w)])
+                                           ld_dst=8, dst_blk_rows=F_total * h * w, nblk=Bo, rows=F * h * w,
+                                           mc=mc + rank * F * h * w * 16 if mc else 0)])
             eps_rows, F = full, F_total
         elif self._shard is not None:  # all-gather the (tiny) noise prediction: [P][B][Fl] -> [B][P Fl]
             import torch.distributed as dist

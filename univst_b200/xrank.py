@@ -37,17 +37,63 @@ class XRank:
         torch.cuda.synchronize(self.device)
         dist.barrier(self.group)
         torch.cuda.synchronize(self.device)
+        self.multicast_ok = self._multicast_selftest()
+
+    def _multicast_selftest(self) -> bool:
+        """One multicast push from rank 0, verified on every rank: only then do later pushes use switch-replicated stores."""
+        import torch.distributed as dist
+        from . import ops
+        self.multicast_ok = True
+        t, ptrs = self.buffer("_mc_selftest", (64, 64))
+        t.zero_()
+        mc = self.multicast("_mc_selftest")
+        ok = torch.ones(1, device=self.device)
+        try:
+            torch.cuda.synchronize(self.device)
+            dist.barrier(self.group)
+            pushes = []
+            if self.rank == 0 and mc:
+                src = (torch.arange(64 * 64, device=self.device) % 251).to(torch.float16).view(64, 64)
+                pushes = [dict(src=src, src_blk_rows=64, dst=[0] * self.world, ld_dst=64, dst_blk_rows=64, nblk=1, rows=64, mc=mc)]
+            ops.xrank_push(self, pushes)
+            torch.cuda.synchronize(self.device)
+            want = (torch.arange(64 * 64, device=self.device) % 251).to(torch.float16).view(64, 64)
+            if not mc or not torch.equal(t, want):
+                ok.zero_()
+        except Exception:  # noqa: BLE001
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        return bool(ok.item() > 0)
 
     def buffer(self, key, shape, dtype=torch.float16):
         """Symmetric buffer ``key`` of ``shape`` (same call sequence on every rank): (local tensor, [device pointer of every
         rank's copy])."""
+        ent = self._entry(key, shape, dtype)
+        return ent[0], ent[1]
+
+    def multicast(self, key) -> int:
+        """Multicast address of an existing symmetric buffer (a store to it lands at the same offset on every rank, replicated
+        by the NVSwitch) or 0 where the fabric has no multicast support (or UNIVST_XRANK_MULTICAST=0)."""
+        return self._buffers[key][3]
+
+    def _entry(self, key, shape, dtype):
         ent = self._buffers.get(key)
         if ent is None:
+            import os
             t = self._symm_mem.empty(*shape, dtype=dtype, device=self.device)
             hdl = self._symm_mem.rendezvous(t, self.group)
             ptrs = [hdl.get_buffer(r, tuple(shape), dtype).data_ptr() for r in range(self.world)]
-            ent = self._buffers[key] = (t, ptrs, hdl)
-        return ent[0], ent[1]
+            mc = 0
+            if os.environ.get("UNIVST_XRANK_MULTICAST", "1") != "0":
+                try:   # multicast_ptr follows the convention of buffer_ptrs (allocation base): add the tensor's offset
+                    base = int(hdl.multicast_ptr or 0)
+                    mc = base + (t.data_ptr() - int(hdl.buffer_ptrs[self.rank])) if base else 0
+                except Exception:  # noqa: BLE001
+                    mc = 0
+            if not getattr(self, "multicast_ok", True):
+                mc = 0
+            ent = self._buffers[key] = (t, ptrs, hdl, mc)
+        return ent
 
     def error(self) -> int:
         """0, or 1 + the rank a wait timed out on (sticky).  Synchronises the device."""
