@@ -441,12 +441,15 @@ def run_ours(args):
                 f"AnimateDiff frame-sharded result differs from one GPU: {ad['frame_sharded']}"
         extra["animatediff_v2_backbone"] = ad
 
-    t = torch.tensor([ms, ms_e2e] + ([fs["clip_parallel_replicas"]["ms_per_clip_per_gpu"]] if fs else []), device=dev,
-                     dtype=torch.float64)
+    # dominant-kernel time: max over ranks (rank 0 holds the clip's first frames, whose [previous, first] sources collapse
+    # to one deduplicated source -- half the keys -- so its launches are not representative)
+    roof_local = dominant_attention(prof, peaks(), None)
+    t = torch.tensor([ms, ms_e2e, roof_local["avg_ms"] if roof_local else 0.0]
+                     + ([fs["clip_parallel_replicas"]["ms_per_clip_per_gpu"]] if fs else []), device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     tl = t.tolist()
-    ms, ms_e2e = tl[0], tl[1]
+    ms, ms_e2e, dom_ms = tl[0], tl[1], tl[2]
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -458,6 +461,12 @@ def run_ours(args):
     fps_e2e = F_FRAMES / (ms_e2e / args.steps / 1e3)
     clk = clocks.summary()
     roof = dominant_attention(prof, pk, clk["sm_mhz"])
+    if roof and world > 1 and dom_ms > 0:
+        roof["avg_ms"] = dom_ms
+        roof["achieved"] = roof["flop_per_launch"] / (dom_ms * 1e-3) / 1e12
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["frac_of_mufu_bound"] = roof["achieved"] / roof["mufu_bound_tflops"]
+        roof["note"] = "launch duration = max over ranks of the per-rank mean (rank 0's sources are deduplicated)"
     attn_ms = sum(m_ for m_, _ in prof.get("sc_attention", [])) / (args.steps if profiling else 1)
     config = {"workload": "SD-v1.5 three-branch localized transfer, 16x512x512, 50 steps, one clip"
                           + (f", frames sharded over {world} GPUs" if world > 1 else ""),
@@ -471,7 +480,7 @@ def run_ours(args):
     if fs is not None:
         fs.pop("clip_parallel_replicas")
         fs["speedup_vs_1gpu_same_box"] = fs["ms_per_clip_1gpu_same_box"] / ms_per_step
-        fs["clip_parallel_replicas"] = {"frames_per_s": world * F_FRAMES / (tl[2] / 1e3), "scaling": "weak",
+        fs["clip_parallel_replicas"] = {"frames_per_s": world * F_FRAMES / (tl[3] / 1e3), "scaling": "weak",
                                         "note": "side number: each rank stylizes its own clip, no communication"}
         config["frame_sharding"] = fs
     line = {
