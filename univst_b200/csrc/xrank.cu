@@ -35,23 +35,37 @@ struct PushArgs {
 };
 
 __global__ void xrank_push_kernel(PushArgs a, XrankPeers P, int rank, int world) {
+  constexpr int U = 4;   // 16-byte pieces in flight per thread: the loads of a batch are issued before its (posted) stores
   for (int k = 0; k < a.n; ++k) {
     const PushDesc& d = a.d[k];
     const int vpr = d.cols >> 3;
     const long long total = (long long)d.nblk * d.rows * vpr;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-      const int v = (int)(i % vpr);
-      const long long rr = i / vpr;
-      const int row = (int)(rr % d.rows), blk = (int)(rr / d.rows);
-      const uint4 val = *reinterpret_cast<const uint4*>(d.src + (blk * d.src_blk + row) * d.ld_src + v * 8);
-      const long long off = (blk * d.dst_blk + row) * d.ld_dst + v * 8;
-      if (d.mc) {
-        multimem_st_v4(d.mc + off, val);
-        continue;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += stride * U) {
+      uint4 val[U];
+      long long off[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const long long i = i0 + u * stride;
+        off[u] = -1;
+        if (i < total) {
+          const int v = (int)(i % vpr);
+          const long long rr = i / vpr;
+          const int row = (int)(rr % d.rows), blk = (int)(rr / d.rows);
+          val[u] = __ldg(reinterpret_cast<const uint4*>(d.src + (blk * d.src_blk + row) * d.ld_src + v * 8));
+          off[u] = (blk * d.dst_blk + row) * d.ld_dst + v * 8;
+        }
       }
-#pragma unroll 4
-      for (int r = 0; r < world; ++r)
-        if (d.dst[r]) *reinterpret_cast<uint4*>(d.dst[r] + off) = val;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (off[u] < 0) continue;
+        if (d.mc) {
+          multimem_st_v4(d.mc + off[u], val[u]);
+        } else {
+          for (int r = 0; r < world; ++r)
+            if (d.dst[r]) *reinterpret_cast<uint4*>(d.dst[r] + off[u]) = val[u];
+        }
+      }
     }
   }
   xrank_kernel_tail(P, rank, world);
