@@ -82,6 +82,25 @@ int univst_gemm_tune(int32_t splitk_max_tiles);
 int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int32_t W, int32_t C1, int32_t C2,
                        const void* Wt, int32_t Cout, int32_t stride, void* Y, int32_t ldy,
                        const univst_epilogue_t* ep, void* stream);
+/* The same implicit GEMM with other tap tables (the VAE around the loop, SURVEY.md 8f row 2 -- third-party diffusers
+ * AutoencoderKLTemporalDecoder, called at stable_diffusion.py:385,810,830 and ddim_inversion.py:29):
+ *   univst_conv3x3_s2_pad_after_f16: 3x3, stride 2, one zero row / column AFTER the image (Downsample2D(padding=0) pads
+ *     (0, 1, 0, 1) before its stride-2 conv); X = the four parity planes, H x W = output size;
+ *   univst_conv_temporal3_f16: the (3, 1, 1) temporal convolutions of the temporal decoder.  X: [NB clips, F frames, HW
+ *     pixels, C] channels-last, Wt: [Cout, 3, C] (tap t = frame offset t - 1), zero frames beyond the clip's ends. */
+int univst_conv3x3_s2_pad_after_f16(const void* X, int32_t NB, int32_t H, int32_t W, int32_t C, const void* Wt, int32_t Cout,
+                                    void* Y, int32_t ldy, const univst_epilogue_t* ep, void* stream);
+int univst_conv_temporal3_f16(const void* X, int32_t NB, int32_t F, int32_t HW, int32_t C, const void* Wt, int32_t Cout,
+                              void* Y, int32_t ldy, const univst_epilogue_t* ep, void* stream);
+/* Small kernels of the VAE legs: in-place softmax(scale * x) over the columns of every row (the single-head mid-block
+ * attention: head dim 512 runs as QK^T GEMM -> softmax -> PV GEMM); decoder rows -> uint8 pixels with the reference's
+ * rounding (stable_diffusion.py:812-814); uint8 pixels -> zero-padded encoder input rows (:826-827); KL posterior sample
+ * (or mode when noise == NULL) of [mean | logvar] moment rows, scaled, in the (C, F, hw) latent layout. */
+int univst_softmax_rows_f16(void* X, int32_t ld, int32_t rows, int32_t cols, float scale, void* stream);
+int univst_frames_to_u8(const void* X, int32_t ld, int64_t pixels, void* out, void* stream);
+int univst_u8_to_frames_f16(const void* in, int64_t pixels, int32_t cpad, void* out, void* stream);
+int univst_vae_sample_f16(const void* moments, int32_t ld, const void* noise, int32_t C, int32_t F, int32_t HW, float scaling,
+                          void* out, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------
  * Fused sparse-causal attention: O[img] = softmax(Q[img] K^T / sqrt(d)) V, where the K/V sequence of image `img` is

@@ -136,3 +136,64 @@ def test_video_style_transfer_non_square_clip(pipe):
     rel, psnr = _rel(out, truth), _psnr(out, truth)
     print(f"non-square clip, {n} steps: rel={rel:.3e} psnr={psnr:.1f} dB")
     assert out.shape == truth.shape and torch.isfinite(out).all() and rel <= 3e-2 and psnr >= 30.0
+
+
+def test_pixel_smoother_branch(pipe):
+    """The sliding-window smoother of stable_diffusion.py:713-758 (hard-coded off in the reference, ``smoother = None``)
+    switched on: steps 0..19 are untouched; step 20 must equal the branch restated from its parts -- predicted x0 (:718),
+    temporal VAE decode to uint8 (:721), the NumPy / cv2-exact window smoothing of the ORACLE on those frames with the mask
+    kept (:725-751), re-encoding (:753), noise recomputed from the stabilised x0 (:782-791), DDIM update (:761).  VAE: the
+    tiny seeded AutoencoderKLTemporalDecoder (parity unpinned, tests/test_vae_gpu.py); flows: analytic, frame-independent."""
+    from oracle import flowwarp_oracle as fo
+    from oracle import vae_oracle as vo
+    from univst_b200 import ops
+    from univst_b200.vae import AutoencoderKLTemporalDecoder
+    g = torch.load(os.path.join(GOLDEN, "style_transfer_tiny.pt"), weights_only=True)
+    n = g["n"]
+    traj_c, traj_s, mask_u8 = po.synthetic_inputs(g["seed"], g["F"], g["hw"], n)
+    H = g["hw"] * 8
+    mask_px = torch.from_numpy(mask_u8)
+    if mask_px.shape[-1] != H:   # the smoother applies the mask at pixel resolution
+        mask_px = torch.nn.functional.interpolate(mask_px[None].float(), size=(H, H), mode="nearest")[0].to(torch.uint8)
+    vae = AutoencoderKLTemporalDecoder(vo.seeded_state_dict(vo.TINY_VAE_CONFIG, seed=55), vo.TINY_VAE_CONFIG)
+    fwd = fo.synthetic_flow(H, H, 3)
+    bwd = fo.synthetic_flow(H, H, 0, backward_of=fwd)
+    fwd_c, bwd_c = torch.from_numpy(fwd).cuda(), torch.from_numpy(bwd).cuda()
+    from univst_b200 import pnp_utils
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    z_T = pnp_utils.latent_adain(traj_c[n].cuda().half(), traj_s[n].cuda().half())
+    kw = dict(num_inference_steps=n, latents=z_T, content_inv_path=[t.half() for t in traj_c],
+              style_inv_path=[t.half() for t in traj_s], mask_path=mask_px, prompt_embeds=g["emb"])
+    plain = {}
+    pipe.video_style_transfer("", callback=lambda i, t, z: plain.__setitem__(i, z.clone()), **kw)
+    rec, eps20 = {}, {}
+
+    def cb(i, t, z):
+        rec[i] = z.clone()
+        if i == 20:
+            eps20["rows"], eps20["branch"] = pipe.unet.last_eps_rows.clone(), pipe.unet.last_edit_branch
+    pipe.vae = vae
+    try:
+        out = pipe.video_style_transfer("", smoother="pixel", flow_fn=lambda a, b: (fwd_c, bwd_c), callback=cb, **kw)
+    finally:
+        pipe.vae = None
+    assert torch.isfinite(out.latents).all()
+    assert all(torch.equal(rec[i], plain[i]) for i in range(20)) and not torch.equal(rec[20], plain[20])
+    # step 20 from its parts
+    t20 = int(pipe.scheduler.timesteps[20])
+    a_t, a_prev = pipe.scheduler.step_alphas(t20)
+    z = rec[19]
+    from univst_b200 import ops as _ops
+    m = pipe._mask(mask_px, g["F"], g["hw"], g["hw"])
+    z = _ops.latent_blend(z, traj_c[n - 20].cuda().half().contiguous(), m)      # the step's mask blend (:687-692), i = 20 <= 45
+    x0 = torch.empty_like(z)
+    _ops.ddim_step(z, eps20["rows"], eps20["branch"], a_t, a_prev, x0_out=x0)
+    frames = vae.decode_latents_u8(x0)
+    keep = (mask_px != 0).numpy().astype(np.uint8)
+    est = fo.sliding_window_smooth(frames.cpu().numpy(), lambda k, nw: (fwd, bwd), keep_mask=keep)
+    x0s = vae.encode_frames_u8(torch.from_numpy(est).cuda(), generator=torch.Generator(device="cuda").manual_seed(0))
+    eps = (z.float() - a_t ** 0.5 * x0s.float()) / (1 - a_t) ** 0.5
+    want = a_prev ** 0.5 * ((z.float() - (1 - a_t) ** 0.5 * eps) / a_t ** 0.5) + (1 - a_prev) ** 0.5 * eps
+    rel = _rel(rec[20], want)
+    print(f"smoothed step 20 vs the branch restated from its parts: rel {rel:.3e}")
+    assert rel < 2e-3

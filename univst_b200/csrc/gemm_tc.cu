@@ -848,11 +848,14 @@ extern "C" int univst_gemm_f16(const void* A, int32_t lda, const void* A2, int32
   return launch(tmA, tmA2, tmB, p, (cudaStream_t)stream);
 }
 
-extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int32_t W, int32_t C1,
-                                  int32_t C2, const void* Wt, int32_t Cout, int32_t stride, void* Y, int32_t ldy,
-                                  const univst_epilogue_t* ep, void* stream) {
+// kind: 0 = 3x3, stride 1, padding 1; 1 = 3x3, stride 2, padding 1 (parity planes); 2 = 3x3, stride 2, padding (0, 1, 0, 1)
+// -- one zero row / column AFTER the image, as diffusers' Downsample2D(padding=0) pads (parity planes); 3 = 3x1 over the
+// image rows only (the (3, 1, 1) temporal convolutions of the temporal VAE decoder: rows = frames, columns = pixels)
+static int conv_taps(const void* X, const void* X2, int32_t NB, int32_t H, int32_t W, int32_t C1, int32_t C2, const void* Wt,
+                     int32_t Cout, int kind, void* Y, int32_t ldy, const univst_epilogue_t* ep, void* stream) {
+  const int stride = (kind == 1 || kind == 2) ? 2 : 1;
+  const int ntaps = kind == 3 ? 3 : 9;
   UV_REQUIRE(X && Wt && Y && NB > 0 && Cout > 0 && C1 > 0, "conv3x3: null pointer or empty shape");
-  UV_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
   UV_REQUIRE(C1 % 8 == 0 && C2 % 8 == 0 && (ldy % 8 == 0 || Cout < 8), "conv3x3: channel counts and ldy must be multiples of 8");
   UV_REQUIRE(!X2 || C1 % kBK == 0, "conv3x3: with a second source, C1 must be a multiple of 64");
   UV_REQUIRE(stride == 1 || !X2, "conv3x3: stride 2 takes a single (parity-plane) source");
@@ -877,17 +880,29 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
   const int cbs2 = X2 ? (C2 + kBK - 1) / kBK : 0;
   p.kb_split = cbs1;
   p.cbs = cbs1 + cbs2;
-  p.num_kb = 9 * p.cbs;
+  p.num_kb = ntaps * p.cbs;
   p.HW = Ho * Wo;
   p.W = Wo;
   p.plane_stride = NB;
-  for (int ky = 0; ky < 3; ++ky)
+  if (kind == 3)
+    for (int t = 0; t < 3; ++t) {
+      p.tap_dy[t] = (int8_t)(t - 1);
+      p.tap_dx[t] = 0;
+      p.tap_plane[t] = 0;
+    }
+  for (int ky = 0; ky < 3 && kind != 3; ++ky)
     for (int kx = 0; kx < 3; ++kx) {
       const int t = ky * 3 + kx;
       if (stride == 1) {
         p.tap_dy[t] = (int8_t)(ky - 1);
         p.tap_dx[t] = (int8_t)(kx - 1);
         p.tap_plane[t] = 0;
+      } else if (kind == 2) {
+        // input row 2*oy + ky: ky=0 -> even row of pair oy; ky=1 -> odd row of pair oy; ky=2 -> even row of pair oy+1
+        const int hp = (ky == 1) ? 1 : 0, wp = (kx == 1) ? 1 : 0;
+        p.tap_dy[t] = (int8_t)(ky == 2 ? 1 : 0);
+        p.tap_dx[t] = (int8_t)(kx == 2 ? 1 : 0);
+        p.tap_plane[t] = (int8_t)(hp * 2 + wp);
       } else {
         // input row 2*oy + ky - 1: ky=0 -> odd row of pair oy-1; ky=1 -> even row of pair oy; ky=2 -> odd row of pair oy
         const int hp = (ky == 1) ? 0 : 1, wp = (kx == 1) ? 0 : 1;
@@ -946,11 +961,29 @@ extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int
   }
   {
     p.cluster = pow2 ? pick_cluster(p.M, p.BN) : 1;
-    uint64_t dims[2] = {(uint64_t)9 * Cin, (uint64_t)Cout};
-    uint64_t str[1] = {(uint64_t)9 * Cin * 2};
+    uint64_t dims[2] = {(uint64_t)ntaps * Cin, (uint64_t)Cout};
+    uint64_t str[1] = {(uint64_t)ntaps * Cin * 2};
     uint32_t box[2] = {kBK, (uint32_t)(p.BN / p.cluster)};
     int r = make_tmap_f16(&tmB, Wt, 2, dims, str, box, true);
     if (r) return r;
   }
   return launch(tmA, tmA2, tmB, p, (cudaStream_t)stream);
+}
+
+extern "C" int univst_conv3x3_f16(const void* X, const void* X2, int32_t NB, int32_t H, int32_t W, int32_t C1,
+                                  int32_t C2, const void* Wt, int32_t Cout, int32_t stride, void* Y, int32_t ldy,
+                                  const univst_epilogue_t* ep, void* stream) {
+  UV_REQUIRE(stride == 1 || stride == 2, "conv3x3: stride must be 1 or 2");
+  return conv_taps(X, X2, NB, H, W, C1, C2, Wt, Cout, stride == 2 ? 1 : 0, Y, ldy, ep, stream);
+}
+
+extern "C" int univst_conv3x3_s2_pad_after_f16(const void* X, int32_t NB, int32_t H, int32_t W, int32_t C, const void* Wt,
+                                               int32_t Cout, void* Y, int32_t ldy, const univst_epilogue_t* ep,
+                                               void* stream) {
+  return conv_taps(X, nullptr, NB, H, W, C, 0, Wt, Cout, 2, Y, ldy, ep, stream);
+}
+
+extern "C" int univst_conv_temporal3_f16(const void* X, int32_t NB, int32_t F, int32_t HW, int32_t C, const void* Wt,
+                                         int32_t Cout, void* Y, int32_t ldy, const univst_epilogue_t* ep, void* stream) {
+  return conv_taps(X, nullptr, NB, F, HW, C, 0, Wt, Cout, 3, Y, ldy, ep, stream);
 }

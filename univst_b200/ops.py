@@ -45,6 +45,12 @@ _lib.register("univst_ddim_step_f16", [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _
 _lib.register("univst_axpby_f16", [_vp, _vp, _f32, _f32, _i64, _vp, _vp])
 _lib.register("univst_halo_push_f16", [_vp, _i32, _i64, C.POINTER(_vp), _i32, _i32, _i64, _i32, _i32, _i32, _vp])
 _lib.register("univst_exchange_push_f16", [_i32, _vp, _i32, C.POINTER(_vp), _i32, _i32, _i32, _i32, _i32, _i32, _vp])
+_lib.register("univst_conv3x3_s2_pad_after_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, C.POINTER(Epilogue), _vp])
+_lib.register("univst_conv_temporal3_f16", [_vp, _i32, _i32, _i32, _i32, _vp, _i32, _vp, _i32, C.POINTER(Epilogue), _vp])
+_lib.register("univst_softmax_rows_f16", [_vp, _i32, _i32, _i32, _f32, _vp])
+_lib.register("univst_frames_to_u8", [_vp, _i32, _i64, _vp, _vp])
+_lib.register("univst_u8_to_frames_f16", [_vp, _i64, _i32, _vp, _vp])
+_lib.register("univst_vae_sample_f16", [_vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp, _vp])
 _lib.register("univst_gemm_set_workspace", [_vp, _i64, _vp])
 _lib.register("univst_gemm_tune", [_i32])
 _lib.register("univst_xrank_ctl_bytes", [], _i64)
@@ -75,6 +81,7 @@ _LAUNCHES = {
     "temporal_attention": 1, "cross_attention": 1, "joint_attention": 1, "rmsnorm_heads": 1, "sd3_attn_shift": 4, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "exchange_push": 1, "halo_push": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
     "xrank_barrier": 1, "xrank_push": 1, "groupnorm_xrank": 3, "set_floats": 1,
+    "conv3x3_s2_pad_after": 1, "conv_temporal3": 1, "softmax_rows": 1, "frames_to_u8": 1, "u8_to_frames": 1, "vae_sample": 1,
 }
 
 
@@ -221,6 +228,89 @@ def conv3x3(x: torch.Tensor, w: torch.Tensor, *, x2: Optional[torch.Tensor] = No
         check(_lib.lib().univst_conv3x3_f16(x.data_ptr(), _ptr(x2), NB, H, W, C1, C2, w.data_ptr(), Cout, stride,
                                             out.data_ptr(), out.stride(0), C.byref(ep), _stream()), "univst_conv3x3_f16")
     _count("conv3x3")
+    return out
+
+
+def conv3x3_s2_pad_after(planes: torch.Tensor, w: torch.Tensor, *, bias=None, out: Optional[torch.Tensor] = None):
+    """3x3 conv, stride 2, zero row / column AFTER the image (diffusers ``Downsample2D(padding=0)``: F.pad (0, 1, 0, 1) then
+    a stride-2 conv).  ``planes``: [4, NB, H/2, W/2, C] from :func:`space_to_depth2`; ``w``: [Cout, 9 C] tap-major."""
+    _lib.require_device()
+    _chk(planes, "planes")
+    _, NB, H, W, C1 = planes.shape
+    Cout = w.shape[0]
+    assert w.is_contiguous() and w.numel() == Cout * 9 * C1
+    if out is None:
+        out = torch.empty((NB * H * W, Cout), dtype=torch.float16, device=planes.device)
+    ep = make_epilogue(bias)
+    _splitk_ready(planes.device)
+    check(_lib.lib().univst_conv3x3_s2_pad_after_f16(planes.data_ptr(), NB, H, W, C1, w.data_ptr(), Cout, out.data_ptr(),
+                                                     out.stride(0), C.byref(ep), _stream()), "univst_conv3x3_s2_pad_after_f16")
+    _count("conv3x3_s2_pad_after")
+    return out
+
+
+def conv_temporal3(x: torch.Tensor, w: torch.Tensor, *, NB: int, F: int, HW: int, bias=None, residual=None,
+                   out: Optional[torch.Tensor] = None):
+    """(3, 1, 1) temporal convolution over the frames of every pixel.  ``x``: [NB * F * HW, C] rows (clip, frame, pixel);
+    ``w``: [Cout, 3 C] (tap t = frame offset t - 1); zero frames beyond the ends of a clip."""
+    _lib.require_device()
+    _chk(x, "x")
+    C1 = x.shape[1]
+    Cout = w.shape[0]
+    assert x.shape[0] == NB * F * HW and w.is_contiguous() and w.numel() == Cout * 3 * C1
+    if out is None:
+        out = torch.empty((NB * F * HW, Cout), dtype=torch.float16, device=x.device)
+    ep = make_epilogue(bias, residual=residual)
+    _splitk_ready(x.device)
+    check(_lib.lib().univst_conv_temporal3_f16(x.data_ptr(), NB, F, HW, C1, w.data_ptr(), Cout, out.data_ptr(), out.stride(0),
+                                               C.byref(ep), _stream()), "univst_conv_temporal3_f16")
+    _count("conv_temporal3")
+    return out
+
+
+def softmax_rows_(x: torch.Tensor, scale: float = 1.0):
+    """In-place softmax(scale * x) over the last dimension of a 2-D fp16 tensor (row stride arbitrary)."""
+    _lib.require_device()
+    assert x.dtype == torch.float16 and x.is_cuda and x.dim() == 2 and x.stride(1) == 1
+    check(_lib.lib().univst_softmax_rows_f16(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(scale), _stream()),
+          "univst_softmax_rows_f16")
+    _count("softmax_rows")
+    return x
+
+
+def frames_to_u8(x: torch.Tensor, pixels: int):
+    """Decoder output rows [pixels, ld >= 3] fp16 -> uint8 [pixels, 3] (stable_diffusion.py:812-814)."""
+    _lib.require_device()
+    assert x.dtype == torch.float16 and x.is_cuda and x.stride(1) == 1 and x.shape[0] >= pixels
+    out = torch.empty((pixels, 3), dtype=torch.uint8, device=x.device)
+    check(_lib.lib().univst_frames_to_u8(x.data_ptr(), x.stride(0), pixels, out.data_ptr(), _stream()), "univst_frames_to_u8")
+    _count("frames_to_u8")
+    return out
+
+
+def u8_to_frames(img: torch.Tensor, cpad: int = 64):
+    """uint8 [pixels, 3] -> fp16 [pixels, cpad] = image / 127.5 - 1 in channels 0..2, zeros beyond (:826-827)."""
+    _lib.require_device()
+    _chk(img, "img", torch.uint8)
+    pixels = img.numel() // 3
+    out = torch.empty((pixels, cpad), dtype=torch.float16, device=img.device)
+    check(_lib.lib().univst_u8_to_frames_f16(img.data_ptr(), pixels, cpad, out.data_ptr(), _stream()), "univst_u8_to_frames_f16")
+    _count("u8_to_frames")
+    return out
+
+
+def vae_sample(moments: torch.Tensor, noise: Optional[torch.Tensor], C_: int, F: int, HW: int, scaling: float):
+    """[mean | logvar] rows [(f) hw, ld] -> (1, C, F, hw) latents: (mean + std * noise) * scaling (``noise`` (F, C, hw) fp16;
+    None = the posterior mode)."""
+    _lib.require_device()
+    assert moments.dtype == torch.float16 and moments.is_cuda and moments.stride(1) == 1 and moments.shape[0] == F * HW
+    if noise is not None:
+        _chk(noise, "noise")
+        assert noise.numel() == F * C_ * HW
+    out = torch.empty((1, C_, F, HW), dtype=torch.float16, device=moments.device)
+    check(_lib.lib().univst_vae_sample_f16(moments.data_ptr(), moments.stride(0), _ptr(noise), C_, F, HW, float(scaling),
+                                           out.data_ptr(), _stream()), "univst_vae_sample_f16")
+    _count("vae_sample")
     return out
 
 

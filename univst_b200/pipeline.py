@@ -71,7 +71,7 @@ class SpatioTemporalStableDiffusionPipeline:
     def video_style_transfer(self, prompt: Union[str, List[str]], num_inference_steps: int = 50, latents=None,
                              content_inv_path=None, style_inv_path=None, mask_path=None, prompt_embeds=None,
                              output_type="tensor", skip_dead_branches: bool = True, callback=None,
-                             inv_prompt_embeds=None, **kwargs):
+                             inv_prompt_embeds=None, smoother=None, flow_fn=None, smoother_generator=None, **kwargs):
         """stable_diffusion.py:631-780.  ``content_inv_path`` / ``style_inv_path``: directory with the inversion's
         ``ddim_latents_{k}.pt`` files (reference format) or an in-memory list [x_0 .. x_n]; ``mask_path``: directory
         of ``%05d.png`` masks or a (F, H, W) tensor (non-zero = keep content).  ``prompt_embeds`` /
@@ -79,7 +79,15 @@ class SpatioTemporalStableDiffusionPipeline:
         conditioned on (:659-668); the latter defaults to ``prompt_embeds`` only when ``prompt`` itself is empty.
         ``skip_dead_branches`` (default on; exact): the content / style branches are evaluated only
         where they can still influence the edit branch -- not at all once the shift window is closed, and up to the
-        last patched attn1 projection while it is open.  The edit latents are bit-identical to the full evaluation."""
+        last patched attn1 projection while it is open.  The edit latents are bit-identical to the full evaluation.
+        ``smoother="pixel"`` switches the sliding-window smoother of :713-758 on (the reference hard-codes
+        ``smoother = None``, :715): on steps 20..24 the predicted x0 is decoded to uint8 frames (``self.vae``), every key
+        frame is replaced in place by the mean of itself and its +-2 flow-warped neighbours, pixels inside the mask keep
+        their value, the frames are re-encoded and the noise prediction is recomputed from the stabilised x0
+        (``return_to_timestep``, :782-791).  ``flow_fn(key_frame, now_frame) -> (fwd, bwd)`` supplies the optical flows
+        ([H, W, 2] fp32 CUDA; the reference asks torchvision's RAFT-large, whose weights are not available offline);
+        ``smoother_generator`` seeds the posterior sample of the re-encoding (default: a fixed seed, so that the ranks of a
+        frame-sharded run, which all evaluate the smoother on the whole clip, stay in lockstep)."""
         n = num_inference_steps
         emb = self._encode_prompt(prompt, prompt_embeds)
         if inv_prompt_embeds is None and prompt_embeds is not None and prompt not in ("", [""]) \
@@ -95,6 +103,18 @@ class SpatioTemporalStableDiffusionPipeline:
         _, C, F, h, w = z.shape
         zc_traj, zs_traj = self._trajectory(content_inv_path, n), self._trajectory(style_inv_path, n)
         m = self._mask(mask_path, F, h, w)
+        keep_u8 = None
+        if smoother is not None:
+            if smoother != "pixel":
+                raise ValueError("smoother must be None or 'pixel' (stable_diffusion.py:719,755)")
+            if self.vae is None or flow_fn is None:
+                raise ValueError("the pixel smoother needs a VAE (univst_b200.vae) and flow_fn(key_frame, now_frame)")
+            if mask_path is None or (isinstance(mask_path, str) and not mask_path):
+                raise ValueError("the pixel smoother needs the mask (stable_diffusion.py:751 reads it unconditionally)")
+            mm = load_mask(mask_path, n_frames=F) if isinstance(mask_path, str) else mask_path
+            keep_u8 = (mm.reshape(-1, mm.shape[-2], mm.shape[-1]) != 0).to(torch.uint8).to(self.device).contiguous()
+            if smoother_generator is None:
+                smoother_generator = torch.Generator(device=self.device).manual_seed(0)
         for i, t in enumerate(timesteps):
             zc, zs = zc_traj[self._traj_index(i, n)], zs_traj[self._traj_index(i, n)]
             if m is not None and i <= 0.9 * n:  # localized latent blending, :687-692
@@ -113,7 +133,18 @@ class SpatioTemporalStableDiffusionPipeline:
                 finally:
                     self.unet.truncate_dead_branches = False
             a_t, a_prev = self.scheduler.step_alphas(t)
-            z = ops.ddim_step(z, self.unet.last_eps_rows, self.unet.last_edit_branch, a_t, a_prev)  # :761, eta = 0
+            if smoother is not None and 20 <= i < 25:   # sliding-window smoothing, :716-758
+                from .flow_warp import sliding_window_smooth
+                x0 = torch.empty_like(z)
+                ops.ddim_step(z, self.unet.last_eps_rows, self.unet.last_edit_branch, a_t, a_prev, x0_out=x0)   # :718
+                frames = self.vae.decode_latents_u8(x0)                                                          # :721
+                est = sliding_window_smooth(frames, keep_mask=keep_u8, flow_fn=flow_fn)                          # :725-751
+                x0s = self.vae.encode_frames_u8(est, generator=smoother_generator)                               # :753
+                eps = ops.axpby(z, x0s, 1.0 / (1.0 - a_t) ** 0.5, -(a_t ** 0.5) / (1.0 - a_t) ** 0.5)           # :782-791
+                x0r = ops.axpby(z, eps, 1.0 / a_t ** 0.5, -((1.0 - a_t) ** 0.5) / a_t ** 0.5)                  # the step's own x0
+                z = ops.axpby(x0r, eps, a_prev ** 0.5, (1.0 - a_prev) ** 0.5)                                    # :761
+            else:
+                z = ops.ddim_step(z, self.unet.last_eps_rows, self.unet.last_edit_branch, a_t, a_prev)  # :761, eta = 0
             if callback is not None:
                 callback(i, t, z)
         images = self.decode_latents(z) if self.vae is not None else None
@@ -135,9 +166,15 @@ class SpatioTemporalStableDiffusionPipeline:
         images = self.decode_latents(z) if self.vae is not None else None
         return SimpleNamespace(images=images, latents=z)
 
-    def decode_latents(self, latents):
-        """stable_diffusion.py:369-394 -- third-party VAE (SVD temporal decoder); runs only when one was supplied."""
+    def decode_latents(self, latents, decode_chunk_size: int = 16):
+        """stable_diffusion.py:369-394: 1 / 0.18215, decode ``decode_chunk_size`` frames at a time (the temporal decoder sees
+        each chunk as one clip), (x / 2 + 0.5).clamp(0, 1) -> (b, f, H, W, 3) float32 on the host.  ``self.vae``:
+        ``univst_b200.vae.AutoencoderKLTemporalDecoder`` or any object with diffusers' ``decode(z, num_frames=)``."""
         lat = (1 / 0.18215 * latents).permute(0, 2, 1, 3, 4).flatten(0, 1)
-        video = self.vae.decode(lat.to(self.vae.dtype), num_frames=lat.shape[0]).sample
+        chunks = []
+        for k in range(0, lat.shape[0], decode_chunk_size):
+            part = lat[k:k + decode_chunk_size].to(self.vae.dtype)
+            chunks.append(self.vae.decode(part, num_frames=part.shape[0]).sample)
+        video = torch.cat(chunks, dim=0)
         video = video.view(latents.shape[0], -1, *video.shape[1:]).permute(0, 1, 3, 4, 2)
         return ((video / 2 + 0.5).clamp(0, 1)).float().cpu()
