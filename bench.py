@@ -97,9 +97,9 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def synthetic_clip(seed_offset: int = 0):
+def synthetic_clip(seed_offset: int = 0, F_FRAMES: int = F_FRAMES, ctx_dim: int = 768):
     """content / style inversion trajectories x_k = sqrt(a_k) x_0 + sqrt(1 - a_k) eps held in
-    memory, a moving-disc mask, a fixed (77, 768) context.  Returned on the host (pinned when CUDA is present)."""
+    memory, a moving-disc mask, a fixed (77, ctx_dim) context.  Returned on the host (pinned when CUDA is present)."""
     from univst_b200.scheduler import DDIMScheduler
     sch = DDIMScheduler.sd15()
     sch.set_timesteps(STEPS_DDIM)
@@ -116,7 +116,7 @@ def synthetic_clip(seed_offset: int = 0):
         traj_s.append(a ** 0.5 * z0_s + (1 - a) ** 0.5 * eps)
     yy, xx = torch.meshgrid(torch.arange(512), torch.arange(512), indexing="ij")
     mask = torch.stack([(((xx - (256 + 6 * f)) ** 2 + (yy - 256) ** 2) <= 128 ** 2) for f in range(F_FRAMES)]).to(torch.uint8) * 255
-    ctx = torch.randn(1, 77, 768, generator=g(7))
+    ctx = torch.randn(1, 77, ctx_dim, generator=g(7))
     pin = (lambda t: t.pin_memory()) if torch.cuda.is_available() else (lambda t: t)
     return {"traj_c": [pin(t.half()) for t in traj_c], "traj_s": [pin(t.half()) for t in traj_s], "mask": pin(mask),
             "ctx": pin(ctx.half())}
@@ -257,6 +257,70 @@ def dominant_attention(prof, pk, clocks_mhz):
                       f"Nkv={Nkv}, H={H}, d={d}, {NI} images)",
             "flop_per_launch": flops, "launches_timed": len(dom), "avg_ms": avg_ms,
             "peak_source": pk["src"] + " (sustained bf16 dense)"}
+
+
+# ------------------------------------------------------------------------------------------------ BASELINE configs[2]
+def run_sd21_smoother(dev, world, rank, args, timed, rel):
+    """BASELINE.json configs[2]: SD-2.1 shapes (head dim 64, 1024-wide context, Linear proj_in / proj_out), 32 frames of
+    512 x 512 sharded over the ranks, sliding-window flow smoothing on (steps 20..24, stable_diffusion.py:713-758): predicted
+    x0 -> temporal VAE decode -> +-2-frame window of flow-warped neighbours -> mask -> VAE encode -> noise recomputed.
+    The UNet is frame-sharded; the smoother legs (VAE + warp pass) are evaluated on the whole clip by every rank (the
+    temporal decoder couples all frames of a 16-frame chunk and the window pass is sequential in the key frame, :731-747).
+    Flows: synthetic (2.5, -1.25) px translation + sinusoidal field (RAFT's weights are not available offline); VAE: SVD VAE
+    shapes with seeded random weights (parity unpinned, univst_b200/vae.py).  Checked against the 1-GPU run of the same clip."""
+    import numpy as np
+    from univst_b200 import ops, pnp_utils
+    from univst_b200.pipeline import SpatioTemporalStableDiffusionPipeline
+    from univst_b200.unet import SD21_CONFIG, UNetPseudo3DConditionModel
+    from univst_b200.vae import AutoencoderKLTemporalDecoder, random_state_dict as vae_state_dict
+    from univst_b200.weights import random_state_dict
+    Fr = 32
+    unet = UNetPseudo3DConditionModel(random_state_dict(SD21_CONFIG, seed=35, device=dev), SD21_CONFIG, device=dev)
+    vae = AutoencoderKLTemporalDecoder(vae_state_dict(seed=55, device=dev), device=dev)
+    pipe = SpatioTemporalStableDiffusionPipeline(unet, vae=vae)
+    pnp_utils.register_spatial_attention_pnp(pipe)
+    c = synthetic_clip(0, F_FRAMES=Fr, ctx_dim=1024)
+    c = {k: ([t.to(dev) for t in v] if isinstance(v, list) else v.to(dev)) for k, v in c.items()}
+    yy, xx = np.mgrid[0:512, 0:512].astype(np.float32)
+    fwd = torch.from_numpy(np.stack([2.5 + 1.5 * np.sin(yy / 37.0), -1.25 + 1.5 * np.cos(xx / 29.0)], -1).astype(np.float32)).to(dev)
+    bwd = (-fwd).clone()
+    bwd[200:232, 300:332] += 4.0          # a patch that violates forward / backward consistency -> occluded
+    flow_fn = lambda key_frame, now_frame: (fwd, bwd)
+
+    def stylize(smoother="pixel"):
+        z_T = ops.latent_adain(c["traj_c"][STEPS_DDIM], c["traj_s"][STEPS_DDIM])
+        return pipe.video_style_transfer("", num_inference_steps=STEPS_DDIM, latents=z_T, content_inv_path=c["traj_c"],
+                                         style_inv_path=c["traj_s"], mask_path=c["mask"], prompt_embeds=c["ctx"],
+                                         smoother=smoother, flow_fn=flow_fn).latents
+
+    stylize()
+    ref, ms_1 = timed(stylize)
+    _, ms_1_plain = timed(lambda: stylize(None))
+    res = {"workload": "SD-v2.1 shapes, 32x512x512, 50 steps, sliding-window flow smoothing on steps 20..24",
+           "one_gpu": {"ms_per_clip": ms_1, "frames_per_s": Fr / (ms_1 / 1e3), "ms_per_clip_without_smoother": ms_1_plain}}
+    if world > 1 and Fr % world == 0:
+        import torch.distributed as dist
+        ok = torch.ones(1, device=dev)
+        try:
+            unet.set_frame_sharding(transport="xrank")
+        except Exception:  # noqa: BLE001
+            ok.zero_()
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item() > 0):
+            unet.set_frame_sharding(transport="nccl", push_halo=False)
+        unet.use_cuda_graphs = bool(ok.item() > 0) and not args.no_cuda_graphs
+        stylize()
+        out, ms_n = timed(stylize, 2)
+        if unet._xr is not None:
+            unet._xr.check()
+        r = rel(out, ref)
+        res["frame_sharded"] = {"n_gpus": world, "frames_per_gpu": Fr // world, "ms_per_clip": ms_n / 2,
+                                "frames_per_s": Fr / (ms_n / 2e3), "speedup_vs_1gpu_same_box": ms_1 / (ms_n / 2),
+                                "rel_l2_vs_1gpu": r, "cuda_graphs": bool(unet.use_cuda_graphs),
+                                "note": "UNet frame-sharded; VAE + warp pass on the whole clip on every rank"}
+        assert r < 1e-2, f"configs[2]: frame-sharded result differs from one GPU: {res}"
+        unet.set_frame_sharding_off()
+    return res
 
 
 # ------------------------------------------------------------------------------------------------ our arm
@@ -441,6 +505,12 @@ def run_ours(args):
                 f"AnimateDiff frame-sharded result differs from one GPU: {ad['frame_sharded']}"
         extra["animatediff_v2_backbone"] = ad
 
+    # ---- extra: BASELINE.json configs[2] (SD-2.1 shapes, 32 frames, smoother on) at the world size it names (4 GPUs); one
+    # GPU with --config2
+    if (world == 4 and not args.no_extras) or args.config2:
+        torch.cuda.empty_cache()
+        extra["sd21_32_frames_flow_smoothing"] = run_sd21_smoother(dev, world, rank, args, timed, rel)
+
     # dominant-kernel time: max over ranks (rank 0 holds the clip's first frames, whose [previous, first] sources collapse
     # to one deduplicated source -- half the keys -- so its launches are not representative)
     roof_local = dominant_attention(prof, peaks(), None)
@@ -516,6 +586,7 @@ def main():
     ap.add_argument("--no-extras", action="store_true", help="skip the supplementary passes (inversion, AnimateDiff, torch eager)")
     ap.add_argument("--no-animatediff", dest="no_extras", action="store_true")
     ap.add_argument("--no-cuda-graphs", action="store_true")
+    ap.add_argument("--config2", action="store_true", help="also run BASELINE configs[2] (SD-2.1, 32 frames, smoother) at this N")
     args = ap.parse_args()
     # stdout carries exactly ONE line, the JSON: libraries that write banners to fd 1 from C (NCCL prints its version there
     # under torchrun) are sent to stderr, and the line itself goes to a duplicate of the original descriptor

@@ -7,8 +7,7 @@
 //                 concat of two tensors (unet_3d_blocks.py:523,618) -- the concat only ever exists as this
 //                 kernel's normalised output.
 //   LayerNorm   : per token over C (attention.py:290,312,329).
-#include "host_util.h"
-#include "ptx.cuh"
+#include "xrank.cuh"
 
 namespace uv {
 
@@ -26,9 +25,18 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, const __half* x
 // the v-th 8-channel vector of rows rl, rl + rows_par, ... of its row range -- a warp reads whole contiguous rows, the
 // per-channel constants of a thread never change, and kGnUnroll independent 16-byte loads are in flight per thread.
 
-// grid (nchunks, NB).  partial[b][chunk][group][2] = (sum, sumsq)
+// arrival counters of the statistics kernels (zero at module load, re-armed by the last block of every launch); the host
+// hands consecutive launches different slots
+__device__ unsigned g_gn_arrivals[64];
+
+// grid (nchunks, NB).  partial[b][chunk][group][2] = (sum, sumsq); the LAST block to finish folds the chunk partials of every
+// batch entry into sums[b][group][2] in a fixed order (deterministic, no float atomics) -- and, when the statistics span
+// the rows of other ranks (world > 1: frame-sharded resnet.py:338,369), exchanges them through the ranks' control blocks
+// (xrank.cuh) and adds the ranks' sums in rank order: one kernel where there used to be a statistics, a fold and a
+// collective launch.
 __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __restrict__ x2, int C1, int C2, int rows,
-                                int groups, int nvec, int rows_par, int rows_per_chunk, float* __restrict__ partial) {
+                                int groups, int nvec, int rows_par, int rows_per_chunk, float* __restrict__ partial,
+                                float* __restrict__ sums, unsigned* __restrict__ arrivals, XrankPeers P, int rank, int world) {
   extern __shared__ float sh[];  // [threads][8] per-thread pair sums, then [groups][2]
   const int b = blockIdx.y, chunk = blockIdx.x;
   const int C = C1 + C2, cpg = C / groups;
@@ -78,32 +86,60 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __r
     out[g * 2] = gs;
     out[g * 2 + 1] = gq;
   }
-}
-
-// sums[b][g][2] = sum over the chunk partials in a fixed order: 16 interleaved partial sums per entry, combined by a
-// fixed tree.  grid NB, block 16 * 64.
-__global__ void gn_fold_kernel(const float* __restrict__ partial, int nchunks, int groups, float* __restrict__ sums) {
-  __shared__ float sh[16][64];
-  const int b = blockIdx.x;
-  const int part = threadIdx.x >> 6, t = threadIdx.x & 63;
-  for (int i0 = 0; i0 < groups * 2; i0 += 64) {
-    const int i = i0 + t;
-    float acc = 0.0f;
-    if (i < groups * 2)
-      for (int c = part; c < nchunks; c += 16) acc += partial[((size_t)b * nchunks + c) * groups * 2 + i];
-    sh[part][t] = acc;
-    __syncthreads();
-    if (part == 0 && i < groups * 2) {
-      float v[16];
-#pragma unroll
-      for (int k = 0; k < 16; ++k) v[k] = sh[k][t];
-#pragma unroll
-      for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-        for (int k = 0; k < w; ++k) v[k] += v[k + w];
-      sums[(size_t)b * groups * 2 + i] = v[0];
+  // ---- last block: fold (and exchange)
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(arrivals, 1u);
+    s_last = (t == gridDim.x * gridDim.y - 1);
+    if (s_last) *reinterpret_cast<volatile unsigned*>(arrivals) = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int NB = gridDim.y, nchunks = gridDim.x, G2 = groups * 2;
+  const int parts = blockDim.x >> 6;                 // blockDim >= 128: at least two interleaved partial sums per entry
+  const int part = threadIdx.x >> 6, tt = threadIdx.x & 63;
+  float* fold = sh;                                   // [parts][64]
+  __shared__ float local[kXrankSlotFloats];
+  for (int bb = 0; bb < NB; ++bb)
+    for (int i0 = 0; i0 < G2; i0 += 64) {
+      const int i = i0 + tt;
+      float acc = 0.0f;
+      if (part < parts && i < G2)
+        for (int c = part; c < nchunks; c += parts) acc += __ldcg(partial + ((size_t)bb * nchunks + c) * G2 + i);
+      if (part < parts) fold[part * 64 + tt] = acc;
+      __syncthreads();
+      if (part == 0 && i < G2) {
+        float v = fold[tt];
+        for (int k = 1; k < parts; ++k) v += fold[k * 64 + tt];
+        if (world > 1)
+          local[bb * G2 + i] = v;
+        else
+          sums[(size_t)bb * G2 + i] = v;
+      }
+      __syncthreads();
     }
-    __syncthreads();
+  if (world <= 1) return;
+  uint32_t* ctl = P.ctl[rank];
+  const uint32_t par = (*reinterpret_cast<volatile uint32_t*>(ctl + kXrEpoch) + 1) & 1u;
+  const int n = NB * G2;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = local[i];
+    for (int r = 0; r < world; ++r)
+      reinterpret_cast<float*>(P.ctl[r] + kXrSlots)[((size_t)par * kXrankMaxRanks + rank) * kXrankSlotFloats + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < 32) xrank_sync_warp(P, rank, world);
+  __syncthreads();
+  const float* slots = reinterpret_cast<const float*>(ctl + kXrSlots) + (size_t)par * kXrankMaxRanks * kXrankSlotFloats;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float acc = 0.0f;
+    for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * kXrankSlotFloats + i);
+    sums[i] = acc;
   }
 }
 
@@ -246,12 +282,19 @@ static GnPlan gn_plan(int C, int rows) {
 }
 
 static int gn_launch_stats(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, float* sums,
-                           void* workspace, cudaStream_t st) {
+                           void* workspace, cudaStream_t st, const XrankPeers* peers = nullptr, int rank = 0, int world = 0) {
   const GnPlan g = gn_plan(C1 + C2, rows);
+  UV_REQUIRE(g.threads >= 128, "groupnorm: at least 128 threads per block (channels %% 8, rows_par) -- internal plan error");
+  UV_REQUIRE(world <= 1 || NB * groups * 2 <= kXrankSlotFloats, "groupnorm: NB * groups * 2 exceeds the exchange slot (%d floats)",
+             kXrankSlotFloats);
+  static unsigned next_slot = 0;
+  static unsigned* arrivals = nullptr;
+  if (!arrivals) UV_CHECK_CUDA(cudaGetSymbolAddress((void**)&arrivals, g_gn_arrivals));
+  const unsigned slot = (next_slot++) & 63u;
+  XrankPeers none{};
   gn_stats_kernel<<<dim3(g.nchunks, NB), g.threads, g.threads * 8 * sizeof(float), st>>>(
-      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace);
-  UV_CHECK_CUDA(cudaGetLastError());
-  gn_fold_kernel<<<NB, 1024, 0, st>>>((const float*)workspace, g.nchunks, groups, sums);
+      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace, sums,
+      arrivals + slot, peers ? *peers : none, rank, world);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }
@@ -267,16 +310,10 @@ static int gn_launch_apply(const void* X1, const void* X2, int C1, int C2, int N
   return UNIVST_OK;
 }
 
-// entry points for the cross-rank form (xrank.cu): chunk partials only / apply only / shape check / folded-sum location
-int gn_stats_partials(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, void* workspace,
-                      int* nchunks, int* nchunks_stride, cudaStream_t st) {
-  const GnPlan g = gn_plan(C1 + C2, rows);
-  gn_stats_kernel<<<dim3(g.nchunks, NB), g.threads, g.threads * 8 * sizeof(float), st>>>(
-      (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace);
-  UV_CHECK_CUDA(cudaGetLastError());
-  *nchunks = g.nchunks;
-  *nchunks_stride = g.nchunks;
-  return UNIVST_OK;
+// entry points for the cross-rank form (xrank.cu): statistics + exchange / apply only / shape check / folded-sum location
+int gn_stats_xrank(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, float* sums, void* workspace,
+                   const XrankPeers& peers, int rank, int world, cudaStream_t st) {
+  return gn_launch_stats(X1, X2, C1, C2, NB, rows, groups, sums, workspace, st, &peers, rank, world);
 }
 int gn_apply_launch(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, const float* sums,
                     int64_t stat_rows, const void* gamma, const void* beta, float eps, int silu, void* Y, cudaStream_t st) {

@@ -71,57 +71,6 @@ __global__ void xrank_push_kernel(PushArgs a, XrankPeers P, int rank, int world)
   xrank_kernel_tail(P, rank, world);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// GroupNorm statistics over the rows of ALL ranks (resnet.py:338,369: the reference's statistics span all frames of a
-// branch): fold the chunk partials of this rank (as gn_fold_kernel), store the NB x groups x 2 sums into slot [rank] of
-// every rank, synchronise, add the P slots in rank order -- the same numbers in the same order on every rank, so the
-// ranks normalise with bit-identical statistics.  One block of 1024 threads.
-__global__ void gn_fold_xrank_kernel(const float* __restrict__ partial, int nchunks, int nchunks_stride, int NB, int groups,
-                                     float* __restrict__ sums, XrankPeers P, int rank, int world) {
-  __shared__ float sh[16][64];
-  __shared__ float local[kXrankSlotFloats];
-  uint32_t* mine = P.ctl[rank];
-  const uint32_t par = (*reinterpret_cast<volatile uint32_t*>(mine + kXrEpoch) + 1) & 1u;
-  const int part = threadIdx.x >> 6, t = threadIdx.x & 63;
-  const int G2 = groups * 2;
-  for (int b = 0; b < NB; ++b)
-    for (int i0 = 0; i0 < G2; i0 += 64) {
-      const int i = i0 + t;
-      float acc = 0.0f;
-      if (i < G2)
-        for (int c = part; c < nchunks; c += 16) acc += partial[((size_t)b * nchunks_stride + c) * G2 + i];
-      sh[part][t] = acc;
-      __syncthreads();
-      if (part == 0 && i < G2) {
-        float v[16];
-#pragma unroll
-        for (int k = 0; k < 16; ++k) v[k] = sh[k][t];
-#pragma unroll
-        for (int w = 8; w > 0; w >>= 1)
-#pragma unroll
-          for (int k = 0; k < w; ++k) v[k] += v[k + w];
-        local[b * G2 + i] = v[0];
-      }
-      __syncthreads();
-    }
-  const int n = NB * G2;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = local[i];
-    for (int r = 0; r < world; ++r)
-      reinterpret_cast<float*>(P.ctl[r] + kXrSlots)[((size_t)par * kXrankMaxRanks + rank) * kXrankSlotFloats + i] = v;
-  }
-  __threadfence_system();
-  __syncthreads();
-  if (threadIdx.x < 32) xrank_sync_warp(P, rank, world);
-  __syncthreads();
-  const float* slots = reinterpret_cast<const float*>(mine + kXrSlots) + (size_t)par * kXrankMaxRanks * kXrankSlotFloats;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    float acc = 0.0f;
-    for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * kXrankSlotFloats + i);
-    sums[i] = acc;
-  }
-}
-
 }  // namespace uv
 
 using namespace uv;
@@ -183,8 +132,8 @@ extern "C" int univst_xrank_push_f16(const univst_push_t* pushes, int32_t npush,
 
 namespace uv {
 // norm.cu
-int gn_stats_partials(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, void* workspace,
-                      int* nchunks, int* nchunks_stride, cudaStream_t st);
+int gn_stats_xrank(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, float* sums, void* workspace,
+                   const XrankPeers& peers, int rank, int world, cudaStream_t st);
 int gn_apply_launch(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, const float* sums,
                     int64_t stat_rows, const void* gamma, const void* beta, float eps, int silu, void* Y, cudaStream_t st);
 int gn_check_shape(const void* X1, const void* X2, int32_t& C1, int32_t& C2, int32_t NB, int32_t rows, int32_t groups);
@@ -201,14 +150,10 @@ extern "C" int univst_groupnorm_xrank_f16(const void* X1, const void* X2, int32_
   if (r) return r;
   r = gn_check_shape(X1, X2, C1, C2, NB, rows, groups);
   if (r) return r;
-  UV_REQUIRE(NB * groups * 2 <= kXrankSlotFloats, "groupnorm_xrank: NB * groups * 2 exceeds the exchange slot (%d floats)",
-             kXrankSlotFloats);
   cudaStream_t st = (cudaStream_t)stream;
-  int nchunks = 0, stride = 0;
-  r = gn_stats_partials(X1, X2, C1, C2, NB, rows, groups, workspace, &nchunks, &stride, st);
-  if (r) return r;
   float* sums = gn_sums_of(workspace, NB, groups);
-  gn_fold_xrank_kernel<<<1, 1024, 0, st>>>((const float*)workspace, nchunks, stride, NB, groups, sums, P, rank, world);
-  UV_CHECK_CUDA(cudaGetLastError());
+  // statistics -> (last block) fold + store into every rank's slot + synchronise + add the slots in rank order
+  r = gn_stats_xrank(X1, X2, C1, C2, NB, rows, groups, sums, workspace, P, rank, world, st);
+  if (r) return r;
   return gn_apply_launch(X1, X2, C1, C2, NB, rows, groups, sums, (int64_t)rows * world, gamma, beta, eps, silu, Y, st);
 }

@@ -227,15 +227,20 @@ class AutoencoderKLTemporalDecoder:
         return SimpleNamespace(sample=out)
 
     @torch.no_grad()
-    def decode_latents_u8(self, latents):
+    def decode_latents_u8(self, latents, decode_chunk_size: int = 16):
         """latents (1, C, F, h, w) (scaled) -> uint8 frames (F, H, W, 3): ``get_images_from_latents`` (stable_diffusion.py:
-        793-819) in one call -- 1 / scaling, decode, (x / 2 + 0.5).clamp(0, 1), round(255 x)."""
+        793-819) in one call -- 1 / scaling, decode ``decode_chunk_size`` frames at a time (each chunk is one clip to the
+        temporal layers, :803-811), (x / 2 + 0.5).clamp(0, 1), round(255 x)."""
         _, C, F_, h, w = latents.shape
-        z = ops.axpby(latents.to(self.device, torch.float16).contiguous(), latents.to(self.device, torch.float16).contiguous(),
-                      1.0 / self.config.scaling_factor, 0.0)
-        rows = ops.pack_latents([z[0]], Cpad=CPAD).view(F_ * h * w, CPAD)
-        px, H, Wd = self._decode_rows(rows, 1, F_, h, w)
-        return ops.frames_to_u8(px, F_ * H * Wd).view(F_, H, Wd, 3)
+        lat = latents.to(self.device, torch.float16).contiguous()
+        z = ops.axpby(lat, lat, 1.0 / self.config.scaling_factor, 0.0)
+        outs = []
+        for k in range(0, F_, decode_chunk_size):
+            n = min(decode_chunk_size, F_ - k)
+            rows = ops.pack_latents([z[0, :, k:k + n].contiguous()], Cpad=CPAD).view(n * h * w, CPAD)
+            px, H, Wd = self._decode_rows(rows, 1, n, h, w)
+            outs.append(ops.frames_to_u8(px, n * H * Wd).view(n, H, Wd, 3))
+        return outs[0] if len(outs) == 1 else torch.cat(outs, 0)
 
 
 def random_state_dict(cfg=None, seed: int = 55, device="cuda"):
