@@ -406,6 +406,7 @@ def run_ours(args):
     assert torch.isfinite(out).all(), "non-finite latents"
 
     # ---- timed region 1: inputs resident in HBM
+    xr_before = unet._xr.wait_stats() if unet._xr is not None else None
     n0 = ops.launch_count
     profiling = not unet.use_cuda_graphs     # per-kernel CUDA events cannot be recorded inside a replayed graph
     if profiling:
@@ -414,6 +415,10 @@ def run_ours(args):
         out, ms = timed(lambda: stylize(resident), args.steps)
     prof = ops.profile_stop() if profiling else {}
     launches = ops.launch_count - n0
+    if xr_before is not None:   # device-side counters of the control block: how long this rank sat in cross-rank waits
+        xr_after = unet._xr.wait_stats()
+        fs["cross_rank_syncs_per_clip"] = (xr_after[0] - xr_before[0]) // args.steps
+        fs["cross_rank_wait_ms_per_clip_rank0"] = (xr_after[1] - xr_before[1]) / args.steps
 
     # ---- timed region 2: end to end through the public call with host buffers
     host_out, ms_e2e = timed(lambda: stylize(to_dev()).cpu(), args.steps)

@@ -47,7 +47,8 @@ typedef struct univst_epilogue {
   const void* rowvec;   /* fp16 [M / rows_per_group, rowvec_ld] or NULL (time-embedding projection per branch) */
   int32_t rows_per_group;
   int32_t rowvec_ld;    /* row stride of rowvec in halves */
-  int32_t act;          /* 1: y = silu(fp16(y)) (time-embedding MLP, unet_3d_condition.py:359-365, resnet.py:355) */
+  int32_t act;          /* 1: y = silu(fp16(y)) (time-embedding MLP, unet_3d_condition.py:359-365, resnet.py:355);
+                           2: y = gelu_tanh(fp16(y)) (feed-forward of the SD3 MMDiT blocks, third-party diffusers) */
   const void* residual; /* fp16 [M, ldr] or NULL */
   int32_t ldr;
   const void* bias2;    /* fp16 [N_out] or NULL */
@@ -195,6 +196,14 @@ int univst_groupnorm_apply_f16(const void* X1, const void* X2, int32_t C1, int32
 /* LayerNorm over the last axis of [rows, C] (attention.py:290,312,329). */
 int univst_layernorm_f16(const void* X, int32_t rows, int32_t C, const void* gamma, const void* beta, float eps, void* Y,
                          void* stream);
+/* The two elementwise pieces of the SD3 / SD3.5 MMDiT blocks around the (built) joint-attention processors -- third-party
+ * diffusers JointTransformerBlock, which backbones/video_diffusion_sd3/models/transformer_3D_model.py:12-113 drives:
+ * adaLN modulation  y = LayerNorm(x, no affine) * (1 + scale[s]) + shift[s]  with per-sample rows scale / shift [samples, ld]
+ * (sample s = row / rows_per_sample), and the gated residual  out = x + gate[s] * y. */
+int univst_layernorm_modulate_f16(const void* X, int32_t rows, int32_t C, const void* scale, const void* shift, int32_t ld,
+                                  int32_t rows_per_sample, float eps, void* Y, void* stream);
+int univst_gated_add_f16(const void* x, const void* y, const void* gate, int32_t ld_gate, int32_t rows_per_sample,
+                         int64_t rows, int32_t C, void* out, void* stream);
 
 /* Nearest x2 upsample of [NB, H, W, C] (resnet.py:145) and the parity-plane rearrangement feeding the stride-2 conv. */
 int univst_upsample2x_f16(const void* X, int32_t NB, int32_t H, int32_t W, int32_t C, void* Y, void* stream);

@@ -98,9 +98,17 @@ def main():
             unet.set_frame_sharding(transport="xrank")
             out_x, t_x = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 3)
             unet.use_cuda_graphs = True
+            unet(x, t, encoder_hidden_states=ctx)                     # capture
+            n0, w0 = unet._xr.wait_stats()
             out_g, t_g = timed(lambda: unet(x, t, encoder_hidden_states=ctx).sample, 5)
+            n1, w1 = unet._xr.wait_stats()
             unet.use_cuda_graphs = False
             unet._xr.check()
+            wt = torch.tensor([(w1 - w0) / 6.0], device="cuda")       # timed() runs the call 1 + 5 times
+            wl = [torch.zeros_like(wt) for _ in range(world)]
+            dist.all_gather(wl, wt)
+            res[f"idx{idx}"].update({"xrank_syncs_per_forward": (n1 - n0) // 6,
+                                     "xrank_wait_ms_per_forward_by_rank": [round(float(w), 3) for w in wl]})
             dx = out_x.float() - ref.float()
             res[f"idx{idx}"].update({"ms_sharded_xrank": t_x, "ms_sharded_xrank_graph": t_g,
                                      "xrank_vs_single_max_abs": float(dx.abs().max()),

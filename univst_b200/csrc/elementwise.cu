@@ -430,6 +430,30 @@ extern "C" int univst_exchange_push_xrank_f16(int32_t dir, const void* src, int3
 }
 
 namespace uv {
+// out = x + gate[row / rows_per_sample] * y   (the gated residuals of the SD3 MMDiT blocks: diffusers JointTransformerBlock)
+__global__ void gated_add_kernel(const __half* __restrict__ x, const __half* __restrict__ y, const __half* __restrict__ gate,
+                                 int ld_gate, int rows_per_sample, long long rows, int C, __half* __restrict__ out) {
+  const int vpr = C >> 3;
+  const long long total = rows * vpr;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / vpr;
+    const int v = (int)(i - row * vpr);
+    const uint4 a = *reinterpret_cast<const uint4*>(x + row * C + v * 8);
+    const uint4 b = *reinterpret_cast<const uint4*>(y + row * C + v * 8);
+    const uint4 g = __ldg(reinterpret_cast<const uint4*>(gate + (row / rows_per_sample) * ld_gate + v * 8));
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, bw[4] = {b.x, b.y, b.z, b.w}, gw[4] = {g.x, g.y, g.z, g.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 fa = unpack_half2(aw[j]), fb = unpack_half2(bw[j]), fg = unpack_half2(gw[j]);
+      // the reference rounds gate * y to fp16 before the add (two tensor ops)
+      const float2 p = unpack_half2(pack_half2(fg.x * fb.x, fg.y * fb.y));
+      o[j] = pack_half2(fa.x + p.x, fa.y + p.y);
+    }
+    *reinterpret_cast<uint4*>(out + row * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+  }
+}
+
 struct FloatVals {
   float v[64];
 };
@@ -437,6 +461,17 @@ __global__ void set_floats_kernel(float* __restrict__ dst, FloatVals vals, int n
   if ((int)threadIdx.x < n) dst[threadIdx.x] = vals.v[threadIdx.x];
 }
 }  // namespace uv
+
+extern "C" int univst_gated_add_f16(const void* x, const void* y, const void* gate, int32_t ld_gate, int32_t rows_per_sample,
+                                    int64_t rows, int32_t C, void* out, void* stream) {
+  UV_REQUIRE(x && y && gate && out && rows > 0 && C > 0 && C % 8 == 0 && ld_gate % 8 == 0 && rows_per_sample > 0 &&
+                 ((uintptr_t)gate & 15) == 0,
+             "gated_add: bad arguments (channels and gate row stride multiples of 8, 16-byte aligned gate)");
+  gated_add_kernel<<<grid_for((size_t)rows * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __half*)x, (const __half*)y, (const __half*)gate, ld_gate, rows_per_sample, rows, C, (__half*)out);
+  UV_CHECK_CUDA(cudaGetLastError());
+  return UNIVST_OK;
+}
 
 extern "C" int univst_set_floats(float* dst, const float* vals, int32_t n, void* stream) {
   UV_REQUIRE(dst && vals && n > 0 && n <= 64, "set_floats: 1..64 values");

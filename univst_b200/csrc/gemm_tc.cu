@@ -78,6 +78,15 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+// tanh-form GELU (diffusers FeedForward(activation_fn="gelu-approximate"), the SD3 MMDiT blocks):
+// 0.5 x (1 + tanh(sqrt(2 / pi) (x + 0.044715 x^3))), tanh through one exponential
+__device__ __forceinline__ float gelu_tanh(float x) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
+  const float e = __expf(2.0f * u);
+  const float th = 1.0f - 2.0f / (e + 1.0f);     // tanh(u); e = inf -> 1, e = 0 -> -1
+  return 0.5f * x * (1.0f + th);
+}
+
 // Per-warp staging tile in shared memory: 32 rows x 32 halves (64 B per row), the 16-byte piece index XOR-swizzled with
 // (row >> 1) & 3 so that both access patterns below are bank-conflict free:
 //   "own row"   : thread r touches row r, pieces 0..3 (the TMEM layout: one accumulator row per thread)
@@ -206,11 +215,17 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
           }
 #pragma unroll
           for (int j = 0; j < 4; ++j) o[g * 4 + j] = pack_half2(v[2 * j] * p.out_scale, v[2 * j + 1] * p.out_scale);
-          if (p.act) {
+          if (p.act == 1) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               float2 y = unpack_half2(o[g * 4 + j]);
               o[g * 4 + j] = pack_half2(y.x / (1.0f + __expf(-y.x)), y.y / (1.0f + __expf(-y.y)));
+            }
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float2 y = unpack_half2(o[g * 4 + j]);
+              o[g * 4 + j] = pack_half2(gelu_tanh(y.x), gelu_tanh(y.y));
             }
           }
           if (p.bias2 && n < p.N_out) {
@@ -239,9 +254,11 @@ __device__ __forceinline__ void epilogue_rows(const GemmParams& p, uint32_t tadd
           if (rv) x += __half2float(rv[n + j]);
           if (res) x += __half2float(res[n + j]);
           __half y = __float2half_rn(x * p.out_scale);
-          if (p.act) {
+          if (p.act == 1) {
             const float yf = __half2float(y);
             y = __float2half_rn(yf / (1.0f + __expf(-yf)));
+          } else if (p.act == 2) {
+            y = __float2half_rn(gelu_tanh(__half2float(y)));
           }
           if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(p.bias2[n + j]));
           drow[n + j] = y;
@@ -366,9 +383,11 @@ __device__ __forceinline__ void split_epilogue(const GemmParams& p, uint32_t tad
       if (rv) x += __half2float(__ldg(rv + col + c));
       if (p.residual) x += __half2float(__ldg(p.residual + (size_t)row * p.ldr + col + c));
       __half y = __float2half_rn(x * p.out_scale);
-      if (p.act) {
+      if (p.act == 1) {
         const float yf = __half2float(y);
         y = __float2half_rn(yf / (1.0f + __expf(-yf)));
+      } else if (p.act == 2) {
+        y = __float2half_rn(gelu_tanh(__half2float(y)));
       }
       if (p.bias2) y = __float2half_rn(__half2float(y) + __half2float(__ldg(p.bias2 + col + c)));
       out[c] = y;

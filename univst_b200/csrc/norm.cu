@@ -211,11 +211,19 @@ __global__ void gn_apply_kernel(const __half* __restrict__ x1, const __half* __r
 
 // One warp per token row, NV = ceil(C / 256) 16-byte vectors per lane; single pass over registers: sum and sum of
 // squares share one shuffle tree.
+// mod_rpg > 0 (adaLN modulation of the SD3 MMDiT blocks, diffusers AdaLayerNormZero / AdaLayerNormContinuous): the norm has
+// no affine parameters; gamma / beta are per-SAMPLE rows [rows / mod_rpg, mod_ld] and y = norm(x) * (1 + gamma) + beta.
 template <int NV>
 __global__ void layernorm_kernel(const __half* __restrict__ x, int rows, int C, const __half* __restrict__ gamma,
-                                 const __half* __restrict__ beta, float eps, __half* __restrict__ y) {
+                                 const __half* __restrict__ beta, float eps, __half* __restrict__ y, int mod_rpg, int mod_ld) {
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
+  float one = 0.0f;
+  if (mod_rpg > 0) {
+    gamma += (size_t)(row / mod_rpg) * mod_ld;
+    beta += (size_t)(row / mod_rpg) * mod_ld;
+    one = 1.0f;
+  }
   const int lane = threadIdx.x & 31;
   const int nvec = C >> 3;
   uint4 buf[NV];
@@ -255,7 +263,7 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int rows, int C, 
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const float2 f = unpack_half2(w[j]), ga = unpack_half2(gw[j]), be = unpack_half2(bw[j]);
-        o[j] = pack_half2((f.x - mean) * rstd * ga.x + be.x, (f.y - mean) * rstd * ga.y + be.y);
+        o[j] = pack_half2((f.x - mean) * rstd * (ga.x + one) + be.x, (f.y - mean) * rstd * (ga.y + one) + be.y);
       }
       *reinterpret_cast<uint4*>(y + (size_t)row * C + v * 8) = make_uint4(o[0], o[1], o[2], o[3]);
     }
@@ -377,8 +385,23 @@ extern "C" int univst_groupnorm_apply_f16(const void* X1, const void* X2, int32_
   return gn_launch_apply(X1, X2, C1, C2, NB, rows, groups, sums, stat_rows, gamma, beta, eps, silu, Y, (cudaStream_t)stream);
 }
 
+static int layernorm_launch(const void* X, int32_t rows, int32_t C, const void* gamma, const void* beta, float eps, void* Y,
+                            int mod_rpg, int mod_ld, void* stream);
+
 extern "C" int univst_layernorm_f16(const void* X, int32_t rows, int32_t C, const void* gamma, const void* beta,
                                     float eps, void* Y, void* stream) {
+  return layernorm_launch(X, rows, C, gamma, beta, eps, Y, 0, 0, stream);
+}
+
+extern "C" int univst_layernorm_modulate_f16(const void* X, int32_t rows, int32_t C, const void* scale, const void* shift,
+                                             int32_t ld, int32_t rows_per_sample, float eps, void* Y, void* stream) {
+  UV_REQUIRE(rows_per_sample > 0 && ld >= C && ld % 8 == 0 && ((uintptr_t)scale & 15) == 0 && ((uintptr_t)shift & 15) == 0,
+             "layernorm_modulate: per-sample scale / shift rows must be 16-byte aligned with a row stride %% 8");
+  return layernorm_launch(X, rows, C, scale, shift, eps, Y, rows_per_sample, ld, stream);
+}
+
+static int layernorm_launch(const void* X, int32_t rows, int32_t C, const void* gamma, const void* beta, float eps, void* Y,
+                            int mod_rpg, int mod_ld, void* stream) {
   UV_REQUIRE(X && Y && gamma && beta, "layernorm: null pointer");
   UV_REQUIRE(rows > 0 && C % 8 == 0 && C <= 2048, "layernorm: C must be a multiple of 8, at most 2048");
   const int warps = 8;
@@ -387,12 +410,12 @@ extern "C" int univst_layernorm_f16(const void* X, int32_t rows, int32_t C, cons
   cudaStream_t st = (cudaStream_t)stream;
   const int nv = (C / 8 + 31) / 32;
   switch (nv) {
-    case 1: layernorm_kernel<1><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
-    case 2: layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
-    case 3: layernorm_kernel<3><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
-    case 4: layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
-    case 5: layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
-    default: layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y); break;
+    case 1: layernorm_kernel<1><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y, mod_rpg, mod_ld); break;
+    case 2: layernorm_kernel<2><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y, mod_rpg, mod_ld); break;
+    case 3: layernorm_kernel<3><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y, mod_rpg, mod_ld); break;
+    case 4: layernorm_kernel<4><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y, mod_rpg, mod_ld); break;
+    case 5: layernorm_kernel<5><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y, mod_rpg, mod_ld); break;
+    default: layernorm_kernel<8><<<grid, warps * 32, 0, st>>>(x, rows, C, g, b, eps, (__half*)Y, mod_rpg, mod_ld); break;
   }
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;

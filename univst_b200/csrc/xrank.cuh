@@ -14,6 +14,8 @@ static constexpr int kXrFlags = 0;                       // [16] flags[src] = la
 static constexpr int kXrEpoch = 16;                      // synchronisations completed (local)
 static constexpr int kXrDone = 17;                       // block-arrival counter of multi-block kernels (local)
 static constexpr int kXrError = 18;                      // sticky: 1 + rank that was waited for when a wait timed out
+static constexpr int kXrWaitNs = 20;                     // (64-bit, words 20-21) nanoseconds spent waiting for peers so far
+static constexpr int kXrSyncs = 22;                      // synchronisations completed (diagnostic twin of the epoch)
 static constexpr int kXrSlots = 32;                      // float slots[2][16][kXrankSlotFloats]
 static constexpr size_t kXrankCtlWords = kXrSlots + 2ull * kXrankMaxRanks * kXrankSlotFloats;
 
@@ -50,6 +52,7 @@ __device__ __forceinline__ void xrank_sync_warp(const XrankPeers& P, int rank, i
   __syncwarp();
   if (lane == 0) *reinterpret_cast<volatile uint32_t*>(mine + kXrEpoch) = e;
   __threadfence_system();
+  unsigned long long waited = 0;
   if (lane < world && lane != rank) {
     st_release_sys(P.ctl[lane] + kXrFlags + rank, e);
     const unsigned long long t0 = global_timer_ns();
@@ -59,6 +62,16 @@ __device__ __forceinline__ void xrank_sync_warp(const XrankPeers& P, int rank, i
         break;
       }
     }
+    waited = global_timer_ns() - t0;
+  }
+  // diagnostics: the longest wait of this synchronisation (= how late the slowest peer was) and a counter
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xffffffffu, waited, o);
+    waited = other > waited ? other : waited;
+  }
+  if (lane == 0) {
+    atomicAdd(reinterpret_cast<unsigned long long*>(mine + kXrWaitNs), waited);
+    atomicAdd(mine + kXrSyncs, 1u);
   }
   __syncwarp();
 }

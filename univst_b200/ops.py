@@ -51,6 +51,8 @@ _lib.register("univst_softmax_rows_f16", [_vp, _i32, _i32, _i32, _f32, _vp])
 _lib.register("univst_frames_to_u8", [_vp, _i32, _i64, _vp, _vp])
 _lib.register("univst_u8_to_frames_f16", [_vp, _i64, _i32, _vp, _vp])
 _lib.register("univst_vae_sample_f16", [_vp, _i32, _vp, _i32, _i32, _i32, _f32, _vp, _vp])
+_lib.register("univst_layernorm_modulate_f16", [_vp, _i32, _i32, _vp, _vp, _i32, _i32, _f32, _vp, _vp])
+_lib.register("univst_gated_add_f16", [_vp, _vp, _vp, _i32, _i32, _i64, _i32, _vp, _vp])
 _lib.register("univst_gemm_set_workspace", [_vp, _i64, _vp])
 _lib.register("univst_gemm_tune", [_i32])
 _lib.register("univst_xrank_ctl_bytes", [], _i64)
@@ -81,6 +83,7 @@ _LAUNCHES = {
     "temporal_attention": 1, "cross_attention": 1, "joint_attention": 1, "rmsnorm_heads": 1, "sd3_attn_shift": 4, "space_to_depth2": 1, "pack_latents": 1, "unpack_latents": 1, "timestep_embedding": 1, "mask_resize": 1,
     "latent_blend": 1, "latent_adain": 1, "ddim_step": 1, "axpby": 1, "exchange_push": 1, "halo_push": 1, "maskprop": 3, "flow_warp_key": 1, "mask_select": 1,
     "xrank_barrier": 1, "xrank_push": 1, "groupnorm_xrank": 3, "set_floats": 1,
+    "layernorm_modulate": 1, "gated_add": 1,
     "conv3x3_s2_pad_after": 1, "conv_temporal3": 1, "softmax_rows": 1, "frames_to_u8": 1, "u8_to_frames": 1, "vae_sample": 1,
 }
 
@@ -148,7 +151,7 @@ def make_epilogue(bias=None, rowvec=None, rows_per_group=1, residual=None, bias2
     ep.rowvec = _ptr(rowvec)
     ep.rows_per_group = rows_per_group
     ep.rowvec_ld = rowvec.stride(0) if rowvec is not None else 0
-    ep.act = 1 if act else 0
+    ep.act = {"silu": 1, "gelu_tanh": 2}[act] if isinstance(act, str) else int(act)   # True / 1 = SiLU, 2 = tanh GELU
     ep.residual = _ptr(residual)
     ep.ldr = residual.stride(0) if residual is not None else 0
     ep.bias2 = _ptr(bias2)
@@ -571,6 +574,38 @@ def layernorm(x: torch.Tensor, gamma, beta, eps: float = 1e-5, out: Optional[tor
     check(_lib.lib().univst_layernorm_f16(x.data_ptr(), rows, C_, gamma.data_ptr(), beta.data_ptr(), eps, out.data_ptr(),
                                           _stream()), "univst_layernorm_f16")
     _count("layernorm")
+    return out
+
+
+def layernorm_modulate(x: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, rows_per_sample: int, eps: float = 1e-6,
+                       out: Optional[torch.Tensor] = None):
+    """adaLN modulation: ``LayerNorm(x, no affine) * (1 + scale[s]) + shift[s]``; ``scale`` / ``shift``: [samples, C] views
+    (column slices of the block's modulation GEMM: one row stride, last dim contiguous); sample of a row = row // rows_per_sample."""
+    _lib.require_device()
+    _chk(x, "x")
+    rows, C_ = x.shape
+    assert scale.shape == shift.shape and scale.shape[1] == C_ and scale.stride(0) == shift.stride(0)
+    assert scale.stride(1) == 1 and shift.stride(1) == 1 and rows == scale.shape[0] * rows_per_sample
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().univst_layernorm_modulate_f16(x.data_ptr(), rows, C_, scale.data_ptr(), shift.data_ptr(), scale.stride(0),
+                                                   rows_per_sample, eps, out.data_ptr(), _stream()),
+          "univst_layernorm_modulate_f16")
+    _count("layernorm_modulate")
+    return out
+
+
+def gated_add(x: torch.Tensor, y: torch.Tensor, gate: torch.Tensor, rows_per_sample: int, out: Optional[torch.Tensor] = None):
+    """``x + gate[s] * y`` with a per-sample gate row ([samples, C] view, last dim contiguous)."""
+    _lib.require_device()
+    _chk(x, "x"), _chk(y, "y")
+    rows, C_ = x.shape
+    assert y.shape == x.shape and gate.shape[1] == C_ and gate.stride(1) == 1 and rows == gate.shape[0] * rows_per_sample
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().univst_gated_add_f16(x.data_ptr(), y.data_ptr(), gate.data_ptr(), gate.stride(0), rows_per_sample, rows, C_,
+                                          out.data_ptr(), _stream()), "univst_gated_add_f16")
+    _count("gated_add")
     return out
 
 

@@ -100,6 +100,13 @@ class XRank:
         torch.cuda.synchronize(self.device)
         return int(self._ctl[72:76].view(torch.int32).item())
 
+    def wait_stats(self):
+        """(synchronisations completed, milliseconds this rank has spent waiting for its peers inside them) since start-up
+        -- the device-side counters of the control block.  Synchronises the device."""
+        torch.cuda.synchronize(self.device)
+        ns = int(self._ctl[80:88].view(torch.int64).item())
+        return int(self._ctl[88:92].view(torch.int32).item()), ns / 1e6
+
     def check(self):
         e = self.error()
         if e:
