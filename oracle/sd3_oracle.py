@@ -49,9 +49,13 @@ def shift_params(idx: int, eta1: float = 0.0, eta2: float = 0.6):
     return active, 0.8, beta, 2.0
 
 
-def joint_attention(w, hidden, enc, heads: int, idx=None, eta1=0.0, eta2=0.6):
+def joint_attention(w, hidden, enc, heads: int, idx=None, eta1=0.0, eta2=0.6, cross_frame=True):
     """Both processors: ``idx is None`` -> CrossFrameProcessor; else AttentionShiftProcessor at step ``idx``.
-    hidden (B*16, N, C), enc (B*16, L, C); w: dict of the attn module's tensors.  Returns (hidden_out, enc_out)."""
+    hidden (B*16, N, C), enc (B*16, L, C); w: dict of the attn module's tensors.  Returns (hidden_out, enc_out).
+    ``enc is None`` (the self-attention ``attn2`` of SD3.5's dual-attention blocks, :92,:120,:134): image tokens only,
+    returns hidden_out.  No ``to_add_out`` in ``w`` = a ``context_pre_only`` attention (:127): the text half of the
+    attention output is returned unprojected.  ``cross_frame=False``: the image K/V are the frame's own (diffusers'
+    stock JointAttnProcessor2_0, third-party)."""
     BF, N, C = hidden.shape
     d = C // heads
     split = lambda t: t.view(BF, -1, heads, d).transpose(1, 2)
@@ -74,14 +78,20 @@ def joint_attention(w, hidden, enc, heads: int, idx=None, eta1=0.0, eta2=0.6):
     first = torch.zeros(Fr, dtype=torch.long)
     prev = (torch.arange(Fr) - 1).clip(0, Fr - 1)
     me = torch.arange(Fr)
-    k = torch.cat([k5[:, s] for s in (first, prev, me)], dim=-2).reshape(BF, heads, 3 * N, d)
-    v = torch.cat([v5[:, s] for s in (first, prev, me)], dim=-2).reshape(BF, heads, 3 * N, d)
+    srcs = (first, prev, me) if cross_frame else (me,)
+    k = torch.cat([k5[:, s] for s in srcs], dim=-2).reshape(BF, heads, len(srcs) * N, d)
+    v = torch.cat([v5[:, s] for s in srcs], dim=-2).reshape(BF, heads, len(srcs) * N, d)
+    if enc is None:
+        o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(BF, -1, C)
+        return F.linear(o, w["to_out.0.weight"], w["to_out.0.bias"])
     eq = rms_norm(split(F.linear(enc, w["add_q_proj.weight"], w["add_q_proj.bias"])), w["norm_added_q.weight"])
     ek = rms_norm(split(F.linear(enc, w["add_k_proj.weight"], w["add_k_proj.bias"])), w["norm_added_k.weight"])
     ev = split(F.linear(enc, w["add_v_proj.weight"], w["add_v_proj.bias"]))
     q, k, v = torch.cat([q, eq], 2), torch.cat([k, ek], 2), torch.cat([v, ev], 2)
     o = F.scaled_dot_product_attention(q, k, v).transpose(1, 2).reshape(BF, -1, C)
     ho, eo = o[:, :N], o[:, N:]
+    if "to_add_out.weight" not in w:
+        return F.linear(ho, w["to_out.0.weight"], w["to_out.0.bias"]), eo
     return (F.linear(ho, w["to_out.0.weight"], w["to_out.0.bias"]),
             F.linear(eo, w["to_add_out.weight"], w["to_add_out.bias"]))
 

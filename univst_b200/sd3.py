@@ -28,9 +28,12 @@ class _Packed:
         h = lambda t: t.detach().to(device=device, dtype=torch.float16).contiguous()
         cat = lambda names, attr: h(torch.cat([getattr(getattr(attn, n), attr) for n in names], 0))
         self.w_qkv, self.b_qkv = cat(("to_q", "to_k", "to_v"), "weight"), cat(("to_q", "to_k", "to_v"), "bias")
-        self.w_add, self.b_add = cat(("add_q_proj", "add_k_proj", "add_v_proj"), "weight"), cat(("add_q_proj", "add_k_proj", "add_v_proj"), "bias")
+        self.w_add = self.b_add = self.w_add_out = self.b_add_out = None
+        if getattr(attn, "add_q_proj", None) is not None:   # absent on the self-attention attn2 of SD3.5's dual blocks
+            self.w_add, self.b_add = cat(("add_q_proj", "add_k_proj", "add_v_proj"), "weight"), cat(("add_q_proj", "add_k_proj", "add_v_proj"), "bias")
         self.w_out, self.b_out = h(attn.to_out[0].weight), h(attn.to_out[0].bias)
-        self.w_add_out, self.b_add_out = h(attn.to_add_out.weight), h(attn.to_add_out.bias)
+        if getattr(attn, "to_add_out", None) is not None:   # absent on a context_pre_only attention (the last block)
+            self.w_add_out, self.b_add_out = h(attn.to_add_out.weight), h(attn.to_add_out.bias)
         nw = lambda n: h(getattr(attn, n).weight) if getattr(attn, n, None) is not None else None
         self.norm_q, self.norm_k, self.norm_added_q, self.norm_added_k = (nw(n) for n in ("norm_q", "norm_k", "norm_added_q", "norm_added_k"))
         self.eps = float(getattr(getattr(attn, "norm_q", None), "eps", 1e-6) or 1e-6)
@@ -40,20 +43,24 @@ class _Packed:
 _tables = {}
 
 
-def _source_table(BF: int, device) -> torch.Tensor:
-    """[first, previous, self] frames of the image K/V (pnp_utils.py:26) + the image's own text tokens (second tensor)."""
-    key = (BF, str(device))
+def _source_table(BF: int, device, cross_frame: bool = True, text: bool = True) -> torch.Tensor:
+    """[first, previous, self] frames of the image K/V (pnp_utils.py:26) -- or the image alone for the stock joint attention
+    -- + the image's own text tokens (second tensor) where the attention is a joint one."""
+    key = (BF, str(device), cross_frame, text)
     if key not in _tables:
         rows = []
         for i in range(BF):
             b, f = divmod(i, CLIP_LENGTH)
-            rows.append([b * CLIP_LENGTH, b * CLIP_LENGTH + max(f - 1, 0), i, BF + i])
+            row = [b * CLIP_LENGTH, b * CLIP_LENGTH + max(f - 1, 0), i] if cross_frame else [i]
+            rows.append(row + ([BF + i] if text else []))
         _tables[key] = torch.tensor(rows, dtype=torch.int32, device=device)
     return _tables[key]
 
 
 class CrossFrameProcessor:
     """pnp_utils.py:9-132."""
+
+    cross_frame = True   # image K/V from the [first, previous, self] frames (pnp_utils.py:26)
 
     def __init__(self):
         self._packed = {}
@@ -64,36 +71,47 @@ class CrossFrameProcessor:
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, idx=-1, *args, **kwargs):
         if attention_mask is not None:
             raise NotImplementedError("attention masks are unused on the UniVST path")
-        if encoder_hidden_states is None:
-            raise NotImplementedError("the SD3 blocks on the UniVST path are joint (text + image) blocks")
         dev = hidden_states.device
         pk = self._packed.get(id(attn))
         if pk is None:
             pk = self._packed[id(attn)] = _Packed(attn, dev)
         BF, N, C = hidden_states.shape
-        L = encoder_hidden_states.shape[1]
         H, d = pk.heads, C // pk.heads
-        if BF % CLIP_LENGTH:
+        if self.cross_frame and BF % CLIP_LENGTH:
             raise ValueError(f"the reference processors assume clips of {CLIP_LENGTH} frames (batch {BF})")
         x = hidden_states.to(torch.float16).reshape(BF * N, C).contiguous()
-        e = encoder_hidden_states.to(torch.float16).reshape(BF * L, C).contiguous()
         qkv = ops.gemm(x, pk.w_qkv, bias=pk.b_qkv)          # [BF N, 3C]
-        tqkv = ops.gemm(e, pk.w_add, bias=pk.b_add)         # [BF L, 3C]
-        ops.rmsnorm_heads_(qkv, H, d, pk.norm_q, pk.norm_k, pk.eps)
-        ops.rmsnorm_heads_(tqkv, H, d, pk.norm_added_q, pk.norm_added_k, pk.eps)
+        if pk.norm_q is not None or pk.norm_k is not None:
+            ops.rmsnorm_heads_(qkv, H, d, pk.norm_q, pk.norm_k, pk.eps)
         shift = self._shift(idx)
         if shift is not None:
             if BF != 3 * CLIP_LENGTH:
                 raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
             ops.sd3_attn_shift_(qkv, CLIP_LENGTH, N, H, d, *shift)
-        table = _source_table(BF, dev)
+        if encoder_hidden_states is None:
+            # the image-only attention (attn2 of SD3.5's dual-attention blocks; pnp_utils.py:92,120,134 skip the text half)
+            table = _source_table(BF, dev, self.cross_frame, text=False)
+            o = ops.sc_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], table, NI=BF, NIkv=BF, H=H, d=d, N=N, Nkv=N)
+            return ops.gemm(o, pk.w_out, bias=pk.b_out).view(BF, N, C)
+        L = encoder_hidden_states.shape[1]
+        e = encoder_hidden_states.to(torch.float16).reshape(BF * L, C).contiguous()
+        tqkv = ops.gemm(e, pk.w_add, bias=pk.b_add)         # [BF L, 3C]
+        if pk.norm_added_q is not None or pk.norm_added_k is not None:
+            ops.rmsnorm_heads_(tqkv, H, d, pk.norm_added_q, pk.norm_added_k, pk.eps)
+        table = _source_table(BF, dev, self.cross_frame)
         kw = dict(NI=BF, NIkv=BF, NIkv2=BF, H=H, d=d, Nkv=N, Nkv2=L)
         o_img = ops.joint_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=N, **kw)
         o_txt = ops.joint_attention(tqkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=L, **kw)
         h_out = ops.gemm(o_img, pk.w_out, bias=pk.b_out).view(BF, N, C)
-        if getattr(attn, "context_pre_only", False):
+        if getattr(attn, "context_pre_only", False) or pk.w_add_out is None:
             return h_out, o_txt.view(BF, L, C)
         return h_out, ops.gemm(o_txt, pk.w_add_out, bias=pk.b_add_out).view(BF, L, C)
+
+
+class JointAttnProcessor(CrossFrameProcessor):
+    """diffusers' stock ``JointAttnProcessor2_0`` (third-party): every image attends to its own tokens + its text tokens.  The
+    default processor of :class:`univst_b200.sd3_transformer.SD3Transformer2DModel` until the reference's are installed."""
+    cross_frame = False
 
 
 class AttentionShiftProcessor(CrossFrameProcessor):
