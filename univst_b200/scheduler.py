@@ -80,3 +80,34 @@ class DDIMScheduler:
         """(alpha_cur, alpha_next) of next_step (inversion_tools/ddim_inversion.py:190-196)."""
         cur = min(int(t) - self.config.num_train_timesteps // self.num_inference_steps, 999)
         return self.alpha(cur), self.alpha(int(t))
+
+
+class FlowMatchEulerDiscreteScheduler:
+    """Host-side scalars of diffusers' ``FlowMatchEulerDiscreteScheduler`` as SD3 / SD3.5 configure it (``shift = 3.0``, no
+    dynamic shifting) -- third-party to the reference, which only reads ``timesteps``, ``sigmas`` and ``config``
+    (custom_pipeline.py:246-262, :336-345; inversion_tools/flow_inversion.py:123-264).  PARITY UNPINNED (restated from the
+    published algorithm, no library here to check against): ``sigma_k = shift s / (1 + (shift - 1) s)`` for ``s`` linearly
+    spaced between the shifted extremes, ``timesteps = 1000 sigma``, a trailing ``sigma = 0``."""
+    order = 1
+
+    def __init__(self, num_train_timesteps: int = 1000, shift: float = 3.0, use_dynamic_shifting: bool = False, **extra):
+        self.config = dict(num_train_timesteps=num_train_timesteps, shift=shift, use_dynamic_shifting=use_dynamic_shifting, **extra)
+        self.config = type("Cfg", (dict,), {"__getattr__": lambda s_, k: s_[k]})(self.config)
+        s = np.linspace(1, num_train_timesteps, num_train_timesteps, dtype=np.float64)[::-1] / num_train_timesteps
+        s = shift * s / (1 + (shift - 1) * s)
+        self.sigma_max, self.sigma_min = float(s[0]), float(s[-1])
+        self.timesteps = torch.from_numpy((s * num_train_timesteps).astype(np.float32))
+        self.sigmas = torch.from_numpy(np.append(s, 0.0).astype(np.float32))
+
+    def set_timesteps(self, num_inference_steps: int, device=None, mu=None, **kwargs):
+        T, shift = self.config["num_train_timesteps"], self.config["shift"]
+        ts = np.linspace(self.sigma_max * T, self.sigma_min * T, num_inference_steps, dtype=np.float64)
+        s = ts / T
+        if self.config["use_dynamic_shifting"]:
+            if mu is None:
+                raise ValueError("use_dynamic_shifting needs mu")
+            s = np.exp(mu) / (np.exp(mu) + (1 / s - 1))
+        else:
+            s = shift * s / (1 + (shift - 1) * s)
+        self.timesteps = torch.from_numpy((s * T).astype(np.float32))          # kept on the host: no device sync when read
+        self.sigmas = torch.from_numpy(np.append(s, 0.0).astype(np.float32))

@@ -43,6 +43,24 @@ class _Packed:
 _tables = {}
 
 
+def _source_table_sharded(B: int, Fl: int, rank: int, device, text: bool = True) -> torch.Tensor:
+    """[first, previous, self] (+ own text tokens) of a frame shard: local images 0 .. B Fl - 1, then the halo banks of the
+    projection buffer -- B Fl + b = last frame of the previous rank, B Fl + B + b = frame 0 of the clip (rank 0 has both
+    locally).  Text K/V live in the second tensor: source (B Fl + 2 B) + image."""
+    key = ("shard", B, Fl, rank, str(device), text)
+    if key not in _tables:
+        NI = B * Fl
+        rows = []
+        for b in range(B):
+            for fl in range(Fl):
+                me = b * Fl + fl
+                first = b * Fl if rank == 0 else NI + B + b
+                prev = me - 1 if fl > 0 else (NI + b if rank > 0 else me)
+                rows.append([first, prev, me] + ([NI + 2 * B + me] if text else []))
+        _tables[key] = torch.tensor(rows, dtype=torch.int32, device=device)
+    return _tables[key]
+
+
 def _source_table(BF: int, device, cross_frame: bool = True, text: bool = True) -> torch.Tensor:
     """[first, previous, self] frames of the image K/V (pnp_utils.py:26) -- or the image alone for the stock joint attention
     -- + the image's own text tokens (second tensor) where the attention is a joint one."""
@@ -77,31 +95,46 @@ class CrossFrameProcessor:
             pk = self._packed[id(attn)] = _Packed(attn, dev)
         BF, N, C = hidden_states.shape
         H, d = pk.heads, C // pk.heads
-        if self.cross_frame and BF % CLIP_LENGTH:
+        # frames sharded over ranks (sd3_transformer.set_frame_sharding): this call sees Fl = 16 / world frames per branch;
+        # the K/V of the neighbouring frames that live on other ranks arrive in two halo banks behind the local images
+        shard = getattr(attn, "_shard", None) if self.cross_frame else None
+        Fl = shard.Fl if shard is not None else CLIP_LENGTH
+        if self.cross_frame and BF % Fl:
             raise ValueError(f"the reference processors assume clips of {CLIP_LENGTH} frames (batch {BF})")
         x = hidden_states.to(torch.float16).reshape(BF * N, C).contiguous()
-        qkv = ops.gemm(x, pk.w_qkv, bias=pk.b_qkv)          # [BF N, 3C]
+        NIkv = BF
+        if shard is None:
+            qkv = kv = ops.gemm(x, pk.w_qkv, bias=pk.b_qkv)          # [BF N, 3C]
+        else:
+            B = BF // Fl
+            NIkv = BF + 2 * B
+            kv, halo_ptrs, halo_mc = shard.buffers.next(NIkv * N, 3 * C)
+            qkv = ops.gemm(x, pk.w_qkv, bias=pk.b_qkv, out=kv[: BF * N])
         if pk.norm_q is not None or pk.norm_k is not None:
             ops.rmsnorm_heads_(qkv, H, d, pk.norm_q, pk.norm_k, pk.eps)
         shift = self._shift(idx)
         if shift is not None:
-            if BF != 3 * CLIP_LENGTH:
+            if BF != 3 * Fl:
                 raise ValueError("the AdaIN-guided shift needs the three-branch batch [content, style, edit]")
-            ops.sd3_attn_shift_(qkv, CLIP_LENGTH, N, H, d, *shift)
+            ops.sd3_attn_shift_(qkv, Fl, N, H, d, *shift)
+        if shard is not None:
+            from .xrank import push_kv_halo
+            push_kv_halo(shard.xr, kv, halo_ptrs, halo_mc, BF // Fl, Fl, N, C)
+        table_of = (lambda text: _source_table_sharded(BF // Fl, Fl, shard.xr.rank, dev, text)) if shard is not None else \
+            (lambda text: _source_table(BF, dev, self.cross_frame, text))
         if encoder_hidden_states is None:
             # the image-only attention (attn2 of SD3.5's dual-attention blocks; pnp_utils.py:92,120,134 skip the text half)
-            table = _source_table(BF, dev, self.cross_frame, text=False)
-            o = ops.sc_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], table, NI=BF, NIkv=BF, H=H, d=d, N=N, Nkv=N)
+            o = ops.sc_attention(qkv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], table_of(False), NI=BF, NIkv=NIkv, H=H, d=d, N=N, Nkv=N)
             return ops.gemm(o, pk.w_out, bias=pk.b_out).view(BF, N, C)
         L = encoder_hidden_states.shape[1]
         e = encoder_hidden_states.to(torch.float16).reshape(BF * L, C).contiguous()
         tqkv = ops.gemm(e, pk.w_add, bias=pk.b_add)         # [BF L, 3C]
         if pk.norm_added_q is not None or pk.norm_added_k is not None:
             ops.rmsnorm_heads_(tqkv, H, d, pk.norm_added_q, pk.norm_added_k, pk.eps)
-        table = _source_table(BF, dev, self.cross_frame)
-        kw = dict(NI=BF, NIkv=BF, NIkv2=BF, H=H, d=d, Nkv=N, Nkv2=L)
-        o_img = ops.joint_attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=N, **kw)
-        o_txt = ops.joint_attention(tqkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=L, **kw)
+        table = table_of(True)
+        kw = dict(NI=BF, NIkv=NIkv, NIkv2=BF, H=H, d=d, Nkv=N, Nkv2=L)
+        o_img = ops.joint_attention(qkv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=N, **kw)
+        o_txt = ops.joint_attention(tqkv[:, :C], kv[:, C:2 * C], kv[:, 2 * C:], tqkv[:, C:2 * C], tqkv[:, 2 * C:], table, N=L, **kw)
         h_out = ops.gemm(o_img, pk.w_out, bias=pk.b_out).view(BF, N, C)
         if getattr(attn, "context_pre_only", False) or pk.w_add_out is None:
             return h_out, o_txt.view(BF, L, C)

@@ -104,6 +104,37 @@ class SD3Transformer2DModel:
         for name, a in self._attentions():
             a.processor = processor[name] if isinstance(processor, dict) else processor
 
+    # ------------------------------------------------------------------------------------------ frame sharding
+    def set_frame_sharding(self, group=None, frames_per_clip: int = 16):
+        """Shard the ``frames_per_clip`` frames of every branch over the ranks of ``group`` (BASELINE.json
+        configs[4]).  Everything in the MMDiT is per image except the cross-frame attention of the reference's processors,
+        whose [first, previous] K/V cross ranks: per attention the boundary frame's K|V go to the next rank's halo bank and
+        the clip's first frame's to every rank's, stored over NVLink by one kernel whose tail is the synchronisation
+        (xrank.push_kv_halo); the velocity prediction of the local frames is stored into every rank's full-batch buffer
+        at the end.  No collective-library call.  The callers keep passing (and receiving) the whole batch."""
+        import torch.distributed as dist
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world == 1:
+            return self.set_frame_sharding_off()
+        if frames_per_clip % world:
+            raise ValueError(f"{frames_per_clip} frames do not shard evenly over {world} ranks")
+        from .xrank import HaloBuffers, XRank
+        if getattr(self, "_xr", None) is None:
+            self._xr = XRank(group, self.device)
+        self._shard = SimpleNamespace(xr=self._xr, Fl=frames_per_clip // world, F=frames_per_clip,
+                                      buffers=HaloBuffers(self._xr, "sd3qkv"))
+        for _, a in self._attentions():
+            a._shard = self._shard
+
+    def set_frame_sharding_off(self):
+        self._shard = None
+        for _, a in self._attentions():
+            a._shard = None
+
+    def _local(self, t, B, F, Fl, rank):
+        """Rows (branch, frame) of a batch-major tensor -> this rank's frames of every branch."""
+        return t.view(B, F, *t.shape[1:])[:, rank * Fl:(rank + 1) * Fl].reshape(B * Fl, *t.shape[1:]).contiguous()
+
     # ------------------------------------------------------------------------------------------ pieces
     def _pos_rows(self, BF, h, w):
         """The cropped sin-cos table (diffusers PatchEmbed.cropped_pos_embed: centre crop of the max x max grid) repeated for
@@ -163,6 +194,18 @@ class SD3Transformer2DModel:
         if "ip_adapter_image_embeds" in kwargs:
             raise NotImplementedError("IP-Adapter inputs are unused on the UniVST path")
         W, cfg, D, dev = self.W, self.config, self.inner_dim, self.device
+        shard = getattr(self, "_shard", None)
+        BF_total = hidden_states.shape[0]
+        if shard is not None:
+            if BF_total % shard.F:
+                raise ValueError(f"the batch must hold whole clips of {shard.F} frames under frame sharding")
+            if ft_path is not None:
+                raise NotImplementedError("feature dumps are not available under frame sharding")
+            Bc, rk = BF_total // shard.F, shard.xr.rank
+            loc = lambda t: self._local(t.to(dev), Bc, shard.F, shard.Fl, rk)
+            hidden_states, encoder_hidden_states, pooled_projections = loc(hidden_states), loc(encoder_hidden_states), loc(pooled_projections)
+            if torch.is_tensor(timestep) and timestep.numel() == BF_total:
+                timestep = loc(timestep.reshape(-1))
         BF, Cin, H, Wd = hidden_states.shape
         p = cfg["patch_size"]
         if H % p or Wd % p:
@@ -202,6 +245,16 @@ class SD3Transformer2DModel:
         out = ops.gemm(hs, W["proj_out.weight"], bias=W["proj_out.bias"])                   # [BF N, p p C_out]
         co = self.out_channels
         out = torch.einsum("nhwpqc->nchpwq", out.view(BF, h, w, p, p, co)).reshape(BF, co, h * p, w * p)
+        if shard is not None:   # my frames -> their place in every rank's full-batch buffer (one multicast store per 16 B)
+            per = co * H * Wd
+            key = ("sd3out", BF_total, per)
+            full, ptrs = shard.xr.buffer(key, (BF_total, per))
+            mc = shard.xr.multicast(key)
+            off = shard.xr.rank * shard.Fl * per * 2
+            ops.xrank_push(shard.xr, [dict(src=out.contiguous().view(BF, per), src_blk_rows=shard.Fl, dst=[q + off for q in ptrs],
+                                           ld_dst=per, dst_blk_rows=shard.F, nblk=BF_total // shard.F, rows=shard.Fl,
+                                           mc=mc + off if mc else 0)])
+            out = full.view(BF_total, co, H, Wd)
         if not return_dict:
             return (out,)
         return SimpleNamespace(sample=out)

@@ -294,22 +294,9 @@ class UNetPseudo3DConditionModel:
         return t[par], [p + par * rows * cols * 2 for p in ptrs], (mc + par * rows * cols * 2 if mc else 0)
 
     def _xr_push_kv_halo(self, qkv, ptrs, mc, B, F, N, C):
-        """xrank transport of the K/V halo: K|V columns (C .. 3C) of my last frame -> bank 1 of rank + 1, of the clip's
-        first frame (rank 0) -> bank 2 of every other rank; the synchronisation is the tail of the same kernel."""
-        _, rank, world = self._shard
-        NI, ld = B * F, qkv.stride(0)
-        kv = qkv[:, C:]
-        pushes = []
-        if rank + 1 < world:
-            dst = [0] * world
-            dst[rank + 1] = ptrs[rank + 1] + (NI * N * ld + C) * 2
-            pushes.append(dict(src=kv[(F - 1) * N:], src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N))
-        if rank == 0:   # one switch-replicated store per 16 bytes where the fabric multicasts, else one store per peer
-            off = ((NI + B) * N * ld + C) * 2
-            dst = [0] + [p + off for p in ptrs[1:]]
-            pushes.append(dict(src=kv, src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N,
-                               mc=mc + off if mc else 0))
-        ops.xrank_push(self._xr, pushes)
+        """xrank transport of the K/V halo (xrank.push_kv_halo): one launch, whose tail is the synchronisation."""
+        from .xrank import push_kv_halo
+        push_kv_halo(self._xr, qkv, ptrs, mc, B, F, N, C)
 
     def set_frame_sharding_off(self):
         self._shard = None

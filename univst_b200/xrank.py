@@ -112,3 +112,42 @@ class XRank:
         if e:
             raise RuntimeError(f"cross-rank wait timed out on rank {self.rank} waiting for rank {e - 1}: the results of "
                                "this process group are invalid")
+
+
+def push_kv_halo(xr: XRank, qkv: torch.Tensor, ptrs, mc: int, B: int, F: int, N: int, C: int):
+    """K/V halo of a frame-sharded sparse-causal / cross-frame attention.  ``qkv``: this rank's fused projection buffer
+    [(B F + 2 B) N, 3 C] in symmetric memory (local images, then bank 1 = "previous frame of my first frame", bank 2 = "first
+    frame of the clip", B images each); ``ptrs`` / ``mc``: every rank's copy / the multicast address of the same buffer.
+    One launch: K|V columns (C .. 3C) of my last frame -> bank 1 of rank + 1; rank 0: its first frame -> bank 2 of every other
+    rank (one switch-replicated store where the fabric multicasts); the kernel's tail is the cross-rank synchronisation."""
+    from . import ops
+    rank, world = xr.rank, xr.world
+    NI, ld = B * F, qkv.stride(0)
+    kv = qkv[:, C:]
+    pushes = []
+    if rank + 1 < world:
+        dst = [0] * world
+        dst[rank + 1] = ptrs[rank + 1] + (NI * N * ld + C) * 2
+        pushes.append(dict(src=kv[(F - 1) * N:], src_blk_rows=F * N, dst=dst, ld_dst=ld, dst_blk_rows=N, nblk=B, rows=N))
+    if rank == 0:
+        off = ((NI + B) * N * ld + C) * 2
+        pushes.append(dict(src=kv, src_blk_rows=F * N, dst=[0] + [p + off for p in ptrs[1:]], ld_dst=ld, dst_blk_rows=N, nblk=B,
+                           rows=N, mc=mc + off if mc else 0))
+    ops.xrank_push(xr, pushes)
+
+
+class HaloBuffers:
+    """Double-buffered symmetric projection buffers with halo banks, one pair per (rows, cols) shape: a buffer is rewritten
+    only two synchronisations after it was last read (see unet.py::_xr_halo)."""
+
+    def __init__(self, xr: XRank, tag: str):
+        self.xr, self.tag, self._par = xr, tag, {}
+
+    def next(self, rows: int, cols: int):
+        key = (self.tag, rows, cols)
+        par = self._par.get(key, 0)
+        self._par[key] = par ^ 1
+        t, ptrs = self.xr.buffer(key, (2, rows, cols))
+        mc = self.xr.multicast(key)
+        off = par * rows * cols * 2
+        return t[par], [p + off for p in ptrs], (mc + off if mc else 0)
