@@ -51,3 +51,18 @@ def test_animatediff_frame_sharded_forward_matches_single_gpu():
     # ... with the NCCL all-to-all and with the rows pushed into the peers' symmetric memory (univst_exchange_push_f16)
     for key in ("idx5", "idx30"):
         assert res[key]["max_abs"] == 0.0 and res[key]["push_vs_single_max_abs"] == 0.0, res
+
+
+@pytest.mark.gpu
+def test_sd3_frame_sharded_forward_matches_single_gpu():
+    """SD3 / SD3.5 MMDiT mirror (BASELINE.json configs[4]): 16 frames per branch over 2 GPUs, the cross-frame attention's
+    [first, previous] K/V through halo banks in peer memory -- bit-identical to one GPU (everything else is per image)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29635",
+                          os.path.join(ROOT, "tools", "check_sd3_sharding.py")], capture_output=True, text=True, timeout=900)
+    assert out.returncode == 0, out.stderr[-3000:]
+    res = json.loads([l for l in out.stdout.splitlines() if l.startswith("{")][-1])
+    for key in ("idx5", "idx40"):
+        assert res[key]["max_abs_vs_single"] == 0.0 and res[key]["second_call_equal"] and res[key]["ranks_agree"], res
