@@ -417,7 +417,9 @@ __device__ __forceinline__ void split_epilogue(const GemmParams& p, uint32_t tad
 // CTA fetches half of every B k-block and multicasts it into both shared memories, so the weight traffic out of L2 --
 // the larger half of what these kernels pull through L2, which is what bounds the 128 x 160 / 224 tiles -- is halved.
 // A stage may be refilled only when both CTAs' MMAs have consumed it: the commit that frees a stage is multicast too.
-template <int CL>
+// SPLIT: the split-K variant (work items = (tile, K slice), split_epilogue) is a separate instantiation so that the plain
+// kernel's epilogue keeps its register allocation (folded into one kernel it spilled: the K = 320 GEMMs ran 1.7x slower).
+template <int CL, bool SPLIT = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -441,7 +443,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   // work items: CL = 1: tiles (m, n), n fastest, one per CTA; CL = 2: pairs of row blocks (2 mm, 2 mm + 1) x n per cluster
   const uint32_t crank = (CL == 2) ? cluster_ctarank() : 0u;
   // (split-K: work item = tile * splits + slice, slice fastest -- the slices of a tile run side by side)
-  const int S = (CL == 2) ? 1 : p.splits;
+  const int S = SPLIT ? p.splits : 1;
   const int num_tiles = (CL == 2 ? (tiles_m + 1) / 2 : tiles_m) * tiles_n * S;
   const int tile_first = (CL == 2) ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int tile_step = (CL == 2) ? (int)(gridDim.x >> 1) : (int)gridDim.x;
@@ -618,7 +620,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       e.lane = lane;
       e.row0 = m0 + (int)(q * 32);
       e.M = m_lim;
-      if (S == 1) {
+      if constexpr (!SPLIT) {
         epilogue_rows(p, taddr, row_ok, rv, res, drow, n0, tile_n, chunk0, e, &tmem_full_bar[a], (uint32_t)((it >> 1) & 1));
       } else {
         split_epilogue(p, taddr, tile, work % S, S, (int)(warp - 2), chunk0, (int)q, (int)lane, m0, m_lim, n0,
@@ -742,6 +744,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   if (smem > configured) {
     UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    UV_CHECK_CUDA(cudaFuncSetAttribute(gemm_tc_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = 227 * 1024;
   }
   const int tiles_m = (p.mode == 2) ? p.gen_tiles_m : (p.M + kBM - 1) / kBM, tiles_n = (p.N + p.BN - 1) / p.BN;
@@ -769,7 +772,10 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmA2, const CUtenso
   pick_splits(p, num_tiles, stream);
   const int num_work = num_tiles * p.splits;
   const int grid = num_work < num_sms() ? num_work : num_sms();
-  gemm_tc_kernel<1><<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
+  if (p.splits > 1)
+    gemm_tc_kernel<1, true><<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
+  else
+    gemm_tc_kernel<1><<<grid, kThreads, smem, stream>>>(tmA, tmA2, tmB, p);
   UV_CHECK_CUDA(cudaGetLastError());
   return UNIVST_OK;
 }

@@ -86,6 +86,7 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __r
     out[g * 2] = gs;
     out[g * 2 + 1] = gq;
   }
+  if (!arrivals) return;   // big tensors: a separate, wider fold kernel follows (gn_launch_stats)
   // ---- last block: fold (and exchange)
   __shared__ int s_last;
   __threadfence();
@@ -136,6 +137,82 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __r
   if (threadIdx.x < 32) xrank_sync_warp(P, rank, world);
   __syncthreads();
   const float* slots = reinterpret_cast<const float*>(ctl + kXrSlots) + (size_t)par * kXrankMaxRanks * kXrankSlotFloats;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    float acc = 0.0f;
+    for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * kXrankSlotFloats + i);
+    sums[i] = acc;
+  }
+}
+
+// Fold of a big tensor's chunk partials (hundreds of chunks: too long a dependent chain for the last block of the statistics
+// kernel): sums[b][g][2] = sum over the chunk partials in a fixed order, 16 interleaved partial sums per entry combined by
+// a fixed tree.  grid NB, block 16 * 64.
+__global__ void gn_fold_kernel(const float* __restrict__ partial, int nchunks, int groups, float* __restrict__ sums) {
+  __shared__ float sh[16][64];
+  const int b = blockIdx.x;
+  const int part = threadIdx.x >> 6, t = threadIdx.x & 63;
+  for (int i0 = 0; i0 < groups * 2; i0 += 64) {
+    const int i = i0 + t;
+    float acc = 0.0f;
+    if (i < groups * 2)
+      for (int c = part; c < nchunks; c += 16) acc += partial[((size_t)b * nchunks + c) * groups * 2 + i];
+    sh[part][t] = acc;
+    __syncthreads();
+    if (part == 0 && i < groups * 2) {
+      float v[16];
+#pragma unroll
+      for (int k = 0; k < 16; ++k) v[k] = sh[k][t];
+#pragma unroll
+      for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+        for (int k = 0; k < w; ++k) v[k] += v[k + w];
+      sums[(size_t)b * groups * 2 + i] = v[0];
+    }
+    __syncthreads();
+  }
+}
+
+// The same for statistics that span the rows of other ranks: fold, store the NB x groups x 2 sums into slot [rank] of every
+// rank, synchronise, add the slots in rank order.  One block of 1024 threads.
+__global__ void gn_fold_xrank_kernel(const float* __restrict__ partial, int nchunks, int nchunks_stride, int NB, int groups,
+                                     float* __restrict__ sums, XrankPeers P, int rank, int world) {
+  __shared__ float sh[16][64];
+  __shared__ float local[kXrankSlotFloats];
+  uint32_t* mine = P.ctl[rank];
+  const uint32_t par = (*reinterpret_cast<volatile uint32_t*>(mine + kXrEpoch) + 1) & 1u;
+  const int part = threadIdx.x >> 6, t = threadIdx.x & 63;
+  const int G2 = groups * 2;
+  for (int b = 0; b < NB; ++b)
+    for (int i0 = 0; i0 < G2; i0 += 64) {
+      const int i = i0 + t;
+      float acc = 0.0f;
+      if (i < G2)
+        for (int c = part; c < nchunks; c += 16) acc += partial[((size_t)b * nchunks_stride + c) * G2 + i];
+      sh[part][t] = acc;
+      __syncthreads();
+      if (part == 0 && i < G2) {
+        float v[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) v[k] = sh[k][t];
+#pragma unroll
+        for (int w = 8; w > 0; w >>= 1)
+#pragma unroll
+          for (int k = 0; k < w; ++k) v[k] += v[k + w];
+        local[b * G2 + i] = v[0];
+      }
+      __syncthreads();
+    }
+  const int n = NB * G2;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float v = local[i];
+    for (int r = 0; r < world; ++r)
+      reinterpret_cast<float*>(P.ctl[r] + kXrSlots)[((size_t)par * kXrankMaxRanks + rank) * kXrankSlotFloats + i] = v;
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < 32) xrank_sync_warp(P, rank, world);
+  __syncthreads();
+  const float* slots = reinterpret_cast<const float*>(mine + kXrSlots) + (size_t)par * kXrankMaxRanks * kXrankSlotFloats;
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
     float acc = 0.0f;
     for (int r = 0; r < world; ++r) acc += __ldcg(slots + (size_t)r * kXrankSlotFloats + i);
@@ -272,8 +349,9 @@ __global__ void layernorm_kernel(const __half* __restrict__ x, int rows, int C, 
 
 struct GnPlan {
   int nvec, rows_par, threads, nchunks, rows_per_chunk, rows_per_block, row_blocks;
+  bool fused;   // the statistics kernel's last block folds (small tensors: few, fat chunks)
 };
-static GnPlan gn_plan(int C, int rows) {
+static GnPlan gn_plan(int C, int rows, int NB = 1) {
   GnPlan g;
   g.nvec = C / 8;
   g.rows_par = g.nvec >= 256 ? 1 : 256 / g.nvec;
@@ -282,6 +360,14 @@ static GnPlan gn_plan(int C, int rows) {
   g.nchunks = (rows + g.rows_par * kGnUnroll * 8 - 1) / (g.rows_par * kGnUnroll * 8);
   if (g.nchunks > kGnMaxChunks) g.nchunks = kGnMaxChunks;
   if (g.nchunks < 1) g.nchunks = 1;
+  // small tensors (<= 32 MB: a frame shard, the deep levels, per-frame norms): a chunk per ~2 SMs' worth of blocks is
+  // plenty, and at most 24 chunks keep the fused fold a short chain -- two launches per GroupNorm instead of three
+  g.fused = (size_t)NB * rows * C * 2 <= (32u << 20);
+  if (g.fused) {
+    int want = (2 * num_sms() + NB - 1) / NB;
+    if (want > 24) want = 24;
+    if (g.nchunks > want) g.nchunks = want;
+  }
   g.rows_per_chunk = (rows + g.nchunks - 1) / g.nchunks;
   // apply: a few unrolled steps per thread and block
   g.rows_per_block = g.rows_par * kGnUnroll * 4;
@@ -291,7 +377,7 @@ static GnPlan gn_plan(int C, int rows) {
 
 static int gn_launch_stats(const void* X1, const void* X2, int C1, int C2, int NB, int rows, int groups, float* sums,
                            void* workspace, cudaStream_t st, const XrankPeers* peers = nullptr, int rank = 0, int world = 0) {
-  const GnPlan g = gn_plan(C1 + C2, rows);
+  const GnPlan g = gn_plan(C1 + C2, rows, NB);
   UV_REQUIRE(g.threads >= 128, "groupnorm: at least 128 threads per block (channels %% 8, rows_par) -- internal plan error");
   UV_REQUIRE(world <= 1 || NB * groups * 2 <= kXrankSlotFloats, "groupnorm: NB * groups * 2 exceeds the exchange slot (%d floats)",
              kXrankSlotFloats);
@@ -302,8 +388,15 @@ static int gn_launch_stats(const void* X1, const void* X2, int C1, int C2, int N
   XrankPeers none{};
   gn_stats_kernel<<<dim3(g.nchunks, NB), g.threads, g.threads * 8 * sizeof(float), st>>>(
       (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace, sums,
-      arrivals + slot, peers ? *peers : none, rank, world);
+      g.fused ? arrivals + slot : nullptr, peers ? *peers : none, rank, world);
   UV_CHECK_CUDA(cudaGetLastError());
+  if (!g.fused) {
+    if (world > 1)
+      gn_fold_xrank_kernel<<<1, 1024, 0, st>>>((const float*)workspace, g.nchunks, g.nchunks, NB, groups, sums, *peers, rank, world);
+    else
+      gn_fold_kernel<<<NB, 1024, 0, st>>>((const float*)workspace, g.nchunks, groups, sums);
+    UV_CHECK_CUDA(cudaGetLastError());
+  }
   return UNIVST_OK;
 }
 
