@@ -11,7 +11,9 @@
  *   - all tensor pointers are DEVICE pointers owned by the caller, fp16 unless the name says otherwise,
  *     16-byte aligned; activations are frames-major / channels-last: [images, H, W, C] == [tokens, C];
  *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
- *   - no global mutable state besides a per-process cache of device properties: thread-compatible.
+ *   - thread-compatible: the only process-wide state is a cache of device properties, the opt-in split-K switch and
+ *     workspace registry (univst_gemm_tune / univst_gemm_set_workspace, keyed by stream) and a ring of arrival counters of
+ *     the GroupNorm statistics kernel in device memory; nothing else outlives a call.
  */
 #ifndef UNIVST_B200_H_
 #define UNIVST_B200_H_
