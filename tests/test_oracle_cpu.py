@@ -84,7 +84,7 @@ def test_library_exports_every_declared_symbol():
     build.build()
     lib = _lib.lib()
     header = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "univst_b200.h")).read()
-    declared = set(re.findall(r"^(?:int|int64_t|const char\*)\s+(univst_[a-z0-9_]+)\s*\(", header, re.M))
+    declared = set(re.findall(r"^(?:int|int32_t|int64_t|const char\*)\s+(univst_[a-z0-9_]+)\s*\(", header, re.M))
     assert len(declared) >= 20
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
@@ -447,7 +447,7 @@ def test_header_is_valid_c_and_links_against_the_library(tmp_path):
     so = build.build()
     root = os.path.abspath(os.path.join(os.path.dirname(GOLDEN), ".."))
     header = open(os.path.join(root, "include", "univst_b200.h")).read()
-    names = sorted(set(re.findall(r"^(?:int|int64_t|const char\*)\s+(univst_[a-z0-9_]+)\s*\(", header, re.M)))
+    names = sorted(set(re.findall(r"^(?:int|int32_t|int64_t|const char\*)\s+(univst_[a-z0-9_]+)\s*\(", header, re.M)))
     src = tmp_path / "abi.c"
     src.write_text(
         '#include <stdio.h>\n#include <string.h>\n#include "univst_b200.h"\n'
