@@ -556,15 +556,20 @@ def run_ours(args):
                                    "bit_identical_to_1gpu": bool(torch.equal(out_ads, out_ad)),
                                    "rel_l2_vs_1gpu": rel(out_ads, out_ad), "split_k": split_k,
                                    "cuda_graphs": bool(unet_ad.use_cuda_graphs)}
-            assert ad["frame_sharded"]["rel_l2_vs_1gpu"] < 5e-3 and (split_k or ad["frame_sharded"]["bit_identical_to_1gpu"]), \
-                f"AnimateDiff frame-sharded result differs from one GPU: {ad['frame_sharded']}"
+            ad["frame_sharded"]["parity_ok"] = bool(ad["frame_sharded"]["rel_l2_vs_1gpu"] < 5e-3
+                                                    and (split_k or ad["frame_sharded"]["bit_identical_to_1gpu"]))
+            assert ad["frame_sharded"]["parity_ok"], f"AnimateDiff frame-sharded result differs from one GPU: {ad['frame_sharded']}"
+            unet_ad.set_frame_sharding_off()   # (also switches the split-K of few-tile GEMMs back off)
         extra["animatediff_v2_backbone"] = ad
 
     # ---- extra: BASELINE.json configs[2] (SD-2.1 shapes, 32 frames, smoother on) at the world size it names (4 GPUs); one
     # GPU with --config2
     if (world == 4 and not args.no_extras) or args.config2:
         torch.cuda.empty_cache()
-        extra["sd21_32_frames_flow_smoothing"] = run_sd21_smoother(dev, world, rank, args, timed, rel)
+        try:   # a supplementary pass must not take the headline line down with it (failures are symmetric across ranks)
+            extra["sd21_32_frames_flow_smoothing"] = run_sd21_smoother(dev, world, rank, args, timed, rel)
+        except Exception as e:  # noqa: BLE001
+            extra["sd21_32_frames_flow_smoothing"] = {"error": repr(e)[:400]}
 
     # ---- extra: BASELINE.json configs[4] (SD-3.5-medium shapes, rectified flow) at the world size it names (8 GPUs); any N
     # with --config5
@@ -572,7 +577,10 @@ def run_ours(args):
         if not args.no_extras:
             unet_ad = pipe_ad = None   # noqa: F841  (free the AnimateDiff model before building the 2.2 B-parameter MMDiT)
         torch.cuda.empty_cache()
-        extra["sd35_medium_rectified_flow"] = run_sd35_rectified_flow(dev, world, rank, args, timed, rel)
+        try:
+            extra["sd35_medium_rectified_flow"] = run_sd35_rectified_flow(dev, world, rank, args, timed, rel)
+        except Exception as e:  # noqa: BLE001
+            extra["sd35_medium_rectified_flow"] = {"error": repr(e)[:400]}
 
     # dominant-kernel time: max over ranks (rank 0 holds the clip's first frames, whose [previous, first] sources collapse
     # to one deduplicated source -- half the keys -- so its launches are not representative)
