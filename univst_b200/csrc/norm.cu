@@ -27,7 +27,9 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, const __half* x
 
 // arrival counters of the statistics kernels (zero at module load, re-armed by the last block of every launch); the host
 // hands consecutive launches different slots
-__device__ unsigned g_gn_arrivals[64];
+static constexpr int kGnFusedChunks = 24;     // a fused fold adds at most this many chunk partials per entry
+static constexpr int kGnMaxFusedNB = 255;     // per-entry counters [0, 255), the all-entries counter at [255]
+__device__ unsigned g_gn_arrivals[64 * 256];
 
 // grid (nchunks, NB).  partial[b][chunk][group][2] = (sum, sumsq); the LAST block to finish folds the chunk partials of every
 // batch entry into sums[b][group][2] in a fixed order (deterministic, no float atomics) -- and, when the statistics span
@@ -87,48 +89,60 @@ __global__ void gn_stats_kernel(const __half* __restrict__ x1, const __half* __r
     out[g * 2 + 1] = gq;
   }
   if (!arrivals) return;   // big tensors: a separate, wider fold kernel follows (gn_launch_stats)
-  // ---- last block: fold (and exchange)
-  __shared__ int s_last;
+  // ---- the last block of batch entry b folds b's chunk partials (<= kGnFusedChunks of them: one round of independent
+  // loads, then a fixed-order sum); with statistics that span other ranks, the block that completes the last entry exchanges
+  __shared__ int s_last, s_last_all;
   __threadfence();
   __syncthreads();
+  const int NB = gridDim.y, nchunks = gridDim.x, G2 = groups * 2;
   if (threadIdx.x == 0) {
-    const unsigned t = atomicAdd(arrivals, 1u);
-    s_last = (t == gridDim.x * gridDim.y - 1);
-    if (s_last) *reinterpret_cast<volatile unsigned*>(arrivals) = 0;
+    const unsigned t = atomicAdd(arrivals + b, 1u);
+    s_last = (t == gridDim.x - 1);
+    if (s_last) *reinterpret_cast<volatile unsigned*>(arrivals + b) = 0;
   }
   __syncthreads();
   if (!s_last) return;
   __threadfence();
-  const int NB = gridDim.y, nchunks = gridDim.x, G2 = groups * 2;
   const int parts = blockDim.x >> 6;                 // blockDim >= 128: at least two interleaved partial sums per entry
   const int part = threadIdx.x >> 6, tt = threadIdx.x & 63;
   float* fold = sh;                                   // [parts][64]
-  __shared__ float local[kXrankSlotFloats];
-  for (int bb = 0; bb < NB; ++bb)
-    for (int i0 = 0; i0 < G2; i0 += 64) {
-      const int i = i0 + tt;
-      float acc = 0.0f;
-      if (part < parts && i < G2)
-        for (int c = part; c < nchunks; c += parts) acc += __ldcg(partial + ((size_t)bb * nchunks + c) * G2 + i);
-      if (part < parts) fold[part * 64 + tt] = acc;
-      __syncthreads();
-      if (part == 0 && i < G2) {
-        float v = fold[tt];
-        for (int k = 1; k < parts; ++k) v += fold[k * 64 + tt];
-        if (world > 1)
-          local[bb * G2 + i] = v;
-        else
-          sums[(size_t)bb * G2 + i] = v;
-      }
-      __syncthreads();
+  float* dst = (world > 1) ? partial + ((size_t)NB * nchunks) * G2 : sums;   // sharded: parked behind the partials first
+  for (int i0 = 0; i0 < G2; i0 += 64) {
+    const int i = i0 + tt;
+    float v[kGnFusedChunks / 2];
+#pragma unroll
+    for (int k = 0; k < kGnFusedChunks / 2; ++k) {
+      const int c = part + k * parts;
+      v[k] = (part < parts && i < G2 && c < nchunks) ? __ldcg(partial + ((size_t)b * nchunks + c) * G2 + i) : 0.0f;
     }
+    float acc = 0.0f;
+#pragma unroll
+    for (int k = 0; k < kGnFusedChunks / 2; ++k) acc += v[k];
+    if (part < parts) fold[part * 64 + tt] = acc;
+    __syncthreads();
+    if (part == 0 && i < G2) {
+      float r = fold[tt];
+      for (int k = 1; k < parts; ++k) r += fold[k * 64 + tt];
+      dst[(size_t)b * G2 + i] = r;
+    }
+    __syncthreads();
+  }
   if (world <= 1) return;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned t = atomicAdd(arrivals + kGnMaxFusedNB, 1u);
+    s_last_all = (t == (unsigned)NB - 1);
+    if (s_last_all) *reinterpret_cast<volatile unsigned*>(arrivals + kGnMaxFusedNB) = 0;
+  }
+  __syncthreads();
+  if (!s_last_all) return;
+  __threadfence();
   uint32_t* ctl = P.ctl[rank];
   const uint32_t par = (*reinterpret_cast<volatile uint32_t*>(ctl + kXrEpoch) + 1) & 1u;
   const int n = NB * G2;
-  __syncthreads();
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const float v = local[i];
+    const float v = __ldcg(dst + i);
     for (int r = 0; r < world; ++r)
       reinterpret_cast<float*>(P.ctl[r] + kXrSlots)[((size_t)par * kXrankMaxRanks + rank) * kXrankSlotFloats + i] = v;
   }
@@ -360,14 +374,12 @@ static GnPlan gn_plan(int C, int rows, int NB = 1) {
   g.nchunks = (rows + g.rows_par * kGnUnroll * 8 - 1) / (g.rows_par * kGnUnroll * 8);
   if (g.nchunks > kGnMaxChunks) g.nchunks = kGnMaxChunks;
   if (g.nchunks < 1) g.nchunks = 1;
-  // small tensors (<= 32 MB: a frame shard, the deep levels, per-frame norms): a chunk per ~2 SMs' worth of blocks is
-  // plenty, and at most 24 chunks keep the fused fold a short chain -- two launches per GroupNorm instead of three
-  g.fused = (size_t)NB * rows * C * 2 <= (32u << 20);
-  if (g.fused) {
-    int want = (2 * num_sms() + NB - 1) / NB;
-    if (want > 24) want = 24;
-    if (g.nchunks > want) g.nchunks = want;
-  }
+  // small statistics spans (<= 8 MB per batch entry: a frame shard, the deep levels, per-frame norms): at most 24 fat
+  // chunks, folded by the entry's last block -- two launches per GroupNorm instead of three.  The plan is a function of
+  // (C, rows) ALONE: the summation order of an entry's statistics must not depend on how many entries share the launch
+  // (a one-branch call must reproduce the edit branch of a three-branch call bit for bit; a frame shard its frames).
+  g.fused = (size_t)rows * C * 2 <= (8u << 20) && NB < kGnMaxFusedNB;
+  if (g.fused && g.nchunks > kGnFusedChunks) g.nchunks = kGnFusedChunks;
   g.rows_per_chunk = (rows + g.nchunks - 1) / g.nchunks;
   // apply: a few unrolled steps per thread and block
   g.rows_per_block = g.rows_par * kGnUnroll * 4;
@@ -384,7 +396,7 @@ static int gn_launch_stats(const void* X1, const void* X2, int C1, int C2, int N
   static unsigned next_slot = 0;
   static unsigned* arrivals = nullptr;
   if (!arrivals) UV_CHECK_CUDA(cudaGetSymbolAddress((void**)&arrivals, g_gn_arrivals));
-  const unsigned slot = (next_slot++) & 63u;
+  const unsigned slot = ((next_slot++) & 63u) * 256u;
   XrankPeers none{};
   gn_stats_kernel<<<dim3(g.nchunks, NB), g.threads, g.threads * 8 * sizeof(float), st>>>(
       (const __half*)X1, (const __half*)X2, C1, C2, rows, groups, g.nvec, g.rows_par, g.rows_per_chunk, (float*)workspace, sums,
