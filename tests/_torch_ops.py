@@ -46,8 +46,10 @@ def _epilogue(acc, bias, rowvec, rows_per_group, residual, bias2, geglu, out_sca
     if residual is not None:
         y = y + _f(residual)
     y = y * out_scale
-    if act:
+    if act in (True, 1, "silu"):
         y = F.silu(y.half().float())
+    elif act in (2, "gelu_tanh"):
+        y = F.gelu(y.half().float(), approximate="tanh")
     if bias2 is not None:
         y = y.half().float() + _f(bias2)
     return y.half()
@@ -185,12 +187,119 @@ def axpby(a, b, wa, wb, out=None):
     return (wa * _f(a) + wb * _f(b)).half()
 
 
+# ------------------------------------------------------------------------------------------------ round 2: VAE / SD3 / xrank-free helpers
+def conv3x3_s2_pad_after(planes, w, *, bias=None, out=None):
+    _, NB, h2, w2, C = planes.shape
+    full = torch.empty(NB, 2 * h2, 2 * w2, C)
+    for hp in range(2):
+        for wp in range(2):
+            full[:, hp::2, wp::2] = _f(planes[hp * 2 + wp])
+    Cout = w.shape[0]
+    w4 = _f(w).view(Cout, 3, 3, -1).permute(0, 3, 1, 2)
+    y = F.conv2d(F.pad(full.permute(0, 3, 1, 2), (0, 1, 0, 1)), w4, None if bias is None else _f(bias), stride=2)
+    y = y.permute(0, 2, 3, 1).reshape(-1, Cout).half()
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def conv_temporal3(x, w, *, NB, F, HW, bias=None, residual=None, out=None):
+    C, Cout = x.shape[1], w.shape[0]
+    x5 = _f(x).view(NB, F, HW, 1, C).permute(0, 4, 1, 2, 3)
+    w5 = _f(w).view(Cout, 3, -1)[:, :, :C].permute(0, 2, 1).reshape(Cout, C, 3, 1, 1)
+    y = torch.nn.functional.conv3d(x5, w5, None if bias is None else _f(bias), padding=(1, 0, 0))
+    y = y.permute(0, 2, 3, 4, 1).reshape(-1, Cout)
+    if residual is not None:
+        y = y + _f(residual)
+    y = y.half()
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def softmax_rows_(x, scale=1.0):
+    x.copy_(torch.softmax(_f(x) * scale, dim=-1).half())
+    return x
+
+
+def frames_to_u8(x, pixels):
+    f = (x[:pixels, :3] / 2 + 0.5).clamp(0, 1).float()
+    return (f * 255).round().to(torch.uint8)
+
+
+def u8_to_frames(img, cpad=64):
+    out = torch.zeros(img.numel() // 3, cpad, dtype=torch.float16)
+    out[:, :3] = (img.reshape(-1, 3).double() / 127.5 - 1.0).half()
+    return out
+
+
+def vae_sample(moments, noise, C_, Fr, HW, scaling):
+    m = _f(moments[:, :2 * C_]).view(Fr, HW, 2 * C_)
+    z = m[..., :C_]
+    if noise is not None:
+        z = z + torch.exp(0.5 * m[..., C_:].clamp(-30, 20)) * _f(noise).view(Fr, C_, HW).transpose(1, 2)
+    return (scaling * z).permute(2, 0, 1).reshape(1, C_, Fr, HW).half()
+
+
+def layernorm_modulate(x, scale, shift, rows_per_sample, eps=1e-6, out=None):
+    y = F.layer_norm(_f(x), (x.shape[-1],), eps=eps)
+    return (y * (1 + _f(scale).repeat_interleave(rows_per_sample, 0)) + _f(shift).repeat_interleave(rows_per_sample, 0)).half()
+
+
+def gated_add(x, y, gate, rows_per_sample, out=None):
+    return (_f(x) + (_f(gate).repeat_interleave(rows_per_sample, 0) * _f(y)).half().float()).half()
+
+
+def rmsnorm_heads_(qkv, H, d, wq, wk, eps=1e-6):
+    C = H * d
+    for blk, w in ((0, wq), (1, wk)):
+        if w is None:
+            continue
+        t = _f(qkv[:, blk * C:(blk + 1) * C]).view(-1, H, d)
+        t = t * torch.rsqrt(t.pow(2).mean(-1, keepdim=True) + eps) * _f(w)
+        qkv[:, blk * C:(blk + 1) * C] = t.reshape(-1, C).half()
+    return qkv
+
+
+def sd3_attn_shift_(qkv, Fr, N, H, d, alpha, beta, gamma):
+    """backbones/video_diffusion_sd3/pnp_utils.py:180-193 + attention_adain :287-300 on the fused [3 F N, 3 H d] buffer."""
+    C = H * d
+
+    def adain(cnt, sty):   # (F, H, N, d): style stats over the tokens, content instance norm over (N, d) per (frame, head)
+        return F.instance_norm(cnt) * sty.std(dim=[-2], keepdim=True) + sty.mean(dim=[-2], keepdim=True)
+    q, k, v = (_f(qkv[:, i * C:(i + 1) * C]).view(3, Fr, N, H, d).permute(0, 1, 3, 2, 4) for i in range(3))
+    q2 = gamma * (alpha * q[0] + (1 - alpha) * q[2])
+    k2 = beta * adain(k[2], k[1]) + (1 - beta) * k[1]
+    v2 = beta * adain(v[2], v[1]) + (1 - beta) * v[1]
+    for i, t in enumerate((q2, k2, v2)):
+        qkv[2 * Fr * N:, i * C:(i + 1) * C] = t.permute(0, 2, 1, 3).reshape(Fr * N, C).half()
+    return qkv
+
+
+def joint_attention(q, k, v, k2, v2, kv_src, *, NI, NIkv, NIkv2, H, d, N, Nkv, Nkv2, out=None):
+    heads = lambda t, img, n: _f(t[img * n:(img + 1) * n]).view(n, H, d).transpose(0, 1)
+    res = torch.empty(NI * N, H * d, dtype=torch.float16)
+    table = kv_src.view(NI, -1).tolist()
+    for i in range(NI):
+        ks = [heads(k, s, Nkv) if s < NIkv else heads(k2, s - NIkv, Nkv2) for s in table[i]]
+        vs = [heads(v, s, Nkv) if s < NIkv else heads(v2, s - NIkv, Nkv2) for s in table[i]]
+        res[i * N:(i + 1) * N] = F.scaled_dot_product_attention(heads(q, i, N), torch.cat(ks, 1), torch.cat(vs, 1)) \
+            .transpose(0, 1).reshape(N, H * d).half()
+    return res
+
+
+ROUND2 = ("conv3x3_s2_pad_after", "conv_temporal3", "softmax_rows_", "frames_to_u8", "u8_to_frames", "vae_sample",
+          "layernorm_modulate", "gated_add", "rmsnorm_heads_", "sd3_attn_shift_", "joint_attention")
+
+
 def install(monkeypatch=None):
     """Swap the definitions into ``univst_b200.ops`` (through ``monkeypatch`` in a test, directly in a worker script)."""
     from univst_b200 import ops
     for name in ("pack_latents", "unpack_latents", "timestep_embedding", "gemm", "conv3x3", "groupnorm", "groupnorm_sharded",
                  "layernorm", "sc_attention", "cross_attention", "temporal_attention", "attn_shift_", "upsample2x",
-                 "space_to_depth2", "mask_resize", "latent_blend", "latent_adain", "ddim_step", "axpby"):
+                 "space_to_depth2", "mask_resize", "latent_blend", "latent_adain", "ddim_step", "axpby") + ROUND2:
         if monkeypatch is not None:
             monkeypatch.setattr(ops, name, globals()[name])
         else:
