@@ -57,6 +57,37 @@ def timed(fn, iters):
     return out, float(t)
 
 
+def op_profile(fn):
+    """Device time by entry point of ``univst_b200.ops`` for one call of ``fn`` (CUDA events around every op call)."""
+    import collections
+    from univst_b200 import ops
+    recs, originals = collections.defaultdict(list), {}
+    for name in list(ops._LAUNCHES):
+        real = name if hasattr(ops, name) else name + "_"
+        f = getattr(ops, real, None)
+        if f is None:
+            continue
+
+        def wrap(f=f, name=name):
+            def inner(*a, **k):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                out = f(*a, **k)
+                e.record()
+                recs[name].append((s, e))
+                return out
+            return inner
+        originals[real] = f
+        setattr(ops, real, wrap())
+    try:
+        fn()
+        torch.cuda.synchronize()
+    finally:
+        for real, f in originals.items():
+            setattr(ops, real, f)
+    return {name: [round(sum(s.elapsed_time(e) for s, e in ev), 3), len(ev)] for name, ev in recs.items()}
+
+
 def main():
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     F = int(args[0]) if len(args) > 0 else 16
@@ -114,6 +145,23 @@ def main():
                                      "xrank_vs_single_max_abs": float(dx.abs().max()),
                                      "xrank_vs_single_rel_l2": float(dx.norm() / ref.float().norm()),
                                      "xrank_graph_vs_eager_max_abs": float((out_g.float() - out_x.float()).abs().max())})
+            if "--profile" in sys.argv:   # where a rank's time goes: per entry point, this rank's shard vs the same shard alone
+                fn = lambda: unet(x, t, encoder_hidden_states=ctx)
+                fn()
+                prof = op_profile(fn)
+                unet.set_frame_sharding_off()
+                Fl = F // world
+                xs = x[:, :, rank * Fl:(rank + 1) * Fl].contiguous()
+                from univst_b200 import ops as _ops
+                _ops.gemm_splitk(74 if world >= 4 else 0)
+                fn1 = lambda: unet(xs, t, encoder_hidden_states=ctx)
+                fn1()
+                prof1 = op_profile(fn1)
+                _ops.gemm_splitk(0)
+                unet.set_frame_sharding(transport="xrank")
+                pl = [None] * world
+                dist.all_gather_object(pl, {"sharded": prof, "alone": prof1})
+                res[f"idx{idx}"]["op_ms_by_rank"] = pl
             # all ranks must hold the same result (the statistics are added in the same order everywhere)
             gathered = [torch.empty_like(out_x) for _ in range(world)]
             dist.all_gather(gathered, out_x.contiguous())
