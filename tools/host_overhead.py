@@ -47,10 +47,13 @@ def main():
     ops._stream = lambda: 0
     torch.cuda.current_stream = lambda *a, **k: SimpleNamespace(cuda_stream=0)   # the only CUDA runtime query on the path
     ops._chk = lambda *a, **k: None            # the CUDA-placement checks (cheap attribute reads) cannot pass on CPU tensors
+    torch.Tensor.is_cuda = property(lambda self: True)   # (the wrappers' own `t.is_cuda` asserts likewise)
     sd = {k: torch.empty(s, dtype=torch.float16) for k, s in unet_param_shapes(SD15_CONFIG).items()}
-    for k in sd:
-        if "attn_temporal.to_out.0.weight" in k:
+    for k in sd:   # the temporal parts at their constructor values (the UNet verifies them at pack time)
+        if "attn_temporal.to_out.0.weight" in k or "conv_temporal" in k:
             sd[k].zero_()
+        if "conv_temporal.weight" in k:
+            sd[k] = torch.nn.init.dirac_(torch.zeros(sd[k].shape)).half()
     unet = UNetPseudo3DConditionModel(sd, SD15_CONFIG, device="cpu")
     pipe = SimpleNamespace(unet=unet)
     pnp_utils.register_spatial_attention_pnp(pipe)
