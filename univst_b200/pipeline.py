@@ -137,9 +137,9 @@ class SpatioTemporalStableDiffusionPipeline:
                 from .flow_warp import sliding_window_smooth
                 x0 = torch.empty_like(z)
                 ops.ddim_step(z, self.unet.last_eps_rows, self.unet.last_edit_branch, a_t, a_prev, x0_out=x0)   # :718
-                frames = self.vae.decode_latents_u8(x0)                                                          # :721
+                frames = self._smoother_decode(x0)                                                               # :721
                 est = sliding_window_smooth(frames, keep_mask=keep_u8, flow_fn=flow_fn)                          # :725-751
-                x0s = self.vae.encode_frames_u8(est, generator=smoother_generator)                               # :753
+                x0s = self._smoother_encode(est, smoother_generator)                                             # :753
                 eps = ops.axpby(z, x0s, 1.0 / (1.0 - a_t) ** 0.5, -(a_t ** 0.5) / (1.0 - a_t) ** 0.5)           # :782-791
                 x0r = ops.axpby(z, eps, 1.0 / a_t ** 0.5, -((1.0 - a_t) ** 0.5) / a_t ** 0.5)                  # the step's own x0
                 z = ops.axpby(x0r, eps, a_prev ** 0.5, (1.0 - a_prev) ** 0.5)                                    # :761
@@ -165,6 +165,64 @@ class SpatioTemporalStableDiffusionPipeline:
             z = ops.ddim_step(z, self.unet.last_eps_rows, 0, a_t, a_prev)
         images = self.decode_latents(z) if self.vae is not None else None
         return SimpleNamespace(images=images, latents=z)
+
+    # ------------------------------------------------------------------------------------------ smoother legs
+    def _smoother_xr(self, F, W):
+        """The cross-rank plumbing of a frame-sharded UNet (xrank transport) when the smoother's VAE legs can be spread over
+        its ranks: decode chunks (16 frames = one clip to the temporal decoder, :803-811) round-robin, encode frames evenly."""
+        shard, xr = getattr(self.unet, "_shard", None), getattr(self.unet, "_xr", None)
+        if shard is None or xr is None or F % xr.world or (W * 3 // 2) % 8 or (W * 3) % 2 or not hasattr(self.vae, "decode_latents_u8"):
+            return None
+        return xr
+
+    def _smoother_decode(self, x0, decode_chunk_size: int = 16):
+        """``get_images_from_latents`` (stable_diffusion.py:793-819).  Frames sharded over GPUs: the 16-frame chunks are
+        independent clips to the temporal decoder, so chunk c is decoded by rank c mod P and its uint8 frames are stored
+        into every rank's full-clip buffer over NVLink (one multicast store per 16 bytes; the kernel's tail synchronises) --
+        the same bits as decoding everything on every rank."""
+        _, C, F, h, w = x0.shape
+        H, W = 8 * h, 8 * w
+        xr = self._smoother_xr(F, W)
+        if xr is None:
+            return self.vae.decode_latents_u8(x0, decode_chunk_size)
+        cols = W * 3 // 2                                              # a uint8 frame row as fp16 pairs
+        key = ("vae_frames", F, H, W)
+        full, ptrs = xr.buffer(key, (F * H, cols))
+        mc = xr.multicast(key)
+        nchunks = (F + decode_chunk_size - 1) // decode_chunk_size
+        for r0 in range(0, nchunks, xr.world):                         # every rank issues the same number of pushes
+            c = r0 + xr.rank
+            pushes = []
+            if c < nchunks:
+                f0, n = c * decode_chunk_size, min(decode_chunk_size, F - c * decode_chunk_size)
+                u8 = self.vae.decode_latents_u8(x0[:, :, f0:f0 + n].contiguous(), decode_chunk_size)
+                src = u8.reshape(n * H, W * 3).view(torch.float16)
+                off = f0 * H * cols * 2
+                pushes = [dict(src=src, src_blk_rows=n * H, dst=[p + off for p in ptrs], ld_dst=cols, dst_blk_rows=n * H, nblk=1,
+                               rows=n * H, mc=mc + off if mc else 0)]
+            ops.xrank_push(xr, pushes)
+        return full.view(torch.uint8).view(F, H, W, 3)
+
+    def _smoother_encode(self, frames_u8, generator):
+        """``get_latent_image`` (:821-834).  The KL encoder is per frame: under frame sharding every rank encodes its own
+        frames with its slice of the clip's posterior noise (drawn identically on every rank) and the latents are stored into
+        every rank's buffer -- bit-identical to encoding the whole clip on every rank."""
+        F, H, W, _ = frames_u8.shape
+        xr = self._smoother_xr(F, W)
+        if xr is None:
+            return self.vae.encode_frames_u8(frames_u8, generator=generator)
+        C, h, w = self.vae.config.latent_channels, H // 8, W // 8
+        noise = torch.randn((F, C, h, w), generator=generator, device=self.device, dtype=torch.float16)
+        Fl = F // xr.world
+        mine = slice(xr.rank * Fl, (xr.rank + 1) * Fl)
+        lat = self.vae.encode_frames_u8(frames_u8[mine].contiguous(), noise=noise[mine])          # (1, C, Fl, h, w)
+        key = ("vae_latents", C, F, h * w)
+        full, ptrs = xr.buffer(key, (C, F * h * w))
+        mc = xr.multicast(key)
+        off = xr.rank * Fl * h * w * 2
+        ops.xrank_push(xr, [dict(src=lat.view(C, Fl * h * w), src_blk_rows=C, dst=[p + off for p in ptrs], ld_dst=F * h * w,
+                                 dst_blk_rows=C, nblk=1, rows=C, mc=mc + off if mc else 0)])
+        return full.view(1, C, F, h, w).clone()
 
     def decode_latents(self, latents, decode_chunk_size: int = 16):
         """stable_diffusion.py:369-394: 1 / 0.18215, decode ``decode_chunk_size`` frames at a time (the temporal decoder sees

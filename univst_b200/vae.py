@@ -173,15 +173,18 @@ class AutoencoderKLTemporalDecoder:
         return SimpleNamespace(latent_dist=_Posterior(self, mom, N, h, w))
 
     @torch.no_grad()
-    def encode_frames_u8(self, frames_u8, generator=None, sample: bool = True):
+    def encode_frames_u8(self, frames_u8, generator=None, sample: bool = True, noise=None):
         """uint8 frames (F, H, W, 3) -> latents (1, C, F, h, w) already multiplied by the scaling factor: the smoother's
-        ``get_latent_image`` (stable_diffusion.py:821-834) and the inversion's encode (ddim_inversion.py:20-31) in one call."""
+        ``get_latent_image`` (stable_diffusion.py:821-834) and the inversion's encode (ddim_inversion.py:20-31) in one call.
+        ``noise`` (F, C, h, w) fp16: the posterior noise of these frames when the caller drew it (a frame shard passes its
+        slice of the clip's noise, so that sharded and unsharded encodes agree bit for bit)."""
         F_, H, Wd, _ = frames_u8.shape
         rows = ops.u8_to_frames(frames_u8.to(self.device).contiguous(), CPAD)
         mom, h, w = self._encode_rows(rows, F_, H, Wd)
         C = self.config.latent_channels
-        noise = None
-        if sample:
+        if noise is not None:
+            noise = noise.to(self.device, torch.float16).contiguous()
+        elif sample:
             noise = torch.randn((F_, C, h, w), generator=generator, device=self.device, dtype=torch.float16).contiguous()
         return ops.vae_sample(mom, noise, C, F_, h * w, self.config.scaling_factor).view(1, C, F_, h, w)
 
