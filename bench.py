@@ -264,8 +264,9 @@ def run_sd21_smoother(dev, world, rank, args, timed, rel):
     """BASELINE.json configs[2]: SD-2.1 shapes (head dim 64, 1024-wide context, Linear proj_in / proj_out), 32 frames of
     512 x 512 sharded over the ranks, sliding-window flow smoothing on (steps 20..24, stable_diffusion.py:713-758): predicted
     x0 -> temporal VAE decode -> +-2-frame window of flow-warped neighbours -> mask -> VAE encode -> noise recomputed.
-    The UNet is frame-sharded; the smoother legs (VAE + warp pass) are evaluated on the whole clip by every rank (the
-    temporal decoder couples all frames of a 16-frame chunk and the window pass is sequential in the key frame, :731-747).
+    The UNet is frame-sharded; of the smoother legs the temporal decoder is spread by 16-frame chunks (one chunk = one clip to
+    its temporal layers, :803-811) and the per-frame encoder by frames, both gathered through peer memory; the window pass,
+    sequential in the key frame (:731-747), is evaluated by every rank.
     Flows: synthetic (2.5, -1.25) px translation + sinusoidal field (RAFT's weights are not available offline); VAE: SVD VAE
     shapes with seeded random weights (parity unpinned, univst_b200/vae.py).  Checked against the 1-GPU run of the same clip."""
     import numpy as np
@@ -317,7 +318,8 @@ def run_sd21_smoother(dev, world, rank, args, timed, rel):
         res["frame_sharded"] = {"n_gpus": world, "frames_per_gpu": Fr // world, "ms_per_clip": ms_n / 2,
                                 "frames_per_s": Fr / (ms_n / 2e3), "speedup_vs_1gpu_same_box": ms_1 / (ms_n / 2),
                                 "rel_l2_vs_1gpu": r, "cuda_graphs": bool(unet.use_cuda_graphs),
-                                "note": "UNet frame-sharded; VAE + warp pass on the whole clip on every rank"}
+                                "note": "UNet frame-sharded; VAE decode by 16-frame chunks round-robin over the ranks, encode by frames, both "
+                                        "gathered through peer memory; the (sequential) warp pass on every rank"}
         assert r < 1e-2, f"configs[2]: frame-sharded result differs from one GPU: {res}"
         unet.set_frame_sharding_off()
     return res
