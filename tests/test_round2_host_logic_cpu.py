@@ -72,3 +72,39 @@ def test_sd3_transformer_host_logic_on_cpu(monkeypatch, case, tmp_path):
     assert out.shape == ref.shape and _rel(out, ref) < 1e-2
     f = torch.load(os.path.join(tmp_path, "inversion_feature_map_0_block_3_step.pt"), weights_only=True)
     assert tuple(f.shape) == tuple(feats[0].shape) and _rel(f, feats[0]) < 1e-2
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_source_tables_name_the_right_frames(world):
+    """The K/V source tables of a frame shard (SD backbone: unet.kv_source_table_sharded; SD3 processors:
+    sd3._source_table_sharded) against the unsharded tables: every local / halo-bank index, mapped back to the global
+    (branch, frame) it holds -- bank 1 = last frame of the previous rank, bank 2 = frame 0 of the clip -- must name the
+    frame the unsharded table names."""
+    from univst_b200 import sd3
+    from univst_b200.unet import kv_source_table, kv_source_table_sharded
+    B, F = 3, 16
+    Fl = F // world
+    for rank in range(world):
+        NI = B * Fl
+
+        def to_global(idx):
+            if idx < NI:                                  # local image (b, fl)
+                b, fl = divmod(idx, Fl)
+                return b * F + rank * Fl + fl
+            if idx < NI + B:                              # bank 1: last frame of the previous rank
+                return (idx - NI) * F + rank * Fl - 1
+            return (idx - NI - B) * F                     # bank 2: frame 0 of the clip
+        for mode in ("prev_first", "prev_self_first", "self"):
+            full = kv_source_table(B, F, mode).tolist()
+            loc = kv_source_table_sharded(B, Fl, mode, rank).tolist()
+            for b in range(B):
+                for fl in range(Fl):
+                    want = full[b * F + rank * Fl + fl]
+                    assert [to_global(i) for i in loc[b * Fl + fl]] == want, (world, rank, mode, b, fl)
+        full3 = sd3._source_table(B * F, "cpu", True, text=False).tolist()
+        loc3 = sd3._source_table_sharded(B, Fl, rank, "cpu", text=True).tolist()
+        for b in range(B):
+            for fl in range(Fl):
+                me = b * Fl + fl
+                assert [to_global(i) for i in loc3[me][:3]] == full3[b * F + rank * Fl + fl], (world, rank, b, fl)
+                assert loc3[me][3] == NI + 2 * B + me          # own text tokens: second K/V tensor, behind all first-tensor images
