@@ -523,8 +523,15 @@ def groupnorm_xrank(x1, gamma, beta, *, NB, rows, xr, groups=32, eps=1e-5, silu=
     check(_lib.lib().univst_groupnorm_xrank_f16(x1.data_ptr(), _ptr(x2), C1, C2, NB, rows, groups, gamma.data_ptr(),
                                                 beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
                                                 xr.ctl, xr.rank, xr.world, _stream()), "univst_groupnorm_xrank_f16")
-    _count("groupnorm_xrank")
+    global launch_count
+    launch_count += _gn_launches(NB, rows, C1 + C2)
     return out
+
+
+def _gn_launches(NB: int, rows: int, C_: int) -> int:
+    """Kernels one GroupNorm launches (mirrors gn_plan in csrc/norm.cu): statistics spans of at most 8 MB are folded by the
+    statistics kernel's last block (statistics + apply); larger ones take the separate fold kernel."""
+    return 2 if rows * C_ * 2 <= (8 << 20) and NB < 255 else 3
 
 
 def groupnorm(x1: torch.Tensor, gamma, beta, *, NB: int, rows: int, groups: int = 32, eps: float = 1e-5,
@@ -539,7 +546,8 @@ def groupnorm(x1: torch.Tensor, gamma, beta, *, NB: int, rows: int, groups: int 
     check(_lib.lib().univst_groupnorm_f16(x1.data_ptr(), _ptr(x2), C1, C2, NB, rows, groups, gamma.data_ptr(),
                                           beta.data_ptr(), eps, 1 if silu else 0, out.data_ptr(), ws.data_ptr(),
                                           _stream()), "univst_groupnorm_f16")
-    _count("groupnorm")
+    global launch_count
+    launch_count += _gn_launches(NB, rows, C1 + C2)
     return out
 
 
