@@ -670,8 +670,12 @@ def main():
     os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
-    else:
-        run_ours(args)
+        return
+    if not torch.cuda.is_available():
+        # the product path is the sm_100a library and nothing else: no CPU fallback, no number without a GPU
+        sys.exit("bench.py: no CUDA device -- the hot path runs only on the sm_100a kernels of univst_b200 "
+                 "(the CPU oracle is timed by --impl reference)")
+    run_ours(args)
 
 
 if __name__ == "__main__":
