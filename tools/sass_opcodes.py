@@ -1,6 +1,8 @@
 """Per-kernel SASS opcode counts of the built library (cuobjdump -sass): the mnemonics that prove which kernels are on the
 Blackwell paths -- UTCHMMA (tcgen05.mma), LDTM / STTM (tcgen05.ld / st), UTMALDG (TMA load), UTCBAR (tcgen05.commit),
-HMMA (mma.sync), MUFU, LDL / STL (register spills), plus registers per thread.
+HMMA (mma.sync), MUFU, LDL / STL (register spills), plus registers per thread.  MULTIMEM counts multimem.ld_reduce / .red
+only: `multimem.st` is an ordinary system-scope STG in SASS (`STG.E.128.STRONG.SYS` in xrank_push_kernel; the switch
+replicates it by address), which tests/test_sass_cpu.py checks.
     python tools/sass_opcodes.py > profiles/r02_sass_opcodes.txt"""
 import collections, hashlib, os, re, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
