@@ -108,3 +108,102 @@ def test_sharded_source_tables_name_the_right_frames(world):
                 me = b * Fl + fl
                 assert [to_global(i) for i in loc3[me][:3]] == full3[b * F + rank * Fl + fl], (world, rank, b, fl)
                 assert loc3[me][3] == NI + 2 * B + me          # own text tokens: second K/V tensor, behind all first-tensor images
+
+
+@pytest.mark.parametrize("world,F", [(2, 32), (4, 32), (8, 32), (4, 16), (8, 48), (3, 18)])
+def test_sharded_smoother_legs_place_every_frame(monkeypatch, world, F):
+    """The smoother's VAE legs under frame sharding (pipeline._smoother_decode / _smoother_encode): 16-frame chunks decoded
+    round-robin, frames encoded evenly, results stored into every rank's full-clip buffer.  Emulated in one process -- the
+    ranks run one after another, `xrank_push` is a strided block copy into the ranks' arenas by address -- against the
+    unsharded legs, incl. the worlds where some ranks have no chunk to decode (4 and 8 ranks on two chunks) and a ragged
+    last chunk."""
+    from types import SimpleNamespace
+    from univst_b200 import ops
+    from univst_b200.pipeline import SpatioTemporalStableDiffusionPipeline as Pipe
+
+    C, h, w = 4, 2, 4
+    H, W = 8 * h, 8 * w                                            # 16 x 32 frames: a uint8 row is 96 bytes = 48 halves
+    g = torch.Generator().manual_seed(world * 100 + F)
+    x0 = torch.randn(1, C, F, h, w, generator=g).half()
+
+    class FakeVAE:
+        config = SimpleNamespace(latent_channels=C)
+        calls = []
+
+        def decode_latents_u8(self, lat, chunk=16):
+            # a chunk is ONE clip to the temporal decoder: make every frame depend on its chunk's content and its place in it
+            outs = []
+            for k in range(0, lat.shape[2], chunk):
+                part = lat[0, :, k:k + chunk].float()
+                FakeVAE.calls.append(part.shape[1])
+                for j in range(part.shape[1]):
+                    v = (part[:, j].sum() * 7 + part.sum() * 3 + j).item()
+                    base = torch.arange(H * W * 3, dtype=torch.float32).view(H, W, 3)
+                    outs.append(((base * 0.37 + v * 11.0) % 251).to(torch.uint8))
+            return torch.stack(outs)
+
+        def encode_frames_u8(self, frames, generator=None, noise=None):
+            assert noise is not None or generator is not None
+            F_ = frames.shape[0]
+            if noise is None:
+                noise = torch.randn((F_, C, h, w), generator=generator, dtype=torch.float16)   # as vae.encode_frames_u8 draws it
+            mean = frames.float().view(F_, h, 8, w, 8, 3).mean(dim=(2, 4, 5))             # per-frame function
+            lat = (mean[:, None] / 255.0 + 0.1 * noise.float()).half()                      # (F, C, h, w)
+            return lat.permute(1, 0, 2, 3).unsqueeze(0).contiguous()
+
+    arenas, cur = {}, {"rank": 0}
+
+    def fake_buffer(key, shape, dtype=torch.float16):
+        for r in range(world):
+            arenas.setdefault((key, r), torch.zeros(*shape, dtype=dtype))
+        return arenas[(key, cur["rank"])], [arenas[(key, r)].data_ptr() for r in range(world)]
+
+    def fake_push(xr, pushes):
+        for p in pushes:
+            src = p["src"]
+            assert p["nblk"] == 1 and src.dtype == torch.float16 and src.shape[0] == p["rows"]
+            for (key, r), a in arenas.items():
+                off = p["dst"][r] - a.data_ptr()
+                if not (0 <= off < a.numel() * 2):
+                    continue                                          # another buffer
+                assert off % 2 == 0 and a.shape[1] == p["ld_dst"]
+                flat = a.view(-1)
+                for row in range(p["rows"]):
+                    o = off // 2 + row * p["ld_dst"]
+                    flat[o:o + src.shape[1]] = src[row]
+
+    monkeypatch.setattr(ops, "xrank_push", fake_push)
+    vae = FakeVAE()
+    plain = SimpleNamespace(vae=vae, unet=SimpleNamespace(), device="cpu")
+    plain._smoother_xr = lambda F_, W_: Pipe._smoother_xr(plain, F_, W_)
+    want_frames = Pipe._smoother_decode(plain, x0)
+    FakeVAE.calls.clear()
+    want_lat = Pipe._smoother_encode(plain, want_frames, torch.Generator().manual_seed(5))
+
+    ranks = []
+    for r in range(world):
+        ns = SimpleNamespace(vae=vae, device="cpu",
+                             unet=SimpleNamespace(_shard=(object(), r, world),
+                                                  _xr=SimpleNamespace(rank=r, world=world, buffer=fake_buffer, multicast=lambda key: 0)))
+        ns._smoother_xr = (lambda ns_: lambda F_, W_: Pipe._smoother_xr(ns_, F_, W_))(ns)
+        ranks.append(ns)
+    if F % world:
+        assert ranks[0]._smoother_xr(F, W) is None                   # not evenly shardable: every rank takes the unsharded legs
+        return
+    outs = []
+    for r in range(world):
+        cur["rank"] = r
+        outs.append(Pipe._smoother_decode(ranks[r], x0))
+    nchunks = (F + 15) // 16
+    assert sorted(FakeVAE.calls) == sorted(min(16, F - 16 * c) for c in range(nchunks))   # every chunk decoded exactly once
+    for r in range(world):
+        assert torch.equal(outs[r], want_frames), (world, F, r)
+    lats = []
+    for r in range(world):
+        cur["rank"] = r
+        lats.append(Pipe._smoother_encode(ranks[r], outs[r], torch.Generator().manual_seed(5)))
+    for r in range(world):                       # clones taken rank by rank: complete once the last rank has pushed
+        cur["rank"] = r
+        full = arenas[(("vae_latents", C, F, h * w), r)].view(1, C, F, h, w)
+        assert torch.equal(full, want_lat), (world, F, r)
+    assert torch.equal(lats[-1], want_lat)
