@@ -1,0 +1,146 @@
+"""The inversion front doors -- ``content_inversion_reconstruction`` / ``style_inversion_reconstruction``
+(inversion_tools/ddim_inversion.py:16-66) -- against the REFERENCE's own two functions (build container only): frame
+folder / style image loading and normalisation, VAE posterior sample -> (1, C, F, h, w) x scaling factor, the inversion
+files, the 50-step reconstruction and the frames handed to the video writer.  Both sides run on the same accelerated UNet
+(kernels replaced by their torch definitions: no GPU here) and the same stand-in VAE; the reference side runs ITS loops,
+ITS pipeline ``reconstruction`` / ``decode_latents`` and ITS ``save_videos_grid``, ours runs the mirrors.  The reference
+runs twice, in fp32 and in fp16 (what its scripts use): ``ddim_latents_0`` (loading, resize, normalisation, posterior
+sample, scaling) must equal the fp16 run bit for bit, and every later file / written frame must be as close to the fp32
+run as the reference's own fp16 run is (this small random UNet amplifies the fp16 rounding of the stored latents to
+~2e-2 over the ten steps, on both sides alike).  In a subprocess so that the test-only shims never leak into the other
+tests' imports."""
+import os
+import subprocess
+import sys
+import textwrap
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+
+SCRIPT = textwrap.dedent("""
+    import os, sys, tempfile, types
+    import numpy as np, torch
+    ROOT, REF = {root!r}, {ref!r}
+    sys.path[:0] = [ROOT, REF, os.path.join(ROOT, "oracle", "_shim"), os.path.join(ROOT, "tests")]
+    torch.cuda.get_device_name = lambda *a, **k: "cpu-shim"
+    torch.Tensor.cuda = lambda self, *a, **k: self            # the reference hard-codes .cuda() (ddim_inversion.py:25,27,51)
+    import imageio
+    written = []
+    imageio.mimsave = lambda path, frames, fps=None: written.append((os.path.basename(path), [f.copy() for f in frames], fps))
+    from PIL import Image
+    from backbones.video_diffusion_sd.models.unet_3d_condition import UNetPseudo3DConditionModel as RefUNet
+    from backbones.video_diffusion_sd.pipelines.stable_diffusion import SpatioTemporalStableDiffusionPipeline as RefPipe
+    import inversion_tools.ddim_inversion as ref_di
+    from diffusers import DDIMScheduler
+    from diffusers.schedulers import SD15_SCHEDULER_CONFIG
+    from oracle import unet_oracle as uo
+    import univst_b200, _torch_ops
+    from univst_b200 import ddim_inversion as our_di
+    from univst_b200.pipeline import SpatioTemporalStableDiffusionPipeline as OurPipe
+    from univst_b200.scheduler import DDIMScheduler as OurScheduler
+
+    class MP:
+        def setattr(self, obj, name, val): setattr(obj, name, val)
+    _torch_ops.install(MP())
+
+    F, HW, steps = 16, 64, 10
+    cfg = uo.TINY_CONFIG
+    g = torch.Generator().manual_seed(4)
+    emb = torch.randn(1, 77, cfg["cross_attention_dim"], generator=g)
+    proj = torch.randn(4, 3, generator=g) * 0.6
+
+    class FakeVAE(torch.nn.Module):                 # third-party member: a fixed 8 x 8 pooling + projection stands in
+        config = types.SimpleNamespace(scaling_factor=0.18215, latent_channels=4)
+        dtype = torch.float16
+        def encode(self, x):
+            mean = torch.einsum("kc,nchw->nkhw", proj, torch.nn.functional.avg_pool2d(x.float(), 8))
+            return types.SimpleNamespace(latent_dist=types.SimpleNamespace(
+                sample=lambda generator=None: (mean + 0.05 * torch.randn(mean.shape)).to(x.dtype)))
+        def forward(self, sample, num_frames=1):
+            return self.decode(sample, num_frames=num_frames)
+        def decode(self, z, num_frames=1):
+            assert z.shape[0] % num_frames == 0
+            px = torch.einsum("kc,nkhw->nchw", proj, z.float()).clamp(-1, 1)
+            return types.SimpleNamespace(sample=torch.nn.functional.interpolate(px, scale_factor=8, mode="nearest").to(z.dtype))
+
+    m = RefUNet(block_out_channels=cfg["block_out_channels"], attention_head_dim=cfg["attention_head_dim"],
+                cross_attention_dim=cfg["cross_attention_dim"], sample_size=8).eval()
+    m.load_state_dict(uo.seeded_state_dict(cfg, seed=33))
+    ref_pipe = RefPipe.__new__(RefPipe)
+    ref_pipe.unet, ref_pipe.scheduler, ref_pipe.vae = m, DDIMScheduler(**SD15_SCHEDULER_CONFIG), FakeVAE()
+    ref_pipe.vae_scale_factor = 64       # reconstruction() is called without height / width (ddim_inversion.py:40): it expects
+                                         # 512 / vae_scale_factor latents; 64 makes that the 8 x 8 of this small clip
+    ref_pipe._encode_prompt = lambda *a, **k: emb.half()
+    univst_b200.accelerate(ref_pipe, device="cpu")
+    ref_di.init_prompt = lambda pipeline, prompt: torch.cat([emb, emb]).half()     # CLIP: third-party, fixed embeddings
+    our_pipe = OurPipe(ref_pipe.unet, OurScheduler.sd15(), vae=ref_pipe.vae)
+
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[0:72, 0:80]
+    rel = lambda a, b: ((a.float() - b.float()).norm() / b.float().norm()).item()
+    with tempfile.TemporaryDirectory() as tmp:
+        fdir = os.path.join(tmp, "frames"); os.makedirs(fdir)
+        for f in range(F):                                      # 80 x 72 files, loaded at 64 x 64: the resize is on the path
+            img = np.stack([127 + 100 * np.sin((xx + 3 * f) / 11.0), 127 + 100 * np.cos(yy / 9.0), 40 + 2 * xx], -1)
+            Image.fromarray((img + rng.integers(0, 9, img.shape)).clip(0, 255).astype(np.uint8)).save(os.path.join(fdir, "%05d.png" % f))
+        style = os.path.join(tmp, "style.png")
+        Image.fromarray(rng.integers(0, 255, (50, 90, 3)).astype(np.uint8)).save(style)
+        for kind in ("content", "style"):
+            dirs = {{}}
+            for side in ("ref32", "ref16", "our"):
+                inv, rec = os.path.join(tmp, kind, side, "inv"), os.path.join(tmp, kind, side, "rec")
+                os.makedirs(inv); os.makedirs(rec)
+                dirs[side] = inv
+                torch.manual_seed(11)                            # the posterior sample draws from the global generator
+                if side != "our":
+                    dt = torch.float32 if side == "ref32" else torch.float16
+                    ref_pipe._encode_prompt = lambda *a, **k: emb.to(dt)
+                    ref_di.init_prompt = lambda pipeline, prompt: torch.cat([emb, emb]).to(dt)   # CLIP: third-party, fixed embeddings
+                    sch = DDIMScheduler(**SD15_SCHEDULER_CONFIG); sch.set_timesteps(steps)
+                    if kind == "content":
+                        ref_di.content_inversion_reconstruction(ref_pipe, sch, fdir, inv, rec, F, HW, HW, steps, dt,
+                                                                ft_indices=[2], ft_timesteps=[301], ft_path=inv, is_opt=True)
+                    else:
+                        ref_di.style_inversion_reconstruction(ref_pipe, sch, style, inv, rec, F, HW, HW, steps, dt, is_opt=True)
+                else:
+                    sch = OurScheduler.sd15(); sch.set_timesteps(steps)
+                    if kind == "content":
+                        our_di.content_inversion_reconstruction(our_pipe, sch, fdir, inv, rec, F, HW, HW, steps, torch.float16,
+                                                                ft_indices=[2], ft_timesteps=[301], ft_path=inv, is_opt=True,
+                                                                prompt_embeds=emb)
+                    else:
+                        our_di.style_inversion_reconstruction(our_pipe, sch, style, inv, rec, F, HW, HW, steps, torch.float16,
+                                                              is_opt=True, prompt_embeds=emb)
+            names = sorted(os.listdir(dirs["ref32"]))
+            assert names == sorted(os.listdir(dirs["ref16"])) == sorted(os.listdir(dirs["our"])), (names, sorted(os.listdir(dirs["our"])))
+            assert ("inversion_feature_map_2_block_301_step.pt" in names) == (kind == "content") and len(names) >= steps + 1
+            worst_our = worst_ref16 = 0.0
+            for name in names:
+                t32, t16, our = (torch.load(os.path.join(dirs[k], name)) for k in ("ref32", "ref16", "our"))
+                assert our.shape == t16.shape == t32.shape and our.dtype == t16.dtype, (name, our.shape, t16.shape, our.dtype, t16.dtype)
+                if name == "ddim_latents_0.pt":
+                    assert torch.equal(our, t16)                  # loading, normalisation, posterior sample, scaling: exact
+                worst_our, worst_ref16 = max(worst_our, rel(our, t32)), max(worst_ref16, rel(t16, t32))
+            (n32, fr32, fps32), (n16, fr16, fps16), (n_our, fr_our, fps_our) = written[-3:]
+            assert n32 == n_our == kind + "_video.mp4" and fps32 == fps_our and len(fr32) == len(fr_our) == F
+            assert fr32[0].shape == fr_our[0].shape == (HW, HW, 3) and fr32[0].dtype == fr_our[0].dtype == np.uint8
+            d_our = np.abs(np.stack(fr32).astype(int) - np.stack(fr_our).astype(int)).mean()
+            d_ref16 = np.abs(np.stack(fr32).astype(int) - np.stack(fr16).astype(int)).mean()
+            print("FRONTDOOR", kind, "latents vs the fp32 reference: ours", worst_our, "reference in fp16", worst_ref16,
+                  "| frames mean abs: ours", d_our, "reference in fp16", d_ref16)
+            # fp16 storage between steps is the floor: ours must be at least as close to the fp32 reference as the
+            # reference's own fp16 run (the dtype its scripts use) is
+            assert worst_our <= max(5e-3, 1.5 * worst_ref16) and d_our <= max(1.0, 1.5 * d_ref16)
+    print("FRONTDOOR OK")
+""")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference checkout (build container only)")
+def test_inversion_front_doors_match_the_reference(tmp_path):
+    script = tmp_path / "frontdoor.py"
+    script.write_text(SCRIPT.format(root=ROOT, ref=REF))
+    out = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0 and "FRONTDOOR OK" in out.stdout, out.stdout[-1500:] + out.stderr[-3000:]
+    print("\n".join(l for l in out.stdout.splitlines() if l.startswith("FRONTDOOR")))

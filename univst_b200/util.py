@@ -22,3 +22,54 @@ def load_mask(mask_path="", n_frames=16):
     files = sorted(f"{mask_path}/%05d.png" % i for i in range(n_frames))
     imgs = np.stack([np.array(Image.open(f)) for f in files])
     return torch.from_numpy((imgs != 0).astype(np.uint8)).unsqueeze(0)
+
+
+def load_video_frames(frames_path, n_frames, image_size=(512, 512)):
+    """src/util.py:63-81: ``%05d.png`` frames -> (F, 3, H, W) float32 in [-1, 1] (``x / 127.5 - 1``).  ``image_size`` is
+    (width, height), PIL's order; each file is resized to it on loading (PIL's default filter, like the reference's
+    ``load_image``, :104) and converted to RGB."""
+    from PIL import Image, ImageOps
+    frames = []
+    for i in range(n_frames):
+        path = f"{frames_path}/%05d.png" % i
+        if not os.path.isfile(path):
+            raise ValueError(f"Incorrect path or URL. URLs must start with `http://` or `https://`, and {path} is not a valid path.")
+        img = ImageOps.exif_transpose(Image.open(path).resize(tuple(image_size))).convert("RGB")
+        if img.size != tuple(image_size):
+            raise ValueError("Frame size does not match config.image_size")
+        frames.append(torch.from_numpy(np.array(img) / 127.5 - 1.0).permute(2, 0, 1).float())
+    return torch.stack(frames)
+
+
+def _grid_frames(videos: torch.Tensor, rescale: bool, n_rows: int):
+    """(b, c, t, h, w) in [0, 1] -> t uint8 (H, W, c) images, the batch tiled ``n_rows`` per row with torchvision's
+    2-pixel padding (src/util.py:35-44; one clip -> the frame itself); ``(x * 255)`` truncated like the reference."""
+    import torchvision
+    outs = []
+    for x in videos.permute(2, 0, 1, 3, 4):
+        x = torchvision.utils.make_grid(x, nrow=n_rows).permute(1, 2, 0)
+        if rescale:
+            x = (x + 1.0) / 2.0
+        outs.append((x * 255).numpy().astype(np.uint8))
+    return outs
+
+
+def save_videos_grid(videos: torch.Tensor, path: str, rescale=False, n_rows=4, fps=8):
+    """src/util.py:34-47.  With ``imageio`` importable the file is written exactly like the reference writes it
+    (``imageio.mimsave(path, frames, fps=fps)``); without it (this image has no imageio / ffmpeg) the frames go to
+    ``<path without extension>/%05d.png`` -- the layout of the reference's ``save_folder`` (:22-31).  Returns the frames."""
+    frames = _grid_frames(videos, rescale, n_rows)
+    os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
+    try:
+        import imageio
+    except ImportError:
+        imageio = None
+    if imageio is not None:
+        imageio.mimsave(path, frames, fps=fps)
+    else:
+        from PIL import Image
+        folder = os.path.splitext(path)[0]
+        os.makedirs(folder, exist_ok=True)
+        for i, x in enumerate(frames):
+            Image.fromarray(x.squeeze(-1) if x.shape[-1] == 1 else x).save(os.path.join(folder, "%05d.png" % i))
+    return frames
