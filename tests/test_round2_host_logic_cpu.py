@@ -207,3 +207,50 @@ def test_sharded_smoother_legs_place_every_frame(monkeypatch, world, F):
         full = arenas[(("vae_latents", C, F, h * w), r)].view(1, C, F, h, w)
         assert torch.equal(full, want_lat), (world, F, r)
     assert torch.equal(lats[-1], want_lat)
+
+
+def test_video_io_helpers_match_the_reference(monkeypatch, tmp_path):
+    """util.load_video_frames / save_videos_grid against src/util.py:34-81 (build container only): the same tensors from a
+    folder of frames that need resizing, the same uint8 grid frames for a batch of two clips (rescale on / off); without
+    imageio the clip is written through OpenCV and reads back with the right frame count and size."""
+    import sys
+    import types
+    import numpy as np
+    from PIL import Image
+    from univst_b200 import util
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs the reference checkout (build container only)")
+    rec = []
+    monkeypatch.setitem(sys.modules, "imageio", types.SimpleNamespace(mimsave=lambda path, frames, fps=None: rec.append((path, frames, fps))))
+    monkeypatch.setitem(sys.modules, "decord", types.SimpleNamespace(bridge=types.SimpleNamespace(set_bridge=lambda n: None)))
+    monkeypatch.syspath_prepend("/root/reference")
+    for m in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
+        monkeypatch.delitem(sys.modules, m)
+    import src.util as ref
+    rng = np.random.default_rng(0)
+    for f in range(3):
+        Image.fromarray(rng.integers(0, 255, (40, 56, 3)).astype(np.uint8)).save(tmp_path / ("%05d.png" % f))
+    want = ref.load_video_frames(str(tmp_path), 3, image_size=(32, 24))
+    got = util.load_video_frames(str(tmp_path), 3, image_size=(32, 24))
+    assert got.shape == (3, 3, 24, 32) and got.dtype == want.dtype and torch.equal(got, want)
+    with pytest.raises(ValueError):
+        util.load_video_frames(str(tmp_path), 4, image_size=(32, 24))       # frame 00003.png does not exist
+    g = torch.Generator().manual_seed(1)
+    for rescale in (False, True):
+        vid = torch.rand(2, 3, 4, 24, 32, generator=g) * (2 if rescale else 1) - (1 if rescale else 0)
+        ref.save_videos_grid(vid.clone(), str(tmp_path / "a" / "ref.mp4"), rescale=rescale, n_rows=4, fps=6)
+        util.save_videos_grid(vid.clone(), str(tmp_path / "b" / "our.mp4"), rescale=rescale, n_rows=4, fps=6)
+        (_, fr_ref, fps_ref), (_, fr_our, fps_our) = rec[-2:]
+        assert fps_ref == fps_our == 6 and len(fr_ref) == len(fr_our) == 4
+        assert all(np.array_equal(a, b) for a, b in zip(fr_ref, fr_our)) and fr_our[0].shape == (28, 70, 3)
+    # no imageio (this image): the OpenCV writer
+    monkeypatch.setitem(sys.modules, "imageio", None)
+    cv2 = pytest.importorskip("cv2")
+    out = util.write_video(str(tmp_path / "c" / "clip.mp4"), [np.full((24, 32, 3), 40 * i, np.uint8) for i in range(5)], fps=8)
+    cap, n = cv2.VideoCapture(out), 0
+    while True:
+        ok, frame = cap.read()
+        if not ok:
+            break
+        n, shape = n + 1, frame.shape
+    assert n == 5 and shape == (24, 32, 3)

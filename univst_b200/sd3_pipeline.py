@@ -44,6 +44,12 @@ class CustomStableDiffusion3Pipeline:
     def device(self):
         return torch.device(getattr(self.host, "_execution_device", None) or getattr(self.host, "device", "cuda"))
 
+    def __getattr__(self, name):
+        # everything else the reference's subclass inherits (encode_prompt, vae, image_processor, ...) lives on the host
+        if name == "host":
+            raise AttributeError(name)
+        return getattr(self.host, name)
+
     # ------------------------------------------------------------------------------------------ helpers
     @staticmethod
     def generate_eta_values(timesteps, start_step, end_step, eta, eta_trend):

@@ -54,22 +54,40 @@ def _grid_frames(videos: torch.Tensor, rescale: bool, n_rows: int):
     return outs
 
 
-def save_videos_grid(videos: torch.Tensor, path: str, rescale=False, n_rows=4, fps=8):
-    """src/util.py:34-47.  With ``imageio`` importable the file is written exactly like the reference writes it
-    (``imageio.mimsave(path, frames, fps=fps)``); without it (this image has no imageio / ffmpeg) the frames go to
-    ``<path without extension>/%05d.png`` -- the layout of the reference's ``save_folder`` (:22-31).  Returns the frames."""
-    frames = _grid_frames(videos, rescale, n_rows)
+def write_video(path: str, frames, fps=8):
+    """``frames``: uint8 RGB (H, W, 3) arrays -> ``path``.  imageio when it is importable (what the reference's
+    ``save_videos_grid`` and diffusers' ``export_to_video`` use), else OpenCV's ``mp4v`` writer (opencv-python is one of the
+    reference's requirements), else PNG frames under ``<path without extension>/%05d.png`` (the layout of the reference's
+    ``save_folder``, src/util.py:22-31)."""
     os.makedirs(os.path.dirname(path) or ".", exist_ok=True)
     try:
         import imageio
-    except ImportError:
-        imageio = None
-    if imageio is not None:
         imageio.mimsave(path, frames, fps=fps)
-    else:
-        from PIL import Image
-        folder = os.path.splitext(path)[0]
-        os.makedirs(folder, exist_ok=True)
-        for i, x in enumerate(frames):
-            Image.fromarray(x.squeeze(-1) if x.shape[-1] == 1 else x).save(os.path.join(folder, "%05d.png" % i))
+        return path
+    except ImportError:
+        pass
+    try:
+        import cv2
+        h, w = frames[0].shape[:2]
+        wr = cv2.VideoWriter(path, cv2.VideoWriter_fourcc(*"mp4v"), float(fps), (w, h))
+        if wr.isOpened():
+            for x in frames:
+                wr.write(cv2.cvtColor(np.ascontiguousarray(x), cv2.COLOR_RGB2BGR) if x.ndim == 3 and x.shape[-1] == 3
+                         else cv2.cvtColor(np.ascontiguousarray(x.squeeze(-1) if x.ndim == 3 else x), cv2.COLOR_GRAY2BGR))
+            wr.release()
+            return path
+    except ImportError:
+        pass
+    from PIL import Image
+    folder = os.path.splitext(path)[0]
+    os.makedirs(folder, exist_ok=True)
+    for i, x in enumerate(frames):
+        Image.fromarray(x.squeeze(-1) if x.ndim == 3 and x.shape[-1] == 1 else x).save(os.path.join(folder, "%05d.png" % i))
+    return folder
+
+
+def save_videos_grid(videos: torch.Tensor, path: str, rescale=False, n_rows=4, fps=8):
+    """src/util.py:34-47: (b, c, t, h, w) in [0, 1] -> one video of the batch tiled per frame.  Returns the frames."""
+    frames = _grid_frames(videos, rescale, n_rows)
+    write_video(path, frames, fps=fps)
     return frames
