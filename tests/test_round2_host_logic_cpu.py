@@ -227,6 +227,8 @@ def test_video_io_helpers_match_the_reference(monkeypatch, tmp_path):
     for m in [k for k in sys.modules if k == "src" or k.startswith("src.")]:
         monkeypatch.delitem(sys.modules, m)
     import src.util as ref
+    for m in [k for k in sys.modules if k == "src" or k.startswith("src.")]:   # do not leave the reference's modules behind
+        monkeypatch.setitem(sys.modules, m, sys.modules.pop(m))
     rng = np.random.default_rng(0)
     for f in range(3):
         Image.fromarray(rng.integers(0, 255, (40, 56, 3)).astype(np.uint8)).save(tmp_path / ("%05d.png" % f))
@@ -254,3 +256,62 @@ def test_video_io_helpers_match_the_reference(monkeypatch, tmp_path):
             break
         n, shape = n + 1, frame.shape
     assert n == 5 and shape == (24, 32, 3)
+
+
+def test_inversion_helpers_keep_the_reference_call_forms(monkeypatch):
+    """ddim_inversion.next_step in the reference's own call form (model_output, timestep, sample, scheduler),
+    init_prompt and get_noise_pred_single (inversion_tools/ddim_inversion.py:171-212) against the reference's functions
+    (build container only), on the diffusers-shim scheduler and stand-in tokenizer / text encoder / UNet."""
+    import sys
+    import types
+    if not os.path.isdir("/root/reference"):
+        pytest.skip("needs the reference checkout (build container only)")
+    import _torch_ops
+    _torch_ops.install(monkeypatch)
+    monkeypatch.setitem(sys.modules, "imageio", types.SimpleNamespace())
+    monkeypatch.setitem(sys.modules, "decord", types.SimpleNamespace(bridge=types.SimpleNamespace(set_bridge=lambda n: None)))
+    monkeypatch.syspath_prepend("/root/reference")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    monkeypatch.syspath_prepend(os.path.join(root, "oracle", "_shim"))
+    shimmed = lambda: [k for k in sys.modules if k.split(".")[0] in ("src", "inversion_tools", "diffusers")]
+    for m in shimmed():
+        monkeypatch.delitem(sys.modules, m)
+    import inversion_tools.ddim_inversion as ref
+    from diffusers import DDIMScheduler as ShimScheduler
+    from diffusers.schedulers import SD15_SCHEDULER_CONFIG
+    for m in shimmed():                       # the test-only shim must not outlive this test: monkeypatch removes at teardown
+        mod = sys.modules.pop(m)              # what it is asked to set now
+        monkeypatch.setitem(sys.modules, m, mod)
+    from univst_b200 import ddim_inversion as ours
+    from univst_b200.scheduler import DDIMScheduler
+
+    g = torch.Generator().manual_seed(0)
+    x, eps = torch.randn(1, 4, 3, 8, 8, generator=g), torch.randn(1, 4, 3, 8, 8, generator=g)
+    rs, os_ = ShimScheduler(**SD15_SCHEDULER_CONFIG), DDIMScheduler.sd15()
+    for n in (10, 50):
+        rs.set_timesteps(n)
+        os_.set_timesteps(n)
+        for t in (1, 481, 981) if n == 50 else (1, 501, 901):
+            want = ref.next_step(eps, t, x, rs)
+            got = ours.next_step(eps.half(), t, x.half(), os_)
+            assert got.dtype == torch.float16 and (got.float() - want).norm() / want.norm() < 1e-3, (n, t)
+
+    class Tok:
+        model_max_length = 7
+        def __call__(self, texts, padding=None, max_length=None, truncation=None, return_tensors=None):
+            ids = torch.tensor([[len(t) + i for i in range(max_length)] for t in texts])
+            return types.SimpleNamespace(input_ids=ids)
+    enc = lambda ids: (torch.sin(ids.float())[..., None] * torch.arange(1, 5.0),)
+    pipe = types.SimpleNamespace(tokenizer=Tok(), text_encoder=enc, device="cpu")
+    assert torch.equal(ours.init_prompt(pipe, "a duck"), ref.init_prompt(pipe, "a duck"))
+    assert ours.init_prompt(pipe, "a duck").shape == (2, 7, 4)
+
+    seen = {}
+    def unet(lat, t, encoder_hidden_states=None, ft_indices=None, ft_timesteps=None, ft_path=None):
+        seen.update(t=t, ft=(ft_indices, ft_timesteps, ft_path))
+        return {"sample": lat * 2 + encoder_hidden_states.sum()}
+    pipe.unet = unet
+    a = ours.get_noise_pred_single(pipe, x, 481, torch.ones(1, 2, 2), ft_indices=[2], ft_timesteps=[301], ft_path="p")
+    first = dict(seen)
+    b = ref.get_noise_pred_single(pipe, x, 481, torch.ones(1, 2, 2), ft_indices=[2], ft_timesteps=[301], ft_path="p")
+    assert torch.equal(a, b) and first == seen == {"t": 481, "ft": ([2], [301], "p")}

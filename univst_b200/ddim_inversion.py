@@ -24,9 +24,35 @@ def _save(latent, inversion_path, k):
 
 
 def next_step(pipeline, t, latent, ddim_scheduler, branch=0):
-    """ddim_inversion.py:190-204 applied to the eps the UNet just produced (kept channels-last on the device)."""
+    """ddim_inversion.py:190-204.  Two call forms: ``next_step(pipeline, t, latent, scheduler)`` -- what the loops below
+    use: the eps the UNet just produced is read where the forward left it (channels-last, on the device) -- and the
+    reference's own ``next_step(model_output, timestep, sample, scheduler)`` on a noise tensor shaped like the sample:
+    ``x_next = sqrt(a') (x - sqrt(1 - a) eps) / sqrt(a) + sqrt(1 - a') eps`` as one fused multiply-add pass."""
+    if torch.is_tensor(pipeline):
+        eps, sample = pipeline, latent
+        a_cur, a_next = ddim_scheduler.inversion_alphas(t)
+        wx = (a_next / a_cur) ** 0.5
+        we = (1.0 - a_next) ** 0.5 - wx * (1.0 - a_cur) ** 0.5
+        return ops.axpby(sample.to(torch.float16).contiguous(), eps.to(sample.device, torch.float16).contiguous(), wx, we)
     a_cur, a_next = ddim_scheduler.inversion_alphas(t)
     return ops.ddim_step(latent, pipeline.unet.last_eps_rows, branch, a_cur, a_next)
+
+
+@torch.no_grad()
+def init_prompt(pipeline, prompt):
+    """ddim_inversion.py:171-187: ``cat([embedding of "", embedding of prompt])`` from the pipeline's own (third-party)
+    tokenizer / text encoder; (2, 77, D)."""
+    tok, enc = pipeline.tokenizer, pipeline.text_encoder
+    un = tok([""], padding="max_length", max_length=tok.model_max_length, return_tensors="pt")
+    tx = tok([prompt], padding="max_length", max_length=tok.model_max_length, truncation=True, return_tensors="pt")
+    dev = pipeline.device
+    return torch.cat([enc(un.input_ids.to(dev))[0], enc(tx.input_ids.to(dev))[0]])
+
+
+def get_noise_pred_single(pipeline, latents, t, context, ft_indices=None, ft_timesteps=None, ft_path=None):
+    """ddim_inversion.py:207-212."""
+    return pipeline.unet(latents, t, encoder_hidden_states=context, ft_indices=ft_indices, ft_timesteps=ft_timesteps,
+                         ft_path=ft_path)["sample"]
 
 
 @torch.no_grad()
