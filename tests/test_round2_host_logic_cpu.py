@@ -245,6 +245,21 @@ def test_video_io_helpers_match_the_reference(monkeypatch, tmp_path):
         (_, fr_ref, fps_ref), (_, fr_our, fps_our) = rec[-2:]
         assert fps_ref == fps_our == 6 and len(fr_ref) == len(fr_our) == 4
         assert all(np.array_equal(a, b) for a, b in zip(fr_ref, fr_our)) and fr_our[0].shape == (28, 70, 3)
+    # save_folder: the reference writes through imageio.imsave, ours through PIL -- same files, same pixels
+    saved = {}
+    sys.modules["imageio"].imsave = lambda p, x: saved.__setitem__(os.path.basename(p), x.copy())
+    vid = torch.rand(1, 3, 3, 24, 32, generator=g)
+    (tmp_path / "f").mkdir()
+    ref.save_folder(vid.clone(), str(tmp_path / "f"))
+    util.save_folder(vid.clone(), str(tmp_path / "f"))
+    assert sorted(saved) == sorted(os.listdir(tmp_path / "f")) == ["00000.png", "00001.png", "00002.png"]
+    for name, x in saved.items():
+        assert np.array_equal(np.array(Image.open(tmp_path / "f" / name)), x)
+    import random
+    util.seed_everything(7)
+    a = (random.random(), np.random.rand(), torch.rand(1).item())
+    ref.seed_everything(7)
+    assert a == (random.random(), np.random.rand(), torch.rand(1).item())
     # no imageio (this image): the OpenCV writer
     monkeypatch.setitem(sys.modules, "imageio", None)
     cv2 = pytest.importorskip("cv2")

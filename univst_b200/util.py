@@ -86,6 +86,24 @@ def write_video(path: str, frames, fps=8):
     return folder
 
 
+def save_folder(videos: torch.Tensor, path: str, rescale=False, n_rows=4, fps=8):
+    """src/util.py:22-31: (b, c, t, h, w) in [0, 1] -> ``path/%05d.png``, one grid image per frame (what the run scripts
+    write the stylized clip with, run_video_style_transfer_sd.py:69).  Returns the frames."""
+    from PIL import Image
+    frames = _grid_frames(videos, rescale, n_rows)
+    for i, x in enumerate(frames):
+        Image.fromarray(x.squeeze(-1) if x.shape[-1] == 1 else x).save(os.path.join(path, "%05d.png" % i))
+    return frames
+
+
+def seed_everything(seed=42):
+    """src/util.py:16-19."""
+    import random
+    random.seed(seed)
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+
+
 def save_videos_grid(videos: torch.Tensor, path: str, rescale=False, n_rows=4, fps=8):
     """src/util.py:34-47: (b, c, t, h, w) in [0, 1] -> one video of the batch tiled per frame.  Returns the frames."""
     frames = _grid_frames(videos, rescale, n_rows)
